@@ -1,0 +1,224 @@
+/*
+ * onb.h -- C ABI of the B200-native Onitama self-play hot path (libonb.so).
+ *
+ * The reference (cyoq/onitama-alphazero) has no FFI of its own: its seam is Rust-level. Every entry
+ * point below names the reference interface it replaces (file:line relative to the reference root).
+ * The Rust-side `extern "C"` block a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every call returns int32_t: 0 = ONB_OK, < 0 = ONB_E*; onb_last_error(ctx) gives a message.
+ *     No C++ exception crosses this boundary. There is NO CPU fallback: without a CUDA device
+ *     onb_create fails with ONB_E_CUDA.
+ *   - a context owns one CUDA device, one stream and all device memory; it is single-threaded
+ *     (one host thread per context, mirroring the reference's one-thread-per-replica self-play,
+ *     alphazero-training/src/train.rs:218-245).
+ *   - board words at this boundary use the reference bit layout: square n (row-major, (0,0) = a5)
+ *     is bit (31 - n) of a uint32_t, low 7 bits zero (onitama-game/src/common/mod.rs:2-4).
+ *   - pointers named *_host are host memory; the call copies. Device buffers are exposed through
+ *     onb_buffer() as borrowed pointers valid until onb_destroy().
+ */
+#ifndef ONB_H_
+#define ONB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONB_VERSION 100
+
+#if defined(__GNUC__)
+#define ONB_API __attribute__((visibility("default")))
+#else
+#define ONB_API
+#endif
+
+/* ---- error codes ---- */
+#define ONB_OK 0
+#define ONB_E_INVALID (-1)   /* bad argument */
+#define ONB_E_CUDA (-2)      /* CUDA runtime error (message has the CUDA error string) */
+#define ONB_E_NOMEM (-3)     /* device allocation failed */
+#define ONB_E_STATE (-4)     /* call out of sequence (e.g. mcts_select before mcts_begin) */
+#define ONB_E_OVERFLOW (-5)  /* a node pool or output buffer was too small */
+
+/* ---- colours, pieces, results (player_color.rs:6-9, piece.rs:6-9, move_result.rs:4-9) ---- */
+#define ONB_RED 0
+#define ONB_BLUE 1
+#define ONB_PAWN 0
+#define ONB_KING 1
+#define ONB_RESULT_IN_PROGRESS 0
+#define ONB_RESULT_RED_WIN 1
+#define ONB_RESULT_BLUE_WIN 2
+
+/* ---- action code (replaces DoneMove{mov: Move{from,to,piece}, used_card_idx}, done_move.rs:4-7) ----
+ *   bits 0-4 to, 5-9 from, 10-11 used_card_idx (deck slot 0..3), bit 12 piece (1 = King),
+ *   bit 13 pass (State::pass(card_idx), state.rs:139-142; only `used_card_idx` is meaningful). */
+typedef uint16_t onb_action;
+#define ONB_ACTION(card_idx, from, to, piece) \
+    ((onb_action)((to) | ((from) << 5) | ((card_idx) << 10) | ((piece) << 12)))
+#define ONB_ACTION_PASS(card_idx) ((onb_action)(((card_idx) << 10) | (1u << 13)))
+#define ONB_ACTION_NONE ((onb_action)0xFFFFu)
+
+/* ---- one game at the boundary (replaces State + GameState::curr_player_color,
+ *      state.rs:51-56, game_state.rs:5-13). 24 bytes. ---- */
+typedef struct onb_state {
+    uint32_t pawns[2]; /* [Red, Blue], reference bit layout */
+    uint32_t kings[2];
+    uint8_t cards[5];  /* card ids 0..15 in deck slots RED1, RED2, BLUE1, BLUE2, NEUTRAL (deck.rs:14-18) */
+    uint8_t side;      /* side to move */
+    uint8_t result;    /* ONB_RESULT_* of the last transition */
+    uint8_t flags;     /* bit0: a pass (zero-legal-move turn) happened since the last reset */
+} onb_state;
+
+/* ---- random policies for onb_env_step_random ---- */
+#define ONB_POLICY_UNIFORM 0 /* uniform over all legal moves, pass if none (ai/mcts/mcts_arena.rs:190-241) */
+#define ONB_POLICY_AGENT 1   /* the `Random` agent incl. its quirks (ai/random.rs:12-43) */
+
+/* ---- outputs of a step ---- */
+#define ONB_OUT_MASKS 1u   /* policy-shaped legal mask of the NEW state, 2 x uint32 per game */
+#define ONB_OUT_PLANES 2u  /* [n,21,5,5] f32 planes of the NEW state (alphazero-training/src/common.rs:26-80) */
+#define ONB_OUT_ACTIONS 4u /* the action taken (random policies) */
+
+/* ---- evaluators that live on the device ---- */
+#define ONB_EVAL_UNIFORM 0 /* policy = f32(1/50) everywhere, value = 0 (BASELINE config 4) */
+#define ONB_EVAL_HASH 1    /* deterministic pseudo-random policy/value from a hash of the planes (parity tests) */
+
+/* ---- device buffers (onb_buffer) ---- */
+#define ONB_BUF_STATES 0      /* packed internal states, 16 B per game (layout in DESIGN.md) */
+#define ONB_BUF_MASKS 1       /* uint32[n][2] */
+#define ONB_BUF_PLANES 2      /* float[n][21][5][5] */
+#define ONB_BUF_ACTIONS 3     /* uint16[n] */
+#define ONB_BUF_LEAF_PLANES 4 /* float[n][21][5][5]   written by onb_mcts_select */
+#define ONB_BUF_POLICY 5      /* float[n][2][25]      read by onb_mcts_expand_backup */
+#define ONB_BUF_VALUE 6       /* float[n]             read by onb_mcts_expand_backup */
+#define ONB_BUF_PI 7          /* float[n][2][25]      written by onb_mcts_finish */
+#define ONB_BUF_BEST 8        /* uint16[n]            written by onb_mcts_finish */
+#define ONB_BUF_STATS 9       /* uint64[ONB_STAT_COUNT] */
+
+#define ONB_STAT_STEPS 0     /* transitions applied */
+#define ONB_STAT_RED_WINS 1
+#define ONB_STAT_BLUE_WINS 2
+#define ONB_STAT_PASSES 3
+#define ONB_STAT_RESETS 4
+#define ONB_STAT_COUNT 8
+
+typedef struct onb_ctx onb_ctx;
+
+typedef struct onb_config {
+    int32_t device;         /* CUDA device ordinal */
+    uint32_t flags;         /* reserved, 0 */
+    int64_t n_games;        /* games (= search trees) owned by this context */
+    uint64_t game_id_base;  /* global id of local game 0; the RNG is keyed by the GLOBAL id, so results
+                               do not depend on how games are sharded over GPUs */
+    uint64_t seed;
+    void* stream;           /* cudaStream_t to launch on; NULL = the context creates its own */
+    uint32_t mcts_max_sims; /* 0 = no search-tree pools */
+    uint32_t mcts_node_cap; /* nodes per tree; 0 = hard bound 1 + 40 * mcts_max_sims */
+    uint32_t alloc_planes;  /* 0/1: allocate the [n,21,5,5] plane buffer */
+    uint32_t reserved;
+} onb_config;
+
+/* ------------------------------------------------------------------------------------------------
+ * lifecycle
+ * ------------------------------------------------------------------------------------------------ */
+ONB_API int32_t onb_version(void);
+ONB_API int32_t onb_create(const onb_config* cfg, onb_ctx** out);
+ONB_API int32_t onb_destroy(onb_ctx* ctx);
+ONB_API const char* onb_last_error(const onb_ctx* ctx);
+ONB_API int32_t onb_sync(onb_ctx* ctx);
+ONB_API int32_t onb_buffer(onb_ctx* ctx, int32_t which, void** dev_ptr, int64_t* bytes);
+
+/* host-side helpers (pure C, no device): */
+/* State::with_deck (state.rs:67-73) + first mover = neutral card's stamp (game_state.rs:34-41) */
+ONB_API int32_t onb_start_states(const uint8_t* decks5, int64_t n, onb_state* out);
+/* the shared counter RNG (project-defined; the reference uses rand::thread_rng) */
+ONB_API uint32_t onb_rand_u32(uint64_t seed, uint64_t game, uint32_t step, uint32_t draw);
+/* random deal = first 5 of a shuffle of the 16 cards (replaces Deck::default, deck.rs:139-151) */
+ONB_API int32_t onb_deal(uint64_t seed, uint64_t game, uint32_t epoch, uint8_t out5[5]);
+/* ATTACK_MAPS[2][16][25] in the reference layout (card.rs:476) as held in __constant__ memory */
+ONB_API int32_t onb_attack_maps(uint32_t out800[800]);
+
+/* ------------------------------------------------------------------------------------------------
+ * env: lockstep batched game dynamics
+ * ------------------------------------------------------------------------------------------------ */
+/* (re)start every game. n_decks = 0: deal from the RNG with `epoch`; 1: the same deck for all games;
+ * n_games: one deck per game. Replaces State::with_deck / GameState::with_deck (train.rs:44-49). */
+ONB_API int32_t onb_env_reset(onb_ctx* ctx, const uint8_t* decks5_host, int64_t n_decks, uint32_t epoch);
+ONB_API int32_t onb_env_set_states(onb_ctx* ctx, const onb_state* states_host, int64_t first, int64_t n);
+ONB_API int32_t onb_env_get_states(onb_ctx* ctx, onb_state* states_host, int64_t first, int64_t n);
+/* State::generate_all_legal_moves (state.rs:301-378) for the side to move of every game.
+ * moves_host: [n][40] action codes in reference order, counts_host: [n]; either may be NULL. */
+ONB_API int32_t onb_env_legal_moves(onb_ctx* ctx, onb_action* moves_host, uint8_t* counts_host);
+/* policy-shaped mask (word s = union of `to` of own hand slot s); masks_host [n][2] may be NULL
+ * (result stays in ONB_BUF_MASKS). */
+ONB_API int32_t onb_env_legal_masks(onb_ctx* ctx, uint32_t* masks_host);
+/* create_tensor_from_state (common.rs:26-80) for every game into ONB_BUF_PLANES; planes_host may be NULL */
+ONB_API int32_t onb_env_encode(onb_ctx* ctx, float* planes_host);
+/* State::make_move / State::pass + side switch (state.rs:139-202, game_state.rs:65-80) with the given
+ * actions. actions_host NULL = use ONB_BUF_ACTIONS as already filled on the device. Finished games are
+ * left untouched. out_flags selects which observation buffers of the new state are written. */
+ONB_API int32_t onb_env_step(onb_ctx* ctx, const onb_action* actions_host, uint32_t out_flags);
+/* one lockstep step of every unfinished game with a random policy drawn from the counter RNG keyed by
+ * (seed, global game id, step). auto_reset: a game that ends is replaced by a fresh deal (epoch step+1). */
+ONB_API int32_t onb_env_step_random(onb_ctx* ctx, uint32_t step, int32_t policy, int32_t auto_reset, uint32_t out_flags);
+/* `n_steps` steps back to back starting at `step0` (no host round trip in between) */
+ONB_API int32_t onb_env_run_random(onb_ctx* ctx, uint32_t step0, uint32_t n_steps, int32_t policy, int32_t auto_reset,
+                           uint32_t out_flags);
+/* BASELINE config 1: every game is played from its current state until it ends or max_plies more plies were
+ * made, entirely in registers (no per-step launch). Equivalent to onb_env_step_random(step0), (step0+1), ...
+ * plies_host [n] and trace_host [n] (a hash chain over the action codes, defined in DESIGN.md) may be NULL.
+ * Replaces the random-vs-random game loop of evaluator.rs:355-399 / ai/mcts/mcts_arena.rs:190-241. */
+ONB_API int32_t onb_env_playout(onb_ctx* ctx, uint32_t step0, uint32_t max_plies, int32_t policy, uint32_t* plies_host,
+                        uint64_t* trace_host);
+ONB_API int32_t onb_env_stats(onb_ctx* ctx, uint64_t stats_host[ONB_STAT_COUNT], int32_t clear);
+
+/* ------------------------------------------------------------------------------------------------
+ * perft-style enumeration (BASELINE config 2)
+ * nodes/wins/zero are host arrays [n][depth]: positions reached by exactly d+1 plies (a line stops at
+ * a win), how many of them are wins, and non-terminal positions at depth d that have no legal move.
+ * ------------------------------------------------------------------------------------------------ */
+ONB_API int32_t onb_perft(onb_ctx* ctx, const onb_state* roots_host, int64_t n, int32_t depth, uint64_t* nodes_host,
+                  uint64_t* wins_host, uint64_t* zero_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * batched AlphaZero PUCT search, one tree per game, rooted at the current env states
+ * (replaces MctsArena::{new,search,playout,select,expand,evaluate,back_propagate},
+ *  alphazero-training/src/alphazero_mcts/mcts_arena.rs:48-323). Eval mode only.
+ * Split phase so the network stays outside:
+ *   onb_mcts_begin; repeat sims times { onb_mcts_select; <evaluator writes POLICY/VALUE from LEAF_PLANES>;
+ *   onb_mcts_expand_backup }; onb_mcts_finish.
+ * or fused with a device evaluator: onb_mcts_begin; onb_mcts_run; onb_mcts_finish.
+ * ------------------------------------------------------------------------------------------------ */
+ONB_API int32_t onb_mcts_begin(onb_ctx* ctx, double c_puct, uint32_t sims);
+ONB_API int32_t onb_mcts_select(onb_ctx* ctx);
+ONB_API int32_t onb_mcts_expand_backup(onb_ctx* ctx);
+ONB_API int32_t onb_mcts_eval(onb_ctx* ctx, int32_t evaluator); /* fills POLICY/VALUE from LEAF_PLANES on the device */
+ONB_API int32_t onb_mcts_run(onb_ctx* ctx, int32_t evaluator, uint32_t sims);
+/* calculate_priors + best child (mcts_arena.rs:83-124). Any host pointer may be NULL.
+ * best [n], pi [n][2][25], root_visits [n], root_q [n], child_visits [n][40] (zero padded, child order) */
+ONB_API int32_t onb_mcts_finish(onb_ctx* ctx, onb_action* best_host, float* pi_host, uint32_t* root_visits_host,
+                        double* root_q_host, uint32_t* child_visits_host);
+/* apply the best action of every tree to its game (self_play: state.make_move(&mov.mov, ...), train.rs:70-72) */
+ONB_API int32_t onb_mcts_play_best(onb_ctx* ctx, uint32_t out_flags);
+
+typedef struct onb_tree_dump { /* host arrays of length cap */
+    uint32_t* visits;
+    double* reward;
+    double* prior;
+    onb_action* action;
+    int32_t* parent;
+    uint32_t* first_child;
+    uint32_t* n_child;
+    uint8_t* flags; /* bit0 expanded, bit1 terminal, bit2 pass child */
+} onb_tree_dump;
+/* copies tree `tree` (arena order == reference arena order); *n_nodes receives the node count */
+ONB_API int32_t onb_mcts_dump_tree(onb_ctx* ctx, int64_t tree, int64_t cap, onb_tree_dump* out, int64_t* n_nodes);
+/* per-tree summary: node counts [n], flags [n] (bit0: a zero-legal-move node was expanded -> parity with the
+ * reference is undefined for that tree, bit1: node pool overflow) */
+ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONB_H_ */

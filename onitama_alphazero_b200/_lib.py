@@ -1,0 +1,102 @@
+"""ctypes binding of libonb.so (include/onb.h). The CUDA library is the product: if it is missing this
+module raises -- there is no CPU fallback and nothing here imports the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libonb.so")
+
+ONB_OK = 0
+E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_OVERFLOW = -1, -2, -3, -4, -5
+POLICY_UNIFORM, POLICY_AGENT = 0, 1
+OUT_MASKS, OUT_PLANES, OUT_ACTIONS = 1, 2, 4
+EVAL_UNIFORM, EVAL_HASH = 0, 1
+(BUF_STATES, BUF_MASKS, BUF_PLANES, BUF_ACTIONS, BUF_LEAF_PLANES, BUF_POLICY, BUF_VALUE, BUF_PI, BUF_BEST,
+ BUF_STATS) = range(10)
+STAT_STEPS, STAT_RED_WINS, STAT_BLUE_WINS, STAT_PASSES, STAT_RESETS, STAT_COUNT = 0, 1, 2, 3, 4, 8
+ACTION_NONE = 0xFFFF
+
+# onb_state (24 bytes)
+STATE_DTYPE = np.dtype([("pawns", "<u4", (2,)), ("kings", "<u4", (2,)), ("cards", "u1", (5,)), ("side", "u1"),
+                        ("result", "u1"), ("flags", "u1")])
+assert STATE_DTYPE.itemsize == 24
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("n_games", C.c_int64), ("game_id_base", C.c_uint64),
+                ("seed", C.c_uint64), ("stream", C.c_void_p), ("mcts_max_sims", C.c_uint32), ("mcts_node_cap", C.c_uint32),
+                ("alloc_planes", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class TreeDump(C.Structure):
+    _fields_ = [("visits", C.c_void_p), ("reward", C.c_void_p), ("prior", C.c_void_p), ("action", C.c_void_p),
+                ("parent", C.c_void_p), ("first_child", C.c_void_p), ("n_child", C.c_void_p), ("flags", C.c_void_p)]
+
+
+# every symbol include/onb.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "onb_version": (C.c_int32, []),
+    "onb_create": (C.c_int32, [C.POINTER(Config), C.POINTER(_P)]),
+    "onb_destroy": (C.c_int32, [_P]),
+    "onb_last_error": (C.c_char_p, [_P]),
+    "onb_sync": (C.c_int32, [_P]),
+    "onb_buffer": (C.c_int32, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "onb_start_states": (C.c_int32, [_P, C.c_int64, _P]),
+    "onb_rand_u32": (C.c_uint32, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]),
+    "onb_deal": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32, _P]),
+    "onb_attack_maps": (C.c_int32, [_P]),
+    "onb_env_reset": (C.c_int32, [_P, _P, C.c_int64, C.c_uint32]),
+    "onb_env_set_states": (C.c_int32, [_P, _P, C.c_int64, C.c_int64]),
+    "onb_env_get_states": (C.c_int32, [_P, _P, C.c_int64, C.c_int64]),
+    "onb_env_legal_moves": (C.c_int32, [_P, _P, _P]),
+    "onb_env_legal_masks": (C.c_int32, [_P, _P]),
+    "onb_env_encode": (C.c_int32, [_P, _P]),
+    "onb_env_step": (C.c_int32, [_P, _P, C.c_uint32]),
+    "onb_env_step_random": (C.c_int32, [_P, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]),
+    "onb_env_run_random": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]),
+    "onb_env_playout": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P, _P]),
+    "onb_env_stats": (C.c_int32, [_P, _P, C.c_int32]),
+    "onb_perft": (C.c_int32, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
+    "onb_mcts_begin": (C.c_int32, [_P, C.c_double, C.c_uint32]),
+    "onb_mcts_select": (C.c_int32, [_P]),
+    "onb_mcts_expand_backup": (C.c_int32, [_P]),
+    "onb_mcts_eval": (C.c_int32, [_P, C.c_int32]),
+    "onb_mcts_run": (C.c_int32, [_P, C.c_int32, C.c_uint32]),
+    "onb_mcts_finish": (C.c_int32, [_P, _P, _P, _P, _P, _P]),
+    "onb_mcts_play_best": (C.c_int32, [_P, C.c_uint32]),
+    "onb_mcts_dump_tree": (C.c_int32, [_P, C.c_int64, C.c_int64, C.POINTER(TreeDump), C.POINTER(C.c_int64)]),
+    "onb_mcts_tree_info": (C.c_int32, [_P, _P, _P]),
+}
+
+_lib = None
+
+
+class OnbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libonb error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    """Load libonb.so; raises if the CUDA extension has not been built (python __graft_entry__.py / build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libonb.so is missing at %s: build the CUDA extension first "
+                              "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)

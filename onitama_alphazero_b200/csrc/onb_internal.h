@@ -1,0 +1,86 @@
+// onb_internal.h -- context layout and launcher prototypes shared by the translation units of libonb.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/onb.h"
+
+namespace onb {
+
+// One search-tree node: exactly one 32-byte sector. A node's children occupy CONTIGUOUS slots (the
+// reference pushes them back to back into its arena, mcts_arena.rs:231-260), so a warp reads a whole
+// children block with one coalesced request and every lane gets (N, W, P, header) of its child at once.
+struct __align__(32) Node {
+    double w;              // MctsNode::reward (sum of backed-up values)      mcts_arena.rs:366-367
+    double p;              // MctsNode::probability                           mcts_arena.rs:372
+    uint32_t n;            // MctsNode::visits                                mcts_arena.rs:364-365
+    uint32_t first_child;  // index of child 0 in this tree's pool
+    uint32_t parent;       // 0xFFFFFFFF for the root
+    uint16_t action;       // move that leads here (onb_action)
+    uint8_t n_child;
+    uint8_t flags;         // bit0 expanded, bit1 terminal, bit2 pass pseudo-child
+};
+static_assert(sizeof(Node) == 32, "node must be one sector");
+constexpr uint8_t kNodeExpanded = 1, kNodeTerminal = 2, kNodePass = 4;
+constexpr uint8_t kTreePassSeen = 1, kTreeOverflow = 2;
+constexpr int kMaxDepth = 32;  // path entries kept in registers (lane l <-> level l); deeper paths spill to the parent chain
+
+struct Ctx {
+    onb_config cfg;
+    cudaStream_t stream;
+    bool own_stream;
+    int64_t n;
+    // env
+    uint4* d_states;
+    uint32_t* d_masks;
+    float* d_planes;
+    uint16_t* d_actions;
+    unsigned long long* d_stats;
+    // scratch for host<->device transfers of boundary structs
+    onb_state* d_io_states;
+    uint16_t* d_moves;  // [n][40]
+    uint8_t* d_counts;  // [n]
+    // mcts
+    Node* d_nodes;          // [n][node_cap]
+    uint32_t node_cap;
+    uint32_t* d_tree_size;  // [n]
+    uint8_t* d_tree_flags;  // [n]
+    uint4* d_roots;         // [n] root states captured by mcts_begin
+    uint32_t* d_leaf_node;  // [n] leaf reached by the last select
+    uint4* d_leaf_state;    // [n]
+    float* d_leaf_planes;   // [n][525]
+    float* d_policy;        // [n][50]
+    float* d_value;         // [n]
+    float* d_pi;            // [n][50]
+    uint16_t* d_best;       // [n]
+    uint32_t* d_root_visits;
+    double* d_root_q;
+    uint32_t* d_child_visits;  // [n][40]
+    double c_puct;
+    uint32_t sims_target, sims_done;
+    int mcts_phase;  // 0 idle, 1 begun/after expand, 2 after select
+    char err[512];
+};
+
+// env (onb_env.cu)
+cudaError_t launch_env_reset(Ctx* c, const uint8_t* d_decks5, int64_t n_decks, uint32_t epoch);
+cudaError_t launch_states_export(Ctx* c, onb_state* d_out, int64_t first, int64_t n);
+cudaError_t launch_states_import(Ctx* c, const onb_state* d_in, int64_t first, int64_t n);
+cudaError_t launch_legal_moves(Ctx* c);
+cudaError_t launch_observe(Ctx* c, uint32_t out_flags);
+cudaError_t launch_env_step(Ctx* c, int mode, uint32_t step, int auto_reset, uint32_t out_flags);
+// perft (onb_perft.cu)
+int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uint64_t* nodes, uint64_t* wins, uint64_t* zero);
+// mcts (onb_mcts.cu)
+cudaError_t launch_mcts_begin(Ctx* c);
+cudaError_t launch_mcts_select(Ctx* c);
+cudaError_t launch_mcts_expand_backup(Ctx* c);
+cudaError_t launch_mcts_eval(Ctx* c, int evaluator);
+cudaError_t launch_mcts_run(Ctx* c, int evaluator, uint32_t sims);
+cudaError_t launch_mcts_finish(Ctx* c);
+cudaError_t launch_mcts_play_best(Ctx* c, uint32_t out_flags);
+
+constexpr int kModeActions = 2;  // env step modes: 0 = ONB_POLICY_UNIFORM, 1 = ONB_POLICY_AGENT, 2 = explicit actions
+
+}  // namespace onb

@@ -1,0 +1,268 @@
+// onb_perft.cu -- perft-style legal-move enumeration (BASELINE config 2).
+//
+// Two phases: (1) lockstep breadth-first frontier expansion in HBM (32 B per node: read parent, write child)
+// until there are enough independent subtrees to fill the machine; (2) every frontier node is finished by a
+// depth-first search held entirely in registers (compile-time depth, so all per-level state is scalar) with
+// bulk counting at the last ply. Phase 2 moves ~0 bytes per node and is issue-bound; see DESIGN.md.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "onb_internal.h"
+#include "onb_rules.cuh"
+
+namespace onb {
+
+struct __align__(16) FrontierItem {
+    uint4 state;
+};
+
+// ---- phase 1: one BFS level -------------------------------------------------------------------------------
+// COUNT_ONLY pass sizes the next frontier exactly; the fill pass writes it (order is irrelevant for perft).
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(128) k_perft_expand(const uint4* __restrict__ in_states, const uint32_t* __restrict__ in_root, int64_t n_in,
+                                                      uint4* __restrict__ out_states, uint32_t* __restrict__ out_root,
+                                                      unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ nodes,
+                                                      unsigned long long* __restrict__ wins, unsigned long long* __restrict__ zero, int depth_total,
+                                                      int level) {
+    __shared__ uint32_t s_att[800];
+    load_attack_table_to_smem(s_att);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n_in;
+    Game g{};
+    uint32_t root = 0, total = 0, nwin = 0;
+    uint32_t own = 0, own_p = 0, win_t = 0, temple = 0, side = 0;
+    if (live) {
+        g = unpack(in_states[i]);
+        root = in_root[i];
+        side = g.side;
+        own_p = side ? g.pawn_b : g.pawn_r;
+        const uint32_t own_k = side ? g.king_b : g.king_r;
+        const uint32_t en_p = side ? g.pawn_r : g.pawn_b, en_k = side ? g.king_r : g.king_b;
+        own = own_p | own_k;
+        win_t = en_k & ~en_p;
+        temple = 1u << (side ? kRedTemple : kBlueTemple);
+        for (uint32_t s = 0; s < 2; ++s) {
+            const uint32_t* Ts = s_att + (side * 16u + card_at(g.cards, side * 2u + s)) * 25u;
+            uint32_t rem = own;
+            while (rem) {
+                const int f = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t a = Ts[f] & ~own;
+                const uint32_t wm = a & (win_t | (((own_p >> f) & 1u) ? 0u : temple));
+                total += __popc(a);
+                nwin += __popc(wm);
+            }
+        }
+    }
+    const uint32_t n_children = total - nwin;  // wins end the line
+    // warp-aggregated reservation of output slots
+    uint32_t incl = n_children;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    if (!live) return;
+    if (COUNT_ONLY) return;
+    atomicAdd(&nodes[(int64_t)root * depth_total + level], (unsigned long long)total);
+    if (nwin) atomicAdd(&wins[(int64_t)root * depth_total + level], (unsigned long long)nwin);
+    if (total == 0) atomicAdd(&zero[(int64_t)root * depth_total + level], 1ull);
+    unsigned long long pos = base + (incl - n_children);
+    for (uint32_t s = 0; s < 2; ++s) {
+        const uint32_t idx = side * 2u + s;
+        const uint32_t* Ts = s_att + (side * 16u + card_at(g.cards, idx)) * 25u;
+        uint32_t rem = own;
+        while (rem) {
+            const int f = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const uint32_t king = ((own_p >> f) & 1u) ^ 1u;
+            uint32_t a = Ts[f] & ~own;
+            a &= ~(win_t | (king ? temple : 0u));
+            while (a) {
+                const uint32_t to = __ffs(a) - 1;
+                a &= a - 1;
+                Game ch = g;
+                apply_move(ch, make_action(idx, (uint32_t)f, to, king));
+                out_states[pos] = pack(ch);
+                out_root[pos] = root;
+                ++pos;
+            }
+        }
+    }
+}
+
+// ---- phase 2: register DFS ---------------------------------------------------------------------------------
+template <int REM>
+struct Dfs {
+    __device__ __forceinline__ static void run(const uint32_t* T, const Game& g, unsigned long long* nodes, unsigned long long* wins, uint32_t* zero) {
+        const uint32_t side = g.side;
+        const uint32_t own_p = side ? g.pawn_b : g.pawn_r, own_k = side ? g.king_b : g.king_r;
+        const uint32_t en_p = side ? g.pawn_r : g.pawn_b, en_k = side ? g.king_r : g.king_b;
+        const uint32_t own = own_p | own_k;
+        const uint32_t win_t = en_k & ~en_p;
+        const uint32_t temple = 1u << (side ? kRedTemple : kBlueTemple);
+        uint32_t total = 0, nwin = 0;
+#pragma unroll 1
+        for (uint32_t s = 0; s < 2; ++s) {
+            const uint32_t idx = side * 2u + s;
+            const uint32_t* Ts = T + (side * 16u + card_at(g.cards, idx)) * 25u;
+            uint32_t rem = own;
+#pragma unroll 1
+            while (rem) {
+                const int f = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t king = ((own_p >> f) & 1u) ^ 1u;
+                const uint32_t a = Ts[f] & ~own;
+                const uint32_t wm = a & (win_t | (king ? temple : 0u));
+                total += __popc(a);
+                nwin += __popc(wm);
+                if constexpr (REM > 1) {
+                    uint32_t b = a & ~wm;
+#pragma unroll 1
+                    while (b) {
+                        const uint32_t to = __ffs(b) - 1;
+                        b &= b - 1;
+                        Game ch = g;
+                        apply_move(ch, make_action(idx, (uint32_t)f, to, king));
+                        Dfs<REM - 1>::run(T, ch, nodes, wins, zero);
+                    }
+                }
+            }
+        }
+        nodes[REM - 1] += total;
+        wins[REM - 1] += nwin;
+        zero[REM - 1] += total == 0 ? 1u : 0u;
+    }
+};
+
+template <int REM>
+__global__ void __launch_bounds__(128) k_perft_dfs(const uint4* __restrict__ states, const uint32_t* __restrict__ roots, int64_t n_items,
+                                                   unsigned long long* __restrict__ nodes, unsigned long long* __restrict__ wins,
+                                                   unsigned long long* __restrict__ zero, int depth_total) {
+    __shared__ uint32_t s_att[800];
+    load_attack_table_to_smem(s_att);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const Game g = unpack(states[i]);
+    unsigned long long ln[REM], lw[REM];
+    uint32_t lz[REM];
+#pragma unroll
+    for (int k = 0; k < REM; ++k) { ln[k] = 0; lw[k] = 0; lz[k] = 0; }
+    Dfs<REM>::run(s_att, g, ln, lw, lz);
+    const int64_t row = (int64_t)roots[i] * depth_total;
+#pragma unroll
+    for (int k = 0; k < REM; ++k) {
+        const int d = depth_total - 1 - k;  // REM-1 == k levels from the bottom
+        if (ln[k]) atomicAdd(&nodes[row + d], ln[k]);
+        if (lw[k]) atomicAdd(&wins[row + d], lw[k]);
+        if (lz[k]) atomicAdd(&zero[row + d], (unsigned long long)lz[k]);
+    }
+}
+
+template <int REM>
+static cudaError_t launch_dfs(Ctx* c, const uint4* st, const uint32_t* rt, int64_t n_items, unsigned long long* nodes, unsigned long long* wins,
+                              unsigned long long* zero, int depth) {
+    k_perft_dfs<REM><<<(unsigned)((n_items + 127) / 128), 128, 0, c->stream>>>(st, rt, n_items, nodes, wins, zero, depth);
+    return cudaGetLastError();
+}
+
+static int32_t perft_fail(Ctx* c, cudaError_t e, const char* what) {
+    snprintf(c->err, sizeof(c->err), "onb_perft: %s: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? ONB_E_NOMEM : ONB_E_CUDA;
+}
+
+constexpr int kMaxDfs = 6;
+
+int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uint64_t* nodes_host, uint64_t* wins_host, uint64_t* zero_host) {
+    cudaError_t e;
+    const size_t cnt = (size_t)n * depth;
+    unsigned long long *d_nodes = nullptr, *d_wins = nullptr, *d_zero = nullptr, *d_cursor = nullptr;
+    onb_state* d_in = nullptr;
+    uint4* cur_s = nullptr; uint32_t* cur_r = nullptr;
+    uint4* nxt_s = nullptr; uint32_t* nxt_r = nullptr;
+    int32_t rc = ONB_OK;
+#define PF(call, what) do { e = (call); if (e != cudaSuccess) { rc = perft_fail(c, e, what); goto done; } } while (0)
+    PF(cudaMalloc(&d_nodes, cnt * 8), "alloc counters");
+    PF(cudaMalloc(&d_wins, cnt * 8), "alloc counters");
+    PF(cudaMalloc(&d_zero, cnt * 8), "alloc counters");
+    PF(cudaMalloc(&d_cursor, 8), "alloc cursor");
+    PF(cudaMemsetAsync(d_nodes, 0, cnt * 8, c->stream), "memset");
+    PF(cudaMemsetAsync(d_wins, 0, cnt * 8, c->stream), "memset");
+    PF(cudaMemsetAsync(d_zero, 0, cnt * 8, c->stream), "memset");
+    {
+        // roots -> internal states. Roots that are already decided (State::current_state is a win) expand to nothing.
+        std::vector<uint4> hs;
+        std::vector<uint32_t> hr;
+        hs.reserve((size_t)n); hr.reserve((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            const onb_state& s = roots_host[i];
+            Game g;
+            auto rev = [](uint32_t v) { uint32_t r = 0; for (int b = 0; b < 25; ++b) if (v & (1u << (31 - b))) r |= 1u << b; return r; };
+            g.pawn_r = rev(s.pawns[0]); g.pawn_b = rev(s.pawns[1]); g.king_r = rev(s.kings[0]); g.king_b = rev(s.kings[1]);
+            g.cards = (s.cards[0] & 15u) | ((s.cards[1] & 15u) << 4) | ((s.cards[2] & 15u) << 8) | ((s.cards[3] & 15u) << 12) | ((s.cards[4] & 15u) << 16);
+            g.side = s.side & 1u; g.result = 0; g.passed = 0;
+            if (current_state(g) != 0) continue;
+            hs.push_back(pack(g)); hr.push_back((uint32_t)i);
+        }
+        int64_t n_cur = (int64_t)hs.size();
+        if (n_cur > 0) {
+            PF(cudaMalloc(&cur_s, (size_t)n_cur * 16), "alloc frontier");
+            PF(cudaMalloc(&cur_r, (size_t)n_cur * 4), "alloc frontier");
+            PF(cudaMemcpyAsync(cur_s, hs.data(), (size_t)n_cur * 16, cudaMemcpyHostToDevice, c->stream), "copy roots");
+            PF(cudaMemcpyAsync(cur_r, hr.data(), (size_t)n_cur * 4, cudaMemcpyHostToDevice, c->stream), "copy roots");
+            PF(cudaStreamSynchronize(c->stream), "sync");
+            int level = 0;
+            // breadth-first while the frontier is too small to fill 148 SMs or the remaining depth exceeds the DFS template range
+            while (n_cur > 0 && ((depth - level) > kMaxDfs || ((depth - level) > 1 && n_cur < (int64_t)(1 << 21)))) {
+                unsigned long long total = 0;
+                PF(cudaMemsetAsync(d_cursor, 0, 8, c->stream), "memset");
+                k_perft_expand<true><<<(unsigned)((n_cur + 127) / 128), 128, 0, c->stream>>>(cur_s, cur_r, n_cur, nullptr, nullptr, d_cursor, d_nodes, d_wins,
+                                                                                            d_zero, depth, level);
+                PF(cudaGetLastError(), "expand(count)");
+                PF(cudaMemcpyAsync(&total, d_cursor, 8, cudaMemcpyDeviceToHost, c->stream), "copy cursor");
+                PF(cudaStreamSynchronize(c->stream), "sync");
+                if (total > (1ull << 31)) { snprintf(c->err, sizeof(c->err), "onb_perft: frontier of %llu nodes is too large", total); rc = ONB_E_OVERFLOW; goto done; }
+                PF(cudaMalloc(&nxt_s, (size_t)(total ? total : 1) * 16), "alloc frontier");
+                PF(cudaMalloc(&nxt_r, (size_t)(total ? total : 1) * 4), "alloc frontier");
+                PF(cudaMemsetAsync(d_cursor, 0, 8, c->stream), "memset");
+                k_perft_expand<false><<<(unsigned)((n_cur + 127) / 128), 128, 0, c->stream>>>(cur_s, cur_r, n_cur, nxt_s, nxt_r, d_cursor, d_nodes, d_wins,
+                                                                                             d_zero, depth, level);
+                PF(cudaGetLastError(), "expand(fill)");
+                PF(cudaStreamSynchronize(c->stream), "sync");
+                cudaFree(cur_s); cudaFree(cur_r);
+                cur_s = nxt_s; cur_r = nxt_r; nxt_s = nullptr; nxt_r = nullptr;
+                n_cur = (int64_t)total;
+                ++level;
+            }
+            const int rem = depth - level;
+            if (n_cur > 0 && rem > 0) {
+                switch (rem) {
+                    case 1: PF(launch_dfs<1>(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, depth), "dfs"); break;
+                    case 2: PF(launch_dfs<2>(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, depth), "dfs"); break;
+                    case 3: PF(launch_dfs<3>(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, depth), "dfs"); break;
+                    case 4: PF(launch_dfs<4>(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, depth), "dfs"); break;
+                    case 5: PF(launch_dfs<5>(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, depth), "dfs"); break;
+                    default: PF(launch_dfs<6>(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, depth), "dfs"); break;
+                }
+            }
+        }
+    }
+    PF(cudaMemcpyAsync(nodes_host, d_nodes, cnt * 8, cudaMemcpyDeviceToHost, c->stream), "copy out");
+    if (wins_host) PF(cudaMemcpyAsync(wins_host, d_wins, cnt * 8, cudaMemcpyDeviceToHost, c->stream), "copy out");
+    if (zero_host) PF(cudaMemcpyAsync(zero_host, d_zero, cnt * 8, cudaMemcpyDeviceToHost, c->stream), "copy out");
+    PF(cudaStreamSynchronize(c->stream), "sync");
+#undef PF
+done:
+    cudaFree(d_nodes); cudaFree(d_wins); cudaFree(d_zero); cudaFree(d_cursor); cudaFree(d_in);
+    cudaFree(cur_s); cudaFree(cur_r); cudaFree(nxt_s); cudaFree(nxt_r);
+    return rc;
+}
+
+}  // namespace onb

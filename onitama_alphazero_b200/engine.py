@@ -1,0 +1,224 @@
+"""Thin Python host layer over the C ABI (include/onb.h). One `Context` per GPU; every method is a direct call
+into libonb.so. numpy is used for host staging only; device buffers can be wrapped zero-copy as torch tensors
+(`Context.tensor`) so a torch module can read the leaf planes and write policy/value in place."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import STATE_DTYPE, OnbError
+
+
+class _DevBuf:
+    """Minimal __cuda_array_interface__ carrier so torch.as_tensor() wraps a borrowed device pointer without a copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class Context:
+    """Owns one onb_ctx (all device memory of `n_games` games / search trees on one GPU and one stream)."""
+
+    def __init__(self, n_games, seed=0, device=0, game_id_base=0, stream=0, mcts_max_sims=0, mcts_node_cap=0, planes=True):
+        self._lib = L.load()
+        cfg = L.Config(device=device, flags=0, n_games=n_games, game_id_base=game_id_base, seed=seed, stream=stream or None,
+                       mcts_max_sims=mcts_max_sims, mcts_node_cap=mcts_node_cap, alloc_planes=1 if planes else 0, reserved=0)
+        h = C.c_void_p()
+        rc = self._lib.onb_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise OnbError(rc, self._lib.onb_last_error(None).decode())
+        self._h = h
+        self.n = int(n_games)
+        self.device = device
+        self.seed = seed
+        self.game_id_base = game_id_base
+        self.mcts_max_sims = mcts_max_sims
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise OnbError(rc, self._lib.onb_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.onb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        self._ck(self._lib.onb_sync(self._h))
+
+    def buffer(self, which):
+        p, b = C.c_void_p(), C.c_int64()
+        self._ck(self._lib.onb_buffer(self._h, which, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def tensor(self, which):
+        """Zero-copy torch view of a device buffer (the network reads LEAF_PLANES and writes POLICY / VALUE in place)."""
+        import torch
+        p, _ = self.buffer(which)
+        n = self.n
+        spec = {L.BUF_MASKS: ((n, 2), "<u4", torch.int32), L.BUF_PLANES: ((n, 21, 5, 5), "<f4", None),
+                L.BUF_ACTIONS: ((n,), "<i2", None), L.BUF_LEAF_PLANES: ((n, 21, 5, 5), "<f4", None),
+                L.BUF_POLICY: ((n, 2, 25), "<f4", None), L.BUF_VALUE: ((n,), "<f4", None), L.BUF_PI: ((n, 2, 25), "<f4", None),
+                L.BUF_BEST: ((n,), "<i2", None), L.BUF_STATES: ((n, 4), "<i4", None), L.BUF_STATS: ((L.STAT_COUNT,), "<i8", None)}[which]
+        shape, typestr, _ = spec
+        if typestr == "<u4":
+            typestr = "<i4"
+        return torch.as_tensor(_DevBuf(p, shape, typestr), device="cuda:%d" % self.device)
+
+    # ------------------------------------------------------------------ env
+    def reset(self, decks=None, epoch=0):
+        """decks: None (deal from the RNG), one deck of 5 card ids, or [n,5]."""
+        if decks is None:
+            self._ck(self._lib.onb_env_reset(self._h, None, 0, epoch))
+            return
+        d = np.ascontiguousarray(decks, dtype=np.uint8).reshape(-1, 5)
+        self._ck(self._lib.onb_env_reset(self._h, L.ptr(d), len(d), epoch))
+
+    def set_states(self, states, first=0):
+        s = np.ascontiguousarray(states, dtype=STATE_DTYPE)
+        self._ck(self._lib.onb_env_set_states(self._h, L.ptr(s), first, len(s)))
+
+    def get_states(self, first=0, n=None):
+        n = self.n - first if n is None else n
+        out = np.zeros(n, dtype=STATE_DTYPE)
+        self._ck(self._lib.onb_env_get_states(self._h, L.ptr(out), first, n))
+        return out
+
+    def legal_moves(self):
+        moves = np.zeros((self.n, 40), dtype=np.uint16)
+        counts = np.zeros(self.n, dtype=np.uint8)
+        self._ck(self._lib.onb_env_legal_moves(self._h, L.ptr(moves), L.ptr(counts)))
+        return moves, counts
+
+    def legal_masks(self, to_host=True):
+        out = np.zeros((self.n, 2), dtype=np.uint32) if to_host else None
+        self._ck(self._lib.onb_env_legal_masks(self._h, L.ptr(out)))
+        return out
+
+    def encode(self, to_host=True):
+        out = np.zeros((self.n, 21, 5, 5), dtype=np.float32) if to_host else None
+        self._ck(self._lib.onb_env_encode(self._h, L.ptr(out)))
+        return out
+
+    def step(self, actions=None, out_flags=0):
+        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.uint16)
+        self._ck(self._lib.onb_env_step(self._h, L.ptr(a), out_flags))
+
+    def step_random(self, step, policy=L.POLICY_UNIFORM, auto_reset=False, out_flags=0):
+        self._ck(self._lib.onb_env_step_random(self._h, step, policy, int(auto_reset), out_flags))
+
+    def run_random(self, step0, n_steps, policy=L.POLICY_UNIFORM, auto_reset=False, out_flags=0):
+        self._ck(self._lib.onb_env_run_random(self._h, step0, n_steps, policy, int(auto_reset), out_flags))
+
+    def playout(self, step0=0, max_plies=1 << 30, policy=L.POLICY_UNIFORM, want_plies=True, want_trace=True):
+        plies = np.zeros(self.n, dtype=np.uint32) if want_plies else None
+        trace = np.zeros(self.n, dtype=np.uint64) if want_trace else None
+        self._ck(self._lib.onb_env_playout(self._h, step0, min(max_plies, 0xFFFFFFFF), policy, L.ptr(plies), L.ptr(trace)))
+        return plies, trace
+
+    def stats(self, clear=False):
+        out = np.zeros(L.STAT_COUNT, dtype=np.uint64)
+        self._ck(self._lib.onb_env_stats(self._h, L.ptr(out), int(clear)))
+        return out
+
+    def read(self, which, dtype, shape):
+        """Copy a device buffer to the host (test helper; uses torch for the D2H copy)."""
+        return self.tensor(which).cpu().numpy().view(dtype).reshape(shape)
+
+    # ------------------------------------------------------------------ perft
+    def perft(self, roots, depth):
+        r = np.ascontiguousarray(roots, dtype=STATE_DTYPE)
+        nodes = np.zeros((len(r), depth), dtype=np.uint64)
+        wins = np.zeros((len(r), depth), dtype=np.uint64)
+        zero = np.zeros((len(r), depth), dtype=np.uint64)
+        self._ck(self._lib.onb_perft(self._h, L.ptr(r), len(r), depth, L.ptr(nodes), L.ptr(wins), L.ptr(zero)))
+        return nodes, wins, zero
+
+    # ------------------------------------------------------------------ mcts
+    def mcts_begin(self, c_puct, sims):
+        self._ck(self._lib.onb_mcts_begin(self._h, float(c_puct), sims))
+
+    def mcts_select(self):
+        self._ck(self._lib.onb_mcts_select(self._h))
+
+    def mcts_eval(self, evaluator):
+        self._ck(self._lib.onb_mcts_eval(self._h, evaluator))
+
+    def mcts_expand_backup(self):
+        self._ck(self._lib.onb_mcts_expand_backup(self._h))
+
+    def mcts_run(self, evaluator, sims):
+        self._ck(self._lib.onb_mcts_run(self._h, evaluator, sims))
+
+    def mcts_finish(self, to_host=True):
+        if not to_host:
+            self._ck(self._lib.onb_mcts_finish(self._h, None, None, None, None, None))
+            return None
+        n = self.n
+        out = dict(best=np.zeros(n, np.uint16), pi=np.zeros((n, 2, 25), np.float32), root_visits=np.zeros(n, np.uint32),
+                   root_q=np.zeros(n, np.float64), child_visits=np.zeros((n, 40), np.uint32))
+        self._ck(self._lib.onb_mcts_finish(self._h, L.ptr(out["best"]), L.ptr(out["pi"]), L.ptr(out["root_visits"]), L.ptr(out["root_q"]),
+                                           L.ptr(out["child_visits"])))
+        return out
+
+    def mcts_play_best(self, out_flags=0):
+        self._ck(self._lib.onb_mcts_play_best(self._h, out_flags))
+
+    def mcts_tree_info(self):
+        nn = np.zeros(self.n, np.uint32)
+        fl = np.zeros(self.n, np.uint8)
+        self._ck(self._lib.onb_mcts_tree_info(self._h, L.ptr(nn), L.ptr(fl)))
+        return nn, fl
+
+    def mcts_dump_tree(self, tree, cap=None):
+        cap = cap or (1 + 40 * self.mcts_max_sims + 2)
+        arrs = dict(visits=np.zeros(cap, np.uint32), reward=np.zeros(cap, np.float64), prior=np.zeros(cap, np.float64),
+                    action=np.zeros(cap, np.uint16), parent=np.zeros(cap, np.int32), first_child=np.zeros(cap, np.uint32),
+                    n_child=np.zeros(cap, np.uint32), flags=np.zeros(cap, np.uint8))
+        td = L.TreeDump(*[L.ptr(arrs[k]) for k, _ in L.TreeDump._fields_])
+        nn = C.c_int64()
+        self._ck(self._lib.onb_mcts_dump_tree(self._h, tree, cap, C.byref(td), C.byref(nn)))
+        return {k: v[:nn.value].copy() for k, v in arrs.items()}
+
+    def search(self, c_puct, sims, evaluator=L.EVAL_UNIFORM, fused=True, net=None):
+        """MctsArena::search for every game at once. net: callable(leaf_planes tensor [n,21,5,5]) -> (policy [n,2,25], value [n])
+        running on this context's stream; it reads/writes the device buffers zero-copy."""
+        self.mcts_begin(c_puct, sims)
+        if net is None and fused:
+            self.mcts_run(evaluator, sims)
+        else:
+            if net is not None:
+                planes, pol, val = self.tensor(L.BUF_LEAF_PLANES), self.tensor(L.BUF_POLICY), self.tensor(L.BUF_VALUE)
+            for _ in range(sims):
+                self.mcts_select()
+                if net is None:
+                    self.mcts_eval(evaluator)
+                else:
+                    p, v = net(planes)
+                    pol.copy_(p.reshape(pol.shape))
+                    val.copy_(v.reshape(val.shape))
+                self.mcts_expand_backup()
+        return self.mcts_finish()
+
+
+def start_states(decks):
+    d = np.ascontiguousarray(decks, dtype=np.uint8).reshape(-1, 5)
+    out = np.zeros(len(d), dtype=STATE_DTYPE)
+    rc = L.load().onb_start_states(L.ptr(d), len(d), L.ptr(out))
+    if rc != 0:
+        raise OnbError(rc, "onb_start_states: invalid deck")
+    return out

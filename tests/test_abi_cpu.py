@@ -1,0 +1,92 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/onb.h declares, its host-side helpers
+agree with the oracle and the golden vectors, and it FAILS LOUDLY without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from onitama_alphazero_b200 import _lib
+    return _lib.load()
+
+
+def test_header_symbols_all_exported(lib):
+    from onitama_alphazero_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "onb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(onb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libonb.so does not export %s" % name
+    # the Python binding table covers exactly the header
+    assert declared == set(_lib.SYMBOLS)
+    assert lib.onb_version() == 100
+
+
+def test_attack_table_matches_reference_hex(lib):
+    out = np.zeros(800, dtype=np.uint32)
+    assert lib.onb_attack_maps(out.ctypes.data) == 0
+    assert out.tolist() == G["attack_maps"]          # parsed from the reference's card.rs by gen_golden.py
+    assert out.tolist() == O.attack_maps().tolist()  # oracle's shift/mask restatement (card.rs:520-604)
+
+
+def test_rng_and_deal_match_oracle_and_golden(lib):
+    for r in G["rng"]:
+        assert lib.onb_rand_u32(r["seed"], r["game"], r["step"], r["draw"]) == r["value"]
+    rs = np.random.RandomState(0)
+    for _ in range(200):
+        seed, game = int(rs.randint(0, 2 ** 62)), int(rs.randint(0, 2 ** 40))
+        step, draw = int(rs.randint(0, 2 ** 31)), int(rs.randint(0, 16))
+        assert lib.onb_rand_u32(seed, game, step, draw) == O.lib().orc_rand_u32(seed, game, step, draw)
+        a = np.zeros(5, np.uint8)
+        b = np.zeros(5, np.uint8)
+        assert lib.onb_deal(seed, game, step, a.ctypes.data) == 0
+        O.lib().orc_deal(seed, game, step, b.ctypes.data)
+        assert a.tolist() == b.tolist() and len(set(a.tolist())) == 5
+    for d in G["deals"]:
+        a = np.zeros(5, np.uint8)
+        lib.onb_deal(d["seed"], d["game"], d["epoch"], a.ctypes.data)
+        assert a.tolist() == d["deck"]
+
+
+def test_start_states_match_oracle(lib):
+    from onitama_alphazero_b200 import start_states
+    decks = np.array([[1, 2, 0, 3, 11], [4, 3, 1, 0, 2], [0, 1, 2, 3, 4], [15, 14, 13, 12, 10]], dtype=np.uint8)
+    s = start_states(decks)
+    for i, d in enumerate(decks):
+        assert s[i:i + 1].tobytes() == O.new_games(1, deck=d).tobytes()
+    bad = np.array([[1, 2, 0, 3, 16]], dtype=np.uint8)
+    out = np.zeros(1, dtype=s.dtype)
+    assert lib.onb_start_states(bad.ctypes.data, 1, out.ctypes.data) == -1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from onitama_alphazero_b200 import Context, OnbError
+    with pytest.raises(OnbError) as e:
+        Context(16)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    assert lib.onb_sync(None) == -1 and lib.onb_env_step(None, None, 0) == -1
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "onitama_alphazero_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle_lib" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/onb_oracle.cpp", ""), f

@@ -1,0 +1,457 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+Bit-exact for states, actions, masks, planes, perft counts, visit counts; |dQ| <= 1e-5 is the stated tolerance for
+Q values (they are in fact compared bit-exactly where noted)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+Q_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def onb():
+    import __graft_entry__ as ge
+    ge.build()
+    import onitama_alphazero_b200 as m
+    return m
+
+
+# ------------------------------------------------------------------ boundary round trip
+def test_state_roundtrip_and_reset(onb):
+    n = 1000  # ragged: not a multiple of the 128-game tile
+    with onb.Context(n, seed=5, game_id_base=77) as ctx:
+        ctx.reset()
+        assert ctx.get_states().tobytes() == O.new_games(n, seed=5, game0=77).tobytes()
+        ctx.reset(decks=[1, 2, 0, 3, 11])
+        assert ctx.get_states().tobytes() == O.new_games(n, deck=[1, 2, 0, 3, 11]).tobytes()
+        rs = np.random.RandomState(1)
+        s = O.new_games(n, seed=9)
+        for i in range(n):  # arbitrary (even illegal) boards survive the packed 16-byte representation
+            s["pawns"][i] = rs.randint(0, 2 ** 25, 2).astype(np.uint32) << 7
+            s["kings"][i] = (1 << (31 - rs.randint(0, 25, 2))).astype(np.uint32)
+            s["side"][i] = rs.randint(0, 2)
+            s["result"][i] = rs.randint(0, 3)
+            s["flags"][i] = rs.randint(0, 2)
+        ctx.set_states(s)
+        assert ctx.get_states().tobytes() == s.tobytes()
+        ctx.set_states(s[10:20], first=500)
+        assert ctx.get_states(500, 10).tobytes() == s[10:20].tobytes()
+
+
+def test_error_paths(onb):
+    with onb.Context(8, planes=False) as ctx:
+        with pytest.raises(onb.OnbError) as e:
+            ctx.encode()
+        assert e.value.code == -4
+        with pytest.raises(onb.OnbError) as e:
+            ctx.mcts_begin(1.0, 10)
+        assert e.value.code == -4
+        with pytest.raises(onb.OnbError) as e:
+            ctx.reset(decks=[[1, 2, 3, 4, 5]] * 3)
+        assert e.value.code == -1
+        with pytest.raises(onb.OnbError):
+            ctx.reset(decks=[1, 2, 3, 4, 99])
+    with onb.Context(8, mcts_max_sims=4) as ctx:
+        ctx.reset()
+        with pytest.raises(onb.OnbError) as e:
+            ctx.mcts_select()
+        assert e.value.code == -4
+        with pytest.raises(onb.OnbError):
+            ctx.mcts_begin(1.0, 5)
+
+
+# ------------------------------------------------------------------ reference known-answer tests through the GPU
+def test_reference_make_move_cases_on_gpu(onb):
+    cases = G["reference_tests"]["make_move"]
+    states = O.new_games(len(cases), deck=cases[0]["deck"])
+    actions = np.zeros(len(cases), dtype=np.uint16)
+    for i, c in enumerate(cases):
+        for k, v in c["set"].items():
+            states[k[:-1]][i][int(k[-1])] = v
+        states["side"][i] = c["color"]
+        frm, to, piece = c["mov"]
+        actions[i] = to | (frm << 5) | (c["card_idx"] << 10) | (piece << 12)
+    with onb.Context(len(cases)) as ctx:
+        ctx.set_states(states)
+        ctx.step(actions)
+        out = ctx.get_states()
+    for i, c in enumerate(cases):
+        want = {"InProgress": 0, "Capture": 0, "RedWin": 1, "BlueWin": 2}[c["result"]]
+        assert int(out["result"][i]) == want, c["cite"]
+        for (field, color, n, bit) in c["bits"]:
+            assert (int(out[field][i][color]) >> (31 - n)) & 1 == bit
+        assert int(out["cards"][i][4]) == c["neutral"]
+        for (field, color, value) in c.get("equals", []):
+            assert int(out[field][i][color]) == value
+    ref = states.copy()
+    O.env_step(ref, actions)
+    assert out.tobytes() == ref.tobytes()
+
+
+def test_reference_move_lists_on_gpu(onb):
+    R = G["reference_tests"]
+    rows = []
+    for c in R["opening_moves"]:
+        s = O.new_games(1, deck=c["deck"])
+        s["side"][0] = c["color"]
+        rows.append(s)
+    for c in R["no_moves"]:
+        rows.append(O.make_state(c["deck"], pawns=c["pawns"], kings=c["kings"], side=c["color"]))
+    s = O.new_games(1, deck=R["expand_order"]["deck"])
+    rows.append(s)
+    states = np.concatenate(rows)
+    with onb.Context(len(states)) as ctx:
+        ctx.set_states(states)
+        moves, counts = ctx.legal_moves()
+        masks = ctx.legal_masks()
+    for i in range(len(states)):
+        want = O.gen_moves(states[i:i + 1])
+        assert counts[i] == len(want)
+        assert moves[i][:counts[i]].tolist() == want.tolist()  # same ORDER as the reference (slot, from, to)
+        assert (moves[i][counts[i]:] == 0xFFFF).all()
+    assert np.array_equal(masks, O.legal_masks(states))
+    assert counts[5] == 0 and masks[5].tolist() == [0, 0]  # state.rs:852-889 no-legal-move position
+
+
+# ------------------------------------------------------------------ lockstep stepping, both random policies
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("auto_reset", [False, True])
+def test_env_step_random_bit_exact(onb, policy, auto_reset):
+    n, seed, base = 3000, 1234 + policy, 1 << 33
+    with onb.Context(n, seed=seed, game_id_base=base) as ctx:
+        ctx.reset()
+        ref = O.new_games(n, seed=seed, game0=base)
+        for step in range(60):
+            ctx.step_random(step, policy=policy, auto_reset=auto_reset, out_flags=onb.OUT_MASKS | onb.OUT_PLANES | onb.OUT_ACTIONS)
+            acts = O.env_step_random(ref, seed, step, policy=policy, auto_reset=auto_reset, game0=base)
+            if step % 7 == 0 or step == 59:
+                assert ctx.get_states().tobytes() == ref.tobytes(), "state mismatch at step %d" % step
+                assert np.array_equal(ctx.read(onb.BUF_ACTIONS, np.uint16, (n,)), acts)
+                assert np.array_equal(ctx.read(onb.BUF_MASKS, np.uint32, (n, 2)), O.legal_masks(ref))
+                assert np.array_equal(ctx.read(onb.BUF_PLANES, np.float32, (n, 21, 5, 5)), O.encode(ref))
+        st = ctx.stats()
+        if auto_reset:
+            assert st[onb.STAT_STEPS] == 60 * n and st[onb.STAT_RESETS] == st[onb.STAT_RED_WINS] + st[onb.STAT_BLUE_WINS] > 0
+        else:
+            done = ref["result"] != 0
+            assert st[onb.STAT_RED_WINS] + st[onb.STAT_BLUE_WINS] == done.sum()
+
+
+def test_env_step_explicit_actions_and_fixed_deck(onb):
+    n, seed = 777, 3
+    deck = [4, 3, 1, 0, 2]
+    with onb.Context(n, seed=seed) as ctx:
+        ctx.reset(decks=deck)
+        ref = O.new_games(n, deck=deck)
+        for step in range(40):
+            # actions chosen by the oracle's policy, applied through onb_env_step on the GPU
+            shadow = ref.copy()
+            acts = O.env_step_random(shadow, seed, step, policy=0, auto_reset=True, deck=deck)
+            ctx.step(acts, out_flags=onb.OUT_MASKS)
+            O.env_step(ref, acts)
+            assert ctx.get_states().tobytes() == ref.tobytes()
+        ctx.reset(decks=deck)
+        ref = O.new_games(n, deck=deck)
+        for step in range(80):  # auto-reset re-deals the SAME deck when the context was reset with one deck
+            ctx.step_random(step, auto_reset=True)
+            O.env_step_random(ref, seed, step, auto_reset=True, deck=deck)
+        assert ctx.get_states().tobytes() == ref.tobytes()
+
+
+def test_config1_playout_4096_games_bit_exact(onb):
+    """BASELINE config 1: random-vs-random, 4096 games to terminal."""
+    n, seed = 4096, 2024
+    with onb.Context(n, seed=seed, planes=False) as ctx:
+        ctx.reset()
+        plies, trace = ctx.playout()
+        fin = ctx.get_states()
+        st = ctx.stats()
+    ref, rplies, rtrace, total = O.playout_games(n, seed)
+    assert fin.tobytes() == ref.tobytes()
+    assert np.array_equal(plies, rplies) and np.array_equal(trace, rtrace)
+    assert st[onb.STAT_STEPS] == total and st[onb.STAT_RED_WINS] + st[onb.STAT_BLUE_WINS] == n
+    for row in G["playouts"]:  # committed golden trajectories (independent Python restatement)
+        g = row["game"]
+        assert int(plies[g]) == row["plies"] and str(int(trace[g])) == row["trace"]
+        assert fin["pawns"][g].tolist() == row["pawns"] and fin["kings"][g].tolist() == row["kings"]
+    # the in-register playout equals lockstep stepping, and a capped playout can be resumed
+    with onb.Context(n, seed=seed, planes=False) as ctx:
+        ctx.reset()
+        ctx.playout(max_plies=20, want_plies=False, want_trace=False)
+        ctx.playout(step0=20, want_plies=False, want_trace=False)
+        assert ctx.get_states().tobytes() == ref.tobytes()
+
+
+def test_sharding_invariance(onb):
+    """Results depend on the GLOBAL game id only: two half-size contexts == one full-size context."""
+    n, seed = 2048, 31
+    with onb.Context(n, seed=seed, planes=False) as ctx:
+        ctx.reset()
+        ctx.playout(want_plies=False, want_trace=False)
+        full = ctx.get_states()
+    parts = []
+    for r in range(2):
+        with onb.Context(n // 2, seed=seed, game_id_base=r * (n // 2), planes=False) as ctx:
+            ctx.reset()
+            ctx.playout(want_plies=False, want_trace=False)
+            parts.append(ctx.get_states())
+    assert np.concatenate(parts).tobytes() == full.tobytes()
+
+
+def test_large_batch_properties(onb):
+    """BASELINE-size batch (1M games): size-independent properties + sampled parity against the oracle."""
+    n, seed = 1 << 20, 99
+    with onb.Context(n, seed=seed) as ctx:
+        ctx.reset()
+        for step in range(24):
+            ctx.step_random(step, auto_reset=True, out_flags=onb.OUT_MASKS | onb.OUT_PLANES)
+        states = ctx.get_states()
+        planes = ctx.tensor(onb.BUF_PLANES)
+        # every plane value is 0/1; plane sums match popcounts of the boards; exactly two card planes are set
+        assert bool(((planes == 0) | (planes == 1)).all())
+        sums = planes.sum(dim=(2, 3)).cpu().numpy()
+        pop = np.vectorize(lambda v: bin(int(v)).count("1"))
+        idx = np.random.RandomState(0).choice(n, 4096, replace=False)
+        assert np.array_equal(sums[idx, 0], pop(states["pawns"][idx, 0]))
+        assert np.array_equal(sums[idx, 2], pop(states["pawns"][idx, 1]))
+        assert (sums[:, 1] == 1).all() and (sums[:, 3] == 1).all()  # auto-reset: both kings always on board
+        assert ((sums[:, 4:20] == 25).sum(axis=1) == 2).all()
+        assert np.array_equal(sums[:, 20] == 25, states["side"] == 1)
+        st = ctx.stats()
+        assert st[onb.STAT_STEPS] == 24 * n
+        # sampled games replayed by the oracle
+        ref = np.zeros(len(idx), dtype=states.dtype)
+        for k, gi in enumerate(idx):
+            g = O.new_games(1, seed=seed, game0=int(gi))
+            for step in range(24):
+                O.env_step_random(g, seed, step, auto_reset=True, game0=int(gi))
+            ref[k] = g[0]
+        assert states[idx].tobytes() == ref.tobytes()
+        assert np.array_equal(planes[idx.tolist()].cpu().numpy(), O.encode(ref))
+        masks = ctx.read(onb.BUF_MASKS, np.uint32, (n, 2))
+        assert np.array_equal(masks[idx], O.legal_masks(ref))
+
+
+# ------------------------------------------------------------------ perft (BASELINE config 2)
+def test_perft_vs_golden_and_oracle(onb):
+    decks = [p["deck"] for p in G["perft"]]
+    roots = onb.start_states(decks)
+    with onb.Context(8, planes=False) as ctx:
+        nodes, wins, zero = ctx.perft(roots, 5)
+        for i, p in enumerate(G["perft"]):
+            assert nodes[i].tolist() == p["nodes"] and wins[i].tolist() == p["wins"]
+        assert zero.sum() == 0
+        nodes6, wins6, _ = ctx.perft(roots, 6)
+        for i, d in enumerate(decks):  # SURVEY Appendix A depth-6 values
+            v = G["survey_appendix_a"]["perft"][",".join(map(str, d))]
+            assert (nodes6[i] - wins6[i]).tolist() == v["leaves"]
+            assert np.cumsum(wins6[i]).tolist() == v["cum_wins"]
+        # shallow depths exercise the pure-DFS / pure-BFS corner cases
+        for depth in (1, 2, 3):
+            nd, wd, _ = ctx.perft(roots, depth)
+            assert nd.tolist() == [p["nodes"][:depth] for p in G["perft"]]
+
+
+def test_perft_midgame_roots_and_zero_move(onb):
+    seed = 17
+    g = O.new_games(64, seed=seed)
+    for step in range(10):
+        O.env_step_random(g, seed, step)
+    case = G["reference_tests"]["no_moves"][1]
+    stuck = O.make_state(case["deck"], pawns=case["pawns"], kings=case["kings"], side=case["color"])
+    roots = np.concatenate([g, stuck])
+    with onb.Context(8, planes=False) as ctx:
+        nodes, wins, zero = ctx.perft(roots, 4)
+    for i in range(len(roots)):
+        n, w, z = O.perft(roots[i:i + 1], 4)
+        assert nodes[i].tolist() == n.tolist() and wins[i].tolist() == w.tolist() and zero[i].tolist() == z.tolist(), i
+    assert zero[-1][0] == 1 and nodes[-1].sum() == 0
+
+
+def test_perft_all_deals_depth2_checksum(onb):
+    """All 131 040 canonical deals: sum of perft(1), perft(2) == the independent restatement's totals."""
+    decks = [[a, b, c, d, e] for a in range(16) for b in range(a + 1, 16) for c in range(16) if c not in (a, b)
+             for d in range(c + 1, 16) if d not in (a, b) for e in range(16) if e not in (a, b, c, d)]
+    assert len(decks) == G["all_deals"]["n_deals"]
+    with onb.Context(8, planes=False) as ctx:
+        nodes, wins, zero = ctx.perft(onb.start_states(decks), 3)
+    assert int(nodes[:, 0].sum()) == G["all_deals"]["sum_perft1"]
+    assert int(nodes[:, 1].sum()) == G["all_deals"]["sum_perft2"]
+    assert zero.sum() == 0
+    sample = np.random.RandomState(3).choice(len(decks), 40, replace=False)
+    for i in sample:
+        n, w, _ = O.perft(O.new_games(1, deck=decks[i]), 3)
+        assert nodes[i].tolist() == n.tolist() and wins[i].tolist() == w.tolist()
+
+
+# ------------------------------------------------------------------ PUCT search (BASELINE config 4)
+def _cfg4_roots(n, seed):
+    """roots = positions after p random plies (p = game id mod 16) of config-1 games"""
+    g = O.new_games(n, seed=seed)
+    for step in range(16):
+        live = (np.arange(n) % 16) > step
+        h = g.copy()
+        O.env_step_random(h, seed, step)
+        g[live] = h[live]
+    return g
+
+
+def _compare_trees(ctx, roots, c, sims, evaluator, trees):
+    for t in trees:
+        if roots["result"][t] != 0:
+            continue
+        want = O.mcts_search(roots[t:t + 1], c, sims, evaluator=evaluator, dump=True)
+        got = ctx.mcts_dump_tree(int(t))
+        wt = want["tree"]
+        assert len(got["visits"]) == want["n_nodes"], t
+        assert np.array_equal(got["visits"], wt["visits"])          # every node's N, bit-exact
+        assert np.array_equal(got["action"], wt["action"])
+        assert np.array_equal(got["parent"], wt["parent"])
+        assert np.array_equal(got["n_child"], wt["n_child"])
+        assert np.array_equal(got["flags"], wt["flags"])
+        assert np.array_equal(got["prior"], wt["prior"])            # f64 priors bit-exact
+        assert np.array_equal(got["reward"], wt["reward"])          # f64 W bit-exact
+        q = np.where(got["visits"] > 0, got["reward"] / np.maximum(got["visits"], 1), 0.0)
+        assert np.abs(q - wt["winrate"]).max() <= Q_TOL
+
+
+@pytest.mark.parametrize("c_puct", [math.sqrt(2.0), 2.0, 5.0])
+def test_mcts_fused_uniform_bit_exact(onb, c_puct):
+    n, sims, seed = 512, 400, 4
+    roots = _cfg4_roots(n, seed)
+    with onb.Context(n, seed=seed, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.set_states(roots)
+        res = ctx.search(c_puct, sims, evaluator=onb.EVAL_UNIFORM, fused=True)
+        want = O.mcts_search_batch(roots, c_puct, sims, evaluator=0, threads=8)
+        live = roots["result"] == 0
+        assert live.sum() > 400
+        assert np.array_equal(res["child_visits"][live], want["child_visits"][live])
+        assert np.array_equal(res["best"][live], want["best"][live])
+        assert np.array_equal(res["root_visits"][live], np.full(live.sum(), sims))
+        assert np.abs(res["root_q"][live] - want["root_q"][live]).max() <= Q_TOL
+        assert np.array_equal(res["root_q"][live], want["root_q"][live])
+        assert np.array_equal(res["pi"][live], want["pi"][live])
+        nn, fl = ctx.mcts_tree_info()
+        assert np.array_equal(nn[live], want["n_nodes"][live]) and (fl[live] & 2).sum() == 0
+        _compare_trees(ctx, roots, c_puct, sims, 0, range(0, n, 37))
+
+
+def test_mcts_golden_start_positions(onb):
+    cases = [c for c in G["puct"] if c["sims"] <= 800]
+    for c in cases:
+        with onb.Context(4, mcts_max_sims=c["sims"], planes=False) as ctx:
+            ctx.reset(decks=c["deck"])
+            res = ctx.search(c["c_puct"], c["sims"])
+            k = len(c["visits"])
+            for t in range(4):
+                assert res["child_visits"][t][:k].tolist() == c["visits"] and res["child_visits"][t][k:].sum() == 0
+                assert int(res["best"][t]) == c["best"]
+                assert res["root_q"][t] == c["root_q"]
+            nn, _ = ctx.mcts_tree_info()
+            assert nn.tolist() == [c["n_nodes"]] * 4
+            tree = ctx.mcts_dump_tree(0)
+            assert tree["prior"][1:1 + k].tolist() == c["child_prior"]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_mcts_hash_evaluator_bit_exact(onb, fused):
+    """non-uniform priors and non-zero leaf values (sign-flipping backup, per-card renormalisation)"""
+    n, sims, seed, c = 192, 150, 8, 1.7
+    roots = _cfg4_roots(n, seed)
+    with onb.Context(n, seed=seed, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.set_states(roots)
+        res = ctx.search(c, sims, evaluator=onb.EVAL_HASH, fused=fused)
+        want = O.mcts_search_batch(roots, c, sims, evaluator=1, threads=8)
+        live = roots["result"] == 0
+        assert np.array_equal(res["child_visits"][live], want["child_visits"][live])
+        assert np.array_equal(res["best"][live], want["best"][live])
+        assert np.abs(res["root_q"][live] - want["root_q"][live]).max() <= Q_TOL
+        assert np.array_equal(res["pi"][live], want["pi"][live])
+        _compare_trees(ctx, roots, c, sims, 1, range(0, n, 23))
+
+
+def test_mcts_split_phase_equals_fused_and_leaf_planes(onb):
+    n, sims, seed, c = 256, 64, 12, 2.0
+    roots = _cfg4_roots(n, seed)
+    with onb.Context(n, seed=seed, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.set_states(roots)
+        fused = ctx.search(c, sims, evaluator=onb.EVAL_UNIFORM, fused=True)
+        ctx.mcts_begin(c, sims)
+        for s in range(sims):
+            ctx.mcts_select()
+            if s in (0, 5, 40):
+                # the leaf planes handed to the evaluator are create_tensor_from_state of the leaf state
+                planes = ctx.read(onb.BUF_LEAF_PLANES, np.float32, (n, 21, 5, 5))
+                assert set(np.unique(planes)) <= {0.0, 1.0}
+                if s == 0:
+                    assert np.array_equal(planes, O.encode(roots))
+                pol, val = O.hash_eval(planes[:8])
+            ctx.mcts_eval(onb.EVAL_UNIFORM)
+            ctx.mcts_expand_backup()
+        split = ctx.mcts_finish()
+        for k in fused:
+            assert np.array_equal(fused[k], split[k]), k
+
+
+def test_mcts_torch_evaluator_zero_copy(onb):
+    """The network stays a black box: a torch callable reads LEAF_PLANES and writes POLICY/VALUE in place."""
+    import torch
+    n, sims, c = 64, 32, 2.0
+    roots = _cfg4_roots(n, 21)
+    with onb.Context(n, mcts_max_sims=sims, planes=False, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        ctx.set_states(roots)
+
+        def net(planes):
+            return torch.full((n, 2, 25), 1.0 / 50.0, device=planes.device), torch.zeros(n, device=planes.device)
+
+        a = ctx.search(c, sims, net=net)
+        b = ctx.search(c, sims, evaluator=onb.EVAL_UNIFORM, fused=True)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_mcts_pass_nodes_and_terminal_roots(onb):
+    case = G["reference_tests"]["no_moves"][1]
+    stuck = O.make_state(case["deck"], pawns=case["pawns"], kings=case["kings"], side=case["color"])
+    won = O.new_games(1, deck=[1, 2, 0, 3, 11])
+    won["kings"][0][1] = 0  # Blue king captured: decided root
+    roots = np.concatenate([stuck, won, O.new_games(2, seed=1)])
+    with onb.Context(4, mcts_max_sims=50, planes=False) as ctx:
+        ctx.set_states(roots)
+        res = ctx.search(1.5, 50)
+        nn, fl = ctx.mcts_tree_info()
+        assert fl[0] & 1 and not (fl[2] & 1)
+        for t in range(4):
+            want = O.mcts_search(roots[t:t + 1], 1.5, 50, dump=True)
+            got = ctx.mcts_dump_tree(t)
+            assert np.array_equal(got["visits"], want["tree"]["visits"]), t
+            assert np.array_equal(got["reward"], want["tree"]["reward"]), t
+            assert np.array_equal(got["action"], want["tree"]["action"]), t
+            assert int(res["best"][t]) == want["best"]
+
+
+def test_selfplay_loop_play_best(onb):
+    """self_play's inner loop (train.rs:55-80): search, play the most visited move, flip side -- all games in lockstep."""
+    n, sims, seed, c = 64, 48, 5, 2.0
+    with onb.Context(n, seed=seed, mcts_max_sims=sims) as ctx:
+        ctx.reset()
+        ref = O.new_games(n, seed=seed)
+        for ply in range(6):
+            res = ctx.search(c, sims)
+            want = O.mcts_search_batch(ref, c, sims, threads=8)
+            live = ref["result"] == 0
+            assert np.array_equal(res["best"][live], want["best"][live])
+            ctx.mcts_play_best(out_flags=onb.OUT_PLANES)
+            acts = want["best"].copy()
+            O.env_step(ref, acts)
+            assert ctx.get_states().tobytes() == ref.tobytes()
+            assert np.array_equal(ctx.read(onb.BUF_PLANES, np.float32, (n, 21, 5, 5)), O.encode(ref))
