@@ -1,0 +1,466 @@
+#!/usr/bin/env python3
+"""bench.py -- env steps/s (and MCTS sims/s) of the B200-native Onitama self-play hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload env|mcts|playout] [--impl ours|reference]
+
+One process per GPU (torchrun for N > 1, NCCL only for the barrier / max-over-ranks of the timings: games shard
+across GPUs with no data-path collective, scaling = weak). A "step" is one pass of the hot path over one batch:
+  env     (BASELINE config 3, the default): one lockstep step of 1 048 576 games/GPU = legal moves -> random action
+          (counter RNG) -> apply -> terminal detection -> auto-reset -> legal mask + 21x5x5 f32 planes of the new state.
+  mcts    (BASELINE config 4): one full search = 16 384 trees/GPU x 400 simulations, uniform-prior evaluator.
+  playout (BASELINE config 1): 4 096 random-vs-random games to terminal.
+The default run measures env as the headline and appends the mcts numbers under "mcts" in the same JSON line.
+--impl reference times the CPU restatement of the reference path (oracle/, all host threads) on the same workload.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_GAMES = 1 << 20
+MCTS_TREES = 1 << 14
+MCTS_SIMS = 400
+MCTS_C = 2.0
+PLAYOUT_GAMES = 4096
+SEED = 20240607
+# algorithmic bytes per unit of work
+ENV_BYTES_PER_STEP = 16 + 16 + 8 + 2100  # state read, state write, legal mask, planes
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def read_traffic(kernel):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def oracle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    return oracle_lib
+
+
+def cpu_env(n_games, steps, threads):
+    O = oracle()
+    sink = ctypes.c_double()
+    dt = O.lib().orc_bench_env(n_games, steps, SEED, threads, 1, ctypes.byref(sink))
+    return n_games * steps / dt, dt
+
+
+def cfg4_roots(O, n, seed):
+    import numpy as np
+    base = O.new_games(n, seed=seed)
+    g = base.copy()
+    for step in range(16):
+        live = (np.arange(n) % 16) > step
+        h = g.copy()
+        O.env_step_random(h, seed, step)
+        g[live] = h[live]
+    dead = g["result"] != 0
+    g[dead] = base[dead]
+    return g
+
+
+def cpu_mcts(n_trees, sims, threads):
+    O = oracle()
+    roots = cfg4_roots(O, n_trees, SEED)
+    sink = ctypes.c_double()
+    dt = O.lib().orc_bench_mcts(roots.ctypes.data, n_trees, MCTS_C, sims, threads, ctypes.byref(sink))
+    return n_trees * sims / dt, dt
+
+
+def cpu_playout(n_games, threads):
+    O = oracle()
+    t0 = time.perf_counter()
+    _, plies, _, total = O.playout_games(n_games, SEED)
+    dt = time.perf_counter() - t0
+    return total / dt, dt
+
+
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path (C++ restatement: the Rust workspace cannot be built here),
+    all host threads, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    wl = args.workload
+    vals = []
+    if wl == "env":
+        n, s = 1 << 18, 12
+        sample = "%d games x %d lockstep steps per timed step (same kernel contents: move gen, random action, apply, reset, mask, planes)" % (n, s)
+        for i in range(args.warmup + args.steps):
+            v, dt = cpu_env(n, s, cores)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        unit, metric = "env_steps/s", "env_steps_per_sec"
+    elif wl == "mcts":
+        n = 1024
+        sample = "%d trees x %d sims per timed step, uniform evaluator" % (n, MCTS_SIMS)
+        for i in range(args.warmup + args.steps):
+            v, dt = cpu_mcts(n, MCTS_SIMS, cores)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        unit, metric = "sims/s", "mcts_sims_per_sec"
+    else:
+        sample = "%d games to terminal, single thread" % PLAYOUT_GAMES
+        cores = 1
+        for i in range(args.warmup + args.steps):
+            v, dt = cpu_playout(PLAYOUT_GAMES, 1)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        unit, metric = "env_steps/s", "env_steps_per_sec"
+    value = sum(v for v, _ in vals) / len(vals)
+    ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32" if wl != "mcts" else "u32+f64",
+            "data": "synthetic", "config": workload_config(wl),
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "C++ restatement of the reference CPU path (oracle/onb_oracle.cpp); the Rust reference cannot be built in this image"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl):
+    if wl == "env":
+        return {"workload": "BASELINE config 3: batched env stepping, %d concurrent games/GPU, legal-move masks + 21x5x5 f32 plane encoding, "
+                            "random policy (counter RNG), auto-reset" % ENV_GAMES, "games_per_gpu": ENV_GAMES,
+                "l2": "per-step output 2.2 GB/GPU >> 126 MB L2 (inputs larger than L2, no flush needed)"}
+    if wl == "mcts":
+        return {"workload": "BASELINE config 4: batched PUCT MCTS, %d sims/move, %d concurrent trees/GPU, uniform-prior evaluator, eval mode"
+                            % (MCTS_SIMS, MCTS_TREES), "trees_per_gpu": MCTS_TREES, "sims": MCTS_SIMS, "c_puct": MCTS_C,
+                "l2": "touched node pools ~2.4 GB/GPU >> 126 MB L2"}
+    return {"workload": "BASELINE config 1: random-vs-random, %d games to terminal" % PLAYOUT_GAMES, "games": PLAYOUT_GAMES,
+            "l2": "L2 flushed between timed iterations (256 MB write)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device. The product path has no CPU fallback (use --impl reference for the CPU arm).")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    import onitama_alphazero_b200 as onb
+
+    stream = torch.cuda.current_stream()
+    peak, peak_src = read_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def timed(fn, warmup, steps, between=None):
+        for i in range(warmup):
+            fn(i)
+            if between:
+                between()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if between is None:
+            e0.record(stream)
+            for i in range(steps):
+                fn(warmup + i)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+        else:  # L2 flush between iterations: time each iteration on its own
+            ms = 0.0
+            for i in range(steps):
+                between()
+                e0.record(stream)
+                fn(warmup + i)
+                e1.record(stream)
+                e1.synchronize()
+                ms += e0.elapsed_time(e1)
+            barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        return max_over_ranks(ms), clocks
+
+    out = {}
+    wl = args.workload
+
+    # ---------------------------------------------------------------- env (config 3)
+    def bench_env(steps, warmup):
+        n = ENV_GAMES
+        flags = onb.OUT_MASKS | onb.OUT_PLANES
+        ctx = onb.Context(n, seed=SEED, game_id_base=rank * n, stream=stream.cuda_stream)
+        ctx.reset()
+        ms, clocks = timed(lambda i: ctx.step_random(i, auto_reset=True, out_flags=flags), warmup, steps)
+        st = ctx.stats()
+        assert int(st[onb.STAT_STEPS]) == n * (steps + warmup), "kernel did not step every game"
+        value = world * n * steps / (ms * 1e-3)
+        kernel_ms = ms / steps  # one k_env_step launch per step
+        achieved = ENV_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic("k_env_step"),
+                "kernel": "k_env_step<uniform,planes>", "algorithmic_bytes_per_launch": ENV_BYTES_PER_STEP * n, "peak_source": peak_src}
+        # e2e: recorded actions replayed from PINNED HOST memory through onb_env_step (H2D inside), masks + stats read back (D2H)
+        k_all = warmup + steps
+        ctx.reset()
+        acts_dev = ctx.tensor(onb.BUF_ACTIONS)
+        host_actions = torch.empty((k_all, n), dtype=torch.int16).pin_memory()
+        for i in range(k_all):
+            ctx.step_random(i, auto_reset=True, out_flags=onb.OUT_ACTIONS)
+            host_actions[i].copy_(acts_dev)
+        torch.cuda.synchronize()
+        ctx.reset()
+        masks_dev = ctx.tensor(onb.BUF_MASKS)
+        stats_dev = ctx.tensor(onb.BUF_STATS)
+        host_masks = torch.empty((n, 2), dtype=torch.int32).pin_memory()
+        host_stats = torch.empty((onb._lib.STAT_COUNT,), dtype=torch.int64).pin_memory()
+
+        def e2e_step(i):
+            ctx.step_from_host_ptr(host_actions[i].data_ptr(), step=i, auto_reset=True, out_flags=flags)
+            host_masks.copy_(masks_dev, non_blocking=True)
+            host_stats.copy_(stats_dev, non_blocking=True)
+            stream.synchronize()  # the host actor needs the masks before it can pick the next actions
+
+        ems, _ = timed(e2e_step, warmup, steps)
+        assert int(host_stats[onb.STAT_STEPS]) >= n * steps
+        e2e = {"value": world * n * steps / (ems * 1e-3), "unit": "env_steps/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 8 * n + 64,
+               "ms_per_step": ems / steps, "path": "onb_env_step(host actions) + D2H of legal masks and stats every step; planes stay in HBM for the network"}
+        ctx.close()
+        return dict(metric="env_steps_per_sec", value=value, unit="env_steps/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
+                    gpu_launches=steps, clocks=clocks)
+
+    # ---------------------------------------------------------------- mcts (config 4)
+    def bench_mcts(steps, warmup):
+        n, sims = MCTS_TREES, MCTS_SIMS
+        ctx = onb.Context(n, seed=SEED, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims, planes=False)
+        # roots = positions after p = (id mod 16) random plies of config-1 games (built with the env kernels);
+        # a game that ended before its p-th ply is searched from its start position instead
+        ctx.reset()
+        base = ctx.get_states()
+        cur = base.copy()
+        for step in range(16):
+            ctx.step_random(step)
+            nxt = ctx.get_states()
+            live = (np.arange(n) % 16) > step
+            cur[live] = nxt[live]
+            ctx.set_states(cur)
+        dead = cur["result"] != 0
+        cur[dead] = base[dead]
+        ctx.set_states(cur)
+        roots_np = cur
+
+        def one(i):
+            ctx.mcts_begin(MCTS_C, sims)
+            ctx.mcts_run(onb.EVAL_UNIFORM, sims)
+            ctx.mcts_finish(to_host=False)
+
+        ms, clocks = timed(one, warmup, steps)
+        nn, fl = ctx.mcts_tree_info()
+        assert int((fl & 2).sum()) == 0, "node pool overflow"
+        value = world * n * sims * steps / (ms * 1e-3)
+        # measured tree shape -> algorithmic bytes per simulation, from the GPU's own trees:
+        # mean select depth d = sum of visits of non-root nodes / sims, mean children k = (nodes - 1) / expanded nodes
+        mean_nodes = float(nn.mean())
+        ds, ks = [], []
+        for t in range(0, n, n // 32):
+            tr = ctx.mcts_dump_tree(int(t))
+            ds.append(float(tr["visits"][1:].sum()) / sims)
+            ks.append((len(tr["visits"]) - 1) / max(1, int((tr["flags"] & 1).sum())))
+        d_mean, kk = float(np.mean(ds)), float(np.mean(ks))
+        bytes_per_sim = d_mean * (16 + kk * 20) + kk * 30 + (d_mean + 1) * 24 + 16
+        run_ms = ms / steps
+        achieved = bytes_per_sim * n * sims / (run_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic("k_mcts_run"),
+                "kernel": "k_mcts_run<uniform>", "algorithmic_bytes_per_sim": bytes_per_sim, "mean_depth": d_mean, "mean_children": kk,
+                "mean_nodes_per_tree": mean_nodes, "peak_source": peak_src,
+                "note": "latency/occupancy-bound pointer chasing; launch time includes k_mcts_begin and k_mcts_finish (<1%)"}
+        # e2e: roots from pinned host memory -> search -> best/pi/visits back on the host
+        roots_host = torch.from_numpy(roots_np.view(np.uint8).reshape(n, 24).copy()).pin_memory()
+        host_view = roots_host.numpy().view(onb.STATE_DTYPE).reshape(n)
+
+        def e2e_one(i):
+            ctx.set_states(host_view)
+            ctx.mcts_begin(MCTS_C, sims)
+            ctx.mcts_run(onb.EVAL_UNIFORM, sims)
+            ctx.mcts_finish(to_host=True)
+
+        ems, _ = timed(e2e_one, 1, max(1, steps))
+        e2e = {"value": world * n * sims * max(1, steps) / (ems * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 24 * n,
+               "d2h_bytes_per_step": n * (2 + 200 + 4 + 8 + 160), "ms_per_step": ems / max(1, steps),
+               "path": "onb_env_set_states(host roots) + onb_mcts_begin/run/finish(host best, pi, visits, q)"}
+        ctx.close()
+        return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=run_ms, dtype="u32+f64", roofline=roof, e2e=e2e,
+                    gpu_launches=3 * steps, clocks=clocks)
+
+    # ---------------------------------------------------------------- playout (config 1)
+    def bench_playout(steps, warmup):
+        n = PLAYOUT_GAMES
+        ctx = onb.Context(n, seed=SEED, game_id_base=rank * n, stream=stream.cuda_stream, planes=False)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        total = {"steps": 0}
+
+        def one(i):
+            ctx.reset()
+            ctx.playout(want_plies=False, want_trace=False)
+
+        ms, clocks = timed(one, warmup, steps, between=lambda: flush.fill_(1))
+        st = ctx.stats()
+        per_iter = int(st[onb.STAT_STEPS]) // (steps + warmup)
+        value = world * per_iter * steps / (ms * 1e-3)
+        ctx.close()
+        roof = {"bound": "hbm", "achieved": 44.0 * per_iter / (ms / steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": 44.0 * per_iter / (ms / steps * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_env_playout",
+                "note": "4096 games cannot fill 148 SMs; launch/latency-bound by construction", "peak_source": peak_src}
+        e2e = {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "path": "same call (reset + playout); timing includes the reset's host sync"}
+        return dict(metric="env_steps_per_sec", value=value, unit="env_steps/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
+                    gpu_launches=2 * steps, clocks=clocks)
+
+    if wl == "env":
+        out = bench_env(args.steps, args.warmup)
+    elif wl == "mcts":
+        out = bench_mcts(args.steps, args.warmup)
+    else:
+        out = bench_playout(args.steps, args.warmup)
+
+    secondary = None
+    if wl == "env" and not args.no_secondary:
+        m = bench_mcts(3, 3)
+        secondary = {k: m[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches")}
+        secondary["config"] = workload_config("mcts")
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        if wl == "env":
+            v, dt = cpu_env(1 << 18, 32, cores)
+            cpu_baseline = {"value": v, "unit": "env_steps/s", "cores": cores, "kind": "port",
+                            "sample": "262144 games x 32 lockstep steps incl. mask + plane encode (%.1f s wall, %d threads)" % (dt, cores)}
+            v1, dt1 = cpu_env(1 << 15, 32, 1)
+            cpu_baseline["single_core_value"] = v1
+            if secondary is not None:
+                vm, dtm = cpu_mcts(8192, MCTS_SIMS, cores)
+                secondary["cpu_baseline"] = {"value": vm, "unit": "sims/s", "cores": cores, "kind": "port",
+                                             "sample": "8192 trees x 400 sims, uniform evaluator (%.1f s wall, %d threads)" % (dtm, cores)}
+        elif wl == "mcts":
+            v, dt = cpu_mcts(8192, MCTS_SIMS, cores)
+            cpu_baseline = {"value": v, "unit": "sims/s", "cores": cores, "kind": "port",
+                            "sample": "8192 trees x 400 sims, uniform evaluator (%.1f s wall, %d threads)" % (dt, cores)}
+        else:
+            v, dt = cpu_playout(PLAYOUT_GAMES, 1)
+            cpu_baseline = {"value": v, "unit": "env_steps/s", "cores": 1, "kind": "port", "sample": "the same 4096 games, one thread (%.2f s)" % dt}
+
+    if rank == 0:
+        line = {"metric": out["metric"], "value": out["value"], "unit": out["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": out["dtype"],
+                "data": "synthetic", "config": workload_config(wl), "roofline": out["roofline"], "cpu_baseline": cpu_baseline, "e2e": out["e2e"],
+                "gpu_launches": out["gpu_launches"], "clocks": out["clocks"], "impl": "ours"}
+        if secondary is not None:
+            line["mcts"] = secondary
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

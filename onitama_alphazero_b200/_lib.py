@@ -54,7 +54,7 @@ SYMBOLS = {
     "onb_env_legal_moves": (C.c_int32, [_P, _P, _P]),
     "onb_env_legal_masks": (C.c_int32, [_P, _P]),
     "onb_env_encode": (C.c_int32, [_P, _P]),
-    "onb_env_step": (C.c_int32, [_P, _P, C.c_uint32]),
+    "onb_env_step": (C.c_int32, [_P, _P, C.c_uint32, C.c_int32, C.c_uint32]),
     "onb_env_step_random": (C.c_int32, [_P, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]),
     "onb_env_run_random": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]),
     "onb_env_playout": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P, _P]),

@@ -307,12 +307,12 @@ int32_t onb_env_encode(onb_ctx* ctx, float* planes_host) {
     return ONB_OK;
 }
 
-int32_t onb_env_step(onb_ctx* ctx, const onb_action* actions_host, uint32_t out_flags) {
+int32_t onb_env_step(onb_ctx* ctx, const onb_action* actions_host, uint32_t step, int32_t auto_reset, uint32_t out_flags) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if ((out_flags & ONB_OUT_PLANES) && !c->d_planes) return fail(c, ONB_E_STATE, "onb_env_step: plane buffer not allocated");
     if (actions_host) ONB_CUDA(c, cudaMemcpyAsync(c->d_actions, actions_host, (size_t)c->n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-    ONB_CUDA(c, launch_env_step(c, kModeActions, 0, 0, out_flags));
+    ONB_CUDA(c, launch_env_step(c, kModeActions, step, auto_reset, out_flags));
     c->mcts_phase = 0;
     return ONB_OK;
 }

@@ -289,7 +289,7 @@ cudaError_t launch_env_step(Ctx* c, int mode, uint32_t step, int auto_reset, uin
     switch (mode) {
         case 0: return launch_step_mode<0>(c, step, auto_reset, fixed, out_flags);
         case 1: return launch_step_mode<1>(c, step, auto_reset, fixed, out_flags);
-        case 2: return launch_step_mode<2>(c, step, 0, fixed, out_flags);
+        case 2: return launch_step_mode<2>(c, step, auto_reset, fixed, out_flags);
         default: return launch_step_mode<3>(c, step, 0, fixed, out_flags);
     }
 }

@@ -114,9 +114,13 @@ class Context:
         self._ck(self._lib.onb_env_encode(self._h, L.ptr(out)))
         return out
 
-    def step(self, actions=None, out_flags=0):
+    def step(self, actions=None, out_flags=0, step=0, auto_reset=False):
         a = None if actions is None else np.ascontiguousarray(actions, dtype=np.uint16)
-        self._ck(self._lib.onb_env_step(self._h, L.ptr(a), out_flags))
+        self._ck(self._lib.onb_env_step(self._h, L.ptr(a), step, int(auto_reset), out_flags))
+
+    def step_from_host_ptr(self, host_ptr, step=0, auto_reset=False, out_flags=0):
+        """onb_env_step with a raw host pointer (e.g. pinned memory owned by the caller)."""
+        self._ck(self._lib.onb_env_step(self._h, C.c_void_p(host_ptr), step, int(auto_reset), out_flags))
 
     def step_random(self, step, policy=L.POLICY_UNIFORM, auto_reset=False, out_flags=0):
         self._ck(self._lib.onb_env_step_random(self._h, step, policy, int(auto_reset), out_flags))

@@ -80,7 +80,7 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(OnbError) as e:
         Context(16)
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
-    assert lib.onb_sync(None) == -1 and lib.onb_env_step(None, None, 0) == -1
+    assert lib.onb_sync(None) == -1 and lib.onb_env_step(None, None, 0, 0, 0) == -1
 
 
 def test_product_does_not_import_oracle():
