@@ -238,7 +238,10 @@ def main():
         dist.barrier()
     import onitama_alphazero_b200 as onb
 
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: the context launches on it, torch's events/copies are ordered with the kernels
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     peak, peak_src = read_peaks()
 
     def barrier():

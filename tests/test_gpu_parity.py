@@ -407,7 +407,9 @@ def test_mcts_torch_evaluator_zero_copy(onb):
     import torch
     n, sims, c = 64, 32, 2.0
     roots = _cfg4_roots(n, 21)
-    with onb.Context(n, mcts_max_sims=sims, planes=False, stream=torch.cuda.current_stream().cuda_stream) as ctx:
+    ts = torch.cuda.Stream()
+    with torch.cuda.stream(ts), onb.Context(n, mcts_max_sims=sims, planes=False, stream=ts.cuda_stream) as ctx:
+        assert ts.cuda_stream != 0
         ctx.set_states(roots)
 
         def net(planes):
