@@ -164,6 +164,9 @@ ONB_API int32_t onb_env_step(onb_ctx* ctx, const onb_action* actions_host, uint3
 /* one lockstep step of every unfinished game with a random policy drawn from the counter RNG keyed by
  * (seed, global game id, step). auto_reset: a game that ends is replaced by a fresh deal (epoch step+1). */
 ONB_API int32_t onb_env_step_random(onb_ctx* ctx, uint32_t step, int32_t policy, int32_t auto_reset, uint32_t out_flags);
+/* the same random policies as agents for the arena loop: write the chosen action of every unfinished game to
+ * ONB_BUF_ACTIONS without playing it (Agent::generate_move of `Random`, ai/random.rs:12-43) */
+ONB_API int32_t onb_env_choose_random(onb_ctx* ctx, uint32_t step, int32_t policy);
 /* `n_steps` steps back to back starting at `step0` (no host round trip in between) */
 ONB_API int32_t onb_env_run_random(onb_ctx* ctx, uint32_t step0, uint32_t n_steps, int32_t policy, int32_t auto_reset,
                            uint32_t out_flags);

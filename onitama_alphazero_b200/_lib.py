@@ -56,6 +56,7 @@ SYMBOLS = {
     "onb_env_encode": (C.c_int32, [_P, _P]),
     "onb_env_step": (C.c_int32, [_P, _P, C.c_uint32, C.c_int32, C.c_uint32]),
     "onb_env_step_random": (C.c_int32, [_P, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]),
+    "onb_env_choose_random": (C.c_int32, [_P, C.c_uint32, C.c_int32]),
     "onb_env_run_random": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]),
     "onb_env_playout": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P, _P]),
     "onb_env_stats": (C.c_int32, [_P, _P, C.c_int32]),

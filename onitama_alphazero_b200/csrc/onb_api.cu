@@ -327,6 +327,14 @@ int32_t onb_env_step_random(onb_ctx* ctx, uint32_t step, int32_t policy, int32_t
     return ONB_OK;
 }
 
+int32_t onb_env_choose_random(onb_ctx* ctx, uint32_t step, int32_t policy) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (policy != ONB_POLICY_UNIFORM && policy != ONB_POLICY_AGENT) return fail(c, ONB_E_INVALID, "onb_env_choose_random: unknown policy %d", policy);
+    ONB_CUDA(c, launch_env_step(c, 4 + policy, step, 0, 0));
+    return ONB_OK;
+}
+
 int32_t onb_env_run_random(onb_ctx* ctx, uint32_t step0, uint32_t n_steps, int32_t policy, int32_t auto_reset, uint32_t out_flags) {
     for (uint32_t s = 0; s < n_steps; ++s) {
         int32_t r = onb_env_step_random(ctx, step0 + s, policy, auto_reset, out_flags);

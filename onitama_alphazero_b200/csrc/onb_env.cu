@@ -110,7 +110,7 @@ template <int MODE, bool PLANES>
 __global__ void __launch_bounds__(kTile) k_env_step(uint4* __restrict__ states, int64_t n, uint16_t* __restrict__ actions,
                                                     uint32_t* __restrict__ masks, float* __restrict__ planes,
                                                     unsigned long long* __restrict__ stats, uint64_t seed, uint64_t game0, uint32_t step,
-                                                    int auto_reset, int32_t fixed_cards, uint32_t out_flags) {
+                                                    int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
     __shared__ uint32_t s_att[800];
     __shared__ uint32_t s_pl[PLANES ? kTile * kPlanes + 1 : 1];
     __shared__ uint32_t s_stat[4];
@@ -132,12 +132,16 @@ __global__ void __launch_bounds__(kTile) k_env_step(uint4* __restrict__ states, 
                 const uint64_t key = game_key(seed, game0 + (uint64_t)i);
                 if (MODE == 2) a = actions[i];
                 else a = choose_action(s_att, g, MODE, key, step);
-                res = apply_move(g, a);
-                stepped = true;
-                passed = (a & kPassBit) != 0;
-                if (MODE != 2 && (out_flags & ONB_OUT_ACTIONS)) actions[i] = (uint16_t)a;
-                if (res && auto_reset) g = start_game(fixed_cards >= 0 ? (uint32_t)fixed_cards : deal_cards(key, step + 1u));
-                states[i] = pack(g);
+                if (MODE != 2 && choose_only) {  // agents for the arena loop: pick, do not play
+                    actions[i] = (uint16_t)a;
+                } else {
+                    res = apply_move(g, a);
+                    stepped = true;
+                    passed = (a & kPassBit) != 0;
+                    if (MODE != 2 && (out_flags & ONB_OUT_ACTIONS)) actions[i] = (uint16_t)a;
+                    if (res && auto_reset) g = start_game(fixed_cards >= 0 ? (uint32_t)fixed_cards : deal_cards(key, step + 1u));
+                    states[i] = pack(g);
+                }
             } else if (MODE != 3 && MODE != 2 && (out_flags & ONB_OUT_ACTIONS)) {
                 actions[i] = 0xFFFFu;
             }
@@ -271,14 +275,14 @@ cudaError_t launch_legal_moves(Ctx* c) {
 }
 
 template <int MODE>
-static cudaError_t launch_step_mode(Ctx* c, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags) {
+static cudaError_t launch_step_mode(Ctx* c, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
     const int grid = grid_for_tiles(c->n);
     if (out_flags & ONB_OUT_PLANES)
         k_env_step<MODE, true><<<grid, kTile, 0, c->stream>>>(c->d_states, c->n, c->d_actions, c->d_masks, c->d_planes, c->d_stats, c->cfg.seed,
-                                                             c->cfg.game_id_base, step, auto_reset, fixed_cards, out_flags);
+                                                             c->cfg.game_id_base, step, auto_reset, fixed_cards, out_flags, choose_only);
     else
         k_env_step<MODE, false><<<grid, kTile, 0, c->stream>>>(c->d_states, c->n, c->d_actions, c->d_masks, c->d_planes, c->d_stats, c->cfg.seed,
-                                                              c->cfg.game_id_base, step, auto_reset, fixed_cards, out_flags);
+                                                              c->cfg.game_id_base, step, auto_reset, fixed_cards, out_flags, choose_only);
     return cudaGetLastError();
 }
 
@@ -287,10 +291,12 @@ int32_t g_fixed_cards_of(Ctx* c);  // onb_api.cu
 cudaError_t launch_env_step(Ctx* c, int mode, uint32_t step, int auto_reset, uint32_t out_flags) {
     const int32_t fixed = g_fixed_cards_of(c);
     switch (mode) {
-        case 0: return launch_step_mode<0>(c, step, auto_reset, fixed, out_flags);
-        case 1: return launch_step_mode<1>(c, step, auto_reset, fixed, out_flags);
-        case 2: return launch_step_mode<2>(c, step, auto_reset, fixed, out_flags);
-        default: return launch_step_mode<3>(c, step, 0, fixed, out_flags);
+        case 0: return launch_step_mode<0>(c, step, auto_reset, fixed, out_flags, 0);
+        case 1: return launch_step_mode<1>(c, step, auto_reset, fixed, out_flags, 0);
+        case 2: return launch_step_mode<2>(c, step, auto_reset, fixed, out_flags, 0);
+        case 4: return launch_step_mode<0>(c, step, 0, fixed, 0, 1);
+        case 5: return launch_step_mode<1>(c, step, 0, fixed, 0, 1);
+        default: return launch_step_mode<3>(c, step, 0, fixed, out_flags, 0);
     }
 }
 cudaError_t launch_observe(Ctx* c, uint32_t out_flags) { return launch_env_step(c, 3, 0, 0, out_flags); }

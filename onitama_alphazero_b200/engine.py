@@ -125,6 +125,9 @@ class Context:
     def step_random(self, step, policy=L.POLICY_UNIFORM, auto_reset=False, out_flags=0):
         self._ck(self._lib.onb_env_step_random(self._h, step, policy, int(auto_reset), out_flags))
 
+    def choose_random(self, step, policy=L.POLICY_UNIFORM):
+        self._ck(self._lib.onb_env_choose_random(self._h, step, policy))
+
     def run_random(self, step0, n_steps, policy=L.POLICY_UNIFORM, auto_reset=False, out_flags=0):
         self._ck(self._lib.onb_env_run_random(self._h, step0, n_steps, policy, int(auto_reset), out_flags))
 
@@ -217,6 +220,25 @@ class Context:
                     val.copy_(v.reshape(val.shape))
                 self.mcts_expand_backup()
         return self.mcts_finish()
+
+
+def _search_device(self, c_puct, sims, evaluator=L.EVAL_UNIFORM, net=None):
+    """Context.search without copying the results to the host (PI / BEST stay in their device buffers)."""
+    self.mcts_begin(c_puct, sims)
+    if net is None:
+        self.mcts_run(evaluator, sims)
+    else:
+        planes, pol, val = self.tensor(L.BUF_LEAF_PLANES), self.tensor(L.BUF_POLICY), self.tensor(L.BUF_VALUE)
+        for _ in range(sims):
+            self.mcts_select()
+            p, v = net(planes)
+            pol.copy_(p.reshape(pol.shape))
+            val.copy_(v.reshape(val.shape))
+            self.mcts_expand_backup()
+    self.mcts_finish(to_host=False)
+
+
+Context.search_device = _search_device
 
 
 def start_states(decks):

@@ -1,0 +1,82 @@
+"""Lockstep batched self-play and arena loops on top of one Context (host glue; all game/search work is in libonb.so).
+
+self_play  <- alphazero-training/src/train.rs:35-98   (per ply: search -> record (pi, planes, colour) -> play best -> flip;
+              stop on a win or after max_plies+2 plies (check-then-decrement, Q15); z = reward(final, sample colour))
+fight      <- alphazero-training/src/evaluator.rs:355-399 (two move sources alternate by side; W/L/D counted per colour)
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def self_play(ctx, c_puct, sims, max_plies=150, evaluator=L.EVAL_UNIFORM, net=None, decks=None):
+    """Plays every game of `ctx` to the end with MCTS moves. Returns device tensors (planes [m,21,5,5], pi [m,2,25], z [m],
+    colour [m], game [m]) for all recorded samples, in ply-major order."""
+    ctx.reset(decks=decks)
+    n = ctx.n
+    dev = "cuda:%d" % ctx.device
+    planes_buf, pi_buf, color_buf, game_buf = [], [], [], []
+    plies_left = max_plies
+    states_t = ctx.tensor(L.BUF_STATES)
+    while True:
+        st = states_t.clone()
+        result = (st[:, 2] >> 29) & 3
+        live = result == 0
+        if not bool(live.any()):
+            break
+        ctx.encode(to_host=False)  # create_tensor_from_state of the position the search starts from (train.rs:58)
+        planes = ctx.tensor(L.BUF_PLANES)
+        ctx.search_device(c_puct, sims, evaluator=evaluator, net=net)
+        pi = ctx.tensor(L.BUF_PI)
+        idx = live.nonzero(as_tuple=True)[0]
+        planes_buf.append(planes[idx].clone())
+        pi_buf.append(pi[idx].clone())
+        color_buf.append(((st[idx, 1] >> 30) & 1).to(torch.int8))
+        game_buf.append(idx)
+        ctx.mcts_play_best()
+        if plies_left < 0:  # train.rs:74-79: checked AFTER the move, then decremented
+            break
+        plies_left -= 1
+    final = states_t.clone()
+    result = ((final[:, 2] >> 29) & 3)  # 0 none, 1 Red won, 2 Blue won
+    planes = torch.cat(planes_buf) if planes_buf else torch.zeros((0, 21, 5, 5), device=dev)
+    pi = torch.cat(pi_buf) if pi_buf else torch.zeros((0, 2, 25), device=dev)
+    color = torch.cat(color_buf) if color_buf else torch.zeros((0,), dtype=torch.int8, device=dev)
+    game = torch.cat(game_buf) if game_buf else torch.zeros((0,), dtype=torch.int64, device=dev)
+    r = result[game]
+    # reward(progress, s.player_color), alphazero_mcts/mod.rs:45-53
+    z = torch.where(r == 0, 0.0, torch.where((r - 1) == color.to(r.dtype), 1.0, -1.0)).to(torch.float32)
+    return dict(planes=planes, pi=pi, z=z, color=color, game=game)
+
+
+def fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies=150):
+    """Arena loop over all games of ctx in lockstep. move_fn_x(ctx) must leave actions for every game in ONB_BUF_ACTIONS
+    (e.g. a search followed by a copy of BEST, or a random policy). a_is_red: bool tensor/array [n], which games agent A
+    plays as Red. Returns (a_wins, b_wins, draws)."""
+    n = ctx.n
+    a_is_red = torch.as_tensor(np.asarray(a_is_red), device="cuda:%d" % ctx.device).bool()
+    states_t = ctx.tensor(L.BUF_STATES)
+    acts = ctx.tensor(L.BUF_ACTIONS)
+    plies_left = max_plies
+    while True:
+        st = states_t.clone()
+        live = ((st[:, 2] >> 29) & 3) == 0
+        if not bool(live.any()):
+            break
+        side = (st[:, 1] >> 30) & 1
+        a_to_move = (side == 0) == a_is_red
+        move_fn_a(ctx)
+        act_a = acts.clone()
+        move_fn_b(ctx)
+        act_b = acts.clone()
+        acts.copy_(torch.where(a_to_move, act_a, act_b))
+        ctx.step(None)
+        if plies_left < 0:
+            break
+        plies_left -= 1
+    res = (states_t.clone()[:, 2] >> 29) & 3
+    red_won, blue_won = res == 1, res == 2
+    a_wins = int((red_won & a_is_red).sum() + (blue_won & ~a_is_red).sum())
+    b_wins = int((red_won & ~a_is_red).sum() + (blue_won & a_is_red).sum())
+    return a_wins, b_wins, int(n - a_wins - b_wins)

@@ -457,3 +457,80 @@ def test_selfplay_loop_play_best(onb):
             O.env_step(ref, acts)
             assert ctx.get_states().tobytes() == ref.tobytes()
             assert np.array_equal(ctx.read(onb.BUF_PLANES, np.float32, (n, 21, 5, 5)), O.encode(ref))
+
+
+# ------------------------------------------------------------------ self_play / fight drivers (train.rs:35-98, evaluator.rs:355-399)
+def _oracle_self_play(n, seed, c, sims, max_plies):
+    g = O.new_games(n, seed=seed)
+    planes, pis, colors, games = [], [], [], []
+    left = max_plies
+    while (g["result"] == 0).any():
+        live = np.flatnonzero(g["result"] == 0)
+        res = O.mcts_search_batch(g, c, sims, threads=8)
+        enc = O.encode(g)
+        planes.append(enc[live]); pis.append(res["pi"][live]); colors.append(g["side"][live].copy()); games.append(live)
+        O.env_step(g, res["best"])
+        if left < 0:
+            break
+        left -= 1
+    games = np.concatenate(games); colors = np.concatenate(colors)
+    r = g["result"][games].astype(np.int64)
+    z = np.where(r == 0, 0.0, np.where((r - 1) == colors, 1.0, -1.0)).astype(np.float32)
+    return dict(planes=np.concatenate(planes), pi=np.concatenate(pis), z=z, color=colors, game=games), g
+
+
+def test_self_play_driver_bit_exact(onb):
+    n, seed, c, sims, max_plies = 48, 77, 2.0, 40, 22
+    with onb.Context(n, seed=seed, mcts_max_sims=sims) as ctx:
+        out = onb.self_play(ctx, c, sims, max_plies=max_plies)
+        final = ctx.get_states()
+    want, g = _oracle_self_play(n, seed, c, sims, max_plies)
+    assert final.tobytes() == g.tobytes()
+    assert np.array_equal(out["game"].cpu().numpy(), want["game"])
+    assert np.array_equal(out["color"].cpu().numpy(), want["color"])
+    assert np.array_equal(out["planes"].cpu().numpy(), want["planes"])
+    assert np.array_equal(out["pi"].cpu().numpy(), want["pi"])
+    assert np.array_equal(out["z"].cpu().numpy(), want["z"])
+    # the 152-ply guard of the reference (max_plies = 150 -> 152 plies) in miniature: max_plies + 2 plies
+    assert out["game"].shape[0] <= n * (max_plies + 2)
+    assert (np.bincount(want["game"], minlength=n) <= max_plies + 2).all()
+
+
+def test_fight_mcts_vs_random(onb):
+    """fight(): agent A = PUCT search (uniform evaluator), agent B = the reference's `Random` agent, colours alternate."""
+    import torch
+    n, seed, c, sims = 64, 9, 2.0, 48
+    a_is_red = (np.arange(n) % 2) == 0
+    step_counter = {"i": 0}
+    with onb.Context(n, seed=seed, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.reset()
+
+        def mcts_agent(cx):
+            cx.search_device(c, sims)
+            cx.tensor(onb.BUF_ACTIONS).copy_(cx.tensor(onb.BUF_BEST))
+
+        def random_agent(cx):
+            cx.choose_random(step_counter["i"], policy=onb.POLICY_AGENT)
+            step_counter["i"] += 1
+
+        a, b, d = onb.fight(ctx, mcts_agent, random_agent, a_is_red, max_plies=150)
+        final = ctx.get_states()
+    # oracle replay of the same arena
+    g = O.new_games(n, seed=seed)
+    left, i = 150, 0
+    while (g["result"] == 0).any():
+        res = O.mcts_search_batch(g, c, sims, threads=8)
+        shadow = g.copy()
+        rnd = O.env_step_random(shadow, seed, i, policy=1)
+        i += 1
+        a_to_move = (g["side"] == 0) == a_is_red
+        acts = np.where(a_to_move, res["best"], rnd).astype(np.uint16)
+        O.env_step(g, acts)
+        if left < 0:
+            break
+        left -= 1
+    assert final.tobytes() == g.tobytes()
+    red, blue = g["result"] == 1, g["result"] == 2
+    assert a == int((red & a_is_red).sum() + (blue & ~a_is_red).sum())
+    assert b == int((red & ~a_is_red).sum() + (blue & a_is_red).sum())
+    assert a + b + d == n and a > b  # 48-sim search beats the random agent
