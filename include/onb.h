@@ -127,6 +127,8 @@ ONB_API int32_t onb_create(const onb_config* cfg, onb_ctx** out);
 ONB_API int32_t onb_destroy(onb_ctx* ctx);
 ONB_API const char* onb_last_error(const onb_ctx* ctx);
 ONB_API int32_t onb_sync(onb_ctx* ctx);
+/* the cudaStream_t every call of this context launches on (so the network and copies can be ordered with it) */
+ONB_API int32_t onb_get_stream(onb_ctx* ctx, void** stream);
 ONB_API int32_t onb_buffer(onb_ctx* ctx, int32_t which, void** dev_ptr, int64_t* bytes);
 
 /* host-side helpers (pure C, no device): */

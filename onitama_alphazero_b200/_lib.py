@@ -43,6 +43,7 @@ SYMBOLS = {
     "onb_destroy": (C.c_int32, [_P]),
     "onb_last_error": (C.c_char_p, [_P]),
     "onb_sync": (C.c_int32, [_P]),
+    "onb_get_stream": (C.c_int32, [_P, C.POINTER(_P)]),
     "onb_buffer": (C.c_int32, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "onb_start_states": (C.c_int32, [_P, C.c_int64, _P]),
     "onb_rand_u32": (C.c_uint32, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]),

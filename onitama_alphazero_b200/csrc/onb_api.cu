@@ -151,6 +151,13 @@ int32_t onb_sync(onb_ctx* ctx) {
     return ONB_OK;
 }
 
+int32_t onb_get_stream(onb_ctx* ctx, void** stream) {
+    ONB_CHECK_CTX(ctx);
+    if (!stream) return ONB_E_INVALID;
+    *stream = reinterpret_cast<void*>(reinterpret_cast<Ctx*>(ctx)->stream);
+    return ONB_OK;
+}
+
 int32_t onb_buffer(onb_ctx* ctx, int32_t which, void** dev_ptr, int64_t* bytes) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);

@@ -60,6 +60,19 @@ class Context:
     def sync(self):
         self._ck(self._lib.onb_sync(self._h))
 
+    def stream_handle(self):
+        p = C.c_void_p()
+        self._ck(self._lib.onb_get_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def torch_stream(self):
+        """The context's CUDA stream as a torch stream: run torch ops that touch its buffers under
+        `with torch.cuda.stream(ctx.torch_stream())` so they are ordered with the kernels."""
+        import torch
+        if getattr(self, "_tstream", None) is None:
+            self._tstream = torch.cuda.ExternalStream(self.stream_handle(), device="cuda:%d" % self.device)
+        return self._tstream
+
     def buffer(self, which):
         p, b = C.c_void_p(), C.c_int64()
         self._ck(self._lib.onb_buffer(self._h, which, C.byref(p), C.byref(b)))
@@ -144,7 +157,9 @@ class Context:
 
     def read(self, which, dtype, shape):
         """Copy a device buffer to the host (test helper; uses torch for the D2H copy)."""
-        return self.tensor(which).cpu().numpy().view(dtype).reshape(shape)
+        import torch
+        with torch.cuda.stream(self.torch_stream()):
+            return self.tensor(which).cpu().numpy().view(dtype).reshape(shape)
 
     # ------------------------------------------------------------------ perft
     def perft(self, roots, depth):
@@ -207,18 +222,21 @@ class Context:
         self.mcts_begin(c_puct, sims)
         if net is None and fused:
             self.mcts_run(evaluator, sims)
-        else:
-            if net is not None:
-                planes, pol, val = self.tensor(L.BUF_LEAF_PLANES), self.tensor(L.BUF_POLICY), self.tensor(L.BUF_VALUE)
+        elif net is None:
             for _ in range(sims):
                 self.mcts_select()
-                if net is None:
-                    self.mcts_eval(evaluator)
-                else:
+                self.mcts_eval(evaluator)
+                self.mcts_expand_backup()
+        else:
+            import torch
+            with torch.cuda.stream(self.torch_stream()):
+                planes, pol, val = self.tensor(L.BUF_LEAF_PLANES), self.tensor(L.BUF_POLICY), self.tensor(L.BUF_VALUE)
+                for _ in range(sims):
+                    self.mcts_select()
                     p, v = net(planes)
                     pol.copy_(p.reshape(pol.shape))
                     val.copy_(v.reshape(val.shape))
-                self.mcts_expand_backup()
+                    self.mcts_expand_backup()
         return self.mcts_finish()
 
 
@@ -228,13 +246,15 @@ def _search_device(self, c_puct, sims, evaluator=L.EVAL_UNIFORM, net=None):
     if net is None:
         self.mcts_run(evaluator, sims)
     else:
-        planes, pol, val = self.tensor(L.BUF_LEAF_PLANES), self.tensor(L.BUF_POLICY), self.tensor(L.BUF_VALUE)
-        for _ in range(sims):
-            self.mcts_select()
-            p, v = net(planes)
-            pol.copy_(p.reshape(pol.shape))
-            val.copy_(v.reshape(val.shape))
-            self.mcts_expand_backup()
+        import torch
+        with torch.cuda.stream(self.torch_stream()):
+            planes, pol, val = self.tensor(L.BUF_LEAF_PLANES), self.tensor(L.BUF_POLICY), self.tensor(L.BUF_VALUE)
+            for _ in range(sims):
+                self.mcts_select()
+                p, v = net(planes)
+                pol.copy_(p.reshape(pol.shape))
+                val.copy_(v.reshape(val.shape))
+                self.mcts_expand_backup()
     self.mcts_finish(to_host=False)
 
 

@@ -11,6 +11,11 @@ from . import _lib as L
 
 
 def self_play(ctx, c_puct, sims, max_plies=150, evaluator=L.EVAL_UNIFORM, net=None, decks=None):
+    with torch.cuda.stream(ctx.torch_stream()):  # torch ops ordered with the context's kernels
+        return _self_play(ctx, c_puct, sims, max_plies, evaluator, net, decks)
+
+
+def _self_play(ctx, c_puct, sims, max_plies, evaluator, net, decks):
     """Plays every game of `ctx` to the end with MCTS moves. Returns device tensors (planes [m,21,5,5], pi [m,2,25], z [m],
     colour [m], game [m]) for all recorded samples, in ply-major order."""
     ctx.reset(decks=decks)
@@ -51,6 +56,11 @@ def self_play(ctx, c_puct, sims, max_plies=150, evaluator=L.EVAL_UNIFORM, net=No
 
 
 def fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies=150):
+    with torch.cuda.stream(ctx.torch_stream()):
+        return _fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies)
+
+
+def _fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies):
     """Arena loop over all games of ctx in lockstep. move_fn_x(ctx) must leave actions for every game in ONB_BUF_ACTIONS
     (e.g. a search followed by a copy of BEST, or a random policy). a_is_red: bool tensor/array [n], which games agent A
     plays as Red. Returns (a_wins, b_wins, draws)."""

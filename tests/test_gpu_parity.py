@@ -215,6 +215,7 @@ def test_large_batch_properties(onb):
         for step in range(24):
             ctx.step_random(step, auto_reset=True, out_flags=onb.OUT_MASKS | onb.OUT_PLANES)
         states = ctx.get_states()
+        ctx.sync()
         planes = ctx.tensor(onb.BUF_PLANES)
         # every plane value is 0/1; plane sums match popcounts of the boards; exactly two card planes are set
         assert bool(((planes == 0) | (planes == 1)).all())
