@@ -106,75 +106,83 @@ __device__ __forceinline__ uint32_t choose_action(const uint32_t* T, const Game&
     return (a & ~(3u << 10)) | (card_idx << 10);
 }
 
-template <int MODE, bool PLANES>
-__global__ void __launch_bounds__(kTile) k_env_step(uint4* __restrict__ states, int64_t n, uint16_t* __restrict__ actions,
-                                                    uint32_t* __restrict__ masks, float* __restrict__ planes,
-                                                    unsigned long long* __restrict__ stats, uint64_t seed, uint64_t game0, uint32_t step,
-                                                    int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
-    __shared__ uint32_t s_att[800];
-    __shared__ uint32_t s_pl[PLANES ? kTile * kPlanes + 1 : 1];
+// GAMES games per CTA are stepped by the first GAMES threads (one thread per game); when planes are written, ALL
+// THREADS (>= GAMES) of the CTA then stream the tile's GAMES x 525 floats. A small tile drained by many threads keeps the
+// chip-wide write front compact, which is what HBM wants (tools/wbench.cu: 8-32 games per CTA reach the memset ceiling,
+// 128 games per 128-thread CTA lose 10-15 %).
+template <int MODE, bool PLANES, int GAMES, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_env_step(uint4* __restrict__ states, int64_t n, uint16_t* __restrict__ actions,
+                                                       uint32_t* __restrict__ masks, float* __restrict__ planes,
+                                                       unsigned long long* __restrict__ stats, uint64_t seed, uint64_t game0, uint32_t step,
+                                                       int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
+    __shared__ __align__(16) uint32_t s_att[800];
+    __shared__ uint32_t s_pl[PLANES ? GAMES * kPlanes + 1 : 1];
     __shared__ uint32_t s_stat[4];
     load_attack_table_to_smem(s_att);
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0;
     __syncthreads();
 
-    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    const int64_t n_tiles = (n + GAMES - 1) / GAMES;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * kTile + threadIdx.x;
-        const bool live = i < n;
-        Game g{};
-        bool stepped = false, passed = false;
-        uint32_t res = 0;
-        if (live) {
-            g = unpack(states[i]);
-            if (MODE != 3 && g.result == 0) {
-                uint32_t a;
-                const uint64_t key = game_key(seed, game0 + (uint64_t)i);
-                if (MODE == 2) a = actions[i];
-                else a = choose_action(s_att, g, MODE, key, step);
-                if (MODE != 2 && choose_only) {  // agents for the arena loop: pick, do not play
-                    actions[i] = (uint16_t)a;
-                } else {
-                    res = apply_move(g, a);
-                    stepped = true;
-                    passed = (a & kPassBit) != 0;
-                    if (MODE != 2 && (out_flags & ONB_OUT_ACTIONS)) actions[i] = (uint16_t)a;
-                    if (res && auto_reset) g = start_game(fixed_cards >= 0 ? (uint32_t)fixed_cards : deal_cards(key, step + 1u));
-                    states[i] = pack(g);
+        if (threadIdx.x < GAMES) {  // warp-uniform: GAMES is a multiple of 32
+            const int64_t i = tile * GAMES + threadIdx.x;
+            const bool live = i < n;
+            Game g{};
+            bool stepped = false, passed = false;
+            uint32_t res = 0;
+            if (live) {
+                g = unpack(states[i]);
+                if (MODE != 3 && g.result == 0) {
+                    uint32_t a;
+                    const uint64_t key = game_key(seed, game0 + (uint64_t)i);
+                    if (MODE == 2) a = actions[i];
+                    else a = choose_action(s_att, g, MODE, key, step);
+                    if (MODE != 2 && choose_only) {  // agents for the arena loop: pick, do not play
+                        actions[i] = (uint16_t)a;
+                    } else {
+                        res = apply_move(g, a);
+                        stepped = true;
+                        passed = (a & kPassBit) != 0;
+                        if (MODE != 2 && (out_flags & ONB_OUT_ACTIONS)) actions[i] = (uint16_t)a;
+                        if (res && auto_reset) g = start_game(fixed_cards >= 0 ? (uint32_t)fixed_cards : deal_cards(key, step + 1u));
+                        states[i] = pack(g);
+                    }
+                } else if (MODE != 3 && MODE != 2 && (out_flags & ONB_OUT_ACTIONS)) {
+                    actions[i] = 0xFFFFu;
                 }
-            } else if (MODE != 3 && MODE != 2 && (out_flags & ONB_OUT_ACTIONS)) {
-                actions[i] = 0xFFFFu;
+                if (out_flags & ONB_OUT_MASKS) {
+                    const MoveSummary s = summarize_moves(s_att, g, g.side);
+                    reinterpret_cast<uint2*>(masks)[i] = make_uint2(__brev(s.m0), __brev(s.m1));
+                }
             }
-            if (out_flags & ONB_OUT_MASKS) {
-                const MoveSummary s = summarize_moves(s_att, g, g.side);
-                reinterpret_cast<uint2*>(masks)[i] = make_uint2(__brev(s.m0), __brev(s.m1));
+            if (MODE != 3) {
+                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, stepped), b1 = __ballot_sync(0xFFFFFFFFu, res == 1),
+                               b2 = __ballot_sync(0xFFFFFFFFu, res == 2), b3 = __ballot_sync(0xFFFFFFFFu, passed);
+                if ((threadIdx.x & 31) == 0) {
+                    if (b0) atomicAdd(&s_stat[0], __popc(b0));
+                    if (b1) atomicAdd(&s_stat[1], __popc(b1));
+                    if (b2) atomicAdd(&s_stat[2], __popc(b2));
+                    if (b3) atomicAdd(&s_stat[3], __popc(b3));
+                }
             }
-        }
-        if (MODE != 3) {
-            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, stepped), b1 = __ballot_sync(0xFFFFFFFFu, res == 1),
-                           b2 = __ballot_sync(0xFFFFFFFFu, res == 2), b3 = __ballot_sync(0xFFFFFFFFu, passed);
-            if ((threadIdx.x & 31) == 0) {
-                if (b0) atomicAdd(&s_stat[0], __popc(b0));
-                if (b1) atomicAdd(&s_stat[1], __popc(b1));
-                if (b2) atomicAdd(&s_stat[2], __popc(b2));
-                if (b3) atomicAdd(&s_stat[3], __popc(b3));
+            if (PLANES) {  // stage the game's 21 plane words (create_tensor_from_state, common.rs:26-80)
+                uint32_t* pl = s_pl + threadIdx.x * kPlanes;
+                const uint32_t c0 = card_at(g.cards, g.side * 2u), c1 = card_at(g.cards, g.side * 2u + 1u);
+                pl[0] = g.pawn_r; pl[1] = g.king_r; pl[2] = g.pawn_b; pl[3] = g.king_b;
+#pragma unroll
+                for (uint32_t c = 0; c < 16; ++c) pl[4 + c] = (c == c0 || c == c1) ? kAll25 : 0u;
+                pl[20] = g.side ? kAll25 : 0u;
+                if (threadIdx.x == 0) s_pl[GAMES * kPlanes] = 0;
             }
         }
         if (PLANES) {
-            // stage the tile's 128 x 21 plane words, then stream them out as one contiguous run of float4
-            uint32_t* pl = s_pl + threadIdx.x * kPlanes;
-            const uint32_t c0 = card_at(g.cards, g.side * 2u), c1 = card_at(g.cards, g.side * 2u + 1u);
-            pl[0] = g.pawn_r; pl[1] = g.king_r; pl[2] = g.pawn_b; pl[3] = g.king_b;
-#pragma unroll
-            for (uint32_t c = 0; c < 16; ++c) pl[4 + c] = (c == c0 || c == c1) ? kAll25 : 0u;
-            pl[20] = g.side ? kAll25 : 0u;
-            if (threadIdx.x == 0) s_pl[kTile * kPlanes] = 0;
             __syncthreads();
-            const int64_t cnt = (n - tile * kTile) < kTile ? (n - tile * kTile) : kTile;
+            // the tile's planes are one contiguous, 16-byte aligned run of GAMES x 525 floats: stream it as float4
+            const int64_t cnt = (n - tile * GAMES) < GAMES ? (n - tile * GAMES) : GAMES;
             const uint32_t n_float = (uint32_t)cnt * kPlaneFloats;
             const uint32_t n_vec = n_float >> 2;
-            float4* __restrict__ dst = reinterpret_cast<float4*>(planes + tile * (int64_t)kTile * kPlaneFloats);
-            for (uint32_t q = threadIdx.x; q < n_vec; q += kTile) {
+            float4* __restrict__ dst = reinterpret_cast<float4*>(planes + tile * (int64_t)GAMES * kPlaneFloats);
+            for (uint32_t q = threadIdx.x; q < n_vec; q += THREADS) {
                 const uint32_t e = q * 4u;
                 const uint32_t G = e / 25u, r = e - G * 25u;
                 const uint32_t v = (s_pl[G] >> r) | (s_pl[G + 1] << (25u - r));
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(kTile) k_env_step(uint4* __restrict__ states, 
             if (threadIdx.x < (n_float & 3u)) {  // ragged tail of the last tile
                 const uint32_t e = n_vec * 4u + threadIdx.x;
                 const uint32_t G = e / 25u, r = e - G * 25u;
-                planes[tile * (int64_t)kTile * kPlaneFloats + e] = (float)((s_pl[G] >> r) & 1u);
+                planes[tile * (int64_t)GAMES * kPlaneFloats + e] = (float)((s_pl[G] >> r) & 1u);
             }
             __syncthreads();
         }
@@ -250,11 +258,24 @@ __global__ void __launch_bounds__(kTile) k_env_playout(uint4* __restrict__ state
 }
 
 // ------------------------------------------------------------------------------------------ launchers
-static inline int grid_for_tiles(int64_t n) {
-    // persistent-style grid: a multiple of the 148 SMs, tiles are grid-strided
-    int64_t tiles = (n + kTile - 1) / kTile;
-    int64_t g = 148 * 8;
-    return (int)(tiles < g ? tiles : g);
+template <int MODE, bool PLANES, int GAMES, int THREADS>
+static cudaError_t launch_step_shape(Ctx* c, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
+    // one tile per CTA (hardware block scheduling balances the load); grid-strided only for absurdly large n
+    const int64_t tiles = (c->n + GAMES - 1) / GAMES;
+    const int64_t cap = (int64_t)1 << 30;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    k_env_step<MODE, PLANES, GAMES, THREADS><<<grid, THREADS, 0, c->stream>>>(c->d_states, c->n, c->d_actions, c->d_masks, c->d_planes, c->d_stats,
+                                                                             c->cfg.seed, c->cfg.game_id_base, step, auto_reset, fixed_cards,
+                                                                             out_flags, choose_only);
+    return cudaGetLastError();
+}
+template <int MODE>
+static cudaError_t launch_step_mode(Ctx* c, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
+    // rules-only variants: 128 games on 128 threads. With planes: 64 games stepped by 2 warps, then 512 threads drain the
+    // 134 KB tile (measured on B200, 1 Mi games: 128g/128t 347 us, 32g/256t 318 us, 64g/256t 321 us, 64g/512t 313 us,
+    // 128g/512t 319 us; a pure fill of the same buffer takes 295 us).
+    if (!(out_flags & ONB_OUT_PLANES)) return launch_step_shape<MODE, false, 128, 128>(c, step, auto_reset, fixed_cards, out_flags, choose_only);
+    return launch_step_shape<MODE, true, 64, 512>(c, step, auto_reset, fixed_cards, out_flags, choose_only);
 }
 
 cudaError_t launch_env_reset(Ctx* c, const uint8_t* d_decks5, int64_t n_decks, uint32_t epoch) {
@@ -271,18 +292,6 @@ cudaError_t launch_states_import(Ctx* c, const onb_state* d_in, int64_t first, i
 }
 cudaError_t launch_legal_moves(Ctx* c) {
     k_legal_moves<<<(unsigned)((c->n + kTile - 1) / kTile), kTile, 0, c->stream>>>(c->d_states, c->n, c->d_moves, c->d_counts);
-    return cudaGetLastError();
-}
-
-template <int MODE>
-static cudaError_t launch_step_mode(Ctx* c, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
-    const int grid = grid_for_tiles(c->n);
-    if (out_flags & ONB_OUT_PLANES)
-        k_env_step<MODE, true><<<grid, kTile, 0, c->stream>>>(c->d_states, c->n, c->d_actions, c->d_masks, c->d_planes, c->d_stats, c->cfg.seed,
-                                                             c->cfg.game_id_base, step, auto_reset, fixed_cards, out_flags, choose_only);
-    else
-        k_env_step<MODE, false><<<grid, kTile, 0, c->stream>>>(c->d_states, c->n, c->d_actions, c->d_masks, c->d_planes, c->d_stats, c->cfg.seed,
-                                                              c->cfg.game_id_base, step, auto_reset, fixed_cards, out_flags, choose_only);
     return cudaGetLastError();
 }
 

@@ -45,7 +45,7 @@ constexpr CardDef kCards[16] = {
 // decides the first mover (game_state.rs:34-41).
 constexpr uint32_t kBlueStampMask = 0x5551u;
 
-struct AttackTable {
+struct alignas(16) AttackTable {
     uint32_t t[2 * 16 * 25];  // [colour][card][from] -> to-mask (internal layout)
 };
 constexpr AttackTable make_attack_table() {
@@ -70,8 +70,14 @@ constexpr AttackTable kAttackHost = make_attack_table();
 // stage it into shared memory once per CTA (load_attack_table_to_smem).
 static __constant__ AttackTable c_attack = make_attack_table();
 
+// Global-memory mirror for the staging copy: lanes read consecutive words (coalesced, L1/L2 resident), whereas
+// lane-divergent reads of __constant__ memory serialise in the constant cache.
+static __device__ AttackTable g_attack = make_attack_table();
+
 __device__ __forceinline__ void load_attack_table_to_smem(uint32_t* s_att) {
-    for (int i = threadIdx.x; i < 800; i += blockDim.x) s_att[i] = c_attack.t[i];
+    const uint4* src = reinterpret_cast<const uint4*>(g_attack.t);
+    uint4* dst = reinterpret_cast<uint4*>(s_att);
+    for (int i = threadIdx.x; i < 200; i += blockDim.x) dst[i] = src[i];
 }
 
 // ---------------------------------------------------------------------------------------------
