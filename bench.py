@@ -137,6 +137,21 @@ def cpu_mcts(n_trees, sims, threads):
     return n_trees * sims / dt, dt
 
 
+def all_deals():
+    return [[a, b, c, d, e] for a in range(16) for b in range(a + 1, 16) for c in range(16) if c not in (a, b)
+            for d in range(c + 1, 16) if d not in (a, b) for e in range(16) if e not in (a, b, c, d)]
+
+
+def cpu_perft(n_decks, depth, threads):
+    import numpy as np
+    O = oracle()
+    decks = np.array(all_deals(), dtype=np.uint8)
+    sel = np.ascontiguousarray(decks[np.random.RandomState(0).choice(len(decks), n_decks, replace=False)])
+    totals = np.zeros(depth, dtype=np.uint64)
+    dt = O.lib().orc_bench_perft(sel.ctypes.data, n_decks, depth, threads, totals.ctypes.data)
+    return float(totals.sum()) / dt, dt
+
+
 def cpu_playout(n_games, threads):
     O = oracle()
     t0 = time.perf_counter()
@@ -169,6 +184,14 @@ def run_reference(args, rank):
             if i >= args.warmup:
                 vals.append((v, dt))
         unit, metric = "sims/s", "mcts_sims_per_sec"
+    elif wl == "perft":
+        nd, dp = 16 * cores, 5
+        sample = "%d deals x depth %d per timed step (same move generation / transition, recursive DFS)" % (nd, dp)
+        for i in range(args.warmup + args.steps):
+            v, dt = cpu_perft(nd, dp, cores)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        unit, metric = "nodes/s", "perft_nodes_per_sec"
     else:
         sample = "%d games to terminal, single thread" % PLAYOUT_GAMES
         cores = 1
@@ -197,6 +220,9 @@ def workload_config(wl):
         return {"workload": "BASELINE config 4: batched PUCT MCTS, %d sims/move, %d concurrent trees/GPU, uniform-prior evaluator, eval mode"
                             % (MCTS_SIMS, MCTS_TREES), "trees_per_gpu": MCTS_TREES, "sims": MCTS_SIMS, "c_puct": MCTS_C,
                 "l2": "touched node pools ~2.4 GB/GPU >> 126 MB L2"}
+    if wl == "perft":
+        return {"workload": "BASELINE config 2: perft-style legal-move enumeration depth 6 from the standard opening over all 131040 canonical "
+                            "card deals, 1 GPU", "deals": 131040, "depth": 6, "l2": "DFS phase is register resident (~0 B/node); L2 flushed between iterations"}
     return {"workload": "BASELINE config 1: random-vs-random, %d games to terminal" % PLAYOUT_GAMES, "games": PLAYOUT_GAMES,
             "l2": "L2 flushed between timed iterations (256 MB write)"}
 
@@ -208,7 +234,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout"])
+    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -418,8 +444,42 @@ def main():
         return dict(metric="env_steps_per_sec", value=value, unit="env_steps/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
                     gpu_launches=2 * steps, clocks=clocks)
 
+    # ---------------------------------------------------------------- perft (config 2)
+    def bench_perft(steps, warmup):
+        decks = np.array(all_deals(), dtype=np.uint8)
+        lo, cnt = rank * len(decks) // world, (rank + 1) * len(decks) // world - rank * len(decks) // world
+        roots = onb.start_states(decks[lo:lo + cnt])  # if sharded (N > 1): deals are partitioned, "strong" scaling
+        ctx = onb.Context(8, stream=stream.cuda_stream, planes=False)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        res = {}
+
+        def one(i):
+            res["nodes"], res["wins"], res["zero"] = ctx.perft(roots, 6)
+
+        ms, clocks = timed(one, warmup, steps, between=lambda: flush.fill_(1))
+        total = int(res["nodes"].sum())
+        tot_t = torch.tensor([total], device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(tot_t)
+        total_all = int(tot_t.item())
+        if world == 1:
+            assert int(res["nodes"][:, 0].sum()) == 1375920 and int(res["nodes"][:, 1].sum()) == 14375088 and int(res["zero"].sum()) == 0
+        value = total_all * steps / (ms * 1e-3)
+        ctx.close()
+        bfs_nodes = int(res["nodes"][:, :2].sum())
+        roof = {"bound": "hbm", "achieved": 32.0 * bfs_nodes / (ms / steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": 32.0 * bfs_nodes / (ms / steps * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_perft_dfs<4>",
+                "note": "only the 2 breadth-first levels touch HBM (32 B/node); the DFS levels are register resident and issue-bound, "
+                        "so the HBM fraction is ~0 by design", "peak_source": peak_src, "nodes_per_call": total}
+        e2e = {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 24 * cnt, "d2h_bytes_per_step": 3 * 8 * 6 * cnt,
+               "path": "onb_perft(host roots) -> host counters (the timed call itself copies both ways)"}
+        return dict(metric="perft_nodes_per_sec", value=value, unit="nodes/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
+                    gpu_launches=5 * steps, clocks=clocks)
+
     if wl == "env":
         out = bench_env(args.steps, args.warmup)
+    elif wl == "perft":
+        out = bench_perft(args.steps, args.warmup)
     elif wl == "mcts":
         out = bench_mcts(args.steps, args.warmup)
     else:
@@ -448,13 +508,17 @@ def main():
             v, dt = cpu_mcts(8192, MCTS_SIMS, cores)
             cpu_baseline = {"value": v, "unit": "sims/s", "cores": cores, "kind": "port",
                             "sample": "8192 trees x 400 sims, uniform evaluator (%.1f s wall, %d threads)" % (dt, cores)}
+        elif wl == "perft":
+            v, dt = cpu_perft(16 * cores, 5, cores)
+            cpu_baseline = {"value": v, "unit": "nodes/s", "cores": cores, "kind": "port",
+                            "sample": "%d random deals x depth 5, recursive DFS (%.1f s wall, %d threads)" % (16 * cores, dt, cores)}
         else:
             v, dt = cpu_playout(PLAYOUT_GAMES, 1)
             cpu_baseline = {"value": v, "unit": "env_steps/s", "cores": 1, "kind": "port", "sample": "the same 4096 games, one thread (%.2f s)" % dt}
 
     if rank == 0:
         line = {"metric": out["metric"], "value": out["value"], "unit": out["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": out["dtype"],
+                "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "strong" if wl == "perft" else "weak", "vs_baseline": None, "dtype": out["dtype"],
                 "data": "synthetic", "config": workload_config(wl), "roofline": out["roofline"], "cpu_baseline": cpu_baseline, "e2e": out["e2e"],
                 "gpu_launches": out["gpu_launches"], "clocks": out["clocks"], "impl": "ours"}
         if secondary is not None:

@@ -131,6 +131,12 @@ ONB_API int32_t onb_sync(onb_ctx* ctx);
 ONB_API int32_t onb_get_stream(onb_ctx* ctx, void** stream);
 ONB_API int32_t onb_buffer(onb_ctx* ctx, int32_t which, void** dev_ptr, int64_t* bytes);
 
+/* copy a whole device buffer to / from host memory on the context's stream (synchronous). Lets a host-side evaluator
+ * (the reference's ConvResNet::forward on CPU tensors, net.rs:215-232) sit between onb_mcts_select and
+ * onb_mcts_expand_backup without any CUDA code on the caller's side. bytes must not exceed the buffer size. */
+ONB_API int32_t onb_read_buffer(onb_ctx* ctx, int32_t which, void* host, int64_t bytes);
+ONB_API int32_t onb_write_buffer(onb_ctx* ctx, int32_t which, const void* host, int64_t bytes);
+
 /* host-side helpers (pure C, no device): */
 /* State::with_deck (state.rs:67-73) + first mover = neutral card's stamp (game_state.rs:34-41) */
 ONB_API int32_t onb_start_states(const uint8_t* decks5, int64_t n, onb_state* out);

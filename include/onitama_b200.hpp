@@ -1,0 +1,466 @@
+// onitama_b200.hpp -- C++17 host-side mirror of the reference's Rust interface for the hot path, header-only, on top of
+// the C ABI (onb.h / libonb.so). Same names, argument meaning and error behaviour as the reference so that tests read
+// like the reference's own tests (tests/cpp/test_host_mirror.cpp). Every game/search operation executes on the GPU
+// through libonb.so; there is no CPU implementation of the rules in this file.
+//
+//   reference (Rust)                                            here
+//   onitama-game/src/game/{player_color,piece,move,done_move,move_result}.rs   PlayerColor, PieceKind, Move, DoneMove, MoveResult
+//   onitama-game/src/game/card.rs (ORIGINAL_CARDS, CARD_NAMES)  Card, TIGER..COBRA, CARD_NAMES
+//   onitama-game/src/game/deck.rs                               Deck
+//   onitama-game/src/game/state.rs                              State
+//   onitama-game/src/game/game_state.rs                         GameState
+//   onitama-game/src/ai/agent.rs, ai/random.rs                  Agent, Random
+//   alphazero-training/src/alphazero_mcts/mod.rs                AlphaZeroMctsConfig, TrainingAlphaZeroMcts, AlphaZeroMcts, reward
+//   alphazero-training/src/train.rs:27-98                       SelfPlayData, TrainConfig (self-play fields), self_play
+//   alphazero-training/src/evaluator.rs:355-399                 EvaluatorConfig, FightStatistics, fight
+//
+// Differences that are deliberate: rand::thread_rng is replaced by the counter RNG of onb.h (seeded, reproducible);
+// search_time is ignored (no wall-clock cut-off); train-mode Dirichlet noise is not implemented (eval mode);
+// where the reference panics (expect/unwrap), this header throws onitama::Error.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "onb.h"
+
+namespace onitama {
+
+struct Error : std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+// ---------------------------------------------------------------------------------------------- small value types
+enum class PlayerColor : int { Red = 0, Blue = 1 };  // player_color.rs:6-9
+inline PlayerColor enemy(PlayerColor c) { return c == PlayerColor::Red ? PlayerColor::Blue : PlayerColor::Red; }
+inline void switch_color(PlayerColor& c) { c = enemy(c); }  // PlayerColor::switch
+
+enum class PieceKind : int { Pawn = 0, King = 1 };  // piece.rs:6-9
+enum class MoveResult { Capture, RedWin, BlueWin, InProgress };  // move_result.rs:4-9
+inline bool is_win(MoveResult r) { return r == MoveResult::RedWin || r == MoveResult::BlueWin; }
+
+struct Move {  // move.rs:21-25 (derived Ord: from, to, piece)
+    uint32_t from, to;
+    PieceKind piece;
+    bool operator==(const Move& o) const { return from == o.from && to == o.to && piece == o.piece; }
+    bool operator<(const Move& o) const {
+        return std::tie(from, to, piece) < std::tie(o.from, o.to, o.piece);
+    }
+    static Move from_2d(std::array<std::array<uint32_t, 2>, 2> rc, PieceKind piece) {  // impl From<([(u32,u32);2], PieceKind)>
+        return Move{rc[0][0] * 5 + rc[0][1], rc[1][0] * 5 + rc[1][1], piece};
+    }
+    static std::string convert_idx_to_notation(uint32_t idx) {  // move.rs:35-47
+        return std::string(1, "abcde"[idx % 5]) + std::to_string(5 - idx / 5);
+    }
+};
+struct DoneMove {  // done_move.rs:4-7
+    Move mov;
+    size_t used_card_idx;
+    bool operator==(const DoneMove& o) const { return mov == o.mov && used_card_idx == o.used_card_idx; }
+};
+inline onb_action to_action(const DoneMove& d) {
+    return ONB_ACTION((uint32_t)d.used_card_idx, d.mov.from, d.mov.to, (uint32_t)d.mov.piece);
+}
+inline DoneMove from_action(onb_action a) {
+    return DoneMove{Move{(uint32_t)((a >> 5) & 31), (uint32_t)(a & 31), ((a >> 12) & 1) ? PieceKind::King : PieceKind::Pawn}, (size_t)((a >> 10) & 3)};
+}
+
+// ---------------------------------------------------------------------------------------------- cards and deck
+static const char* const CARD_NAMES[16] = {"Tiger", "Dragon", "Frog", "Rabbit", "Crab", "Elephant", "Goose", "Rooster",
+                                           "Monkey", "Mantis", "Crane", "Horse", "Ox", "Boar", "Eel", "Cobra"};  // card.rs:471-474
+struct Card {  // card.rs:7-16; the move patterns live in the library's __constant__ table, addressed by `index`
+    size_t index;
+    PlayerColor player_color() const { return ((0x5551u >> index) & 1u) ? PlayerColor::Blue : PlayerColor::Red; }
+    const char* name() const { return CARD_NAMES[index]; }
+    bool operator==(const Card& o) const { return index == o.index; }
+};
+static const Card TIGER{0}, DRAGON{1}, FROG{2}, RABBIT{3}, CRAB{4}, ELEPHANT{5}, GOOSE{6}, ROOSTER{7}, MONKEY{8}, MANTIS{9}, CRANE{10},
+    HORSE{11}, OX{12}, BOAR{13}, EEL{14}, COBRA{15};
+
+constexpr size_t RED_CARD1 = 0, RED_CARD2 = 1, BLUE_CARD1 = 2, BLUE_CARD2 = 3, NEUTRAL = 4;  // deck.rs:14-18
+struct Deck {
+    std::array<Card, 5> cards;
+    Deck() : cards{TIGER, DRAGON, FROG, RABBIT, CRAB} {}
+    explicit Deck(std::array<Card, 5> c) : cards(c) {}
+    std::array<const Card*, 2> get_player_cards(PlayerColor c) const {
+        return c == PlayerColor::Red ? std::array<const Card*, 2>{&cards[0], &cards[1]} : std::array<const Card*, 2>{&cards[2], &cards[3]};
+    }
+    std::array<size_t, 2> get_player_cards_idx(PlayerColor c) const { return c == PlayerColor::Red ? std::array<size_t, 2>{0, 1} : std::array<size_t, 2>{2, 3}; }
+    const Card& neutral_card() const { return cards[NEUTRAL]; }
+    const Card& get_card(size_t i) const {
+        if (i >= 5) throw Error(ONB_E_INVALID, "card_idx < 5");
+        return cards[i];
+    }
+    void rotate(size_t idx) {  // deck.rs:87-90
+        if (idx >= 4) throw Error(ONB_E_INVALID, "idx < 4");
+        std::swap(cards[idx], cards[NEUTRAL]);
+    }
+    /// Deck::default (deck.rs:139-151) with the counter RNG instead of thread_rng
+    static Deck random(uint64_t seed, uint64_t game, uint32_t epoch = 0) {
+        uint8_t d[5];
+        onb_deal(seed, game, epoch, d);
+        return Deck({Card{d[0]}, Card{d[1]}, Card{d[2]}, Card{d[3]}, Card{d[4]}});
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- engine (RAII over onb_ctx)
+class Engine {
+public:
+    explicit Engine(int64_t n_games, uint32_t max_sims = 0, uint64_t seed = 0, int device = 0, bool planes = true, uint64_t game_id_base = 0) : n_(n_games) {
+        onb_config cfg{};
+        cfg.device = device; cfg.n_games = n_games; cfg.seed = seed; cfg.game_id_base = game_id_base;
+        cfg.mcts_max_sims = max_sims; cfg.alloc_planes = planes ? 1 : 0;
+        int32_t rc = onb_create(&cfg, &ctx_);
+        if (rc != ONB_OK) throw Error(rc, onb_last_error(nullptr));
+    }
+    ~Engine() { if (ctx_) onb_destroy(ctx_); }
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+    onb_ctx* ctx() const { return ctx_; }
+    int64_t n() const { return n_; }
+    void check(int32_t rc) const { if (rc != ONB_OK) throw Error(rc, onb_last_error(ctx_)); }
+    /// one-game engine shared by the single-state methods of State / the agents (thread local: a context is single threaded)
+    static Engine& single(uint32_t min_sims = 0) {
+        thread_local std::unique_ptr<Engine> e;
+        thread_local uint32_t sims = 0;
+        if (!e || sims < min_sims) { e.reset(); sims = std::max<uint32_t>(min_sims, 64); e = std::make_unique<Engine>(1, sims); }
+        return *e;
+    }
+private:
+    onb_ctx* ctx_ = nullptr;
+    int64_t n_;
+};
+
+// ---------------------------------------------------------------------------------------------- State (state.rs)
+constexpr uint32_t RED_KING_SP = 0x00000200u, BLUE_KING_SP = 0x20000000u, BLUE_PAWNS_SP = 0xD8000000u, RED_PAWNS_SP = 0x00000D80u;  // state.rs:24-45
+constexpr size_t BLUE_TEMPLE = 2, RED_TEMPLE = 22;                                                                                  // state.rs:48-49
+inline uint32_t get_bit(uint32_t x, size_t n) { return (x >> (31 - n)) & 1u; }  // common/mod.rs:2-4
+
+struct State {
+    Deck deck;
+    uint32_t kings[2];
+    uint32_t pawns[2];
+
+    static State with_deck(const Deck& deck) {  // state.rs:67-73
+        State s;
+        s.deck = deck;
+        s.kings[0] = RED_KING_SP; s.kings[1] = BLUE_KING_SP;
+        s.pawns[0] = RED_PAWNS_SP; s.pawns[1] = BLUE_PAWNS_SP;
+        return s;
+    }
+    onb_state to_onb(PlayerColor side) const {
+        onb_state o{};
+        o.pawns[0] = pawns[0]; o.pawns[1] = pawns[1]; o.kings[0] = kings[0]; o.kings[1] = kings[1];
+        for (int i = 0; i < 5; ++i) o.cards[i] = (uint8_t)deck.cards[i].index;
+        o.side = (uint8_t)side;
+        return o;
+    }
+    void from_onb(const onb_state& o) {
+        pawns[0] = o.pawns[0]; pawns[1] = o.pawns[1]; kings[0] = o.kings[0]; kings[1] = o.kings[1];
+        for (int i = 0; i < 5; ++i) deck.cards[i] = Card{o.cards[i]};
+    }
+    bool is_terminal() const {  // state.rs:111-117
+        return kings[0] == 0 || kings[1] == 0 || kings[0] == BLUE_KING_SP || kings[1] == RED_KING_SP;
+    }
+    MoveResult current_state() const {  // state.rs:120-134
+        if (kings[0] == 0 || kings[1] == RED_KING_SP) return MoveResult::BlueWin;
+        if (kings[1] == 0 || kings[0] == BLUE_KING_SP) return MoveResult::RedWin;
+        return MoveResult::InProgress;
+    }
+    /// state.rs:301-310, executed by k_legal_moves on the GPU; order = slot, from, to as in the reference
+    std::vector<std::pair<size_t, Move>> generate_all_legal_moves(PlayerColor player_color) const {
+        Engine& e = Engine::single();
+        onb_state o = to_onb(player_color);
+        e.check(onb_env_set_states(e.ctx(), &o, 0, 1));
+        onb_action moves[40];
+        uint8_t count = 0;
+        e.check(onb_env_legal_moves(e.ctx(), moves, &count));
+        std::vector<std::pair<size_t, Move>> out;
+        for (int i = 0; i < count; ++i) { DoneMove d = from_action(moves[i]); out.emplace_back(d.used_card_idx, d.mov); }
+        return out;
+    }
+    /// state.rs:323-378: moves of one card for `player_color` (the card does not have to be in that player's hand)
+    std::vector<Move> generate_legal_moves(PlayerColor player_color, const Card& card) const {
+        State tmp = *this;
+        const size_t slot = player_color == PlayerColor::Red ? RED_CARD1 : BLUE_CARD1;
+        tmp.deck.cards[slot] = card;
+        std::vector<Move> out;
+        for (auto& cm : tmp.generate_all_legal_moves(player_color))
+            if (cm.first == slot) out.push_back(cm.second);
+        return out;
+    }
+    std::vector<Move> generate_legal_moves_card_idx(PlayerColor player_color, size_t card_idx) const {
+        return generate_legal_moves(player_color, deck.get_card(card_idx));
+    }
+    /// state.rs:145-202 (no legality check), executed by k_env_step on the GPU
+    MoveResult make_move(const Move& mov, PlayerColor player_color, size_t used_card_idx) {
+        Engine& e = Engine::single();
+        onb_state o = to_onb(player_color);
+        const uint32_t enemy_pawns_before = pawns[(int)enemy(player_color)];
+        e.check(onb_env_set_states(e.ctx(), &o, 0, 1));
+        onb_action a = to_action(DoneMove{mov, used_card_idx});
+        e.check(onb_env_step(e.ctx(), &a, 0, 0, 0));
+        e.check(onb_env_get_states(e.ctx(), &o, 0, 1));
+        from_onb(o);
+        if (o.result == ONB_RESULT_RED_WIN) return MoveResult::RedWin;
+        if (o.result == ONB_RESULT_BLUE_WIN) return MoveResult::BlueWin;
+        return pawns[(int)enemy(player_color)] != enemy_pawns_before ? MoveResult::Capture : MoveResult::InProgress;
+    }
+    MoveResult pass(size_t card_idx) {  // state.rs:139-142
+        deck.rotate(card_idx);
+        return MoveResult::InProgress;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- GameState (game_state.rs)
+struct GameState {
+    State state;
+    std::vector<State> history;
+    size_t curr_agent_idx;
+    PlayerColor curr_player_color;
+
+    static GameState with_deck(const Deck& deck) {  // game_state.rs:34-49: first mover = the neutral card's stamp
+        GameState g;
+        g.state = State::with_deck(deck);
+        g.curr_player_color = g.state.deck.neutral_card().player_color();
+        g.curr_agent_idx = g.curr_player_color == PlayerColor::Red ? 0 : 1;
+        return g;
+    }
+    MoveResult progress(const DoneMove& done_move) {  // game_state.rs:65-80
+        history.push_back(state);
+        MoveResult r = state.make_move(done_move.mov, curr_player_color, done_move.used_card_idx);
+        curr_agent_idx = (curr_agent_idx + 1) % 2;
+        switch_color(curr_player_color);
+        return r;
+    }
+    void undo() {  // game_state.rs:82-89
+        if (!history.empty()) { state = history.back(); history.pop_back(); }
+        curr_agent_idx = (curr_agent_idx + 1) % 2;
+        switch_color(curr_player_color);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- agents
+struct Agent {  // ai/agent.rs:7-17
+    virtual ~Agent() = default;
+    virtual std::pair<DoneMove, double> generate_move(const GameState& game_state) = 0;
+    virtual const char* name() const = 0;
+    virtual std::unique_ptr<Agent> clone_dyn() const = 0;
+    virtual uint64_t id() const = 0;
+};
+
+/// ai/random.rs:12-43 including its quirks (fabricated a5->a4 pawn move when the drawn card has no move; used_card_idx is
+/// the 0/1 slot number even for Blue). Draws come from the counter RNG keyed by (seed, game = 0, step = call number).
+struct Random : Agent {
+    uint64_t seed;
+    uint32_t calls = 0;
+    explicit Random(uint64_t seed_ = 0) : seed(seed_) {}
+    std::pair<DoneMove, double> generate_move(const GameState& gs) override {
+        thread_local std::unique_ptr<Engine> e;
+        thread_local uint64_t e_seed = ~0ull;
+        if (!e || e_seed != seed) { e = std::make_unique<Engine>(1, 0, seed); e_seed = seed; }
+        onb_state o = gs.state.to_onb(gs.curr_player_color);
+        e->check(onb_env_set_states(e->ctx(), &o, 0, 1));
+        e->check(onb_env_choose_random(e->ctx(), calls++, ONB_POLICY_AGENT));
+        onb_action a = 0;
+        e->check(onb_read_buffer(e->ctx(), ONB_BUF_ACTIONS, &a, sizeof(a)));
+        return {from_action(a), 0.};
+    }
+    const char* name() const override { return "Random AI"; }
+    std::unique_ptr<Agent> clone_dyn() const override { return std::make_unique<Random>(*this); }
+    uint64_t id() const override { return seed; }
+};
+
+struct AlphaZeroMctsConfig {  // alphazero_mcts/mod.rs:26-43
+    double search_time_ms = 400.;  // ignored: the search always runs max_playouts simulations
+    double exploration_c = 1.4142135623730951;
+    uint32_t max_playouts = 5000;
+    bool train = false;  // Dirichlet noise is not implemented; must be false
+};
+inline double reward(MoveResult r, PlayerColor c) {  // alphazero_mcts/mod.rs:45-53
+    if (c == PlayerColor::Red) return r == MoveResult::RedWin ? 1. : r == MoveResult::BlueWin ? -1. : 0.;
+    return r == MoveResult::RedWin ? -1. : r == MoveResult::BlueWin ? 1. : 0.;
+}
+
+/// The policy/value network as a black box on host memory: planes [n][21][5][5] -> policy [n][2][25], value [n]
+/// (ConvResNet::forward, net.rs:215-232). nullptr selects a device evaluator (ONB_EVAL_*).
+using HostEvaluator = std::function<void(const float* planes, int64_t n, float* policy, float* value)>;
+
+namespace detail {
+inline void run_search(Engine& e, const AlphaZeroMctsConfig& cfg, int32_t device_eval, const HostEvaluator& net) {
+    if (cfg.train) throw Error(ONB_E_INVALID, "train-mode Dirichlet noise is not implemented");
+    e.check(onb_mcts_begin(e.ctx(), cfg.exploration_c, cfg.max_playouts));
+    if (!net) {
+        e.check(onb_mcts_run(e.ctx(), device_eval, cfg.max_playouts));
+    } else {
+        const int64_t n = e.n();
+        std::vector<float> planes((size_t)n * 525), pol((size_t)n * 50), val((size_t)n);
+        for (uint32_t s = 0; s < cfg.max_playouts; ++s) {
+            e.check(onb_mcts_select(e.ctx()));
+            e.check(onb_read_buffer(e.ctx(), ONB_BUF_LEAF_PLANES, planes.data(), n * 2100));
+            net(planes.data(), n, pol.data(), val.data());
+            e.check(onb_write_buffer(e.ctx(), ONB_BUF_POLICY, pol.data(), n * 200));
+            e.check(onb_write_buffer(e.ctx(), ONB_BUF_VALUE, val.data(), n * 4));
+            e.check(onb_mcts_expand_backup(e.ctx()));
+        }
+    }
+}
+}  // namespace detail
+
+struct TrainingAlphaZeroMcts {  // alphazero_mcts/mod.rs:55-79
+    AlphaZeroMctsConfig config;
+    int32_t device_evaluator = ONB_EVAL_UNIFORM;
+    HostEvaluator model;  // optional host network
+    /// generate_move_tensor(&State, PlayerColor) -> (DoneMove, Tensor[2,25])
+    std::pair<DoneMove, std::array<float, 50>> generate_move_tensor(const State& state, PlayerColor curr_player_color) const {
+        Engine& e = Engine::single(config.max_playouts);
+        onb_state o = state.to_onb(curr_player_color);
+        e.check(onb_env_set_states(e.ctx(), &o, 0, 1));
+        detail::run_search(e, config, device_evaluator, model);
+        onb_action best = 0;
+        std::array<float, 50> pi{};
+        e.check(onb_mcts_finish(e.ctx(), &best, pi.data(), nullptr, nullptr, nullptr));
+        if (best == ONB_ACTION_NONE) throw Error(ONB_E_STATE, "Must find the best child");  // mcts_arena.rs:94
+        return {from_action(best), pi};
+    }
+};
+
+struct AlphaZeroMcts : Agent {  // alphazero_mcts/mod.rs:81-161
+    AlphaZeroMctsConfig config;
+    int32_t device_evaluator = ONB_EVAL_UNIFORM;
+    HostEvaluator model;
+    std::pair<DoneMove, double> generate_move(const GameState& gs) override {
+        TrainingAlphaZeroMcts t{config, device_evaluator, model};
+        auto r = t.generate_move_tensor(gs.state, gs.curr_player_color);
+        // the reference reports the network's value of the root position (mod.rs:136-142): one extra evaluation of the root
+        Engine& e = Engine::single(config.max_playouts);
+        double value = 0.;
+        e.check(onb_mcts_begin(e.ctx(), config.exploration_c, config.max_playouts));
+        e.check(onb_mcts_select(e.ctx()));
+        float v = 0.f;
+        if (model) {
+            std::vector<float> planes(525), pol(50);
+            e.check(onb_read_buffer(e.ctx(), ONB_BUF_LEAF_PLANES, planes.data(), 2100));
+            model(planes.data(), 1, pol.data(), &v);
+        } else {
+            e.check(onb_mcts_eval(e.ctx(), device_evaluator));
+            e.check(onb_read_buffer(e.ctx(), ONB_BUF_VALUE, &v, 4));
+        }
+        value = (double)v;
+        return {r.first, value};
+    }
+    const char* name() const override { return "AlphaZero MCTS AI"; }
+    std::unique_ptr<Agent> clone_dyn() const override { return std::make_unique<AlphaZeroMcts>(*this); }
+    uint64_t id() const override { return (uint64_t)config.exploration_c + config.max_playouts + (uint64_t)config.train; }
+};
+
+// ---------------------------------------------------------------------------------------------- self_play (train.rs:27-98)
+struct SelfPlayData {
+    std::array<float, 50> pi;      // [2,25]
+    float z;
+    std::array<float, 525> state;  // [21,5,5]
+    PlayerColor player_color;
+};
+struct TrainConfig {  // the self-play fields of train.rs:100-154
+    AlphaZeroMctsConfig mcts_config;
+    size_t self_play_game_amnt = 100;
+    long max_plies = 150;
+    std::optional<Deck> deck;
+    uint64_t seed = 0;
+};
+/// All `self_play_game_amnt` games are played in lockstep on one engine (the reference plays them one after another on one
+/// thread); samples are returned game-major, ply-minor like the reference's play_buffer.
+inline std::vector<SelfPlayData> self_play(const TrainingAlphaZeroMcts& mcts, const TrainConfig& config) {
+    const int64_t n = (int64_t)config.self_play_game_amnt;
+    Engine e(n, mcts.config.max_playouts, config.seed);
+    if (config.deck) {
+        uint8_t d[5];
+        for (int i = 0; i < 5; ++i) d[i] = (uint8_t)config.deck->cards[i].index;
+        e.check(onb_env_reset(e.ctx(), d, 1, 0));
+    } else {
+        e.check(onb_env_reset(e.ctx(), nullptr, 0, 0));  // State::new(): random deal
+    }
+    std::vector<std::vector<SelfPlayData>> per_game((size_t)n);
+    std::vector<onb_state> st((size_t)n);
+    std::vector<float> planes((size_t)n * 525), pi((size_t)n * 50);
+    long max_plies = config.max_plies;
+    for (;;) {
+        e.check(onb_env_get_states(e.ctx(), st.data(), 0, n));
+        bool any = false;
+        for (auto& s : st) any |= s.result == 0;
+        if (!any) break;
+        e.check(onb_env_encode(e.ctx(), planes.data()));
+        detail::run_search(e, mcts.config, mcts.device_evaluator, mcts.model);
+        e.check(onb_mcts_finish(e.ctx(), nullptr, pi.data(), nullptr, nullptr, nullptr));
+        for (int64_t g = 0; g < n; ++g) {
+            if (st[(size_t)g].result != 0) continue;
+            SelfPlayData d;
+            std::memcpy(d.pi.data(), &pi[(size_t)g * 50], 200);
+            std::memcpy(d.state.data(), &planes[(size_t)g * 525], 2100);
+            d.z = 0.f;
+            d.player_color = (PlayerColor)st[(size_t)g].side;
+            per_game[(size_t)g].push_back(d);
+        }
+        e.check(onb_mcts_play_best(e.ctx(), 0));
+        if (max_plies < 0) break;  // train.rs:74-79 (check, then decrement: max_plies + 2 plies in total)
+        max_plies -= 1;
+    }
+    e.check(onb_env_get_states(e.ctx(), st.data(), 0, n));
+    std::vector<SelfPlayData> out;
+    for (int64_t g = 0; g < n; ++g) {
+        const uint8_t r = st[(size_t)g].result;
+        const MoveResult progress = r == 1 ? MoveResult::RedWin : r == 2 ? MoveResult::BlueWin : MoveResult::InProgress;
+        for (auto& d : per_game[(size_t)g]) { d.z = (float)reward(progress, d.player_color); out.push_back(d); }  // train.rs:83-85
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------- fight (evaluator.rs:355-399)
+struct EvaluatorConfig {
+    size_t game_amnt = 20;
+    long max_plies = 150;
+    std::optional<Deck> deck;
+    uint64_t seed = 0;
+};
+struct FightStatistics {  // the counters of evaluator.rs:38-56
+    size_t wins = 0, losses = 0, draws = 0, wins_red = 0, wins_blue = 0, games_red = 0, games_blue = 0;
+    void update(MoveResult progress, PlayerColor agent_color) {
+        (agent_color == PlayerColor::Red ? games_red : games_blue) += 1;
+        if (!is_win(progress)) { draws += 1; return; }
+        const bool agent_won = (progress == MoveResult::RedWin) == (agent_color == PlayerColor::Red);
+        if (agent_won) { wins += 1; (agent_color == PlayerColor::Red ? wins_red : wins_blue) += 1; }
+        else losses += 1;
+    }
+};
+inline FightStatistics fight(const EvaluatorConfig& config, std::unique_ptr<Agent> agent, std::unique_ptr<Agent> opponent) {
+    std::array<std::unique_ptr<Agent>, 2> agents{std::move(agent), std::move(opponent)};
+    PlayerColor agent_color = PlayerColor::Red;
+    FightStatistics statistics;
+    for (size_t game = 0; game < config.game_amnt; ++game) {
+        Deck deck = config.deck ? *config.deck : Deck::random(config.seed, game);
+        GameState state = GameState::with_deck(deck);
+        MoveResult progress = MoveResult::InProgress;
+        long max_plies = config.max_plies;
+        while (!is_win(progress)) {
+            auto mv = agents[state.curr_agent_idx]->generate_move(state);
+            progress = state.progress(mv.first);
+            if (max_plies < 0) break;
+            max_plies -= 1;
+        }
+        statistics.update(progress, agent_color);
+        switch_color(agent_color);
+        std::swap(agents[0], agents[1]);
+    }
+    return statistics;
+}
+
+}  // namespace onitama

@@ -45,6 +45,8 @@ SYMBOLS = {
     "onb_sync": (C.c_int32, [_P]),
     "onb_get_stream": (C.c_int32, [_P, C.POINTER(_P)]),
     "onb_buffer": (C.c_int32, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "onb_read_buffer": (C.c_int32, [_P, C.c_int32, _P, C.c_int64]),
+    "onb_write_buffer": (C.c_int32, [_P, C.c_int32, _P, C.c_int64]),
     "onb_start_states": (C.c_int32, [_P, C.c_int64, _P]),
     "onb_rand_u32": (C.c_uint32, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]),
     "onb_deal": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32, _P]),

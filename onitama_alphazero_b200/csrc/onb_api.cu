@@ -183,6 +183,31 @@ int32_t onb_buffer(onb_ctx* ctx, int32_t which, void** dev_ptr, int64_t* bytes) 
     return ONB_OK;
 }
 
+int32_t onb_read_buffer(onb_ctx* ctx, int32_t which, void* host, int64_t bytes) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    void* p = nullptr;
+    int64_t cap = 0;
+    int32_t r = onb_buffer(ctx, which, &p, &cap);
+    if (r) return r;
+    if (!host || bytes < 0 || bytes > cap) return fail(c, ONB_E_INVALID, "onb_read_buffer: bad size %lld (buffer has %lld bytes)", (long long)bytes, (long long)cap);
+    ONB_CUDA(c, cudaMemcpyAsync(host, p, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    ONB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ONB_OK;
+}
+int32_t onb_write_buffer(onb_ctx* ctx, int32_t which, const void* host, int64_t bytes) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    void* p = nullptr;
+    int64_t cap = 0;
+    int32_t r = onb_buffer(ctx, which, &p, &cap);
+    if (r) return r;
+    if (!host || bytes < 0 || bytes > cap) return fail(c, ONB_E_INVALID, "onb_write_buffer: bad size %lld (buffer has %lld bytes)", (long long)bytes, (long long)cap);
+    ONB_CUDA(c, cudaMemcpyAsync(p, host, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    ONB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ONB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- host helpers
 int32_t onb_start_states(const uint8_t* decks5, int64_t n, onb_state* out) {
     if (!decks5 || !out || n < 0) return ONB_E_INVALID;

@@ -1,0 +1,165 @@
+// The reference's own unit tests re-expressed against the C++ host mirror (include/onitama_b200.hpp); every rules call
+// below executes on the GPU through libonb.so. Sources: onitama-game/src/game/state.rs:420-889,
+// onitama-game/src/ai/mcts/mcts_arena.rs:403-457. Exit code 0 + "ALL OK" on success.
+#include <cstdio>
+#include <cmath>
+#include "onitama_b200.hpp"
+
+using namespace onitama;
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); ++failures; } } while (0)
+
+static Move mv(uint32_t r0, uint32_t c0, uint32_t r1, uint32_t c1, PieceKind p) { return Move::from_2d({{{r0, c0}, {r1, c1}}}, p); }
+
+static void create_all_legal_moves_for_red_in_starting_position() {  // state.rs:420-455
+    State state = State::with_deck(Deck({CRAB, RABBIT, DRAGON, TIGER, FROG}));
+    auto cards = state.deck.get_player_cards(PlayerColor::Red);
+    std::vector<Move> crab_expected = {mv(4, 0, 3, 0, PieceKind::Pawn), mv(4, 1, 3, 1, PieceKind::Pawn), mv(4, 2, 3, 2, PieceKind::King),
+                                       mv(4, 3, 3, 3, PieceKind::Pawn), mv(4, 4, 3, 4, PieceKind::Pawn)};
+    auto crab_moves = state.generate_legal_moves(PlayerColor::Red, *cards[0]);
+    std::sort(crab_moves.begin(), crab_moves.end()); std::sort(crab_expected.begin(), crab_expected.end());
+    CHECK(crab_moves == crab_expected);
+    std::vector<Move> rabbit_expected = {mv(4, 0, 3, 1, PieceKind::Pawn), mv(4, 1, 3, 2, PieceKind::Pawn), mv(4, 2, 3, 3, PieceKind::King),
+                                         mv(4, 3, 3, 4, PieceKind::Pawn)};
+    auto rabbit_moves = state.generate_legal_moves(PlayerColor::Red, *cards[1]);
+    std::sort(rabbit_moves.begin(), rabbit_moves.end()); std::sort(rabbit_expected.begin(), rabbit_expected.end());
+    CHECK(rabbit_moves == rabbit_expected);
+}
+static void create_all_legal_moves_for_blue_in_starting_position() {  // state.rs:457-492
+    State state = State::with_deck(Deck({DRAGON, TIGER, CRAB, RABBIT, FROG}));
+    auto cards = state.deck.get_player_cards(PlayerColor::Blue);
+    std::vector<Move> crab_expected = {mv(0, 0, 1, 0, PieceKind::Pawn), mv(0, 1, 1, 1, PieceKind::Pawn), mv(0, 2, 1, 2, PieceKind::King),
+                                       mv(0, 3, 1, 3, PieceKind::Pawn), mv(0, 4, 1, 4, PieceKind::Pawn)};
+    auto crab_moves = state.generate_legal_moves(PlayerColor::Blue, *cards[0]);
+    std::sort(crab_moves.begin(), crab_moves.end()); std::sort(crab_expected.begin(), crab_expected.end());
+    CHECK(crab_moves == crab_expected);
+    std::vector<Move> rabbit_expected = {mv(0, 1, 1, 0, PieceKind::Pawn), mv(0, 2, 1, 1, PieceKind::King), mv(0, 3, 1, 2, PieceKind::Pawn),
+                                         mv(0, 4, 1, 3, PieceKind::Pawn)};
+    auto rabbit_moves = state.generate_legal_moves(PlayerColor::Blue, *cards[1]);
+    std::sort(rabbit_moves.begin(), rabbit_moves.end()); std::sort(rabbit_expected.begin(), rabbit_expected.end());
+    CHECK(rabbit_moves == rabbit_expected);
+}
+static State base() { return State::with_deck(Deck({CRAB, RABBIT, DRAGON, TIGER, FROG})); }
+
+static void make_move_tests() {  // state.rs:495-816
+    {   // make_move_as_red
+        State s = base(); Card crab = *s.deck.get_player_cards(PlayerColor::Red)[0];
+        CHECK(s.make_move(Move{20, 15, PieceKind::Pawn}, PlayerColor::Red, 0) == MoveResult::InProgress);
+        CHECK(get_bit(s.pawns[0], 15) == 1 && get_bit(s.pawns[0], 20) == 0 && s.deck.neutral_card() == crab);
+    }
+    {   // make_move_as_blue
+        State s = base(); Card tiger = *s.deck.get_player_cards(PlayerColor::Blue)[1];
+        CHECK(s.make_move(Move{1, 11, PieceKind::Pawn}, PlayerColor::Blue, 3) == MoveResult::InProgress);
+        CHECK(get_bit(s.pawns[1], 11) == 1 && get_bit(s.pawns[1], 1) == 0 && s.deck.neutral_card() == tiger);
+    }
+    {   // capture_as_red
+        State s = base(); s.pawns[1] = 0x58010000u; Card crab = *s.deck.get_player_cards(PlayerColor::Red)[0];
+        CHECK(s.make_move(Move{20, 15, PieceKind::Pawn}, PlayerColor::Red, 0) == MoveResult::Capture);
+        CHECK(get_bit(s.pawns[0], 15) == 1 && get_bit(s.pawns[0], 20) == 0 && s.deck.neutral_card() == crab && s.pawns[1] == 0x58000000u);
+    }
+    {   // capture_as_blue
+        State s = base(); s.pawns[1] = 0x58200000u; Card tiger = *s.deck.get_player_cards(PlayerColor::Blue)[1];
+        CHECK(s.make_move(Move{10, 20, PieceKind::Pawn}, PlayerColor::Blue, 3) == MoveResult::Capture);
+        CHECK(get_bit(s.pawns[1], 20) == 1 && get_bit(s.pawns[1], 10) == 0 && s.deck.neutral_card() == tiger && s.pawns[0] == 0x00000580u);
+    }
+    {   // capture_win_as_red
+        State s = base(); s.pawns[0] = 0x01000680u;
+        CHECK(s.make_move(Move{7, 2, PieceKind::Pawn}, PlayerColor::Red, 0) == MoveResult::RedWin);
+        CHECK(get_bit(s.pawns[0], 2) == 1 && get_bit(s.pawns[0], 7) == 0 && s.kings[1] == 0);
+    }
+    {   // capture_win_as_blue
+        State s = base(); s.pawns[1] = 0x58080000u;
+        CHECK(s.make_move(Move{12, 22, PieceKind::Pawn}, PlayerColor::Blue, 3) == MoveResult::BlueWin);
+        CHECK(get_bit(s.pawns[1], 22) == 1 && get_bit(s.pawns[1], 12) == 0 && s.kings[0] == 0);
+    }
+    {   // king_in_temple_as_blue
+        State s = base(); s.kings[1] = 0x00080000u; s.kings[0] = 0x00002000u;
+        CHECK(s.make_move(Move{12, 22, PieceKind::King}, PlayerColor::Blue, 3) == MoveResult::BlueWin);
+        CHECK(get_bit(s.kings[1], 22) == 1 && get_bit(s.kings[1], 12) == 0 && s.kings[0] > 0);
+    }
+    {   // king_in_temple_as_red
+        State s = base(); s.kings[1] = 0x00080000u; s.kings[0] = 0x01000000u;
+        CHECK(s.make_move(Move{7, 2, PieceKind::King}, PlayerColor::Red, 0) == MoveResult::RedWin);
+        CHECK(get_bit(s.kings[0], 2) == 1 && get_bit(s.kings[0], 7) == 0 && s.kings[1] > 0);
+    }
+}
+static void no_legal_moves() {  // state.rs:819-889
+    State a = State::with_deck(Deck({DRAGON, TIGER, RABBIT, HORSE, FROG}));
+    a.kings[1] = 67108864; a.kings[0] = 512; a.pawns[0] = 61568; a.pawns[1] = 3221225472u;
+    CHECK(a.generate_legal_moves(PlayerColor::Blue, *a.deck.get_player_cards(PlayerColor::Blue)[0]).empty());
+    State b = State::with_deck(Deck({DRAGON, RABBIT, TIGER, HORSE, FROG}));
+    b.kings[1] = 131072; b.kings[0] = 16384; b.pawns[0] = 2148009984u; b.pawns[1] = 138416256;
+    auto cards = b.deck.get_player_cards(PlayerColor::Blue);
+    CHECK(b.generate_legal_moves(PlayerColor::Blue, *cards[0]).empty());
+    CHECK(b.generate_legal_moves(PlayerColor::Blue, *cards[1]).empty());
+    CHECK(b.generate_all_legal_moves(PlayerColor::Blue).empty());
+}
+static void expand_order() {  // ai/mcts/mcts_arena.rs:403-457: enumeration order after expand
+    State s = State::with_deck(Deck({DRAGON, FROG, TIGER, RABBIT, HORSE}));
+    const char* expected[] = {"Dragon a1-c2", "Dragon b1-d2", "Dragon c1-a2", "Dragon c1-e2", "Dragon d1-b2", "Dragon e1-c2",
+                              "Frog b1-a2", "Frog c1-b2", "Frog d1-c2", "Frog e1-d2"};
+    auto moves = s.generate_all_legal_moves(PlayerColor::Red);
+    CHECK(moves.size() == 10);
+    for (size_t i = 0; i < moves.size() && i < 10; ++i) {
+        std::string str = std::string(s.deck.get_card(moves[i].first).name()) + " " + Move::convert_idx_to_notation(moves[i].second.from) + "-" +
+                          Move::convert_idx_to_notation(moves[i].second.to);
+        CHECK(str == expected[i]);
+    }
+}
+static void search_and_drivers() {
+    // deck Dragon,Frog,Tiger,Rabbit,Horse, c = sqrt(2), 400 playouts, uniform evaluator -> best = (slot 1, 24 -> 18)
+    TrainingAlphaZeroMcts mcts;
+    mcts.config.max_playouts = 400;
+    State s = State::with_deck(Deck({DRAGON, FROG, TIGER, RABBIT, HORSE}));
+    auto r = mcts.generate_move_tensor(s, PlayerColor::Red);
+    CHECK((r.first == DoneMove{Move{24, 18, PieceKind::Pawn}, 1}));
+    float sum = 0.f; for (float p : r.second) sum += p;
+    CHECK(std::fabs(sum - 1.f) < 1e-5f);
+    CHECK(r.second[25 + 18] == 46.f / 400.f);  // pi[slot 1][to 18] = visits / total, f32 division
+    // the same search with the network as a host-side black box (uniform policy, value 0) must be identical
+    TrainingAlphaZeroMcts host = mcts;
+    host.config.max_playouts = 60;
+    TrainingAlphaZeroMcts dev = host;
+    host.model = [](const float*, int64_t n, float* pol, float* val) { for (int64_t i = 0; i < n * 50; ++i) pol[i] = 1.0f / 50.0f; for (int64_t i = 0; i < n; ++i) val[i] = 0.f; };
+    auto rh = host.generate_move_tensor(s, PlayerColor::Red), rd = dev.generate_move_tensor(s, PlayerColor::Red);
+    CHECK(rh.first == rd.first && rh.second == rd.second);
+    // self_play: sample invariants (train.rs:55-88)
+    TrainConfig tc; tc.mcts_config.max_playouts = 32; tc.self_play_game_amnt = 8; tc.max_plies = 10; tc.seed = 3;
+    TrainingAlphaZeroMcts sp; sp.config = tc.mcts_config;
+    auto data = self_play(sp, tc);
+    CHECK(!data.empty() && data.size() <= 8 * 12);
+    for (auto& d : data) {
+        float ps = 0.f; for (float p : d.pi) ps += p;
+        CHECK(std::fabs(ps - 1.f) < 1e-5f);
+        CHECK(d.z == 0.f || d.z == 1.f || d.z == -1.f);
+        float side_plane = d.state[20 * 25];
+        CHECK(side_plane == (d.player_color == PlayerColor::Blue ? 1.f : 0.f));
+    }
+    // fight: AlphaZero MCTS (uniform evaluator, 64 playouts) against the Random agent, colours alternate
+    EvaluatorConfig ec; ec.game_amnt = 4; ec.seed = 11;
+    auto az = std::make_unique<AlphaZeroMcts>(); az->config.max_playouts = 64;
+    FightStatistics fs = fight(ec, std::move(az), std::make_unique<Random>(5));
+    CHECK(fs.wins + fs.losses + fs.draws == 4 && fs.games_red == 2 && fs.games_blue == 2);
+    CHECK(fs.wins >= fs.losses);
+    // error behaviour: the reference panics, the mirror throws
+    bool threw = false;
+    try { Deck d; d.rotate(4); } catch (const Error&) { threw = true; }
+    CHECK(threw);
+}
+
+int main() {
+    try {
+        create_all_legal_moves_for_red_in_starting_position();
+        create_all_legal_moves_for_blue_in_starting_position();
+        make_move_tests();
+        no_legal_moves();
+        expand_order();
+        search_and_drivers();
+    } catch (const Error& e) {
+        std::printf("FAIL exception %d: %s\n", e.code, e.what());
+        return 2;
+    }
+    if (failures) { std::printf("%d FAILURES\n", failures); return 1; }
+    std::printf("ALL OK\n");
+    return 0;
+}

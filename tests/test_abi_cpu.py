@@ -90,3 +90,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/onb_oracle.cpp", ""), f
+
+
+def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(lib):
+    """include/onitama_b200.hpp compiles against the C ABI; without a device its first GPU call throws (no CPU fallback)."""
+    import subprocess
+    import torch
+    import __graft_entry__ as ge
+    exe = ge.build_cpp_mirror_test()
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "no CPU fallback" in r.stdout

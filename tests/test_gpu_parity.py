@@ -535,3 +535,12 @@ def test_fight_mcts_vs_random(onb):
     assert a == int((red & a_is_red).sum() + (blue & ~a_is_red).sum())
     assert b == int((red & ~a_is_red).sum() + (blue & a_is_red).sum())
     assert a + b + d == n and a > b  # 48-sim search beats the random agent
+
+
+def test_cpp_host_mirror_reference_tests(onb):
+    """The reference's unit tests re-expressed in C++ against include/onitama_b200.hpp, run on the GPU."""
+    import subprocess
+    import __graft_entry__ as ge
+    exe = ge.build_cpp_mirror_test()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
