@@ -319,7 +319,7 @@ def main():
     def bench_env(steps, warmup):
         n = ENV_GAMES
         flags = onb.OUT_MASKS | onb.OUT_PLANES
-        ctx = onb.Context(n, seed=SEED, game_id_base=rank * n, stream=stream.cuda_stream)
+        ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream)
         ctx.reset()
         ms, clocks = timed(lambda i: ctx.step_random(i, auto_reset=True, out_flags=flags), warmup, steps)
         st = ctx.stats()
@@ -361,7 +361,7 @@ def main():
     # ---------------------------------------------------------------- mcts (config 4)
     def bench_mcts(steps, warmup):
         n, sims = MCTS_TREES, MCTS_SIMS
-        ctx = onb.Context(n, seed=SEED, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims, planes=False)
+        ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims, planes=False)
         # roots = positions after p = (id mod 16) random plies of config-1 games (built with the env kernels);
         # a game that ended before its p-th ply is searched from its start position instead
         ctx.reset()
@@ -424,7 +424,7 @@ def main():
     # ---------------------------------------------------------------- playout (config 1)
     def bench_playout(steps, warmup):
         n = PLAYOUT_GAMES
-        ctx = onb.Context(n, seed=SEED, game_id_base=rank * n, stream=stream.cuda_stream, planes=False)
+        ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, planes=False)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         total = {"steps": 0}
 
@@ -449,7 +449,7 @@ def main():
         decks = np.array(all_deals(), dtype=np.uint8)
         lo, cnt = rank * len(decks) // world, (rank + 1) * len(decks) // world - rank * len(decks) // world
         roots = onb.start_states(decks[lo:lo + cnt])  # if sharded (N > 1): deals are partitioned, "strong" scaling
-        ctx = onb.Context(8, stream=stream.cuda_stream, planes=False)
+        ctx = onb.Context(8, device=local_rank, stream=stream.cuda_stream, planes=False)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         res = {}
 

@@ -115,7 +115,7 @@ static void search_and_drivers() {
     CHECK((r.first == DoneMove{Move{24, 18, PieceKind::Pawn}, 1}));
     float sum = 0.f; for (float p : r.second) sum += p;
     CHECK(std::fabs(sum - 1.f) < 1e-5f);
-    CHECK(r.second[25 + 18] == 46.f / 400.f);  // pi[slot 1][to 18] = visits / total, f32 division
+    CHECK(r.second[25 + 18] == 46.f / 399.f);  // pi[slot 1][to 18] = visits / sum of child visits (399), f32 division
     // the same search with the network as a host-side black box (uniform policy, value 0) must be identical
     TrainingAlphaZeroMcts host = mcts;
     host.config.max_playouts = 60;
