@@ -30,6 +30,8 @@ MCTS_TREES = 1 << 14
 MCTS_SIMS = 400
 MCTS_C = 2.0
 PLAYOUT_GAMES = 4096
+SELFPLAY_GAMES = 4096
+SELFPLAY_SIMS = 800
 SEED = 20240607
 # algorithmic bytes per unit of work
 ENV_BYTES_PER_STEP = 16 + 16 + 8 + 2100  # state read, state write, legal mask, planes
@@ -220,6 +222,11 @@ def workload_config(wl):
         return {"workload": "BASELINE config 4: batched PUCT MCTS, %d sims/move, %d concurrent trees/GPU, uniform-prior evaluator, eval mode"
                             % (MCTS_SIMS, MCTS_TREES), "trees_per_gpu": MCTS_TREES, "sims": MCTS_SIMS, "c_puct": MCTS_C,
                 "l2": "touched node pools ~2.4 GB/GPU >> 126 MB L2"}
+    if wl == "selfplay":
+        return {"workload": "BASELINE config 5: AlphaZero self-play, %d sims/move, 3-block ConvResNet (64 ch, random init, fixed seed) as a torch "
+                            "black box reading the leaf buffer zero-copy, %d concurrent games/GPU, one ply per step, replay samples gathered to GPU 0"
+                            % (SELFPLAY_SIMS, SELFPLAY_GAMES), "games_per_gpu": SELFPLAY_GAMES, "sims": SELFPLAY_SIMS, "c_puct": MCTS_C,
+                "l2": "node pools + leaf batches >> L2"}
     if wl == "perft":
         return {"workload": "BASELINE config 2: perft-style legal-move enumeration depth 6 from the standard opening over all 131040 canonical "
                             "card deals, 1 GPU", "deals": 131040, "depth": 6, "l2": "DFS phase is register resident (~0 B/node); L2 flushed between iterations"}
@@ -234,7 +241,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft"])
+    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -476,8 +483,43 @@ def main():
         return dict(metric="perft_nodes_per_sec", value=value, unit="nodes/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
                     gpu_launches=5 * steps, clocks=clocks)
 
+    # ---------------------------------------------------------------- self-play with the network (config 5)
+    def bench_selfplay(steps, warmup):
+        from onitama_alphazero_b200.net import ConvResNet, make_evaluator
+        n, sims = SELFPLAY_GAMES, SELFPLAY_SIMS
+        torch.manual_seed(1234)
+        net = make_evaluator(ConvResNet(64, 21, 3).cuda(local_rank))
+        ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims)
+        ctx.reset()
+        planes_t, pi_t = ctx.tensor(onb.BUF_PLANES), ctx.tensor(onb.BUF_PI)
+        got = {"samples": 0}
+
+        def one_ply(i):
+            ctx.encode(to_host=False)                      # sample planes of the searched position (train.rs:58)
+            ctx.search_device(MCTS_C, sims, net=net, use_graph=True)  # select -> ConvResNet (zero-copy leaf batch) -> expand/backup, x sims
+            z = torch.zeros(n, device=planes_t.device)
+            out_s = onb.gather_replay(planes_t, pi_t, z, dst=0)   # NCCL gather of the ply's samples to the trainer GPU
+            if out_s is not None:
+                got["samples"] = int(out_s[0].shape[0])
+            ctx.mcts_play_best()
+
+        ms, clocks = timed(one_ply, warmup, steps)
+        value = world * n * sims * steps / (ms * 1e-3)
+        ctx.close()
+        per_sim = 1217.0 + 2100 + 204
+        roof = {"bound": "hbm", "achieved": per_sim * n * sims * steps / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": per_sim * n * sims * steps / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_mcts_select + k_mcts_expand_backup",
+                "note": "the step is dominated by the black-box network (library kernels, ~11.7 MFLOP per evaluation), not by these kernels",
+                "peak_source": peak_src}
+        e2e = {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "path": "device-resident self-play ply (search + sample gather + play); nothing crosses PCIe by design"}
+        return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=ms / steps, dtype="u32+f64 (search), f32/tf32 (network)",
+                    roofline=roof, e2e=e2e, gpu_launches=(2 * sims + 4) * steps, clocks=clocks, samples_per_ply=got["samples"])
+
     if wl == "env":
         out = bench_env(args.steps, args.warmup)
+    elif wl == "selfplay":
+        out = bench_selfplay(args.steps, args.warmup)
     elif wl == "perft":
         out = bench_perft(args.steps, args.warmup)
     elif wl == "mcts":

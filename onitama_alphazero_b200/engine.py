@@ -240,21 +240,44 @@ class Context:
         return self.mcts_finish()
 
 
-def _search_device(self, c_puct, sims, evaluator=L.EVAL_UNIFORM, net=None):
-    """Context.search without copying the results to the host (PI / BEST stay in their device buffers)."""
+def _search_device(self, c_puct, sims, evaluator=L.EVAL_UNIFORM, net=None, use_graph=False):
+    """Context.search without copying the results to the host (PI / BEST stay in their device buffers).
+    use_graph: capture one simulation round (select -> network -> expand/backup) in a CUDA graph on the context's stream and
+    replay it; the round is launch-bound otherwise (~40 small network kernels per round)."""
     self.mcts_begin(c_puct, sims)
     if net is None:
         self.mcts_run(evaluator, sims)
     else:
         import torch
-        with torch.cuda.stream(self.torch_stream()):
+        ts = self.torch_stream()
+        with torch.cuda.stream(ts):
             planes, pol, val = self.tensor(L.BUF_LEAF_PLANES), self.tensor(L.BUF_POLICY), self.tensor(L.BUF_VALUE)
-            for _ in range(sims):
+
+            def one_round():
                 self.mcts_select()
                 p, v = net(planes)
                 pol.copy_(p.reshape(pol.shape))
                 val.copy_(v.reshape(val.shape))
                 self.mcts_expand_backup()
+
+            if not use_graph or sims < 3:
+                for _ in range(sims):
+                    one_round()
+            else:
+                key = (id(net), float(c_puct))
+                cache = self.__dict__.setdefault("_graphs", {})
+                done = 0
+                if key not in cache:
+                    one_round()  # eager warm-up round (lazy cuDNN/cuBLAS initialisation must not happen during capture)
+                    done = 1
+                    ts.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=ts):
+                        one_round()  # captured, not executed
+                    cache[key] = g
+                g = cache[key]
+                for _ in range(sims - done):
+                    g.replay()
     self.mcts_finish(to_host=False)
 
 

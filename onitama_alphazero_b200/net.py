@@ -1,0 +1,83 @@
+"""Stand-in for the reference's policy/value network (alphazero-training/src/net.rs:14-232), kept a BLACK BOX by the
+hot path: it reads ONB_BUF_LEAF_PLANES [n,21,5,5] and produces policy [n,2,25] (softmax over 50) and value [n,1] (tanh).
+Harness only (plain PyTorch, library kernels): the product is the search/env path around it. Parameter names follow the
+reference's VarStore paths ('resnet_0|resnet_small_block1|small_block_conv|weight', ...) so the shipped .ot archives load."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class _SmallBlock(nn.Module):  # net.rs:9-38
+    def __init__(self, c_in, c_out):
+        super().__init__()
+        self.small_block_conv = nn.Conv2d(c_in, c_out, 3, stride=1, padding=1)
+        self.small_block_bn = nn.BatchNorm2d(c_out)
+
+    def forward(self, x):
+        return self.small_block_bn(self.small_block_conv(x))
+
+
+class _ResNetBlock(nn.Module):  # net.rs:40-66
+    def __init__(self, c):
+        super().__init__()
+        self.resnet_small_block1 = _SmallBlock(c, c)
+        self.resnet_small_block2 = _SmallBlock(c, c)
+
+    def forward(self, x):
+        return F.relu(self.resnet_small_block2(F.relu(self.resnet_small_block1(x))) + x)
+
+
+class ConvResNet(nn.Module):
+    """ConvResNetConfig{hidden_channels, input_channels, resnet_block_amnt} (net.rs:74-90)."""
+
+    def __init__(self, hidden_channels=64, input_channels=21, resnet_block_amnt=3):
+        super().__init__()
+        h = hidden_channels
+        self.conv_init_1 = nn.Conv2d(input_channels, h, 3, stride=1, padding=1)
+        self.bn1 = nn.BatchNorm2d(h)
+        for i in range(resnet_block_amnt):
+            setattr(self, "resnet_%d" % i, _ResNetBlock(h))
+        self.n_blocks = resnet_block_amnt
+        self.vh_conv = nn.Conv2d(h, 1, 1)
+        self.vh_bn = nn.BatchNorm2d(1)
+        self.vh_linear1 = nn.Linear(25, h)
+        self.vh_linear2 = nn.Linear(h, 1)
+        self.policy_conv = nn.Conv2d(h, 2, 1)
+        self.policy_bn = nn.BatchNorm2d(2)
+        self.ph_linear2 = nn.Linear(50, 50)
+
+    def forward(self, x):
+        """x [n,21,5,5] -> (policy [n,2,25], value [n,1])  (net.rs:215-232; the batch dimension replaces unsqueeze(0))"""
+        y = F.relu(self.bn1(self.conv_init_1(x)))
+        for i in range(self.n_blocks):
+            y = getattr(self, "resnet_%d" % i)(y)
+        v = F.relu(self.vh_bn(self.vh_conv(y))).flatten(1)
+        v = torch.tanh(self.vh_linear2(F.relu(self.vh_linear1(v))))
+        p = F.relu(self.policy_bn(self.policy_conv(y))).flatten(1)
+        p = torch.softmax(self.ph_linear2(p), dim=-1).reshape(-1, 2, 25)
+        return p, v
+
+    def load_ot(self, path):
+        """Load a libtorch named-tensor archive saved by VarStore::save (train.rs:414-430)."""
+        arch = torch.jit.load(path, map_location="cpu")
+        src = {n.replace("|", "."): p.detach() for n, p in arch.named_parameters()}
+        own = self.state_dict()
+        missing = [k for k in own if k not in src and not k.endswith("num_batches_tracked")]
+        if missing:
+            raise KeyError("tensors missing from %s: %s" % (path, missing[:5]))
+        for k in own:
+            if k in src:
+                own[k].copy_(src[k])
+        return self
+
+
+def make_evaluator(model):
+    """Wrap a module as the `net` callable of Context.search / self_play: planes tensor -> (policy, value)."""
+    model.eval()
+
+    @torch.no_grad()
+    def net(planes):
+        p, v = model(planes)
+        return p, v.reshape(-1)
+
+    return net

@@ -160,7 +160,11 @@ def perft(g, depth):
     return nodes, wins, zero
 
 
-def mcts_search(g, c_puct, sims, evaluator=0, dump=False):
+EVAL_CB = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
+
+
+def mcts_search(g, c_puct, sims, evaluator=0, dump=False, callback=None):
+    """callback(planes[525] float32 ndarray) -> (policy[50], value): a host evaluator (the network as a black box)."""
     best = np.zeros(1, dtype=np.uint16)
     pi = np.zeros(50, dtype=np.float32)
     rv = np.zeros(1, dtype=np.uint32)
@@ -176,7 +180,16 @@ def mcts_search(g, c_puct, sims, evaluator=0, dump=False):
                     prior=np.zeros(cap, np.float64), action=np.zeros(cap, np.uint16), parent=np.zeros(cap, np.int32),
                     first_child=np.zeros(cap, np.uint32), n_child=np.zeros(cap, np.uint32), flags=np.zeros(cap, np.uint8))
         td = TreeDump(*[_p(arrs[k]) for k, _ in TreeDump._fields_])
-    n = lib().orc_mcts_search(_p(g), c_puct, sims, evaluator, None, None, _p(best), _p(pi), _p(rv), _p(rq), _p(ps), _p(md),
+    cb = None
+    if callback is not None:
+        def _cb(planes_p, pol_p, val_p, _user):
+            planes = np.ctypeslib.as_array(planes_p, shape=(525,)).copy()
+            pol, val = callback(planes)
+            np.ctypeslib.as_array(pol_p, shape=(50,))[:] = np.asarray(pol, dtype=np.float32).reshape(50)
+            val_p[0] = float(val)
+        cb = EVAL_CB(_cb)
+        evaluator = 2
+    n = lib().orc_mcts_search(_p(g), c_puct, sims, evaluator, C.cast(cb, C.c_void_p) if cb else None, None, _p(best), _p(pi), _p(rv), _p(rq), _p(ps), _p(md),
                               _p(mc), C.byref(td) if td is not None else None, cap)
     res.update(n_nodes=int(n), best=int(best[0]), pi=pi.reshape(2, 25), root_visits=int(rv[0]), root_q=float(rq[0]),
                pass_seen=int(ps[0]), mean_depth=float(md[0]), mean_children=float(mc[0]))

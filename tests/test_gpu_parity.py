@@ -544,3 +544,69 @@ def test_cpp_host_mirror_reference_tests(onb):
     exe = ge.build_cpp_mirror_test()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_search_with_network_black_box_bit_exact(onb):
+    """BASELINE config 5 in miniature: the 3-block ConvResNet (random init, fixed seed) drives the split-phase search.
+    Both sides see bit-identical network outputs (the same CPU module evaluated sample by sample), so visit counts, priors
+    and W must be bit-exact; this exercises select -> leaf planes -> policy/value buffers -> expand/backup end to end."""
+    import torch
+    from onitama_alphazero_b200.net import ConvResNet
+    torch.manual_seed(1234)
+    model = ConvResNet(64, 21, 3).eval()
+    for m in model.modules():  # non-trivial BatchNorm statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+
+    @torch.no_grad()
+    def eval_one(planes525):
+        p, v = model(torch.from_numpy(np.asarray(planes525, dtype=np.float32)).reshape(1, 21, 5, 5))
+        return p.reshape(50).numpy(), float(v.reshape(()))
+
+    n, sims, c = 6, 40, 2.0
+    roots = _cfg4_roots(16, 5)[[1, 3, 6, 9, 12, 15]]
+    with onb.Context(n, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.set_states(roots)
+
+        def net(planes_dev):
+            host = planes_dev.cpu().numpy()
+            outs = [eval_one(host[i]) for i in range(n)]
+            pol = torch.from_numpy(np.stack([o[0] for o in outs])).to(planes_dev.device)
+            val = torch.tensor([o[1] for o in outs], dtype=torch.float32, device=planes_dev.device)
+            return pol, val
+
+        res = ctx.search(c, sims, net=net)
+        for t in range(n):
+            if roots["result"][t] != 0:
+                continue
+            want = O.mcts_search(roots[t:t + 1], c, sims, dump=True, callback=eval_one)
+            got = ctx.mcts_dump_tree(t)
+            assert np.array_equal(got["visits"], want["tree"]["visits"]), t
+            assert np.array_equal(got["prior"], want["tree"]["prior"])
+            assert np.array_equal(got["reward"], want["tree"]["reward"])
+            assert int(res["best"][t]) == want["best"]
+            assert np.array_equal(res["pi"][t], want["pi"])
+            assert abs(res["root_q"][t] - want["root_q"]) <= Q_TOL
+
+
+def test_selfplay_with_gpu_network_runs(onb):
+    """The same network on the GPU, zero-copy on the context's stream (statistical check only: GPU conv != CPU conv bitwise)."""
+    import torch
+    from onitama_alphazero_b200.net import ConvResNet, make_evaluator
+    torch.manual_seed(7)
+    net = make_evaluator(ConvResNet(64, 21, 3).cuda())
+    n, sims = 32, 16
+    with onb.Context(n, seed=2, mcts_max_sims=sims) as ctx:
+        out = onb.self_play(ctx, 2.0, sims, max_plies=6, net=net)
+        # one simulation round captured in a CUDA graph and replayed gives the same search as eager launches
+        ctx.reset()
+        ctx.search_device(2.0, sims, net=net)
+        eager = ctx.mcts_finish()
+        ctx.search_device(2.0, sims, net=net, use_graph=True)
+        ctx.search_device(2.0, sims, net=net, use_graph=True)  # second call reuses the cached graph
+        graphed = ctx.mcts_finish()
+        assert np.array_equal(eager["child_visits"], graphed["child_visits"]) and np.array_equal(eager["best"], graphed["best"])
+    m = out["planes"].shape[0]
+    assert m == n * 8 or m <= n * 8
+    assert torch.allclose(out["pi"].sum(dim=(1, 2)), torch.ones(m, device=out["pi"].device), atol=1e-5)
+    assert set(out["z"].unique().tolist()) <= {-1.0, 0.0, 1.0}

@@ -1,0 +1,30 @@
+"""The network stand-in: architecture restated from net.rs; loads the reference's .ot archives when they are available
+(build container only -- /root/reference does not exist on the GPU box)."""
+import os
+
+import pytest
+import torch
+
+
+def test_shapes_and_param_count():
+    from onitama_alphazero_b200.net import ConvResNet
+    m = ConvResNet(64, 21, 3).eval()
+    n_elems = sum(v.numel() for k, v in m.state_dict().items() if not k.endswith("num_batches_tracked"))
+    assert n_elems == 240006  # model_5e-3_3_resnet.ot = 60 tensors / 240 006 elements
+    p, v = m(torch.zeros(7, 21, 5, 5))
+    assert p.shape == (7, 2, 25) and v.shape == (7, 1)
+    assert torch.allclose(p.reshape(7, -1).sum(-1), torch.ones(7), atol=1e-6) and (v.abs() <= 1).all()
+    assert sum(v.numel() for k, v in ConvResNet(64, 21, 5).state_dict().items() if not k.endswith("num_batches_tracked")) == 388742
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/model_5e-3_3_resnet.ot"), reason="reference weights not present")
+def test_loads_reference_ot_archive():
+    from onitama_alphazero_b200.net import ConvResNet, make_evaluator
+    m = ConvResNet(64, 21, 3).load_ot("/root/reference/models/model_5e-3_3_resnet.ot")
+    net = make_evaluator(m)
+    x = torch.zeros(2, 21, 5, 5)
+    x[:, 0, 4, :] = 1
+    p, v = net(x)
+    assert p.shape == (2, 2, 25) and v.shape == (2,) and torch.isfinite(p).all() and torch.equal(p[0], p[1])
+    m5 = ConvResNet(64, 21, 5).load_ot("/root/reference/models/model_5e-3.ot")
+    assert m5.n_blocks == 5
