@@ -120,8 +120,8 @@ __host__ __device__ __forceinline__ uint32_t card_at(uint32_t cards, uint32_t sl
 // Deck::rotate (deck.rs:87-90): swap hand slot `idx` with the neutral slot 4.
 __host__ __device__ __forceinline__ uint32_t rotate_cards(uint32_t cards, uint32_t idx) {
     const uint32_t sh = 4u * idx;
-    const uint32_t a = (cards >> sh) & 15u, b = (cards >> 16) & 15u;
-    return (cards & 0xFFFFu & ~(15u << sh)) | (b << sh) | (a << 16);
+    const uint32_t d = ((cards >> sh) ^ (cards >> 16)) & 15u;  // xor-swap of the two nibbles
+    return cards ^ (d << sh) ^ (d << 16);
 }
 
 // start position (state.rs:24-45) in the internal layout
@@ -211,6 +211,48 @@ __host__ __device__ __forceinline__ uint32_t apply_move(Game& g, uint32_t action
     }
     g.side = side ^ 1u;
     g.result = res;
+    return res;
+}
+
+// The same transition on a mover-relative view (own / enemy boards instead of Red / Blue), used by the search descent where
+// the per-ply colour selects of apply_move would dominate: after the move the roles are swapped, so the view is again
+// relative to the side to move.
+struct RelGame {
+    uint32_t op, ok, ep, ek;  // own pawns, own king, enemy pawns, enemy king (of the side to move)
+    uint32_t cards, side;
+};
+__host__ __device__ __forceinline__ RelGame to_rel(const Game& g) {
+    RelGame r;
+    r.op = g.side ? g.pawn_b : g.pawn_r; r.ok = g.side ? g.king_b : g.king_r;
+    r.ep = g.side ? g.pawn_r : g.pawn_b; r.ek = g.side ? g.king_r : g.king_b;
+    r.cards = g.cards; r.side = g.side;
+    return r;
+}
+__host__ __device__ __forceinline__ Game from_rel(const RelGame& r) {
+    Game g;
+    g.pawn_r = r.side ? r.ep : r.op; g.king_r = r.side ? r.ek : r.ok;
+    g.pawn_b = r.side ? r.op : r.ep; g.king_b = r.side ? r.ok : r.ek;
+    g.cards = r.cards; g.side = r.side; g.result = 0; g.passed = 0;
+    return g;
+}
+__host__ __device__ __forceinline__ uint32_t apply_move_rel(RelGame& g, uint32_t action) {
+    const uint32_t to = action & 31u, from = (action >> 5) & 31u, idx = (action >> 10) & 3u, king = (action >> 12) & 1u;
+    uint32_t res = 0;
+    if (!(action & kPassBit)) {
+        const uint32_t fb = 1u << from, tb = 1u << to;
+        const uint32_t km = 0u - king;  // all ones if the mover is the king
+        g.ok = (g.ok & ~(fb & km)) | (tb & km);
+        g.op = (g.op & ~(fb & ~km)) | (tb & ~km);
+        const uint32_t hit_p = g.ep & tb;
+        g.ep &= ~tb;
+        const uint32_t hit_k = hit_p ? 0u : (g.ek & tb);
+        g.ek &= ~hit_k;
+        if (hit_k || (king && to == (g.side ? kRedTemple : kBlueTemple))) res = 1u + g.side;
+    }
+    g.cards = rotate_cards(g.cards, idx);
+    uint32_t t = g.op; g.op = g.ep; g.ep = t;
+    t = g.ok; g.ok = g.ek; g.ek = t;
+    g.side ^= 1u;
     return res;
 }
 

@@ -610,3 +610,35 @@ def test_selfplay_with_gpu_network_runs(onb):
     assert m == n * 8 or m <= n * 8
     assert torch.allclose(out["pi"].sum(dim=(1, 2)), torch.ones(m, device=out["pi"].device), atol=1e-5)
     assert set(out["z"].unique().tolist()) <= {-1.0, 0.0, 1.0}
+
+
+def test_mcts_deep_paths_bit_exact(onb):
+    """Many simulations from late positions: descents deeper than the lane-held path (8 levels with 8 lanes per tree) use the
+    parent-chain backup; more children than lanes are scanned in several rounds. Every node must still match the oracle."""
+    seed, sims, c = 41, 1500, 0.1  # a small c_puct with non-zero leaf values digs deep (20 levels with the hash evaluator)
+    g = O.new_games(96, seed=seed)
+    for step in range(30):
+        O.env_step_random(g, seed, step)
+    roots = g[g["result"] == 0][:40]
+    assert len(roots) >= 20
+    with onb.Context(len(roots), seed=seed, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.set_states(roots)
+        for ev in (onb.EVAL_UNIFORM, onb.EVAL_HASH):
+            res = ctx.search(c, sims, evaluator=ev, fused=True)
+            want = O.mcts_search_batch(roots, c, sims, evaluator=ev, threads=8)
+            assert np.array_equal(res["child_visits"], want["child_visits"])
+            assert np.array_equal(res["best"], want["best"])
+            assert np.array_equal(res["root_q"], want["root_q"])
+            deepest = 0
+            for t in range(0, len(roots), 3):
+                w = O.mcts_search(roots[t:t + 1], c, sims, evaluator=ev, dump=True)
+                got = ctx.mcts_dump_tree(t)
+                assert np.array_equal(got["visits"], w["tree"]["visits"]) and np.array_equal(got["reward"], w["tree"]["reward"])
+                assert np.array_equal(got["parent"], w["tree"]["parent"]) and np.array_equal(got["flags"], w["tree"]["flags"])
+                par = w["tree"]["parent"]
+                depth = np.zeros(len(par), dtype=np.int32)
+                for i in range(1, len(par)):
+                    depth[i] = depth[par[i]] + 1
+                deepest = max(deepest, int(depth.max()))
+            if ev == onb.EVAL_HASH:
+                assert deepest >= 12, "test positions did not produce a path deeper than the lane-held levels (%d)" % deepest
