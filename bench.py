@@ -100,7 +100,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": "warm-up + timed region"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -238,13 +238,18 @@ def workload_config(wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default per workload: env 200, mcts 20, perft 5, selfplay 3, playout 50)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default per workload, >= 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    dflt = {"env": (200, 20), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5)}[args.workload]
+    if args.impl == "reference":
+        dflt = (3, 1)
+    args.steps = dflt[0] if args.steps is None else args.steps
+    args.warmup = dflt[1] if args.warmup is None else args.warmup
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -290,14 +295,16 @@ def main():
         return ms
 
     def timed(fn, warmup, steps, between=None):
+        # the clock sampler (nvidia-smi, 100 ms period) runs from the first warm-up step to the end of the timed region:
+        # the timed region alone can be shorter than one sampling period
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
         for i in range(warmup):
             fn(i)
             if between:
                 between()
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if between is None:
             e0.record(stream)
@@ -337,31 +344,63 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic("k_env_step"),
                 "kernel": "k_env_step<uniform,planes>", "algorithmic_bytes_per_launch": ENV_BYTES_PER_STEP * n, "peak_source": peak_src}
         # e2e: recorded actions replayed from PINNED HOST memory through onb_env_step (H2D inside), masks + stats read back (D2H)
-        k_all = warmup + steps
-        ctx.reset()
-        acts_dev = ctx.tensor(onb.BUF_ACTIONS)
-        host_actions = torch.empty((k_all, n), dtype=torch.int16).pin_memory()
-        for i in range(k_all):
-            ctx.step_random(i, auto_reset=True, out_flags=onb.OUT_ACTIONS)
-            host_actions[i].copy_(acts_dev)
-        torch.cuda.synchronize()
-        ctx.reset()
-        masks_dev = ctx.tensor(onb.BUF_MASKS)
-        stats_dev = ctx.tensor(onb.BUF_STATS)
-        host_masks = torch.empty((n, 2), dtype=torch.int32).pin_memory()
-        host_stats = torch.empty((onb._lib.STAT_COUNT,), dtype=torch.int64).pin_memory()
-
-        def e2e_step(i):
-            ctx.step_from_host_ptr(host_actions[i].data_ptr(), step=i, auto_reset=True, out_flags=flags)
-            host_masks.copy_(masks_dev, non_blocking=True)
-            host_stats.copy_(stats_dev, non_blocking=True)
-            stream.synchronize()  # the host actor needs the masks before it can pick the next actions
-
-        ems, _ = timed(e2e_step, warmup, steps)
-        assert int(host_stats[onb.STAT_STEPS]) >= n * steps
-        e2e = {"value": world * n * steps / (ems * 1e-3), "unit": "env_steps/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 8 * n + 64,
-               "ms_per_step": ems / steps, "path": "onb_env_step(host actions) + D2H of legal masks and stats every step; planes stay in HBM for the network"}
+        # every step. The batch is split into two half-size contexts on two streams, as a host actor would do: while the host
+        # waits for (and consumes) the masks of one half, the other half is stepping, so PCIe copies overlap with compute.
         ctx.close()
+        k_all = warmup + steps
+        half = n // 2
+        hstreams = [torch.cuda.Stream(device=local_rank) for _ in range(2)]
+        hctx = [onb.Context(half, seed=SEED, device=local_rank, game_id_base=rank * n + h * half, stream=hstreams[h].cuda_stream) for h in range(2)]
+        host_actions = [torch.empty((k_all, half), dtype=torch.int16).pin_memory() for _ in range(2)]
+        host_masks = [torch.empty((half, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
+        host_stats = [torch.empty((onb._lib.STAT_COUNT,), dtype=torch.int64).pin_memory() for _ in range(2)]
+        masks_dev = [c.tensor(onb.BUF_MASKS) for c in hctx]
+        stats_dev = [c.tensor(onb.BUF_STATS) for c in hctx]
+        for h in range(2):
+            with torch.cuda.stream(hstreams[h]):
+                hctx[h].reset()
+                acts_dev = hctx[h].tensor(onb.BUF_ACTIONS)
+                for i in range(k_all):
+                    hctx[h].step_random(i, auto_reset=True, out_flags=onb.OUT_ACTIONS)
+                    host_actions[h][i].copy_(acts_dev)
+                hstreams[h].synchronize()
+                hctx[h].reset()
+                hctx[h].stats(clear=True)
+
+        def issue(h, i):
+            with torch.cuda.stream(hstreams[h]):
+                hctx[h].step_from_host_ptr(host_actions[h][i].data_ptr(), step=i, auto_reset=True, out_flags=flags)
+                host_masks[h].copy_(masks_dev[h], non_blocking=True)
+                host_stats[h].copy_(stats_dev[h], non_blocking=True)
+
+        def run(i0, k):
+            for h in range(2):
+                issue(h, i0)
+            for i in range(i0 + 1, i0 + k):
+                for h in range(2):
+                    hstreams[h].synchronize()  # the host actor has the masks of step i-1 of this half and picks its next actions
+                    issue(h, i)
+            for h in range(2):
+                hstreams[h].synchronize()
+
+        run(0, warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for h in range(2):
+            hstreams[h].wait_stream(stream)
+        run(warmup, steps)
+        for h in range(2):
+            stream.wait_stream(hstreams[h])
+        e1.record(stream)
+        barrier()
+        ems = max_over_ranks(e0.elapsed_time(e1))
+        assert int(host_stats[0][onb.STAT_STEPS]) + int(host_stats[1][onb.STAT_STEPS]) == n * k_all
+        e2e = {"value": world * n * steps / (ems * 1e-3), "unit": "env_steps/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 8 * n + 128,
+               "ms_per_step": ems / steps, "path": "onb_env_step(host actions in pinned memory) + D2H of legal masks and stats every step, two half-batches "
+                                                   "pipelined on two streams; planes stay in HBM for the network"}
+        for c in hctx:
+            c.close()
         return dict(metric="env_steps_per_sec", value=value, unit="env_steps/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
                     gpu_launches=steps, clocks=clocks)
 
@@ -529,7 +568,7 @@ def main():
 
     secondary = None
     if wl == "env" and not args.no_secondary:
-        m = bench_mcts(3, 3)
+        m = bench_mcts(10, 3)
         secondary = {k: m[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches")}
         secondary["config"] = workload_config("mcts")
 
