@@ -642,3 +642,48 @@ def test_mcts_deep_paths_bit_exact(onb):
                 deepest = max(deepest, int(depth.max()))
             if ev == onb.EVAL_HASH:
                 assert deepest >= 12, "test positions did not produce a path deeper than the lane-held levels (%d)" % deepest
+
+
+# ------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 63, 65, 129])
+def test_ragged_sizes(onb, n):
+    """tiny and ragged batch sizes: partial tiles, partial warps, partial 8-lane groups"""
+    seed = 100 + n
+    with onb.Context(n, seed=seed, mcts_max_sims=24) as ctx:
+        ctx.reset()
+        ref = O.new_games(n, seed=seed)
+        for step in range(9):
+            ctx.step_random(step, auto_reset=True, out_flags=onb.OUT_MASKS | onb.OUT_PLANES)
+            O.env_step_random(ref, seed, step, auto_reset=True)
+        assert ctx.get_states().tobytes() == ref.tobytes()
+        assert np.array_equal(ctx.read(onb.BUF_PLANES, np.float32, (n, 21, 5, 5)), O.encode(ref))
+        assert np.array_equal(ctx.read(onb.BUF_MASKS, np.uint32, (n, 2)), O.legal_masks(ref))
+        res = ctx.search(1.9, 24)
+        want = O.mcts_search_batch(ref, 1.9, 24)
+        assert np.array_equal(res["child_visits"], want["child_visits"]) and np.array_equal(res["best"], want["best"])
+        split = ctx.search(1.9, 24, fused=False)
+        assert np.array_equal(split["child_visits"], want["child_visits"])
+
+
+def test_mcts_in_chunks_and_pool_overflow(onb):
+    """onb_mcts_run may be called several times per search (sims accumulate); a too-small node pool is reported, not fatal."""
+    n, c = 40, 2.0
+    roots = _cfg4_roots(n, 3)
+    with onb.Context(n, mcts_max_sims=200, planes=False) as ctx:
+        ctx.set_states(roots)
+        ctx.mcts_begin(c, 200)
+        for chunk in (1, 7, 92, 100):
+            ctx.mcts_run(onb.EVAL_UNIFORM, chunk)
+        a = ctx.mcts_finish()
+        b = ctx.search(c, 200)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        with pytest.raises(onb.OnbError):
+            ctx.mcts_run(onb.EVAL_UNIFORM, 1)  # more simulations than mcts_max_sims
+    with onb.Context(n, mcts_max_sims=200, mcts_node_cap=300, planes=False) as ctx:
+        ctx.set_states(roots)
+        res = ctx.search(c, 200)
+        nn, fl = ctx.mcts_tree_info()
+        assert (nn <= 300).all() and (fl & 2).any()           # overflow flagged per tree
+        assert (res["root_visits"] == 200).all()               # the search still completes every simulation
+        assert (res["child_visits"].sum(axis=1) == 199)[roots["result"] == 0].all()
