@@ -15,7 +15,7 @@
 //   alphazero-training/src/evaluator.rs:355-399                 EvaluatorConfig, FightStatistics, fight
 //
 // Differences that are deliberate: rand::thread_rng is replaced by the counter RNG of onb.h (seeded, reproducible);
-// search_time is ignored (no wall-clock cut-off); train-mode Dirichlet noise is not implemented (eval mode);
+// search_time is ignored (no wall-clock cut-off); train-mode root noise is drawn from the counter RNG (statistical parity);
 // where the reference panics (expect/unwrap), this header throws onitama::Error.
 #pragma once
 #include <algorithm>
@@ -284,7 +284,8 @@ struct AlphaZeroMctsConfig {  // alphazero_mcts/mod.rs:26-43
     double search_time_ms = 400.;  // ignored: the search always runs max_playouts simulations
     double exploration_c = 1.4142135623730951;
     uint32_t max_playouts = 5000;
-    bool train = false;  // Dirichlet noise is not implemented; must be false
+    bool train = false;  // root exploration noise, epsilon 0.25 / Dirichlet alpha 0.03 (mcts_arena.rs:186-202)
+    uint64_t noise_seed = 0;
 };
 inline double reward(MoveResult r, PlayerColor c) {  // alphazero_mcts/mod.rs:45-53
     if (c == PlayerColor::Red) return r == MoveResult::RedWin ? 1. : r == MoveResult::BlueWin ? -1. : 0.;
@@ -297,7 +298,7 @@ using HostEvaluator = std::function<void(const float* planes, int64_t n, float* 
 
 namespace detail {
 inline void run_search(Engine& e, const AlphaZeroMctsConfig& cfg, int32_t device_eval, const HostEvaluator& net) {
-    if (cfg.train) throw Error(ONB_E_INVALID, "train-mode Dirichlet noise is not implemented");
+    e.check(onb_mcts_set_noise(e.ctx(), cfg.train ? 1 : 0, 0.25, 0.03, cfg.noise_seed));
     e.check(onb_mcts_begin(e.ctx(), cfg.exploration_c, cfg.max_playouts));
     if (!net) {
         e.check(onb_mcts_run(e.ctx(), device_eval, cfg.max_playouts));

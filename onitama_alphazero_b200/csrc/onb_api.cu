@@ -424,6 +424,16 @@ int32_t onb_mcts_begin(onb_ctx* ctx, double c_puct, uint32_t sims) {
     c->mcts_phase = 1;
     return ONB_OK;
 }
+int32_t onb_mcts_set_noise(onb_ctx* ctx, int32_t enabled, double epsilon, double alpha, uint64_t seed) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (enabled && (!(epsilon >= 0.0 && epsilon <= 1.0) || !(alpha > 0.0))) return fail(c, ONB_E_INVALID, "onb_mcts_set_noise: need 0 <= epsilon <= 1 and alpha > 0");
+    c->noise_on = enabled ? 1 : 0;
+    c->noise_eps = epsilon;
+    c->noise_alpha = alpha;
+    c->noise_seed = seed;
+    return ONB_OK;
+}
 int32_t onb_mcts_select(onb_ctx* ctx) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);

@@ -58,6 +58,9 @@ struct Ctx {
     double* d_root_q;
     uint32_t* d_child_visits;  // [n][40]
     double c_puct;
+    int noise_on;           // train mode: Dirichlet-like exploration noise at the root (mcts_arena.rs:186-202)
+    double noise_eps, noise_alpha;
+    uint64_t noise_seed;
     uint32_t sims_target, sims_done;
     int mcts_phase;  // 0 idle, 1 begun/after expand, 2 after select
     char err[512];

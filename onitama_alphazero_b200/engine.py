@@ -174,6 +174,10 @@ class Context:
     def mcts_begin(self, c_puct, sims):
         self._ck(self._lib.onb_mcts_begin(self._h, float(c_puct), sims))
 
+    def mcts_set_noise(self, enabled, epsilon=0.25, alpha=0.03, seed=0):
+        """train mode: root exploration noise (AlphaZeroMctsConfig::train); statistical parity only."""
+        self._ck(self._lib.onb_mcts_set_noise(self._h, int(bool(enabled)), float(epsilon), float(alpha), int(seed)))
+
     def mcts_select(self):
         self._ck(self._lib.onb_mcts_select(self._h))
 

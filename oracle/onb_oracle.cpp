@@ -226,6 +226,39 @@ static void deal(uint64_t seed, uint64_t game, uint32_t epoch, uint8_t out[5]) {
     for (int i = 0; i < 5; ++i) out[i] = ids[i];
 }
 
+// ------------------------------------------------------------------ root exploration noise (train mode)
+// The reference adds Dirichlet(0.03) noise at the root in train mode, drawn from thread_rng with a FRESH Dirichlet sample per
+// uct() call (alphazero_mcts/mcts_arena.rs:186-202): not reproducible, statistical parity only. Project-defined restatement:
+// the noise of child i in one uct() call is component i of a fresh Dirichlet(alpha; k) sample, i.e. g1 / (g1 + g2) with
+// g1 ~ Gamma(alpha), g2 ~ Gamma((k-1) alpha) (rand_distr 0.4.3 normalises k independent Gamma(alpha) draws), sampled with
+// Marsaglia-Tsang (+ the U^(1/shape) boost for shape < 1, as rand_distr::Gamma does) from the counter RNG.
+static inline double noise_uniform(uint64_t key, uint32_t step, uint32_t code) {
+    return ((double)(uint32_t)(mix64(key ^ (((uint64_t)step << 32) | code)) >> 32) + 0.5) * (1.0 / 4294967296.0);
+}
+static double noise_gamma(double shape, uint64_t key, uint32_t step, uint32_t base) {
+    const bool boost = shape < 1.0;
+    const double a = boost ? shape + 1.0 : shape;
+    const double d = a - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
+    double g = d;
+    for (uint32_t attempt = 0; attempt < 15; ++attempt) {
+        const double u1 = noise_uniform(key, step, base | (attempt << 2) | 0u), u2 = noise_uniform(key, step, base | (attempt << 2) | 1u),
+                     u3 = noise_uniform(key, step, base | (attempt << 2) | 2u);
+        const double x = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+        const double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        const double v3 = v * v * v;
+        if (std::log(u3) < 0.5 * x * x + d * (1.0 - v3 + std::log(v3))) { g = d * v3; break; }
+    }
+    if (boost) g *= std::exp(std::log(noise_uniform(key, step, base | 63u)) / shape);
+    return g;
+}
+static double noise_beta(uint32_t k, double alpha, uint64_t key, uint32_t step, uint32_t sample) {
+    const uint32_t base = 0x80000000u | (sample << 8);
+    const double g1 = noise_gamma(alpha, key, step, base), g2 = noise_gamma((double)(k - 1) * alpha, key, step, base | (1u << 6));
+    const double tot = g1 + g2;
+    return tot > 0.0 ? g1 / tot : 0.0;
+}
+
 // ------------------------------------------------------------------ boundary structs (C layout)
 }  // namespace orc
 
@@ -392,6 +425,9 @@ struct MctsArena {  // mcts_arena.rs:37-73
     uint32_t playouts = 0;
     eval_fn eval; void* user;
     bool pass_seen = false;
+    bool train = false;          // root Dirichlet noise (mcts_arena.rs:186-202)
+    double epsilon = 0.25, eta = 0.03;
+    uint64_t noise_key = 0;
     uint64_t depth_sum = 0;      // instrumentation for DESIGN.md's d and k
     uint64_t expanded_children = 0, expansions = 0;
 
@@ -408,6 +444,22 @@ struct MctsArena {  // mcts_arena.rs:37-73
     // mcts_arena.rs:183-223, eval mode (train-mode Dirichlet noise is thread_rng driven -> not restated)
     uint32_t select(const MctsNode& parent) const {
         const auto& children = parent.children;
+        if (parent.parent < 0 && train && children.size() > 1) {
+            // max_by folds left to right and evaluates uct() of BOTH operands afresh at every comparison, each call with a
+            // new noise sample; the last maximal element wins.
+            const uint32_t k = (uint32_t)children.size();
+            auto uct_noisy = [&](const MctsNode& child, uint32_t sample) {
+                const double noise = noise_beta(k, eta, noise_key, parent.visits, sample);
+                return child.winrate + exploration_c * (child.probability * (1. - epsilon) + noise * epsilon) *
+                                           (std::sqrt((double)parent.visits) / (double)(child.visits + 1));
+            };
+            uint32_t best = children[0];
+            for (uint32_t i = 1; i < k; ++i) {
+                const double ua = uct_noisy(arena[best], 2 * (i - 1)), ub = uct_noisy(arena[children[i]], 2 * (i - 1) + 1);
+                if (total_key(ua) <= total_key(ub)) best = children[i];
+            }
+            return best;
+        }
         auto uct = [&](const MctsNode& child) {
             return child.winrate + exploration_c * child.probability * (std::sqrt((double)parent.visits) / (double)(child.visits + 1));
         };
@@ -642,11 +694,24 @@ struct orc_tree_dump {  // flat copies of the arena, length = n_nodes
 
 // One PUCT search (eval mode, no wall clock). evaluator: 0 uniform, 1 hash_eval, 2 callback `cb`.
 // Returns the number of nodes; out_* may be NULL. If dump != NULL and cap >= n_nodes the arena is copied out.
+static double g_noise_eps = 0.25, g_noise_alpha = 0.03;
+static uint64_t g_noise_seed = 0, g_noise_game0 = 0;
+static int g_noise_on = 0;
+// train-mode switch for the searches below (global: the oracle is single-purpose test code)
+void orc_mcts_set_noise(int enabled, double epsilon, double alpha, uint64_t seed, uint64_t game0) {
+    g_noise_on = enabled; g_noise_eps = epsilon; g_noise_alpha = alpha; g_noise_seed = seed; g_noise_game0 = game0;
+}
+static void apply_noise_cfg(orc::MctsArena& a, uint64_t tree) {
+    a.train = g_noise_on != 0; a.epsilon = g_noise_eps; a.eta = g_noise_alpha;
+    a.noise_key = orc::mix64(g_noise_seed + 0x9E3779B97F4A7C15ull * (g_noise_game0 + tree + 1));
+}
+
 int64_t orc_mcts_search(const orc_state* g, double c_puct, uint32_t sims, int evaluator, orc::eval_fn cb, void* user,
                         uint16_t* best_action, float* pi50, uint32_t* root_visits, double* root_q, int32_t* pass_seen,
                         double* mean_depth, double* mean_children, orc_tree_dump* dump, int64_t cap) {
     orc::eval_fn e = evaluator == 0 ? orc::uniform_eval : evaluator == 1 ? orc::hash_eval : cb;
     orc::MctsArena arena(orc::to_state(*g), g->side, c_puct, sims, e, user);
+    apply_noise_cfg(arena, 0);
     float pi[50];
     uint32_t best = arena.search(pi);
     if (best_action) {
@@ -692,6 +757,7 @@ void orc_mcts_search_batch(const orc_state* roots, int64_t n, double c_puct, uin
             if (i >= n) break;
             orc::eval_fn e = evaluator == 0 ? orc::uniform_eval : orc::hash_eval;
             orc::MctsArena arena(orc::to_state(roots[i]), roots[i].side, c_puct, sims, e, nullptr);
+            apply_noise_cfg(arena, (uint64_t)i);
             float pi[50];
             uint32_t best = arena.search(pi);
             const auto& ch = arena.arena[0].children;

@@ -61,6 +61,7 @@ def lib():
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int64]
         L.orc_hash_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_mcts_set_noise.argtypes = [C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint64]
         L.orc_mcts_search_batch.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_bench_env.restype = C.c_double
@@ -208,6 +209,11 @@ def mcts_search_batch(roots, c_puct, sims, evaluator=0, threads=1):
     ps = np.zeros(n, dtype=np.int32)
     lib().orc_mcts_search_batch(_p(roots), n, c_puct, sims, evaluator, threads, _p(best), _p(cv), _p(nn), _p(rq), _p(pi), _p(ps))
     return dict(best=best, child_visits=cv, n_nodes=nn, root_q=rq, pi=pi, pass_seen=ps)
+
+
+def mcts_set_noise(enabled, epsilon=0.25, alpha=0.03, seed=0, game0=0):
+    """train-mode root noise for the searches that follow (tree i of a batch uses global tree id game0 + i)"""
+    lib().orc_mcts_set_noise(int(bool(enabled)), epsilon, alpha, seed, game0)
 
 
 def hash_eval(planes):

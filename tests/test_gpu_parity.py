@@ -687,3 +687,43 @@ def test_mcts_in_chunks_and_pool_overflow(onb):
         assert (nn <= 300).all() and (fl & 2).any()           # overflow flagged per tree
         assert (res["root_visits"] == 200).all()               # the search still completes every simulation
         assert (res["child_visits"].sum(axis=1) == 199)[roots["result"] == 0].all()
+
+
+# ------------------------------------------------------------------ train mode: root exploration noise (statistical parity)
+@pytest.mark.parametrize("fused", [True, False])
+def test_mcts_train_mode_noise_statistical(onb, fused):
+    """AlphaZeroMctsConfig::train: the reference's noise comes from thread_rng, so only the DISTRIBUTION can be compared. GPU and
+    oracle share the counter RNG and the sampling algorithm; libm vs CUDA math may flip a rare comparison, so: (a) the large
+    majority of trees must be identical, (b) the mean root visit vectors must agree closely, (c) the noise must matter."""
+    n, sims, c, seed = 512, 120, 2.0, 77
+    roots = O.new_games(n, deck=[1, 2, 0, 3, 11])
+    with onb.Context(n, mcts_max_sims=sims, planes=False, game_id_base=1000) as ctx:
+        ctx.set_states(roots)
+        quiet = ctx.search(c, sims, fused=fused)
+        ctx.mcts_set_noise(True, 0.25, 0.03, seed)
+        noisy = ctx.search(c, sims, fused=fused)
+        again = ctx.search(c, sims, fused=fused)
+        ctx.mcts_set_noise(False)
+        quiet2 = ctx.search(c, sims, fused=fused)
+    try:
+        O.mcts_set_noise(True, 0.25, 0.03, seed, game0=1000)
+        want = O.mcts_search_batch(roots, c, sims, threads=8)
+    finally:
+        O.mcts_set_noise(False)
+    assert np.array_equal(noisy["child_visits"], again["child_visits"])      # repeatable (counter RNG)
+    assert np.array_equal(quiet["child_visits"], quiet2["child_visits"])     # switching it off restores eval mode
+    assert (noisy["child_visits"] != quiet["child_visits"]).any(axis=1).mean() > 0.9   # the noise changes almost every tree
+    assert len({tuple(r) for r in noisy["child_visits"]}) > n // 4                      # and differs between trees
+    same = (noisy["child_visits"] == want["child_visits"]).all(axis=1).mean()
+    assert same >= 0.9, "only %.1f%% of the trees match the oracle" % (100 * same)
+    assert np.abs(noisy["child_visits"][:, :10].mean(axis=0) - want["child_visits"][:, :10].mean(axis=0)).max() < 0.25
+    assert (noisy["child_visits"].sum(axis=1) == sims - 1).all()
+
+
+def test_self_play_train_mode(onb):
+    n, sims = 64, 32
+    with onb.Context(n, seed=4, mcts_max_sims=sims) as ctx:
+        ctx.mcts_set_noise(True, 0.25, 0.03, 9)
+        out = onb.self_play(ctx, 2.0, sims, max_plies=8)
+        assert out["planes"].shape[0] > 0
+        assert abs(float(out["pi"].sum()) - out["pi"].shape[0]) < 1e-3
