@@ -164,8 +164,8 @@ ONB_API int32_t onb_env_legal_masks(onb_ctx* ctx, uint32_t* masks_host);
 /* create_tensor_from_state (common.rs:26-80) for every game into ONB_BUF_PLANES; planes_host may be NULL */
 ONB_API int32_t onb_env_encode(onb_ctx* ctx, float* planes_host);
 /* State::make_move / State::pass + side switch (state.rs:139-202, game_state.rs:65-80) with the given
- * actions. actions_host NULL = use ONB_BUF_ACTIONS as already filled on the device. Finished games are
- * left untouched. auto_reset: a game that ends is replaced by a fresh deal (RNG epoch step+1; `step` is only
+ * actions. actions_host NULL = use ONB_BUF_ACTIONS as already filled on the device. Finished games and games
+ * whose action is ONB_ACTION_NONE are left untouched. auto_reset: a game that ends is replaced by a fresh deal (RNG epoch step+1; `step` is only
  * used for that). out_flags selects which observation buffers of the new state are written. */
 ONB_API int32_t onb_env_step(onb_ctx* ctx, const onb_action* actions_host, uint32_t step, int32_t auto_reset,
                              uint32_t out_flags);

@@ -132,11 +132,12 @@ __global__ void __launch_bounds__(THREADS) k_env_step(uint4* __restrict__ states
             uint32_t res = 0;
             if (live) {
                 g = unpack(states[i]);
-                if (MODE != 3 && g.result == 0) {
-                    uint32_t a;
+                uint32_t a = 0xFFFFu;
+                if (MODE == 2) a = actions[i];
+                // explicit actions: ONB_ACTION_NONE leaves the game untouched (e.g. the best move of a tree whose root was decided)
+                if (MODE != 3 && g.result == 0 && !(MODE == 2 && a == 0xFFFFu)) {
                     const uint64_t key = game_key(seed, game0 + (uint64_t)i);
-                    if (MODE == 2) a = actions[i];
-                    else a = choose_action(s_att, g, MODE, key, step);
+                    if (MODE != 2) a = choose_action(s_att, g, MODE, key, step);
                     if (MODE != 2 && choose_only) {  // agents for the arena loop: pick, do not play
                         actions[i] = (uint16_t)a;
                     } else {

@@ -641,7 +641,7 @@ void orc_encode(const orc_state* g, int64_t n, float* out525n) {
 
 // lockstep env step with explicit actions. Finished games (result != 0) are left untouched.
 void orc_env_step(orc_state* g, int64_t n, const uint16_t* actions) {
-    for (int64_t i = 0; i < n; ++i) if (g[i].result == 0) orc::apply_action(g[i], actions[i]);
+    for (int64_t i = 0; i < n; ++i) if (g[i].result == 0 && actions[i] != 0xFFFF) orc::apply_action(g[i], actions[i]);
 }
 // lockstep env step with the counter-RNG random policy; writes the chosen actions (0xFFFF for finished games).
 // auto_reset: a game that ends at `step` is replaced by a fresh deal with epoch step+1.

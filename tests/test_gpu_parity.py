@@ -665,6 +665,22 @@ def test_ragged_sizes(onb, n):
         assert np.array_equal(split["child_visits"], want["child_visits"])
 
 
+def test_action_none_is_a_noop(onb):
+    n = 200
+    with onb.Context(n, seed=6) as ctx:
+        ctx.reset()
+        ref = O.new_games(n, seed=6)
+        shadow = ref.copy()
+        acts = O.env_step_random(shadow, 6, 0)
+        acts[::3] = 0xFFFF
+        ctx.step(acts, out_flags=onb.OUT_MASKS | onb.OUT_PLANES)
+        O.env_step(ref, acts)
+        got = ctx.get_states()
+        assert got.tobytes() == ref.tobytes()
+        assert got[::3].tobytes() == O.new_games(n, seed=6)[::3].tobytes()
+        assert np.array_equal(ctx.read(onb.BUF_PLANES, np.float32, (n, 21, 5, 5)), O.encode(ref))
+
+
 def test_mcts_in_chunks_and_pool_overflow(onb):
     """onb_mcts_run may be called several times per search (sims accumulate); a too-small node pool is reported, not fatal."""
     n, c = 40, 2.0
