@@ -10,6 +10,58 @@ import torch
 from . import _lib as L
 
 
+class EloRating:
+    """elo_rating.rs:53-70 (K = 32, 1/400 scale)"""
+    K = 32.0
+    C_ELO = 2.5e-3
+
+    @staticmethod
+    def elo_change(ra, rb, is_a_win):
+        ea = 1.0 / (1.0 + 10.0 ** (EloRating.C_ELO * (rb - ra)))
+        eb = 1.0 / (1.0 + 10.0 ** (EloRating.C_ELO * (ra - rb)))
+        sa = 1.0 if is_a_win else 0.0
+        sb = 1.0 - sa
+        return ra + EloRating.K * (sa - ea), rb + EloRating.K * (sb - eb)
+
+
+class FightStatistics:
+    """evaluator.rs:38-110: W/L/D in total and per colour of agent A, win rates, sequential Elo updates game by game."""
+
+    def __init__(self, rating_a=800.0, rating_b=800.0):
+        self.general = dict(wins=0, loses=0, draws=0)
+        self.color = [dict(wins=0, loses=0, draws=0), dict(wins=0, loses=0, draws=0)]
+        self.winrate = 0.0
+        self.color_winrate = [0.0, 0.0]
+        self.rating_a, self.rating_b = rating_a, rating_b
+        self.rating_change_history = []
+
+    def update(self, result, player_color):
+        """result: 0 none/draw, 1 RedWin, 2 BlueWin; player_color: colour agent A played (0 Red, 1 Blue)"""
+        before = (self.rating_a, self.rating_b)
+        if result in (1, 2):
+            a_won = (result - 1) == player_color
+            self.rating_a, self.rating_b = EloRating.elo_change(self.rating_a, self.rating_b, a_won)
+            key = "wins" if a_won else "loses"
+        else:
+            key = "draws"
+        self.rating_change_history.append((before[0], self.rating_a, before[1], self.rating_b))
+        self.general[key] += 1
+        self.color[player_color][key] += 1
+        tot = sum(self.general.values())
+        self.winrate = self.general["wins"] / tot
+        for c in (0, 1):
+            t = sum(self.color[c].values())
+            self.color_winrate[c] = self.color[c]["wins"] / t if t else float("nan")
+
+
+def fight_statistics(results, a_is_red, rating_a=800.0, rating_b=800.0):
+    """Fold the per-game results of a lockstep arena (game order = the reference's sequential order) into FightStatistics."""
+    st = FightStatistics(rating_a, rating_b)
+    for r, red in zip(results, a_is_red):
+        st.update(int(r), 0 if red else 1)
+    return st
+
+
 def self_play(ctx, c_puct, sims, max_plies=150, evaluator=L.EVAL_UNIFORM, net=None, decks=None):
     with torch.cuda.stream(ctx.torch_stream()):  # torch ops ordered with the context's kernels
         return _self_play(ctx, c_puct, sims, max_plies, evaluator, net, decks)
@@ -89,4 +141,5 @@ def _fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies):
     red_won, blue_won = res == 1, res == 2
     a_wins = int((red_won & a_is_red).sum() + (blue_won & ~a_is_red).sum())
     b_wins = int((red_won & ~a_is_red).sum() + (blue_won & a_is_red).sum())
+    ctx.last_fight_results = res.cpu().numpy()  # per-game results for fight_statistics()
     return a_wins, b_wins, int(n - a_wins - b_wins)
