@@ -10,16 +10,6 @@
 
 namespace onb {
 
-struct CtxExtra {
-    int32_t fixed_cards;  // -1: auto-reset deals from the RNG, else nibble-packed deck used for every reset
-};
-// Ctx is followed in memory by CtxExtra (kept out of the header so the kernels' TU does not depend on it)
-struct CtxFull {
-    Ctx c;
-    CtxExtra x;
-};
-int32_t g_fixed_cards_of(Ctx* c) { return reinterpret_cast<CtxFull*>(c)->x.fixed_cards; }
-
 cudaError_t launch_env_playout(Ctx* c, uint32_t* d_plies, unsigned long long* d_trace, uint32_t step0, uint32_t max_plies, int mode);
 
 static int32_t fail(Ctx* c, int32_t code, const char* fmt, ...) {
@@ -74,11 +64,10 @@ int32_t onb_create(const onb_config* cfg, onb_ctx** out) {
                  e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
         return ONB_E_CUDA;
     }
-    CtxFull* full = new (std::nothrow) CtxFull();
-    if (!full) return ONB_E_NOMEM;
-    memset(full, 0, sizeof(*full));
-    Ctx* c = &full->c;
-    full->x.fixed_cards = -1;
+    Ctx* c = new (std::nothrow) Ctx();
+    if (!c) return ONB_E_NOMEM;
+    memset(c, 0, sizeof(*c));
+    c->fixed_cards = -1;
     c->cfg = *cfg;
     c->n = cfg->n_games;
 #define ONB_CREATE_CUDA(call)                                                                       \
@@ -140,7 +129,7 @@ int32_t onb_destroy(onb_ctx* ctx) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-    delete reinterpret_cast<CtxFull*>(c);
+    delete c;
     return ONB_OK;
 }
 
@@ -265,11 +254,10 @@ int32_t onb_env_reset(onb_ctx* ctx, const uint8_t* decks5_host, int64_t n_decks,
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (d_decks) cudaFree(d_decks);
     if (e != cudaSuccess) return cuda_fail(c, e, "onb_env_reset");
-    CtxFull* f = reinterpret_cast<CtxFull*>(c);
-    f->x.fixed_cards = -1;
+    c->fixed_cards = -1;
     if (n_decks == 1) {
         const uint8_t* d = decks5_host;
-        f->x.fixed_cards = (int32_t)((d[0]) | (d[1] << 4) | (d[2] << 8) | (d[3] << 12) | (d[4] << 16));
+        c->fixed_cards = (int32_t)((d[0]) | (d[1] << 4) | (d[2] << 8) | (d[3] << 12) | (d[4] << 16));
     }
     c->mcts_phase = 0;
     return ONB_OK;

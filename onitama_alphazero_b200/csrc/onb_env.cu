@@ -110,8 +110,17 @@ __device__ __forceinline__ uint32_t choose_action(const uint32_t* T, const Game&
 // THREADS (>= GAMES) of the CTA then stream the tile's GAMES x 525 floats. A small tile drained by many threads keeps the
 // chip-wide write front compact, which is what HBM wants (tools/wbench.cu: 8-32 games per CTA reach the memset ceiling,
 // 128 games per 128-thread CTA lose 10-15 %).
+// plane-writing variant: 64 games per CTA on 640 threads, 3 CTAs per SM (<= 34 registers). Measured per 1 Mi-game step on B200:
+// 512 thr x 4 CTAs 314.8 us, 384 x 5 317.0, 640 x 3 311.1, 320 x 6 319.8, 1024 x 2 382; without the min-blocks bound ptxas takes
+// more registers and the kernel drops to 2 CTAs per SM (405 us).
+#ifndef ONB_ENV_MINB
+#define ONB_ENV_MINB 3
+#endif
+#ifndef ONB_ENV_THREADS
+#define ONB_ENV_THREADS 640
+#endif
 template <int MODE, bool PLANES, int GAMES, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_env_step(uint4* __restrict__ states, int64_t n, uint16_t* __restrict__ actions,
+__global__ void __launch_bounds__(THREADS, (PLANES ? ONB_ENV_MINB : 1)) k_env_step(uint4* __restrict__ states, int64_t n, uint16_t* __restrict__ actions,
                                                        uint32_t* __restrict__ masks, float* __restrict__ planes,
                                                        unsigned long long* __restrict__ stats, uint64_t seed, uint64_t game0, uint32_t step,
                                                        int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
@@ -272,11 +281,11 @@ static cudaError_t launch_step_shape(Ctx* c, uint32_t step, int auto_reset, int3
 }
 template <int MODE>
 static cudaError_t launch_step_mode(Ctx* c, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
-    // rules-only variants: 128 games on 128 threads. With planes: 64 games stepped by 2 warps, then 512 threads drain the
-    // 134 KB tile (measured on B200, 1 Mi games: 128g/128t 347 us, 32g/256t 318 us, 64g/256t 321 us, 64g/512t 313 us,
-    // 128g/512t 319 us; a pure fill of the same buffer takes 295 us).
+    // rules-only variants: 128 games on 128 threads. With planes: 64 games stepped by 2 warps, then all threads of the CTA drain
+    // the 134 KB tile (measured on B200, 1 Mi games: 128g/128t 347 us, 32g/256t 318 us, 64g/256t 321 us, 64g/512t 313 us,
+    // 128g/512t 319 us, 64g/640t 311 us; a pure fill of the same buffer takes 295 us).
     if (!(out_flags & ONB_OUT_PLANES)) return launch_step_shape<MODE, false, 128, 128>(c, step, auto_reset, fixed_cards, out_flags, choose_only);
-    return launch_step_shape<MODE, true, 64, 512>(c, step, auto_reset, fixed_cards, out_flags, choose_only);
+    return launch_step_shape<MODE, true, 64, ONB_ENV_THREADS>(c, step, auto_reset, fixed_cards, out_flags, choose_only);
 }
 
 cudaError_t launch_env_reset(Ctx* c, const uint8_t* d_decks5, int64_t n_decks, uint32_t epoch) {
@@ -296,10 +305,8 @@ cudaError_t launch_legal_moves(Ctx* c) {
     return cudaGetLastError();
 }
 
-int32_t g_fixed_cards_of(Ctx* c);  // onb_api.cu
-
 cudaError_t launch_env_step(Ctx* c, int mode, uint32_t step, int auto_reset, uint32_t out_flags) {
-    const int32_t fixed = g_fixed_cards_of(c);
+    const int32_t fixed = c->fixed_cards;
     switch (mode) {
         case 0: return launch_step_mode<0>(c, step, auto_reset, fixed, out_flags, 0);
         case 1: return launch_step_mode<1>(c, step, auto_reset, fixed, out_flags, 0);

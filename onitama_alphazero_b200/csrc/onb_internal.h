@@ -37,6 +37,7 @@ struct Ctx {
     float* d_planes;
     uint16_t* d_actions;
     unsigned long long* d_stats;
+    int32_t fixed_cards;  // -1: auto-reset deals from the RNG, else the nibble-packed deck every reset re-deals (onb_env_reset with one deck)
     // scratch for host<->device transfers of boundary structs
     onb_state* d_io_states;
     uint16_t* d_moves;  // [n][40]
