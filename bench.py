@@ -30,7 +30,7 @@ MCTS_TREES = 1 << 14
 MCTS_SIMS = 400
 MCTS_C = 2.0
 PLAYOUT_GAMES = 4096
-SELFPLAY_GAMES = 4096
+SELFPLAY_GAMES = 16384
 SELFPLAY_SIMS = 800
 SEED = 20240607
 # algorithmic bytes per unit of work

@@ -71,12 +71,19 @@ class ConvResNet(nn.Module):
         return self
 
 
-def make_evaluator(model):
-    """Wrap a module as the `net` callable of Context.search / self_play: planes tensor -> (policy, value)."""
+def make_evaluator(model, channels_last=True):
+    """Wrap a module as the `net` callable of Context.search / self_play: planes tensor -> (policy, value).
+    channels_last: run the convolutions in NHWC (same f32/TF32 arithmetic, ~2.7x faster in cuDNN for these 5x5 maps:
+    0.64 ms vs 1.76 ms per 4 096 positions on B200); the NCHW leaf buffer is re-laid-out by one small copy per call."""
     model.eval()
+    on_gpu = next(model.parameters()).is_cuda
+    if channels_last and on_gpu:
+        model.to(memory_format=torch.channels_last)
 
     @torch.no_grad()
     def net(planes):
+        if channels_last and on_gpu:
+            planes = planes.contiguous(memory_format=torch.channels_last)
         p, v = model(planes)
         return p, v.reshape(-1)
 
