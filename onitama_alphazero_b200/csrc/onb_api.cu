@@ -128,6 +128,8 @@ int32_t onb_destroy(onb_ctx* ctx) {
                     c->d_pi, c->d_best, c->d_root_visits, c->d_root_q, c->d_child_visits};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (void* p : c->scratch)
+        if (p) cudaFree(p);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return ONB_OK;

@@ -64,6 +64,10 @@ struct Ctx {
     uint64_t noise_seed;
     uint32_t sims_target, sims_done;
     int mcts_phase;  // 0 idle, 1 begun/after expand, 2 after select
+    // grow-only device scratch reused across onb_perft calls (counters, cursor, two ping-pong frontiers): repeated
+    // cudaMalloc/cudaFree of several hundred MB made the call time vary by +-50 %
+    void* scratch[8];
+    size_t scratch_cap[8];
     char err[512];
 };
 

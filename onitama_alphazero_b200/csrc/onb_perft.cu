@@ -180,19 +180,34 @@ static int32_t perft_fail(Ctx* c, cudaError_t e, const char* what) {
 
 constexpr int kMaxDfs = 6;
 
+static cudaError_t scratch_get(Ctx* c, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (c->scratch_cap[slot] < bytes) {
+        if (c->scratch[slot]) cudaFree(c->scratch[slot]);
+        c->scratch[slot] = nullptr;
+        c->scratch_cap[slot] = 0;
+        const size_t want = bytes + bytes / 8;  // a little headroom so similar calls do not reallocate
+        cudaError_t e = cudaMalloc(&c->scratch[slot], want);
+        if (e != cudaSuccess) return e;
+        c->scratch_cap[slot] = want;
+    }
+    *out = c->scratch[slot];
+    return cudaSuccess;
+}
+
 int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uint64_t* nodes_host, uint64_t* wins_host, uint64_t* zero_host) {
     cudaError_t e;
     const size_t cnt = (size_t)n * depth;
     unsigned long long *d_nodes = nullptr, *d_wins = nullptr, *d_zero = nullptr, *d_cursor = nullptr;
-    onb_state* d_in = nullptr;
     uint4* cur_s = nullptr; uint32_t* cur_r = nullptr;
     uint4* nxt_s = nullptr; uint32_t* nxt_r = nullptr;
+    int pair = 0;  // which scratch pair (4/5 or 6/7) holds the current frontier
     int32_t rc = ONB_OK;
 #define PF(call, what) do { e = (call); if (e != cudaSuccess) { rc = perft_fail(c, e, what); goto done; } } while (0)
-    PF(cudaMalloc(&d_nodes, cnt * 8), "alloc counters");
-    PF(cudaMalloc(&d_wins, cnt * 8), "alloc counters");
-    PF(cudaMalloc(&d_zero, cnt * 8), "alloc counters");
-    PF(cudaMalloc(&d_cursor, 8), "alloc cursor");
+    PF(scratch_get(c, 0, cnt * 8, (void**)&d_nodes), "alloc counters");
+    PF(scratch_get(c, 1, cnt * 8, (void**)&d_wins), "alloc counters");
+    PF(scratch_get(c, 2, cnt * 8, (void**)&d_zero), "alloc counters");
+    PF(scratch_get(c, 3, 8, (void**)&d_cursor), "alloc cursor");
     PF(cudaMemsetAsync(d_nodes, 0, cnt * 8, c->stream), "memset");
     PF(cudaMemsetAsync(d_wins, 0, cnt * 8, c->stream), "memset");
     PF(cudaMemsetAsync(d_zero, 0, cnt * 8, c->stream), "memset");
@@ -213,8 +228,8 @@ int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uin
         }
         int64_t n_cur = (int64_t)hs.size();
         if (n_cur > 0) {
-            PF(cudaMalloc(&cur_s, (size_t)n_cur * 16), "alloc frontier");
-            PF(cudaMalloc(&cur_r, (size_t)n_cur * 4), "alloc frontier");
+            PF(scratch_get(c, 4, (size_t)n_cur * 16, (void**)&cur_s), "alloc frontier");
+            PF(scratch_get(c, 5, (size_t)n_cur * 4, (void**)&cur_r), "alloc frontier");
             PF(cudaMemcpyAsync(cur_s, hs.data(), (size_t)n_cur * 16, cudaMemcpyHostToDevice, c->stream), "copy roots");
             PF(cudaMemcpyAsync(cur_r, hr.data(), (size_t)n_cur * 4, cudaMemcpyHostToDevice, c->stream), "copy roots");
             PF(cudaStreamSynchronize(c->stream), "sync");
@@ -229,15 +244,16 @@ int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uin
                 PF(cudaMemcpyAsync(&total, d_cursor, 8, cudaMemcpyDeviceToHost, c->stream), "copy cursor");
                 PF(cudaStreamSynchronize(c->stream), "sync");
                 if (total > (1ull << 31)) { snprintf(c->err, sizeof(c->err), "onb_perft: frontier of %llu nodes is too large", total); rc = ONB_E_OVERFLOW; goto done; }
-                PF(cudaMalloc(&nxt_s, (size_t)(total ? total : 1) * 16), "alloc frontier");
-                PF(cudaMalloc(&nxt_r, (size_t)(total ? total : 1) * 4), "alloc frontier");
+                const int other = pair ^ 1;
+                PF(scratch_get(c, 4 + 2 * other, (size_t)total * 16, (void**)&nxt_s), "alloc frontier");
+                PF(scratch_get(c, 5 + 2 * other, (size_t)total * 4, (void**)&nxt_r), "alloc frontier");
                 PF(cudaMemsetAsync(d_cursor, 0, 8, c->stream), "memset");
                 k_perft_expand<false><<<(unsigned)((n_cur + 127) / 128), 128, 0, c->stream>>>(cur_s, cur_r, n_cur, nxt_s, nxt_r, d_cursor, d_nodes, d_wins,
                                                                                              d_zero, depth, level);
                 PF(cudaGetLastError(), "expand(fill)");
                 PF(cudaStreamSynchronize(c->stream), "sync");
-                cudaFree(cur_s); cudaFree(cur_r);
-                cur_s = nxt_s; cur_r = nxt_r; nxt_s = nullptr; nxt_r = nullptr;
+                cur_s = nxt_s; cur_r = nxt_r;
+                pair = other;
                 n_cur = (int64_t)total;
                 ++level;
             }
@@ -260,8 +276,6 @@ int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uin
     PF(cudaStreamSynchronize(c->stream), "sync");
 #undef PF
 done:
-    cudaFree(d_nodes); cudaFree(d_wins); cudaFree(d_zero); cudaFree(d_cursor); cudaFree(d_in);
-    cudaFree(cur_s); cudaFree(cur_r); cudaFree(nxt_s); cudaFree(nxt_r);
     return rc;
 }
 
