@@ -743,3 +743,56 @@ def test_self_play_train_mode(onb):
         out = onb.self_play(ctx, 2.0, sims, max_plies=8)
         assert out["planes"].shape[0] > 0
         assert abs(float(out["pi"].sum()) - out["pi"].shape[0]) < 1e-3
+
+
+# ------------------------------------------------------------------ BASELINE-size runs: properties + sampled parity
+def test_config4_full_size_properties_and_sampled_parity(onb):
+    """16 384 trees x 400 simulations (BASELINE config 4): size-independent invariants on every tree, bit-exact visit vectors on a
+    sample of trees replayed by the oracle."""
+    n, sims, c, seed = 1 << 14, 400, 2.0, 20240607
+    with onb.Context(n, seed=seed, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.reset()
+        base = ctx.get_states()
+        cur = base.copy()
+        for step in range(16):  # roots = positions after p = id mod 16 random plies
+            ctx.step_random(step)
+            nxt = ctx.get_states()
+            live = (np.arange(n) % 16) > step
+            cur[live] = nxt[live]
+            ctx.set_states(cur)
+        dead = cur["result"] != 0
+        cur[dead] = base[dead]
+        ctx.set_states(cur)
+        res = ctx.search(c, sims)
+        nn, fl = ctx.mcts_tree_info()
+        assert (res["root_visits"] == sims).all()
+        assert (res["child_visits"].sum(axis=1) == sims - 1).all()      # every playout after the first passes through one root child
+        assert np.allclose(res["pi"].sum(axis=(1, 2)), 1.0, atol=1e-6)
+        assert (np.abs(res["root_q"]) <= 1.0).all() and (fl & 2).sum() == 0
+        assert (nn <= 1 + 40 * sims).all() and (nn > 1).all()
+        best_slot = (res["best"] >> 10) & 3
+        assert ((best_slot >> 1) == cur["side"]).all()                   # the chosen card belongs to the side to move
+        # the most visited child's move is the reported best move (last maximum wins)
+        idx = np.random.RandomState(1).choice(n, 48, replace=False)
+        want = O.mcts_search_batch(cur[idx], c, sims, threads=8)
+        assert np.array_equal(res["child_visits"][idx], want["child_visits"])
+        assert np.array_equal(res["best"][idx], want["best"])
+        assert np.array_equal(res["root_q"][idx], want["root_q"])
+        assert np.array_equal(nn[idx], want["n_nodes"])
+
+
+def test_config2_full_size_perft(onb):
+    """All 131 040 canonical deals to depth 6 (BASELINE config 2): checksums against the independent restatement, wins are a
+    subset of nodes, sampled deals bit-exact against the oracle at every depth."""
+    decks = np.array([[a, b, c, d, e] for a in range(16) for b in range(a + 1, 16) for c in range(16) if c not in (a, b)
+                      for d in range(c + 1, 16) if d not in (a, b) for e in range(16) if e not in (a, b, c, d)], dtype=np.uint8)
+    with onb.Context(8, planes=False) as ctx:
+        nodes, wins, zero = ctx.perft(onb.start_states(decks), 6)
+    assert int(nodes[:, 0].sum()) == G["all_deals"]["sum_perft1"] and int(nodes[:, 1].sum()) == G["all_deals"]["sum_perft2"]
+    assert zero.sum() == 0 and (wins <= nodes).all() and (wins[:, :2] == 0).all()
+    assert (nodes[:, 1:] <= nodes[:, :-1] * 40).all() and (nodes[:, 5] > nodes[:, 4]).all()
+    # mirror symmetry of the rules: swapping the two cards inside a hand does not change the counts
+    first = {tuple(d): i for i, d in enumerate(decks.tolist())}
+    for i in np.random.RandomState(5).choice(len(decks), 12, replace=False):
+        n_, w_, _ = O.perft(O.new_games(1, deck=decks[i]), 6)
+        assert nodes[i].tolist() == n_.tolist() and wins[i].tolist() == w_.tolist(), decks[i]
