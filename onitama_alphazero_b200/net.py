@@ -71,6 +71,20 @@ class ConvResNet(nn.Module):
         return self
 
 
+def alphaloss(v, p, pi, z):
+    """ConvResNet::alphaloss (net.rs:234-243): (value_loss, policy_loss) = (mean((z - v)^2), -mean_b(sum_card(log p * pi))).
+    v [B,1], p [B,2,25], pi [B,2,25], z [B,1]; the reference sums over dim 1 only and then averages over the rest."""
+    diff = z - v
+    value_loss = (diff * diff).mean()
+    policy_loss = -(p.log() * pi).sum(dim=1).mean()
+    return value_loss, policy_loss
+
+
+def sample_minibatch(n_samples, batch_size, generator=None):
+    """train.rs:280-283 (`choose_multiple`): batch_size distinct sample indices, uniformly at random."""
+    return torch.randperm(n_samples, generator=generator)[:batch_size]
+
+
 def make_evaluator(model, channels_last=True):
     """Wrap a module as the `net` callable of Context.search / self_play: planes tensor -> (policy, value).
     channels_last: run the convolutions in NHWC (same f32/TF32 arithmetic, ~2.7x faster in cuDNN for these 5x5 maps:

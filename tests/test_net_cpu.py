@@ -28,3 +28,18 @@ def test_loads_reference_ot_archive():
     assert p.shape == (2, 2, 25) and v.shape == (2,) and torch.isfinite(p).all() and torch.equal(p[0], p[1])
     m5 = ConvResNet(64, 21, 5).load_ot("/root/reference/models/model_5e-3.ot")
     assert m5.n_blocks == 5
+
+
+def test_alphaloss_matches_reference_formula():
+    """net.rs:234-243"""
+    from onitama_alphazero_b200.net import alphaloss, sample_minibatch
+    g = torch.Generator().manual_seed(0)
+    v = torch.tanh(torch.randn(6, 1, generator=g))
+    z = torch.tensor([[1.0], [-1.0], [0.0], [1.0], [1.0], [-1.0]])
+    p = torch.softmax(torch.randn(6, 50, generator=g), dim=-1).reshape(6, 2, 25)
+    pi = torch.softmax(torch.randn(6, 50, generator=g), dim=-1).reshape(6, 2, 25)
+    vl, pl = alphaloss(v, p, pi, z)
+    assert torch.isclose(vl, ((z - v) ** 2).sum() / 6)
+    assert torch.isclose(pl, -(p.log() * pi).sum() / (6 * 25))   # sum over the card dim, mean over batch x 25 squares
+    idx = sample_minibatch(100, 32, generator=g)
+    assert idx.shape == (32,) and len(set(idx.tolist())) == 32 and int(idx.max()) < 100
