@@ -103,3 +103,15 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(lib):
         pytest.skip("a CUDA device is present")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 2 and "no CPU fallback" in r.stdout
+
+
+def test_header_is_c99_clean_and_links_from_c(lib):
+    """include/onb.h compiles as strict C99 (-Wall -Wextra -Werror -pedantic); a pure C program links libonb.so, uses the
+    host-side helpers and sees onb_create fail loudly without a device (or round-trips a reset with one)."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "c", "abi_host_only.c")
+    exe = os.path.join(ROOT, "tests", "c", "abi_host_only")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L" + os.path.join(ROOT, "onitama_alphazero_b200"), "-lonb", "-Wl,-rpath,$ORIGIN/../../onitama_alphazero_b200"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C ABI OK" in r.stdout, r.stdout + r.stderr
