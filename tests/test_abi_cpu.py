@@ -115,3 +115,20 @@ def test_header_is_c99_clean_and_links_from_c(lib):
                            "-L" + os.path.join(ROOT, "onitama_alphazero_b200"), "-lonb", "-Wl,-rpath,$ORIGIN/../../onitama_alphazero_b200"])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "C ABI OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_rust_bindings_cover_the_header():
+    """include/onb_sys.rs (the unbuilt Rust side of the boundary) binds every symbol onb.h declares, with the
+    same arity."""
+    hdr = open(os.path.join(ROOT, "include", "onb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    rs = open(os.path.join(ROOT, "include", "onb_sys.rs")).read()
+    decls = re.findall(r"ONB_API\s+[^;]+?\s+(onb_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+    assert len(decls) >= 36
+    for name, args in decls:
+        m = re.search(r"pub fn %s\(([^)]*)\)" % name, rs)
+        assert m, "onb_sys.rs does not bind %s" % name
+        n_c = 0 if args.strip() in ("", "void") else len(args.split(","))
+        n_rs = 0 if not m.group(1).strip() else len(m.group(1).split(","))
+        assert n_c == n_rs, name
+    assert "pub struct onb_state" in rs and "pub struct onb_config" in rs
