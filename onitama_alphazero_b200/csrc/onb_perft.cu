@@ -166,10 +166,144 @@ __global__ void __launch_bounds__(128) k_perft_dfs(const uint4* __restrict__ sta
     }
 }
 
+// ---- phase 2, flattened: one move per loop iteration -----------------------------------------------------------------------
+// The nested-loop DFS above keeps everything in registers but its lanes drift apart (each lane sits at a different nesting
+// level with a different trip count): ~14 % SIMT efficiency. This variant runs the same search as a state machine whose
+// iteration either advances the (slot, piece) iterator of the current node or plays ONE move; positions at the last interior
+// level are bulk-counted immediately. The per-level stack lives in shared memory ([level][word][thread], conflict free), the
+// current level in registers, so every lane executes the same short instruction stream in every iteration.
+constexpr int kFlatThreads = 128;
+constexpr int kFlatWords = 7;  // op, ok, ep, ek, cards|side<<20, iterator, current destination mask | from << 25
+
+struct BulkCount { uint32_t total, wins; };
+__device__ __forceinline__ BulkCount bulk_count(const uint32_t* T, const RelGame& g) {
+    const uint32_t own = g.op | g.ok;
+    const uint32_t win_t = g.ek & ~g.ep;
+    const uint32_t temple = 1u << (g.side ? kRedTemple : kBlueTemple);
+    const uint32_t* T0 = T + (g.side * 16u + card_at(g.cards, g.side * 2u)) * 25u;
+    const uint32_t* T1 = T + (g.side * 16u + card_at(g.cards, g.side * 2u + 1u)) * 25u;
+    BulkCount c{0, 0};
+    uint32_t rem = own;
+    while (rem) {
+        const int f = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const uint32_t wm = win_t | (((g.op >> f) & 1u) ? 0u : temple);
+        const uint32_t a0 = T0[f] & ~own, a1 = T1[f] & ~own;
+        c.total += __popc(a0) + __popc(a1);
+        c.wins += __popc(a0 & wm) + __popc(a1 & wm);
+    }
+    return c;
+}
+
+#ifndef ONB_PERFT_MINB
+#define ONB_PERFT_MINB 1
+#endif
+template <int REM>
+__global__ void __launch_bounds__(kFlatThreads, ONB_PERFT_MINB) k_perft_flat(const uint4* __restrict__ states, const uint32_t* __restrict__ roots, int64_t n_items,
+                                                             unsigned long long* __restrict__ nodes, unsigned long long* __restrict__ wins,
+                                                             unsigned long long* __restrict__ zero, int depth_total) {
+    __shared__ __align__(16) uint32_t s_att[800];
+    __shared__ uint32_t s_stk[(REM > 2 ? REM - 2 : 1) * kFlatWords * kFlatThreads];  // levels 0 .. REM-3 can have a level below them
+    load_attack_table_to_smem(s_att);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int64_t row = (int64_t)roots[i] * depth_total;
+    const int d0 = depth_total - REM;  // the counters of the frontier node's children live at index d0
+    RelGame g = to_rel(unpack(states[i]));
+    if constexpr (REM == 1) {
+        const BulkCount c = bulk_count(s_att, g);
+        if (c.total) atomicAdd(&nodes[row + d0], (unsigned long long)c.total);
+        if (c.wins) atomicAdd(&wins[row + d0], (unsigned long long)c.wins);
+        if (c.total == 0) atomicAdd(&zero[row + d0], 1ull);
+    } else {
+    unsigned long long cnt_n[REM], cnt_w[REM];  // index = level of the PARENT whose children are counted
+    uint32_t cnt_z[REM];
+#pragma unroll
+    for (int k = 0; k < REM; ++k) { cnt_n[k] = 0; cnt_w[k] = 0; cnt_z[k] = 0; }
+    auto add_counts = [&](int lv, uint32_t tot, uint32_t w, uint32_t z) {  // level-indexed without dynamic register indexing
+#pragma unroll
+        for (int k = 0; k < REM - 1; ++k)
+            if (k == lv) { cnt_n[k] += tot; cnt_w[k] += w; cnt_z[k] += z; }
+    };
+    int level = 0;
+    uint32_t it = g.op | g.ok;        // own pieces of the current hand slot that were not visited yet
+    uint32_t cur = 0, cur_f = 0;      // unplayed, non-winning destinations of the current piece, and its square
+    uint32_t cur_slot = 0, had = 0;   // hand slot being enumerated; whether this node had any move so far
+    uint32_t n_total = 0, n_wins = 0; // running child counts of the current node
+    bool done = false;
+    for (;;) {
+        // (1) find the next move: advance over pieces and hand slots, leave finished nodes. Light and rarely more than one round,
+        //     so that step (2), which dominates, is executed by all lanes of the warp together.
+        while (cur == 0) {
+            if (it) {  // next piece of the current hand slot
+                const uint32_t own = g.op | g.ok;
+                const int f = __ffs(it) - 1;
+                it &= it - 1;
+                const uint32_t wm = (g.ek & ~g.ep) | (((g.op >> f) & 1u) ? 0u : (1u << (g.side ? kRedTemple : kBlueTemple)));
+                const uint32_t a = s_att[(g.side * 16u + card_at(g.cards, g.side * 2u + cur_slot)) * 25u + f] & ~own;
+                n_total += __popc(a);
+                n_wins += __popc(a & wm);
+                had |= a ? 1u : 0u;
+                cur = a & ~wm;  // a winning move ends its line
+                cur_f = (uint32_t)f;
+            } else if (cur_slot == 0) {  // second hand slot
+                cur_slot = 1;
+                it = g.op | g.ok;
+            } else {  // node finished
+                add_counts(level, n_total, n_wins, had ? 0u : 1u);
+                if (level == 0) { done = true; break; }
+                --level;
+                const uint32_t* p = s_stk + (level * kFlatWords) * kFlatThreads + threadIdx.x;
+                g.op = p[0 * kFlatThreads]; g.ok = p[1 * kFlatThreads]; g.ep = p[2 * kFlatThreads]; g.ek = p[3 * kFlatThreads];
+                const uint32_t cs = p[4 * kFlatThreads];
+                g.cards = cs & 0xFFFFFu; g.side = cs >> 20;
+                const uint32_t itw = p[5 * kFlatThreads];
+                it = itw & kAll25; cur_slot = (itw >> 25) & 1u; had = (itw >> 26) & 1u;
+                const uint32_t cw = p[6 * kFlatThreads];
+                cur = cw & kAll25; cur_f = cw >> 25;
+                n_total = 0; n_wins = 0;  // the part counted before the descent was flushed then
+            }
+        }
+        if (done) break;
+        // (2) play one move
+        const uint32_t to = __ffs(cur) - 1;
+        cur &= cur - 1;
+        RelGame ch = g;
+        apply_move_rel(ch, make_action(g.side * 2u + cur_slot, cur_f, to, ((g.op >> cur_f) & 1u) ^ 1u));
+        if (level == REM - 2) {  // the child is on the last interior level: count its children in bulk, do not descend
+            const BulkCount c = bulk_count(s_att, ch);
+            cnt_n[REM - 1] += c.total; cnt_w[REM - 1] += c.wins; cnt_z[REM - 1] += c.total == 0 ? 1u : 0u;
+        } else {
+            add_counts(level, n_total, n_wins, 0);
+            uint32_t* p = s_stk + (level * kFlatWords) * kFlatThreads + threadIdx.x;
+            p[0 * kFlatThreads] = g.op; p[1 * kFlatThreads] = g.ok; p[2 * kFlatThreads] = g.ep; p[3 * kFlatThreads] = g.ek;
+            p[4 * kFlatThreads] = g.cards | (g.side << 20);
+            p[5 * kFlatThreads] = it | (cur_slot << 25) | (had << 26);
+            p[6 * kFlatThreads] = cur | (cur_f << 25);
+            ++level;
+            g = ch;
+            it = g.op | g.ok; cur = 0; cur_f = 0; cur_slot = 0; had = 0; n_total = 0; n_wins = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < REM; ++k) {
+        if (cnt_n[k]) atomicAdd(&nodes[row + d0 + k], cnt_n[k]);
+        if (cnt_w[k]) atomicAdd(&wins[row + d0 + k], cnt_w[k]);
+        if (cnt_z[k]) atomicAdd(&zero[row + d0 + k], (unsigned long long)cnt_z[k]);
+    }
+    }
+}
+
 template <int REM>
 static cudaError_t launch_dfs(Ctx* c, const uint4* st, const uint32_t* rt, int64_t n_items, unsigned long long* nodes, unsigned long long* wins,
                               unsigned long long* zero, int depth) {
-    k_perft_dfs<REM><<<(unsigned)((n_items + 127) / 128), 128, 0, c->stream>>>(st, rt, n_items, nodes, wins, zero, depth);
+    const char* legacy = getenv("ONB_PERFT_NESTED");  // exploration knob: the nested-loop register DFS
+    if (legacy && legacy[0] == '1')
+        k_perft_dfs<REM><<<(unsigned)((n_items + 127) / 128), 128, 0, c->stream>>>(st, rt, n_items, nodes, wins, zero, depth);
+    else
+        k_perft_flat<REM><<<(unsigned)((n_items + kFlatThreads - 1) / kFlatThreads), kFlatThreads, 0, c->stream>>>(st, rt, n_items, nodes, wins, zero,
+                                                                                                                 depth);
     return cudaGetLastError();
 }
 
