@@ -1,9 +1,10 @@
 // onb_perft.cu -- perft-style legal-move enumeration (BASELINE config 2).
 //
 // Two phases: (1) lockstep breadth-first frontier expansion in HBM (32 B per node: read parent, write child)
-// until there are enough independent subtrees to fill the machine; (2) every frontier node is finished by a
-// depth-first search held entirely in registers (compile-time depth, so all per-level state is scalar) with
-// bulk counting at the last ply. Phase 2 moves ~0 bytes per node and is issue-bound; see DESIGN.md.
+// until there are enough independent subtrees to fill the machine; (2) every frontier node is finished by one
+// thread's depth-first search with bulk counting at the last ply: k_perft_flat (flat state machine, stack in shared
+// memory, the shipped path) or k_perft_dfs (nested loops in registers, kept for comparison). Phase 2 moves ~0 bytes
+// per node and is issue-bound; see DESIGN.md.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
