@@ -453,11 +453,23 @@ def main():
         roots_host = torch.from_numpy(roots_np.view(np.uint8).reshape(n, 24).copy()).pin_memory()
         host_view = roots_host.numpy().view(onb.STATE_DTYPE).reshape(n)
 
+        def pinned(shape, tdtype, ndtype):
+            t = torch.empty(shape, dtype=tdtype).pin_memory()
+            return t, t.numpy().view(ndtype)
+        keep = []
+        outs = {}
+        for key, shape, td, nd in (("best", (n,), torch.int16, np.uint16), ("pi", (n, 2, 25), torch.float32, np.float32),
+                                   ("root_visits", (n,), torch.int32, np.uint32), ("root_q", (n,), torch.float64, np.float64),
+                                   ("child_visits", (n, 40), torch.int32, np.uint32)):
+            t, a = pinned(shape, td, nd)
+            keep.append(t)
+            outs[key] = a
+
         def e2e_one(i):
             ctx.set_states(host_view)
             ctx.mcts_begin(MCTS_C, sims)
             ctx.mcts_run(onb.EVAL_UNIFORM, sims)
-            ctx.mcts_finish(to_host=True)
+            ctx.mcts_finish(to_host=True, out=outs)
 
         ems, _ = timed(e2e_one, 1, max(1, steps))
         e2e = {"value": world * n * sims * max(1, steps) / (ems * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 24 * n,

@@ -190,13 +190,15 @@ class Context:
     def mcts_run(self, evaluator, sims):
         self._ck(self._lib.onb_mcts_run(self._h, evaluator, sims))
 
-    def mcts_finish(self, to_host=True):
+    def mcts_finish(self, to_host=True, out=None):
+        """out: optional dict of preallocated arrays (e.g. views of pinned memory) with the keys below; reused across calls."""
         if not to_host:
             self._ck(self._lib.onb_mcts_finish(self._h, None, None, None, None, None))
             return None
         n = self.n
-        out = dict(best=np.zeros(n, np.uint16), pi=np.zeros((n, 2, 25), np.float32), root_visits=np.zeros(n, np.uint32),
-                   root_q=np.zeros(n, np.float64), child_visits=np.zeros((n, 40), np.uint32))
+        if out is None:
+            out = dict(best=np.zeros(n, np.uint16), pi=np.zeros((n, 2, 25), np.float32), root_visits=np.zeros(n, np.uint32),
+                       root_q=np.zeros(n, np.float64), child_visits=np.zeros((n, 40), np.uint32))
         self._ck(self._lib.onb_mcts_finish(self._h, L.ptr(out["best"]), L.ptr(out["pi"]), L.ptr(out["root_visits"]), L.ptr(out["root_q"]),
                                            L.ptr(out["child_visits"])))
         return out
