@@ -796,3 +796,33 @@ def test_config2_full_size_perft(onb):
     for i in np.random.RandomState(5).choice(len(decks), 12, replace=False):
         n_, w_, _ = O.perft(O.new_games(1, deck=decks[i]), 6)
         assert nodes[i].tolist() == n_.tolist() and wins[i].tolist() == w_.tolist(), decks[i]
+
+
+def test_mcts_wide_nodes_more_than_32_children(onb):
+    """Roots with 33-36 legal moves: more children than a warp has lanes (two rounds in the warp-per-tree kernels, five rounds
+    of 8 lanes in the fused kernel); both paths must match the oracle node for node."""
+    seed = 123
+    g = O.new_games(4096, seed=seed)
+    picks = {12: [627], 16: [3247, 320], 14: [2338], 20: [462], 32: [185, 3256], 34: [2725]}
+    roots = []
+    for step in range(35):
+        O.env_step_random(g, seed, step)
+        for i in picks.get(step, []):
+            roots.append(g[i:i + 1].copy())
+    roots = np.concatenate(roots)
+    counts = [len(O.gen_moves(roots[i:i + 1])) for i in range(len(roots))]
+    assert min(counts) >= 33 and max(counts) >= 36
+    sims, c = 300, 2.0
+    with onb.Context(len(roots), mcts_max_sims=sims, planes=False) as ctx:
+        ctx.set_states(roots)
+        for fused in (True, False):
+            for ev in (onb.EVAL_UNIFORM, onb.EVAL_HASH):
+                res = ctx.search(c, sims, evaluator=ev, fused=fused)
+                want = O.mcts_search_batch(roots, c, sims, evaluator=ev)
+                assert np.array_equal(res["child_visits"], want["child_visits"]), (fused, ev)
+                assert np.array_equal(res["best"], want["best"]) and np.array_equal(res["pi"], want["pi"])
+                for t in range(len(roots)):
+                    w = O.mcts_search(roots[t:t + 1], c, sims, evaluator=ev, dump=True)
+                    got = ctx.mcts_dump_tree(t)
+                    assert np.array_equal(got["visits"], w["tree"]["visits"]) and np.array_equal(got["prior"], w["tree"]["prior"])
+                    assert got["n_child"].max() >= 33
