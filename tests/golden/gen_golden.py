@@ -376,8 +376,9 @@ def main():
     ref = {}
     # common/mod.rs:95-134
     ref["from_2d_to_bitboard"] = [[[0, 0], 0x80000000], [[2, 1], 0x00100000], [[4, 4], 0x00000080]]
-    # common/mod.rs:82-92: value 0x8000_0001... (bit order): get_bit(x, 0) is the MSB
-    ref["get_bit_msb_first"] = True
+    # common/mod.rs:82-92: get_bit(bits, i) for i in 0..32, i = 0 is the MSB
+    ref["get_bit"] = dict(cite="common/mod.rs:82-92", bits=0b00001111000011110000111100001111,
+                          expected=[0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1])
     # state.rs:420-492 (moves given as [[r0,c0],[r1,c1],piece])
     ref["opening_moves"] = [
         dict(cite="state.rs:420-455", deck=[4, 3, 1, 0, 2], color=RED, card=4,

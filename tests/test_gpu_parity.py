@@ -69,6 +69,19 @@ def test_error_paths(onb):
             ctx.mcts_begin(1.0, 5)
 
 
+def test_get_bit_order_on_gpu(onb):
+    """common/mod.rs:82-92 through the CUDA encoder and the boundary conversion"""
+    gb = G["reference_tests"]["get_bit"]
+    s = O.new_games(3, deck=[4, 3, 1, 0, 2])
+    s["pawns"][1][0] = gb["bits"] & 0xFFFFFF80
+    with onb.Context(3) as ctx:
+        ctx.set_states(s)
+        planes = ctx.encode()
+        assert ctx.get_states().tobytes() == s.tobytes()
+    assert planes[1, 0].reshape(25).tolist() == [float(b) for b in gb["expected"][:25]]
+    assert np.array_equal(planes, O.encode(s))
+
+
 # ------------------------------------------------------------------ reference known-answer tests through the GPU
 def test_reference_make_move_cases_on_gpu(onb):
     cases = G["reference_tests"]["make_move"]

@@ -34,6 +34,15 @@ def test_bit_layout_from_2d():
     assert list(g["kings"][0]) == REF["start_position"]["kings"]
 
 
+def test_get_bit_order_through_the_encoder():
+    """common/mod.rs:82-92 (get_bit, i = 0 is the MSB) pinned through get_bit_array / create_tensor_from_state"""
+    gb = REF["get_bit"]
+    g = O.new_games(1, deck=[4, 3, 1, 0, 2])
+    g["pawns"][0][0] = gb["bits"] & 0xFFFFFF80
+    plane0 = O.encode(g)[0, 0].reshape(25)
+    assert plane0.tolist() == [float(b) for b in gb["expected"][:25]]
+
+
 # ------------------------------------------------------------------ attack maps (card.rs:476-604)
 def test_attack_maps_match_golden_and_survey():
     att = O.attack_maps()
