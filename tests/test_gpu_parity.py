@@ -839,3 +839,24 @@ def test_mcts_wide_nodes_more_than_32_children(onb):
                     got = ctx.mcts_dump_tree(t)
                     assert np.array_equal(got["visits"], w["tree"]["visits"]) and np.array_equal(got["prior"], w["tree"]["prior"])
                     assert got["n_child"].max() >= 33
+
+
+def test_reference_tactical_positions(onb):
+    """The two tactical sanity positions of the reference's plain-MCTS tests (ai/mcts/mcts_arena.rs:460-523: take the king with
+    the Dragon card; the only king move that does not lose). They pin a different agent statistically; the PUCT search with the
+    uniform evaluator finds the same moves, on the GPU and in the oracle alike."""
+    def bb(r, c):
+        return 0x80000000 >> (r * 5 + c)
+    a = O.make_state([3, 2, 0, 1, 11], side=1)           # Dragon,Frog,Tiger,Rabbit,Horse with slots 0 and 3 swapped
+    a["kings"][0][0] = bb(1, 3)
+    b = O.make_state([12, 8, 3, 11, 1], side=1)          # Ox,Monkey | Rabbit,Horse | Dragon
+    b["kings"][0][1] = bb(0, 4); b["pawns"][0][1] = 0; b["pawns"][0][0] = bb(0, 3) | bb(1, 4)
+    roots = np.concatenate([a, b])
+    expected = [1 << 5 | 8 | (3 << 10), 4 << 5 | 2 | (2 << 10) | (1 << 12)]   # (from 1 -> 8 pawn, card idx 3), (king 4 -> 2, card idx 2)
+    for sims in (400, 2000):
+        with onb.Context(2, mcts_max_sims=sims, planes=False) as ctx:
+            ctx.set_states(roots)
+            res = ctx.search(math.sqrt(2.0), sims)
+        want = O.mcts_search_batch(roots, math.sqrt(2.0), sims)
+        assert res["best"].tolist() == expected == want["best"].tolist()
+        assert np.array_equal(res["child_visits"], want["child_visits"])
