@@ -39,6 +39,8 @@ static cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
 }
 
+// message of the last failed onb_create (no context exists yet to hold it); onb_create is expected to be called from one
+// thread at a time per process
 static char g_create_err[512] = "";
 
 }  // namespace onb

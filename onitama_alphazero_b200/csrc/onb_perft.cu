@@ -14,10 +14,6 @@
 
 namespace onb {
 
-struct __align__(16) FrontierItem {
-    uint4 state;
-};
-
 // ---- phase 1: one BFS level -------------------------------------------------------------------------------
 // COUNT_ONLY pass sizes the next frontier exactly; the fill pass writes it (order is irrelevant for perft).
 template <bool COUNT_ONLY>
