@@ -205,7 +205,7 @@ ONB_API int32_t onb_perft(onb_ctx* ctx, const onb_state* roots_host, int64_t n, 
  * ------------------------------------------------------------------------------------------------ */
 ONB_API int32_t onb_mcts_begin(onb_ctx* ctx, double c_puct, uint32_t sims);
 /* train mode (AlphaZeroMctsConfig::train, alphazero_mcts/mod.rs:26-43): at the ROOT every uct() evaluation uses
- * P' = P (1 - epsilon) + noise epsilon with a fresh Dirichlet(alpha; k) component per evaluation and a left-to-right max_by
+ * P' = P (1 - epsilon) + noise epsilon with a fresh Dirichlet(alpha; k) component (a Beta(alpha, (k-1) alpha) variate) per evaluation and a left-to-right max_by
  * fold (mcts_arena.rs:186-220). The reference draws from thread_rng (not reproducible); here the draws come from the counter RNG
  * keyed by (seed, global tree id, root visit count), so a run is repeatable. Reference values: epsilon 0.25, alpha 0.03.
  * Applies to the searches started after the call; enabled = 0 restores eval mode. Statistical parity only. */

@@ -229,34 +229,23 @@ static void deal(uint64_t seed, uint64_t game, uint32_t epoch, uint8_t out[5]) {
 // ------------------------------------------------------------------ root exploration noise (train mode)
 // The reference adds Dirichlet(0.03) noise at the root in train mode, drawn from thread_rng with a FRESH Dirichlet sample per
 // uct() call (alphazero_mcts/mcts_arena.rs:186-202): not reproducible, statistical parity only. Project-defined restatement:
-// the noise of child i in one uct() call is component i of a fresh Dirichlet(alpha; k) sample, i.e. g1 / (g1 + g2) with
-// g1 ~ Gamma(alpha), g2 ~ Gamma((k-1) alpha) (rand_distr 0.4.3 normalises k independent Gamma(alpha) draws), sampled with
-// Marsaglia-Tsang (+ the U^(1/shape) boost for shape < 1, as rand_distr::Gamma does) from the counter RNG.
-static inline double noise_uniform(uint64_t key, uint32_t step, uint32_t code) {
-    return ((double)(uint32_t)(mix64(key ^ (((uint64_t)step << 32) | code)) >> 32) + 0.5) * (1.0 / 4294967296.0);
+// the noise of child i in one uct() call is component i of a fresh Dirichlet(alpha; k) sample (rand_distr 0.4.3 normalises k
+// independent Gamma(alpha) draws), i.e. a Beta(alpha, (k-1) alpha) variate, sampled from the counter RNG.
+static inline float noise_uniform(uint64_t key, uint32_t step, uint32_t code) {
+    const uint32_t r = (uint32_t)(mix64(key ^ (((uint64_t)step << 32) | code)) >> 32);
+    return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
-static double noise_gamma(double shape, uint64_t key, uint32_t step, uint32_t base) {
-    const bool boost = shape < 1.0;
-    const double a = boost ? shape + 1.0 : shape;
-    const double d = a - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
-    double g = d;
-    for (uint32_t attempt = 0; attempt < 15; ++attempt) {
-        const double u1 = noise_uniform(key, step, base | (attempt << 2) | 0u), u2 = noise_uniform(key, step, base | (attempt << 2) | 1u),
-                     u3 = noise_uniform(key, step, base | (attempt << 2) | 2u);
-        const double x = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
-        const double v = 1.0 + c * x;
-        if (v <= 0.0) continue;
-        const double v3 = v * v * v;
-        if (std::log(u3) < 0.5 * x * x + d * (1.0 - v3 + std::log(v3))) { g = d * v3; break; }
+// Beta(alpha, (k-1) alpha) by Joehnk's method in log space, single precision (see the comment in csrc/onb_mcts.cu).
+static float noise_beta(uint32_t k, float alpha, uint64_t key, uint32_t step, uint32_t sample) {
+    const float inv_a = 1.0f / alpha, inv_b = 1.0f / ((float)(k - 1) * alpha);
+    float lx = 0.f, ly = 0.f;
+    for (uint32_t attempt = 0; attempt < 16; ++attempt) {
+        const uint32_t code = 0x80000000u | (sample << 8) | (attempt << 2);
+        lx = std::log(noise_uniform(key, step, code)) * inv_a;
+        ly = std::log(noise_uniform(key, step, code | 1u)) * inv_b;
+        if (std::exp(lx) + std::exp(ly) <= 1.0f) break;
     }
-    if (boost) g *= std::exp(std::log(noise_uniform(key, step, base | 63u)) / shape);
-    return g;
-}
-static double noise_beta(uint32_t k, double alpha, uint64_t key, uint32_t step, uint32_t sample) {
-    const uint32_t base = 0x80000000u | (sample << 8);
-    const double g1 = noise_gamma(alpha, key, step, base), g2 = noise_gamma((double)(k - 1) * alpha, key, step, base | (1u << 6));
-    const double tot = g1 + g2;
-    return tot > 0.0 ? g1 / tot : 0.0;
+    return 1.0f / (1.0f + std::exp(ly - lx));
 }
 
 // ------------------------------------------------------------------ boundary structs (C layout)
@@ -449,7 +438,7 @@ struct MctsArena {  // mcts_arena.rs:37-73
             // new noise sample; the last maximal element wins.
             const uint32_t k = (uint32_t)children.size();
             auto uct_noisy = [&](const MctsNode& child, uint32_t sample) {
-                const double noise = noise_beta(k, eta, noise_key, parent.visits, sample);
+                const double noise = (double)noise_beta(k, (float)eta, noise_key, parent.visits, sample);
                 return child.winrate + exploration_c * (child.probability * (1. - epsilon) + noise * epsilon) *
                                            (std::sqrt((double)parent.visits) / (double)(child.visits + 1));
             };
