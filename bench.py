@@ -475,6 +475,11 @@ def main():
         e2e = {"value": world * n * sims * max(1, steps) / (ems * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 24 * n,
                "d2h_bytes_per_step": n * (2 + 200 + 4 + 8 + 160), "ms_per_step": ems / max(1, steps),
                "path": "onb_env_set_states(host roots) + onb_mcts_begin/run/finish(host best, pi, visits, q)"}
+        # train mode (root exploration noise, AlphaZeroMctsConfig::train) for reference: same search with onb_mcts_set_noise
+        ctx.mcts_set_noise(True, 0.25, 0.03, SEED)
+        tms, _ = timed(one, 2, 3)
+        ctx.mcts_set_noise(False)
+        roof["train_mode_noise"] = {"value": world * n * sims * 3 / (tms * 1e-3), "unit": "sims/s", "ms_per_step": tms / 3}
         ctx.close()
         return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=run_ms, dtype="u32+f64", roofline=roof, e2e=e2e,
                     gpu_launches=3 * steps, clocks=clocks)
