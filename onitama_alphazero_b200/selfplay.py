@@ -143,3 +143,37 @@ def _fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies):
     b_wins = int((red_won & ~a_is_red).sum() + (blue_won & a_is_red).sum())
     ctx.last_fight_results = res.cpu().numpy()  # per-game results for fight_statistics()
     return a_wins, b_wins, int(n - a_wins - b_wins)
+
+
+class ReplayBuffer:
+    """Fixed-capacity ring buffer of self-play samples on one device (train.rs:180-339 keeps a Vec<SelfPlayData> and drains the
+    oldest samples when it outgrows buffer_size; a ring does the same without reallocation). 2 304 B per sample."""
+
+    def __init__(self, capacity, device="cpu"):
+        self.capacity = int(capacity)
+        self.planes = torch.zeros((self.capacity, 21, 5, 5), dtype=torch.float32, device=device)
+        self.pi = torch.zeros((self.capacity, 2, 25), dtype=torch.float32, device=device)
+        self.z = torch.zeros((self.capacity,), dtype=torch.float32, device=device)
+        self.size = 0
+        self.head = 0  # next write position
+
+    def add(self, planes, pi, z):
+        """Append m samples (newest overwrite the oldest once full). Accepts the dict fields returned by self_play()."""
+        m = int(planes.shape[0])
+        if m == 0:
+            return
+        if m >= self.capacity:  # keep only the newest `capacity` samples
+            planes, pi, z = planes[-self.capacity:], pi[-self.capacity:], z[-self.capacity:]
+            m = self.capacity
+        idx = (self.head + torch.arange(m, device=self.planes.device)) % self.capacity
+        self.planes[idx] = planes.to(self.planes.device)
+        self.pi[idx] = pi.to(self.pi.device)
+        self.z[idx] = z.to(self.z.device)
+        self.head = (self.head + m) % self.capacity
+        self.size = min(self.capacity, self.size + m)
+
+    def sample(self, batch_size, generator=None):
+        """train.rs:280-283: `choose_multiple` -> batch_size distinct samples, uniformly at random."""
+        b = min(int(batch_size), self.size)
+        idx = torch.randperm(self.size, generator=generator, device="cpu")[:b].to(self.planes.device)
+        return self.planes[idx], self.pi[idx], self.z[idx].unsqueeze(1)
