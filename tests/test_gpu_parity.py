@@ -860,3 +860,15 @@ def test_reference_tactical_positions(onb):
         want = O.mcts_search_batch(roots, math.sqrt(2.0), sims)
         assert res["best"].tolist() == expected == want["best"].tolist()
         assert np.array_equal(res["child_visits"], want["child_visits"])
+
+
+def test_example_training_iteration_runs(onb):
+    """examples/selfplay_train_loop.py: self-play (train mode, network) -> replay ring -> alphaloss SGD -> arena vs Random."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("selfplay_train_loop", os.path.join(ROOT, "examples", "selfplay_train_loop.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    log = mod.main(["--games", "48", "--sims", "16", "--iters", "1", "--max-plies", "12", "--batch", "64", "--sgd-steps", "3",
+                    "--eval-games", "16"])
+    assert len(log) == 1 and log[0]["samples"] > 0 and log[0]["wins"] + log[0]["losses"] + log[0]["draws"] == 16
+    assert np.isfinite(log[0]["value_loss"]) and np.isfinite(log[0]["policy_loss"])
