@@ -132,3 +132,13 @@ def test_rust_bindings_cover_the_header():
         n_rs = 0 if not m.group(1).strip() else len(m.group(1).split(","))
         assert n_c == n_rs, name
     assert "pub struct onb_state" in rs and "pub struct onb_config" in rs
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    """Without the built CUDA library the package refuses to work (no silent fallback of any kind)."""
+    from onitama_alphazero_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "onitama_alphazero_b200", "does_not_exist.so"))
+    with pytest.raises(ImportError) as e:
+        _lib.load()
+    assert "no CPU fallback" in str(e.value)
