@@ -237,6 +237,14 @@ ONB_API int32_t onb_mcts_dump_tree(onb_ctx* ctx, int64_t tree, int64_t cap, onb_
  * reference is undefined for that tree, bit1: node pool overflow) */
 ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_host);
 
+/* ---- device self-tests -------------------------------------------------------------------------------------- */
+/* Arithmetic identities the kernels rely on, checked on the device itself. which = ONB_SELFTEST_DIV: the PUCT score
+ * (mcts_arena.rs:204-207) divides by visit counts through a reciprocal table; this compares that division with the
+ * correctly rounded IEEE quotient over every sqrt(N_parent) / (n + 1) with both below 4096 and over 2^25 pseudo-random
+ * W / n. *mismatches receives the number of quotients whose bits differ (0 on a correct build). */
+#define ONB_SELFTEST_DIV 0
+ONB_API int32_t onb_selftest(onb_ctx* ctx, int32_t which, uint64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

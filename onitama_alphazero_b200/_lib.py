@@ -74,6 +74,7 @@ SYMBOLS = {
     "onb_mcts_play_best": (C.c_int32, [_P, C.c_uint32]),
     "onb_mcts_dump_tree": (C.c_int32, [_P, C.c_int64, C.c_int64, C.POINTER(TreeDump), C.POINTER(C.c_int64)]),
     "onb_mcts_tree_info": (C.c_int32, [_P, _P, _P]),
+    "onb_selftest": (C.c_int32, [_P, C.c_int32, _P]),
 }
 
 _lib = None

@@ -522,4 +522,22 @@ int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_
     return ONB_OK;
 }
 
+int32_t onb_selftest(onb_ctx* ctx, int32_t which, uint64_t* mismatches) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (which != ONB_SELFTEST_DIV) return fail(c, ONB_E_INVALID, "onb_selftest: unknown test");
+    if (!mismatches) return fail(c, ONB_E_INVALID, "onb_selftest: null output");
+    unsigned long long* d = nullptr;
+    ONB_CUDA(c, cudaMalloc(&d, 8));
+    cudaError_t e = cudaMemsetAsync(d, 0, 8, c->stream);
+    if (e == cudaSuccess) e = launch_selftest_div(c, d);
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    ONB_CUDA(c, e);
+    *mismatches = (uint64_t)h;
+    return ONB_OK;
+}
+
 }  // extern "C"

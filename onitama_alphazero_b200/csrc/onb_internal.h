@@ -81,6 +81,7 @@ cudaError_t launch_env_step(Ctx* c, int mode, uint32_t step, int auto_reset, uin
 // perft (onb_perft.cu)
 int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uint64_t* nodes, uint64_t* wins, uint64_t* zero);
 // mcts (onb_mcts.cu)
+cudaError_t launch_selftest_div(Ctx* c, unsigned long long* d_mismatches);
 cudaError_t launch_mcts_begin(Ctx* c);
 cudaError_t launch_mcts_select(Ctx* c);
 cudaError_t launch_mcts_expand_backup(Ctx* c);

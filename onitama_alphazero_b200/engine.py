@@ -206,6 +206,12 @@ class Context:
     def mcts_play_best(self, out_flags=0):
         self._ck(self._lib.onb_mcts_play_best(self._h, out_flags))
 
+    def selftest(self, which=0):
+        """onb_selftest: number of results that differ from the IEEE answer (0 on a correct build)"""
+        bad = C.c_uint64(0)
+        self._ck(self._lib.onb_selftest(self._h, which, C.byref(bad)))
+        return int(bad.value)
+
     def mcts_tree_info(self):
         nn = np.zeros(self.n, np.uint32)
         fl = np.zeros(self.n, np.uint8)

@@ -872,3 +872,11 @@ def test_example_training_iteration_runs(onb):
                     "--eval-games", "16"])
     assert len(log) == 1 and log[0]["samples"] > 0 and log[0]["wins"] + log[0]["losses"] + log[0]["draws"] == 16
     assert np.isfinite(log[0]["value_loss"]) and np.isfinite(log[0]["policy_loss"])
+
+
+@pytest.mark.gpu
+def test_table_division_is_ieee_exact(onb):
+    """The PUCT score divides through a reciprocal table (onb_mcts.cu div_by_rcp); the device compares it with the correctly
+    rounded quotient over every sqrt(Np)/(n+1), Np and n+1 < 4096, and 2^25 pseudo-random W/n (include/onb.h onb_selftest)."""
+    with onb.Context(1, planes=False) as ctx:
+        assert ctx.selftest(0) == 0
