@@ -83,6 +83,7 @@ typedef struct onb_state {
 /* ---- evaluators that live on the device ---- */
 #define ONB_EVAL_UNIFORM 0 /* policy = f32(1/50) everywhere, value = 0 (BASELINE config 4) */
 #define ONB_EVAL_HASH 1    /* deterministic pseudo-random policy/value from a hash of the planes (parity tests) */
+#define ONB_EVAL_NET 2     /* the ConvResNet loaded with onb_net_load, evaluated on the tensor cores */
 
 /* ---- device buffers (onb_buffer) ---- */
 #define ONB_BUF_STATES 0      /* packed internal states, 16 B per game (layout in DESIGN.md) */
@@ -236,6 +237,21 @@ ONB_API int32_t onb_mcts_dump_tree(onb_ctx* ctx, int64_t tree, int64_t cap, onb_
 /* per-tree summary: node counts [n], flags [n] (bit0: a zero-legal-move node was expanded -> parity with the
  * reference is undefined for that tree, bit1: node pool overflow) */
 ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_host);
+
+/* ---- policy/value network on the device ---------------------------------------------------------------------
+ * ConvResNet::forward (alphazero-training/src/net.rs:215-232) for every position of a plane buffer, as one fused
+ * tensor-core kernel (BatchNorm in eval mode folded into the convolutions; tf32 products with f32 accumulation,
+ * i.e. what libtorch's cuDNN convolutions compute by default on this GPU; heads in f32). This is the evaluator the
+ * search would otherwise get from tch as a black box; with it a whole search needs no host round trip.
+ * onb_net_load takes the parameters under the reference's VarStore names (net.rs:118-213, `|` or `.` separators),
+ * e.g. "conv_init_1|weight", "bn1|running_var", "resnet_0|resnet_small_block1|small_block_conv|weight",
+ * "policy_conv|bias", "ph_linear2|weight", "vh_linear1|weight": host f32 arrays in libtorch layout (OIHW, [out][in]).
+ * The number of residual blocks is taken from the names; hidden_channels must be 64 and input_channels 21
+ * (ConvResNetConfig of train.rs) -- anything else is rejected with ONB_E_INVALID.
+ * onb_net_forward reads planes_buffer (ONB_BUF_LEAF_PLANES or ONB_BUF_PLANES, [n][21][5][5] f32) and writes
+ * ONB_BUF_POLICY [n][2][25] (softmax over 50) and ONB_BUF_VALUE [n]. onb_mcts_eval / onb_mcts_run accept ONB_EVAL_NET. */
+ONB_API int32_t onb_net_load(onb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel);
+ONB_API int32_t onb_net_forward(onb_ctx* ctx, int32_t planes_buffer);
 
 /* ---- device self-tests -------------------------------------------------------------------------------------- */
 /* Arithmetic identities the kernels rely on, checked on the device itself. which = ONB_SELFTEST_DIV: the PUCT score

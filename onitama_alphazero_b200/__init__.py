@@ -4,7 +4,7 @@ The product is libonb.so (csrc/, include/onb.h); this package is the Python host
 Importing it does not touch the oracle. Every compute call requires the built CUDA library and a CUDA device."""
 from . import _lib
 from ._lib import (ACTION_NONE, BUF_ACTIONS, BUF_BEST, BUF_LEAF_PLANES, BUF_MASKS, BUF_PI, BUF_PLANES, BUF_POLICY, BUF_STATES,
-                   BUF_STATS, BUF_VALUE, EVAL_HASH, EVAL_UNIFORM, OUT_ACTIONS, OUT_MASKS, OUT_PLANES, POLICY_AGENT, POLICY_UNIFORM,
+                   BUF_STATS, BUF_VALUE, EVAL_HASH, EVAL_NET, EVAL_UNIFORM, OUT_ACTIONS, OUT_MASKS, OUT_PLANES, POLICY_AGENT, POLICY_UNIFORM,
                    STAT_BLUE_WINS, STAT_PASSES, STAT_RED_WINS, STAT_RESETS, STAT_STEPS, STATE_DTYPE, OnbError)
 from .engine import Context, start_states
 from .selfplay import EloRating, FightStatistics, ReplayBuffer, fight, fight_statistics, self_play

@@ -12,7 +12,7 @@ ONB_OK = 0
 E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_OVERFLOW = -1, -2, -3, -4, -5
 POLICY_UNIFORM, POLICY_AGENT = 0, 1
 OUT_MASKS, OUT_PLANES, OUT_ACTIONS = 1, 2, 4
-EVAL_UNIFORM, EVAL_HASH = 0, 1
+EVAL_UNIFORM, EVAL_HASH, EVAL_NET = 0, 1, 2
 (BUF_STATES, BUF_MASKS, BUF_PLANES, BUF_ACTIONS, BUF_LEAF_PLANES, BUF_POLICY, BUF_VALUE, BUF_PI, BUF_BEST,
  BUF_STATS) = range(10)
 STAT_STEPS, STAT_RED_WINS, STAT_BLUE_WINS, STAT_PASSES, STAT_RESETS, STAT_COUNT = 0, 1, 2, 3, 4, 8
@@ -75,6 +75,8 @@ SYMBOLS = {
     "onb_mcts_dump_tree": (C.c_int32, [_P, C.c_int64, C.c_int64, C.POINTER(TreeDump), C.POINTER(C.c_int64)]),
     "onb_mcts_tree_info": (C.c_int32, [_P, _P, _P]),
     "onb_selftest": (C.c_int32, [_P, C.c_int32, _P]),
+    "onb_net_load": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
+    "onb_net_forward": (C.c_int32, [_P, C.c_int32]),
 }
 
 _lib = None

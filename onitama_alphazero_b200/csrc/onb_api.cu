@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <new>
+#include <string>
 
 #include "onb_internal.h"
 #include "onb_rules.cuh"
@@ -127,7 +129,7 @@ int32_t onb_destroy(onb_ctx* ctx) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_states, c->d_masks, c->d_planes, c->d_actions, c->d_stats, c->d_io_states, c->d_moves, c->d_counts, c->d_nodes,
                     c->d_tree_size, c->d_tree_flags, c->d_roots, c->d_leaf_node, c->d_leaf_state, c->d_leaf_planes, c->d_policy, c->d_value,
-                    c->d_pi, c->d_best, c->d_root_visits, c->d_root_q, c->d_child_visits};
+                    c->d_pi, c->d_best, c->d_root_visits, c->d_root_q, c->d_child_visits, c->d_net_w, c->d_net_bias, c->d_net_head};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->scratch)
@@ -438,6 +440,11 @@ int32_t onb_mcts_eval(onb_ctx* ctx, int32_t evaluator) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (c->mcts_phase != 2) return fail(c, ONB_E_STATE, "onb_mcts_eval: no leaves selected");
+    if (evaluator == ONB_EVAL_NET) {
+        if (!c->net_loaded) return fail(c, ONB_E_STATE, "onb_mcts_eval: no network loaded (onb_net_load)");
+        ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value));
+        return ONB_OK;
+    }
     if (evaluator != ONB_EVAL_UNIFORM && evaluator != ONB_EVAL_HASH) return fail(c, ONB_E_INVALID, "onb_mcts_eval: unknown evaluator %d", evaluator);
     ONB_CUDA(c, launch_mcts_eval(c, evaluator));
     return ONB_OK;
@@ -455,8 +462,20 @@ int32_t onb_mcts_run(onb_ctx* ctx, int32_t evaluator, uint32_t sims) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (c->mcts_phase != 1) return fail(c, ONB_E_STATE, "onb_mcts_run: call onb_mcts_begin first");
-    if (evaluator != ONB_EVAL_UNIFORM && evaluator != ONB_EVAL_HASH) return fail(c, ONB_E_INVALID, "onb_mcts_run: unknown evaluator %d", evaluator);
+    if (evaluator != ONB_EVAL_UNIFORM && evaluator != ONB_EVAL_HASH && evaluator != ONB_EVAL_NET)
+        return fail(c, ONB_E_INVALID, "onb_mcts_run: unknown evaluator %d", evaluator);
     if (c->sims_done + sims > c->cfg.mcts_max_sims) return fail(c, ONB_E_INVALID, "onb_mcts_run: more simulations than mcts_max_sims");
+    if (evaluator == ONB_EVAL_NET) {
+        // the network sits between select and expand: three launches per simulation round, all on the context's stream
+        if (!c->net_loaded) return fail(c, ONB_E_STATE, "onb_mcts_run: no network loaded (onb_net_load)");
+        for (uint32_t s = 0; s < sims; ++s) {
+            ONB_CUDA(c, launch_mcts_select(c));
+            ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value));
+            ONB_CUDA(c, launch_mcts_expand_backup(c));
+        }
+        c->sims_done += sims;
+        return ONB_OK;
+    }
     ONB_CUDA(c, launch_mcts_run(c, evaluator, sims));
     c->sims_done += sims;
     return ONB_OK;
@@ -519,6 +538,34 @@ int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_
     if (n_nodes_host) ONB_CUDA(c, cudaMemcpyAsync(n_nodes_host, c->d_tree_size, (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (flags_host) ONB_CUDA(c, cudaMemcpyAsync(flags_host, c->d_tree_flags, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
     ONB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ONB_OK;
+}
+
+int32_t onb_net_load(onb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (n_tensors <= 0 || !names || !data || !numel) return fail(c, ONB_E_INVALID, "onb_net_load: null argument");
+    c->net_loaded = 0;
+    std::string err;
+    int32_t rc = ONB_E_INVALID;
+    try {
+        rc = net_load(c, n_tensors, names, data, numel, err);
+    } catch (const std::exception& ex) {  // nothing may cross the C boundary
+        err = ex.what();
+        rc = ONB_E_NOMEM;
+    }
+    if (rc != ONB_OK) return fail(c, rc, "onb_net_load: %s", err.c_str());
+    c->net_loaded = 1;
+    return ONB_OK;
+}
+int32_t onb_net_forward(onb_ctx* ctx, int32_t planes_buffer) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c->net_loaded) return fail(c, ONB_E_STATE, "onb_net_forward: no network loaded (onb_net_load)");
+    const float* planes = planes_buffer == ONB_BUF_LEAF_PLANES ? c->d_leaf_planes : planes_buffer == ONB_BUF_PLANES ? c->d_planes : nullptr;
+    if (planes_buffer != ONB_BUF_LEAF_PLANES && planes_buffer != ONB_BUF_PLANES) return fail(c, ONB_E_INVALID, "onb_net_forward: not a plane buffer");
+    if (!planes || !c->d_policy) return fail(c, ONB_E_STATE, "onb_net_forward: plane or policy/value buffers were not allocated by onb_create");
+    ONB_CUDA(c, launch_net_forward(c, planes, c->d_policy, c->d_value));
     return ONB_OK;
 }
 

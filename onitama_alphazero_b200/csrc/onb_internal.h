@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <string>
 
 #include "../../include/onb.h"
 
@@ -64,6 +65,12 @@ struct Ctx {
     uint64_t noise_seed;
     uint32_t sims_target, sims_done;
     int mcts_phase;  // 0 idle, 1 begun/after expand, 2 after select
+    // policy/value network (onb_net.cu): weights in tensor-core operand layout, folded biases, head parameters
+    float* d_net_w;
+    float* d_net_bias;
+    float* d_net_head;
+    int net_blocks;
+    int net_loaded;
     // grow-only device scratch reused across onb_perft calls (counters, cursor, two ping-pong frontiers): repeated
     // cudaMalloc/cudaFree of several hundred MB made the call time vary by +-50 %
     void* scratch[8];
@@ -89,6 +96,10 @@ cudaError_t launch_mcts_eval(Ctx* c, int evaluator);
 cudaError_t launch_mcts_run(Ctx* c, int evaluator, uint32_t sims);
 cudaError_t launch_mcts_finish(Ctx* c);
 cudaError_t launch_mcts_play_best(Ctx* c, uint32_t out_flags);
+
+// network (onb_net.cu)
+int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel, std::string& err);
+cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value);
 
 constexpr int kModeActions = 2;  // env step modes: 0 = ONB_POLICY_UNIFORM, 1 = ONB_POLICY_AGENT, 2 = explicit actions
 

@@ -1,0 +1,581 @@
+// onb_net.cu -- the policy/value network of the search (ConvResNet, alphazero-training/src/net.rs:118-232) as ONE fused
+// kernel on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, weights streamed by bulk TMA).
+//
+// What the reference computes per position (net.rs:215-232, restated in onitama_alphazero_b200/net.py):
+//   y = relu(bn1(conv3x3(x)))                                  21 -> 64 channels on the 5x5 board
+//   y = relu(bn(conv3x3(relu(bn(conv3x3(y))))) + y)            x resnet_block_amnt
+//   policy = softmax(linear50x50(flatten(relu(bn(conv1x1 64->2 (y))))))   value = tanh(linear(relu(linear25->64(flatten(relu(bn(conv1x1 64->1 (y))))))))
+// BatchNorm runs in eval mode (running statistics) and is folded into the convolution weights and a per-channel bias on the host.
+//
+// Mapping. A 3x3 convolution over N boards is the GEMM  out[cell][co] = sum_{tap, ci} act[cell + shift(tap)][ci] * W[tap][co][ci].
+// Boards are laid out as a continuous sequence of CELLS, 36 per board: one row of 6 zero cells, then 5 rows of (5 squares + 1 zero
+// cell). Every out-of-board neighbour of a square is then one of those zero cells (of this board or the next), so a tap is nothing
+// but a ROW SHIFT of the activation matrix by dy*6+dx cells. The activations live in shared memory in the tensor core's K-major
+// no-swizzle layout with all rows 16 bytes apart (core matrices of 8 rows x 16 B back to back, one 16-byte channel chunk after the
+// other): a shifted window is just a different start address in the shared-memory descriptor -- no im2col copy is ever made.
+// One CTA keeps NB boards (NACC accumulators of 128 cells x 64 channels in TMEM) on chip through ALL layers; only the input planes
+// are read from and only policy/value are written to global memory. The residual input of a block is parked in TMEM (pre-loaded
+// into the accumulator of the block's second convolution together with that layer's bias), so the skip connection costs nothing.
+// Weights (tf32-rounded, BN folded, already in the operand layout) are streamed tap by tap through a small ring by one producer
+// thread with cp.async.bulk + mbarriers; one thread issues the MMAs; all 8 warps run the epilogues (TMEM -> bias/ReLU -> tf32 ->
+// shared memory). Arithmetic: tf32 products, f32 accumulation -- what libtorch's cuDNN convolutions use by default on this GPU.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "onb_internal.h"
+
+namespace onb {
+namespace {
+
+constexpr int kHid = 64;             // hidden channels (ConvResNetConfig::hidden_channels) the kernel is built for
+constexpr int kInPlanes = 21;        // input planes (common.rs:26-80)
+constexpr int kInPad = 24;           // padded to a multiple of 8: one tf32 MMA consumes K = 8
+constexpr int kCellsPerBoard = 36;
+constexpr int kLead = 8, kTrail = 8;                // zero rows before the first / after the last cell (|shift| <= 7)
+constexpr int kTapFloats0 = (kInPad / 4) * 64 * 4;  // one tap of the first layer: [6 chunks][64 co][4 ci]
+constexpr int kTapFloats = 16 * 64 * 4;             // one tap of a 64 -> 64 layer: [16 chunks][64 co][4 ci]
+constexpr int kMaxBlocks = 16;
+// head parameter blob (floats)
+constexpr int kHP0 = 0, kHP1 = 64, kHV = 128, kHB = 192, kPhW = 196, kPhB = 2696, kV1W = 2748, kV1B = 4348, kV2W = 4412, kV2B = 4476,
+              kHeadFloats = 4480;
+
+template <int NACC>
+struct Geo {
+    static constexpr int NB = NACC == 2 ? 6 : 14;  // boards per pass
+    static constexpr int CELLS = NB * kCellsPerBoard;
+    static constexpr int R = kLead + CELLS + kTrail;  // rows of the activation matrix
+    static constexpr int NSLOT = NACC == 2 ? 3 : 4;   // weight ring slots (one tap each)
+    static constexpr int ACT_BYTES = R * 256;
+    static constexpr int OFF_RING = ACT_BYTES;
+    static constexpr int RING_BYTES = NSLOT * kTapFloats * 4;
+    static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
+    static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;
+    static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
+    static constexpr int SMEM = OFF_BAR + (2 * NSLOT + 1) * 8 + 16;
+    static constexpr int TMEM_COLS = NACC * 128;  // NACC accumulators + NACC residual accumulators of 64 columns
+    static_assert(CELLS <= NACC * 128, "cells must fit the accumulators");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "power of two");
+};
+
+struct NetDev {
+    const float* wconv;  // all conv taps in operand layout
+    const float* bias;   // [1 + 2 * n_blocks][64] folded biases
+    const float* head;   // kHeadFloats
+    int n_blocks;
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol error must end in a trap (the launch fails with an error), never in a hang
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: 8-row x 16-byte core matrices; `lbo` = byte distance between the two
+// 16-byte K chunks one MMA consumes, `sbo` = byte distance between consecutive 8-row groups (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, tf32 x tf32, both K-major, M = 128, N = 64
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// cell -> (board in pass, square 0..24) or pad
+struct Cell {
+    int board, pos;
+    bool real;
+};
+__device__ __forceinline__ Cell decode_cell(int cell, int n_cells) {
+    Cell c;
+    c.board = cell / kCellsPerBoard;
+    const int k = cell - c.board * kCellsPerBoard;  // 0..35: row of 6 zero cells, then 5 x (5 squares + 1 zero cell)
+    const int row = k / 6, col = k - row * 6;
+    c.real = cell < n_cells && row >= 1 && col < 5;
+    c.pos = (row - 1) * 5 + col;
+    return c;
+}
+
+template <int NACC>
+__global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
+    k_net_forward(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
+    using G = Geo<NACC>;
+    constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = G::NSLOT;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t s_act = smem_u32(smem), s_ring = s_act + G::OFF_RING, s_bar = s_act + G::OFF_BAR;
+    float* s_head = reinterpret_cast<float*>(smem + G::OFF_HEAD);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + G::OFF_BAR + (2 * NSLOT + 1) * 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = 1 + 2 * net.n_blocks;
+    const int64_t n_groups = (n + NB - 1) / NB;
+    if ((int64_t)blockIdx.x >= n_groups) return;  // whole CTA, before any allocation
+    const int64_t my_groups = (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t total_taps = (uint32_t)my_groups * 9u * (uint32_t)L;
+    auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
+    auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
+    const uint32_t bar_acc = s_bar + 2 * NSLOT * 8u;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
+    for (int i = tid; i < G::ACT_BYTES / 16; i += 256) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero for good
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+
+    uint32_t q0 = 0;      // ring position of the current layer's first tap (all threads)
+    uint32_t q_prod = 0;  // taps requested so far (producer thread)
+    uint32_t acc_par = 0;
+    for (int64_t gi = 0; gi < my_groups; ++gi) {
+        const int64_t board0 = ((int64_t)blockIdx.x + gi * gridDim.x) * NB;
+        // ---- input planes -> channel chunks 0..5 of the activation matrix (create_tensor_from_state layout [21][5][5])
+        for (int cell = tid; cell < CELLS; cell += 256) {
+            const Cell c = decode_cell(cell, CELLS);
+            if (!c.real) continue;
+            const int64_t gb = board0 + c.board;
+            const float* src = planes + gb * 525 + c.pos;
+#pragma unroll
+            for (int kc = 0; kc < kInPad / 4; ++kc) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ch = kc * 4 + e;
+                    w[e] = (ch < kInPlanes && gb < n) ? to_tf32(__ldg(src + ch * 25)) : 0u;
+                }
+                st_shared_v4(s_act + (uint32_t)(kc * R + kLead + cell) * 16u, w[0], w[1], w[2], w[3]);
+            }
+        }
+        fence_proxy_async();
+        for (int l = 0; l < L; ++l) {
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
+            const bool last = l == L - 1;
+            if (tid == 0) {
+                // ---- MMA issue: 9 taps x K steps x NACC accumulators
+                const int ksteps = l == 0 ? kInPad / 8 : kHid / 8;
+                const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
+                for (int t = 0; t < 9; ++t) {
+                    const uint32_t q = q0 + t, slot = q % NSLOT, use = q / NSLOT;
+                    mbar_wait(bar_full(slot), use & 1u);
+                    tc_fence_after();
+                    const int shift = (t / 3 - 1) * 6 + (t % 3 - 1);
+                    const uint32_t a0 = s_act + (uint32_t)(kLead + shift) * 16u;
+                    const uint32_t b0 = s_ring + slot * (uint32_t)(kTapFloats * 4);
+                    for (int j = 0; j < ksteps; ++j) {
+                        const uint64_t bdesc = smem_desc(b0 + (uint32_t)j * 2048u, 1024u, 128u);
+#pragma unroll
+                        for (int a = 0; a < NACC; ++a) {
+                            const uint64_t adesc = smem_desc(a0 + (uint32_t)(j * 2 * R + a * 128) * 16u, (uint32_t)R * 16u, 128u);
+                            mma_tf32(dcol + a * 64, adesc, bdesc, (use_s || t > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
+                }
+                umma_commit(bar_acc);
+            } else if (tid == 32) {
+                // ---- weight producer: keeps the ring NSLOT taps ahead of the MMAs (weights do not depend on the data)
+                const uint32_t target = min(q0 + 9u + (uint32_t)NSLOT, total_taps);
+                while (q_prod < target) {
+                    const uint32_t slot = q_prod % NSLOT, use = q_prod / NSLOT;
+                    if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
+                    const uint32_t ql = q_prod % (9u * (uint32_t)L), layer = ql / 9u, tap = ql - layer * 9u;
+                    const float* src = net.wconv + (layer == 0 ? (size_t)tap * kTapFloats0
+                                                                : (size_t)9 * kTapFloats0 + ((size_t)(layer - 1) * 9 + tap) * kTapFloats);
+                    const uint32_t bytes = (layer == 0 ? kTapFloats0 : kTapFloats) * 4u;
+                    mbar_expect_tx(bar_full(slot), bytes);
+                    bulk_g2s(s_ring + slot * (uint32_t)(kTapFloats * 4), src, bytes, bar_full(slot));
+                    ++q_prod;
+                }
+            }
+            __syncwarp();
+            mbar_wait(bar_acc, acc_par);
+            acc_par ^= 1u;
+            tc_fence_after();
+            // ---- epilogue: this thread owns one cell (TMEM lane) of accumulator(s) warp/4 (+2)
+            const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
+            const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
+            const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
+            const float4* hw = reinterpret_cast<const float4*>(net.head);
+#pragma unroll
+            for (int ai = 0; ai < NACC / 2; ++ai) {
+                const int a = (warp >> 2) + 2 * ai;
+                const int cell = a * 128 + (warp & 3) * 32 + lane;
+                const Cell c = decode_cell(cell, CELLS);
+                const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+                const uint32_t tsrc = tlane + (use_s ? NACC * 64 : 0) + a * 64;
+                const uint32_t tskip = tlane + NACC * 64 + a * 64;
+                float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(tsrc + h * 32, v);
+                    float o[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!use_s) b = __ldg(bias_l + h * 8 + i);
+                        o[4 * i + 0] = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f);
+                        o[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f);
+                        o[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f);
+                        o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
+                    }
+                    if (!last && c.real) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            st_shared_v4(s_act + (uint32_t)((h * 8 + i) * R + kLead + cell) * 16u, to_tf32(o[4 * i + 0]), to_tf32(o[4 * i + 1]),
+                                         to_tf32(o[4 * i + 2]), to_tf32(o[4 * i + 3]));
+                    }
+                    if (preload) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b = __ldg(bias_n + h * 8 + i);
+                            v[4 * i + 0] = __float_as_uint(o[4 * i + 0] + b.x);
+                            v[4 * i + 1] = __float_as_uint(o[4 * i + 1] + b.y);
+                            v[4 * i + 2] = __float_as_uint(o[4 * i + 2] + b.z);
+                            v[4 * i + 3] = __float_as_uint(o[4 * i + 3] + b.w);
+                        }
+                        tmem_st32(tskip + h * 32, v);
+                    }
+                    if (last) {  // 1x1 convolutions of both heads (net.rs: policy_conv 64 -> 2, vh_conv 64 -> 1)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 w0 = __ldg(hw + (kHP0 / 4) + h * 8 + i), w1 = __ldg(hw + (kHP1 / 4) + h * 8 + i),
+                                         w2 = __ldg(hw + (kHV / 4) + h * 8 + i);
+                            hp0 = fmaf(o[4 * i + 0], w0.x, fmaf(o[4 * i + 1], w0.y, fmaf(o[4 * i + 2], w0.z, fmaf(o[4 * i + 3], w0.w, hp0))));
+                            hp1 = fmaf(o[4 * i + 0], w1.x, fmaf(o[4 * i + 1], w1.y, fmaf(o[4 * i + 2], w1.z, fmaf(o[4 * i + 3], w1.w, hp1))));
+                            hv = fmaf(o[4 * i + 0], w2.x, fmaf(o[4 * i + 1], w2.y, fmaf(o[4 * i + 2], w2.z, fmaf(o[4 * i + 3], w2.w, hv))));
+                        }
+                    }
+                }
+                if (last && c.real) {
+                    float* hb = s_head + c.board * 75;
+                    hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
+                    hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
+                    hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+                }
+            }
+            if (preload) tmem_wait_st();
+            fence_proxy_async();
+            q0 += 9u;
+        }
+        // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
+        __syncthreads();
+        for (int b = warp; b < NB; b += 8) {
+            const int64_t gb = board0 + b;
+            if (gb >= n) continue;
+            const float* hb = s_head + b * 75;
+            const bool two = lane + 32 < 50;
+            float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+            for (int i = 0; i < 50; ++i) {
+                const float x = hb[i];
+                l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
+                if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+            }
+            const float m = warp_max(two ? fmaxf(l0, l1) : l0);
+            const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
+            const float s = warp_sum(e0 + e1);
+            policy[gb * 50 + lane] = e0 / s;
+            if (two) policy[gb * 50 + 32 + lane] = e1 / s;
+            float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+            for (int i = 0; i < 25; ++i) {
+                const float x = hb[50 + i];
+                h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
+                h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+            }
+            float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+            acc = warp_sum(acc);
+            if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
+}
+
+// ---- host side: fold BatchNorm, round to tf32, lay the weights out as the tensor core reads them ------------------------------
+struct Named {
+    std::string name;
+    const float* data;
+    int64_t numel;
+};
+const Named* find(const std::vector<Named>& ts, const std::string& name, int64_t numel, std::string& err) {
+    for (const Named& t : ts)
+        if (t.name == name) {
+            if (t.numel != numel) {
+                err = "tensor " + name + " has " + std::to_string(t.numel) + " elements, expected " + std::to_string(numel);
+                return nullptr;
+            }
+            return &t;
+        }
+    err = "tensor " + name + " is missing";
+    return nullptr;
+}
+float tf32_round_host(float x) {  // cvt.rna.tf32.f32: nearest, ties away from zero, on the 13 dropped mantissa bits
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;
+    u &= 0xFFFFE000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
+struct BnFold {
+    std::vector<double> scale, shift;  // y = conv_nobias * scale + shift
+};
+bool fold_bn(const std::vector<Named>& ts, const std::string& conv, const std::string& bn, int c_out, double eps, BnFold& f, std::string& err) {
+    const Named *cb = find(ts, conv + ".bias", c_out, err), *w = cb ? find(ts, bn + ".weight", c_out, err) : nullptr,
+                *b = w ? find(ts, bn + ".bias", c_out, err) : nullptr, *m = b ? find(ts, bn + ".running_mean", c_out, err) : nullptr,
+                *v = m ? find(ts, bn + ".running_var", c_out, err) : nullptr;
+    if (!v) return false;
+    f.scale.resize(c_out);
+    f.shift.resize(c_out);
+    for (int i = 0; i < c_out; ++i) {
+        const double s = (double)w->data[i] / std::sqrt((double)v->data[i] + eps);
+        f.scale[i] = s;
+        f.shift[i] = ((double)cb->data[i] - (double)m->data[i]) * s + (double)b->data[i];
+    }
+    return true;
+}
+
+}  // namespace
+
+// Parameters by the reference's VarStore names (net.rs:118-213; '|' or '.' as separator), OIHW / [out][in] f32 as libtorch stores them.
+int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel, std::string& err) {
+    std::vector<Named> ts;
+    for (int32_t i = 0; i < n_tensors; ++i) {
+        if (!names[i] || !data[i]) {
+            err = "null tensor name or data";
+            return ONB_E_INVALID;
+        }
+        std::string s(names[i]);
+        for (char& ch : s)
+            if (ch == '|') ch = '.';
+        ts.push_back(Named{s, data[i], numel[i]});
+    }
+    int n_blocks = 0;
+    for (;; ++n_blocks) {
+        bool present = false;
+        const std::string key = "resnet_" + std::to_string(n_blocks) + ".resnet_small_block1.small_block_conv.weight";
+        for (const Named& t : ts) present |= t.name == key;
+        if (!present) break;
+    }
+    if (n_blocks > kMaxBlocks) {
+        err = "more residual blocks than supported";
+        return ONB_E_INVALID;
+    }
+    const double eps = 1e-5;  // nn::BatchNormConfig default of tch 0.10 / torch
+    const int L = 1 + 2 * n_blocks;
+    std::vector<float> wconv((size_t)9 * kTapFloats0 + (size_t)(L - 1) * 9 * kTapFloats, 0.f), bias((size_t)(L + 2) * 64, 0.f),
+        head(kHeadFloats, 0.f);
+    for (int l = 0; l < L; ++l) {
+        std::string conv, bn;
+        if (l == 0) {
+            conv = "conv_init_1";
+            bn = "bn1";
+        } else {
+            const std::string blk = "resnet_" + std::to_string((l - 1) / 2) + ".resnet_small_block" + std::to_string(((l - 1) & 1) + 1);
+            conv = blk + ".small_block_conv";
+            bn = blk + ".small_block_bn";
+        }
+        const int c_in = l == 0 ? kInPlanes : kHid;
+        const Named* w = find(ts, conv + ".weight", (int64_t)kHid * c_in * 9, err);
+        if (!w) {
+            if (l == 0) err += " (this build supports ConvResNetConfig{hidden_channels: 64, input_channels: 21})";
+            return ONB_E_INVALID;
+        }
+        BnFold f;
+        if (!fold_bn(ts, conv, bn, kHid, eps, f, err)) return ONB_E_INVALID;
+        const int chunks = l == 0 ? kInPad / 4 : 16;
+        float* dst = wconv.data() + (l == 0 ? 0 : (size_t)9 * kTapFloats0 + (size_t)(l - 1) * 9 * kTapFloats);
+        const size_t tap_floats = l == 0 ? kTapFloats0 : kTapFloats;
+        for (int tap = 0; tap < 9; ++tap)
+            for (int kc = 0; kc < chunks; ++kc)
+                for (int co = 0; co < kHid; ++co)
+                    for (int e = 0; e < 4; ++e) {
+                        const int ci = kc * 4 + e;
+                        float x = 0.f;
+                        if (ci < c_in) x = tf32_round_host((float)((double)w->data[((size_t)co * c_in + ci) * 9 + tap] * f.scale[co]));
+                        dst[tap * tap_floats + ((size_t)kc * 64 + co) * 4 + e] = x;
+                    }
+        for (int co = 0; co < kHid; ++co) bias[(size_t)l * 64 + co] = (float)f.shift[co];
+    }
+    {   // heads
+        const Named *pw = find(ts, "policy_conv.weight", 2 * kHid, err), *vw = pw ? find(ts, "vh_conv.weight", kHid, err) : nullptr;
+        if (!vw) return ONB_E_INVALID;
+        BnFold fp, fv;
+        if (!fold_bn(ts, "policy_conv", "policy_bn", 2, eps, fp, err) || !fold_bn(ts, "vh_conv", "vh_bn", 1, eps, fv, err)) return ONB_E_INVALID;
+        for (int ci = 0; ci < kHid; ++ci) {
+            head[kHP0 + ci] = (float)((double)pw->data[ci] * fp.scale[0]);
+            head[kHP1 + ci] = (float)((double)pw->data[kHid + ci] * fp.scale[1]);
+            head[kHV + ci] = (float)((double)vw->data[ci] * fv.scale[0]);
+        }
+        head[kHB + 0] = (float)fp.shift[0];
+        head[kHB + 1] = (float)fp.shift[1];
+        head[kHB + 2] = (float)fv.shift[0];
+        const Named *p2w = find(ts, "ph_linear2.weight", 2500, err), *p2b = p2w ? find(ts, "ph_linear2.bias", 50, err) : nullptr,
+                    *v1w = p2b ? find(ts, "vh_linear1.weight", (int64_t)kHid * 25, err) : nullptr,
+                    *v1b = v1w ? find(ts, "vh_linear1.bias", kHid, err) : nullptr, *v2w = v1b ? find(ts, "vh_linear2.weight", kHid, err) : nullptr,
+                    *v2b = v2w ? find(ts, "vh_linear2.bias", 1, err) : nullptr;
+        if (!v2b) return ONB_E_INVALID;
+        for (int j = 0; j < 50; ++j) {
+            for (int i = 0; i < 50; ++i) head[kPhW + i * 50 + j] = p2w->data[j * 50 + i];
+            head[kPhB + j] = p2b->data[j];
+        }
+        for (int j = 0; j < kHid; ++j) {
+            for (int i = 0; i < 25; ++i) head[kV1W + i * 64 + j] = v1w->data[j * 25 + i];
+            head[kV1B + j] = v1b->data[j];
+            head[kV2W + j] = v2w->data[j];
+        }
+        head[kV2B] = v2b->data[0];
+    }
+    for (float** p : {&c->d_net_w, &c->d_net_bias, &c->d_net_head})
+        if (*p) {
+            cudaFree(*p);
+            *p = nullptr;
+        }
+    c->net_blocks = -1;
+    cudaError_t e = cudaMalloc(&c->d_net_w, wconv.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_net_bias, bias.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_net_head, head.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_w, wconv.data(), wconv.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        err = std::string("CUDA: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? ONB_E_NOMEM : ONB_E_CUDA;
+    }
+    c->net_blocks = n_blocks;
+    return ONB_OK;
+}
+
+cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value) {
+    NetDev nd{c->d_net_w, c->d_net_bias, c->d_net_head, c->net_blocks};
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* wide = getenv("ONB_NET_WIDE");  // exploration knob: 14 boards per CTA, one CTA per SM
+    if (wide && wide[0] == '1') {
+        using G = Geo<4>;
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(k_net_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+            if (e != cudaSuccess) return e;
+            attr = true;
+        }
+        const int64_t groups = (c->n + G::NB - 1) / G::NB;
+        const unsigned grid = (unsigned)(groups < sms ? groups : sms);
+        k_net_forward<4><<<grid, 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
+    } else {
+        using G = Geo<2>;
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(k_net_forward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+            if (e != cudaSuccess) return e;
+            attr = true;
+        }
+        const int64_t groups = (c->n + G::NB - 1) / G::NB;
+        const unsigned grid = (unsigned)(groups < 2 * sms ? groups : 2 * sms);
+        k_net_forward<2><<<grid, 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace onb

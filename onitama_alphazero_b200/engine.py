@@ -206,6 +206,29 @@ class Context:
     def mcts_play_best(self, out_flags=0):
         self._ck(self._lib.onb_mcts_play_best(self._h, out_flags))
 
+    def net_load(self, params):
+        """onb_net_load: params = a torch module / state_dict / dict name -> array with the reference's VarStore names
+        (net.rs:118-213; '.' or '|' separators). Folds BatchNorm, lays the weights out for the tensor cores, uploads them."""
+        if hasattr(params, "state_dict"):
+            params = params.state_dict()
+        names, arrays = [], []
+        for k, v in params.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            if hasattr(v, "detach"):
+                v = v.detach().float().cpu().numpy()
+            names.append(k.encode())
+            arrays.append(np.ascontiguousarray(v, dtype=np.float32))
+        n = len(names)
+        c_names = (C.c_char_p * n)(*names)
+        c_data = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        c_numel = (C.c_int64 * n)(*[a.size for a in arrays])
+        self._ck(self._lib.onb_net_load(self._h, n, c_names, c_data, c_numel))
+
+    def net_forward(self, planes_buffer=L.BUF_LEAF_PLANES):
+        """onb_net_forward: planes buffer -> ONB_BUF_POLICY / ONB_BUF_VALUE on the device (async on the context's stream)"""
+        self._ck(self._lib.onb_net_forward(self._h, planes_buffer))
+
     def selftest(self, which=0):
         """onb_selftest: number of results that differ from the IEEE answer (0 on a correct build)"""
         bad = C.c_uint64(0)
