@@ -240,9 +240,11 @@ ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t
 
 /* ---- policy/value network on the device ---------------------------------------------------------------------
  * ConvResNet::forward (alphazero-training/src/net.rs:215-232) for every position of a plane buffer, as one fused
- * tensor-core kernel (BatchNorm in eval mode folded into the convolutions; tf32 products with f32 accumulation,
- * i.e. what libtorch's cuDNN convolutions compute by default on this GPU; heads in f32). This is the evaluator the
- * search would otherwise get from tch as a black box; with it a whole search needs no host round trip.
+ * tensor-core kernel (BatchNorm in eval mode folded into the convolutions; f32 accumulation of products of operands
+ * rounded to an 11-bit significand: ONB_NET_F16 (default) or ONB_NET_TF32, the latter being what libtorch's cuDNN
+ * convolutions compute by default on this GPU; heads in f32). This is the evaluator the search would otherwise get
+ * from tch as a black box; with it a whole search needs no host round trip.
+ * onb_net_precision selects the operand format used by the NEXT onb_net_load.
  * onb_net_load takes the parameters under the reference's VarStore names (net.rs:118-213, `|` or `.` separators),
  * e.g. "conv_init_1|weight", "bn1|running_var", "resnet_0|resnet_small_block1|small_block_conv|weight",
  * "policy_conv|bias", "ph_linear2|weight", "vh_linear1|weight": host f32 arrays in libtorch layout (OIHW, [out][in]).
@@ -250,6 +252,9 @@ ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t
  * (ConvResNetConfig of train.rs) -- anything else is rejected with ONB_E_INVALID.
  * onb_net_forward reads planes_buffer (ONB_BUF_LEAF_PLANES or ONB_BUF_PLANES, [n][21][5][5] f32) and writes
  * ONB_BUF_POLICY [n][2][25] (softmax over 50) and ONB_BUF_VALUE [n]. onb_mcts_eval / onb_mcts_run accept ONB_EVAL_NET. */
+#define ONB_NET_F16 0
+#define ONB_NET_TF32 1
+ONB_API int32_t onb_net_precision(onb_ctx* ctx, int32_t mode);
 ONB_API int32_t onb_net_load(onb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel);
 ONB_API int32_t onb_net_forward(onb_ctx* ctx, int32_t planes_buffer);
 

@@ -71,6 +71,8 @@ struct Ctx {
     float* d_net_head;
     int net_blocks;
     int net_loaded;
+    int net_tf32;  // requested operand format for the next onb_net_load: 0 = f16 (default), 1 = tf32
+    int net_f16;   // format of the loaded weights
     // grow-only device scratch reused across onb_perft calls (counters, cursor, two ping-pong frontiers): repeated
     // cudaMalloc/cudaFree of several hundred MB made the call time vary by +-50 %
     void* scratch[8];

@@ -18,7 +18,11 @@
 // into the accumulator of the block's second convolution together with that layer's bias), so the skip connection costs nothing.
 // Weights (tf32-rounded, BN folded, already in the operand layout) are streamed tap by tap through a small ring by one producer
 // thread with cp.async.bulk + mbarriers; one thread issues the MMAs; all 8 warps run the epilogues (TMEM -> bias/ReLU -> tf32 ->
-// shared memory). Arithmetic: tf32 products, f32 accumulation -- what libtorch's cuDNN convolutions use by default on this GPU.
+// shared memory). Arithmetic: f32 accumulation of products of operands rounded to an 11-bit significand -- either tf32 (what
+// libtorch's cuDNN convolutions use by default on this GPU) or f16 (same significand, half the shared-memory bytes per MMA, twice
+// the tensor rate; the kernel is bound by the shared-memory reads of the MMA operands, so this is the default). Heads in f32.
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -31,36 +35,48 @@ namespace {
 
 constexpr int kHid = 64;             // hidden channels (ConvResNetConfig::hidden_channels) the kernel is built for
 constexpr int kInPlanes = 21;        // input planes (common.rs:26-80)
-constexpr int kInPad = 24;           // padded to a multiple of 8: one tf32 MMA consumes K = 8
 constexpr int kCellsPerBoard = 36;
-constexpr int kLead = 8, kTrail = 8;                // zero rows before the first / after the last cell (|shift| <= 7)
-constexpr int kTapFloats0 = (kInPad / 4) * 64 * 4;  // one tap of the first layer: [6 chunks][64 co][4 ci]
-constexpr int kTapFloats = 16 * 64 * 4;             // one tap of a 64 -> 64 layer: [16 chunks][64 co][4 ci]
+constexpr int kLead = 8, kTrail = 8;  // zero rows before the first / after the last cell (|shift| <= 7)
 constexpr int kMaxBlocks = 16;
+// operand format: a 16-byte chunk holds CPC channels; one MMA consumes two chunks of every row (K = 32 bytes)
+template <bool F16>
+struct Op {
+    static constexpr int ELT = F16 ? 2 : 4;
+    static constexpr int CPC = 16 / ELT;               // 8 | 4 channels per chunk
+    static constexpr int KCH = kHid / CPC;             // 8 | 16 chunks per 64 channels
+    static constexpr int IN_PAD = F16 ? 32 : 24;       // input planes padded to a multiple of the MMA's K (16 | 8)
+    static constexpr int KCH0 = IN_PAD / CPC;          // 4 | 6
+    static constexpr int TAP_BYTES = KCH * 64 * 16;    // one tap of a 64 -> 64 layer: [chunks][64 co][16 B]
+    static constexpr int TAP_BYTES0 = KCH0 * 64 * 16;  // one tap of the first layer
+    // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, A/B format, both K-major, N = 64, M = 128
+    static constexpr uint32_t IDESC = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+};
 // head parameter blob (floats)
 constexpr int kHP0 = 0, kHP1 = 64, kHV = 128, kHB = 192, kPhW = 196, kPhB = 2696, kV1W = 2748, kV1B = 4348, kV2W = 4412, kV2B = 4476,
               kHeadFloats = 4480;
 
-template <int NACC>
+template <int NACC, bool F16>
 struct Geo {
-    static constexpr int NB = NACC == 2 ? 6 : 14;  // boards per pass
+    static constexpr int NB = NACC == 2 ? (F16 ? 7 : 6) : 14;  // boards per pass (two CTAs per SM when NACC == 2)
     static constexpr int CELLS = NB * kCellsPerBoard;
     static constexpr int R = kLead + CELLS + kTrail;  // rows of the activation matrix
-    static constexpr int NSLOT = NACC == 2 ? 3 : 4;   // weight ring slots (one tap each)
-    static constexpr int ACT_BYTES = R * 256;
+    static constexpr int NSLOT = F16 ? 4 : (NACC == 2 ? 3 : 4);  // weight ring slots (one tap each)
+    static constexpr int ACT_BYTES = R * Op<F16>::KCH * 16;
     static constexpr int OFF_RING = ACT_BYTES;
-    static constexpr int RING_BYTES = NSLOT * kTapFloats * 4;
+    static constexpr int RING_BYTES = NSLOT * Op<F16>::TAP_BYTES;
     static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
     static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;
     static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
-    static constexpr int SMEM = OFF_BAR + (2 * NSLOT + 1) * 8 + 16;
+    static constexpr int SMEM_USED = OFF_BAR + (2 * NSLOT + 1) * 8 + 16;
+    // TMEM holds two CTAs of 256 columns: ask for enough shared memory that a third CTA can never become resident and block in tcgen05.alloc
+    static constexpr int SMEM = NACC == 2 && SMEM_USED < 78 * 1024 ? 78 * 1024 : SMEM_USED;
     static constexpr int TMEM_COLS = NACC * 128;  // NACC accumulators + NACC residual accumulators of 64 columns
     static_assert(CELLS <= NACC * 128, "cells must fit the accumulators");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "power of two");
 };
 
 struct NetDev {
-    const float* wconv;  // all conv taps in operand layout
+    const uint8_t* wconv;  // all conv taps in operand layout
     const float* bias;   // [1 + 2 * n_blocks][64] folded biases
     const float* head;   // kHeadFloats
     int n_blocks;
@@ -115,15 +131,22 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
            (1ull << 46);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, tf32 x tf32, both K-major, M = 128, N = 64
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-        : "memory");
+template <bool F16>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    if (F16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(Op<true>::IDESC), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(Op<false>::IDESC), "r"(accumulate)
+            : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -155,8 +178,29 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ uint32_t to_f16x2(float lo, float hi) {  // post-ReLU values: only the upper end can overflow
+    const __half2 h = __floats2half2_rn(fminf(lo, 65504.f), fminf(hi, 65504.f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+// store 32 consecutive channels [c0, c0 + 32) of one cell as operand chunks
+template <bool F16>
+__device__ __forceinline__ void store_channels(uint32_t s_act, int R, int row, int c0, const float (&o)[32]);
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+template <>
+__device__ __forceinline__ void store_channels<true>(uint32_t s_act, int R, int row, int c0, const float (&o)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        st_shared_v4(s_act + (uint32_t)((c0 / 8 + i) * R + row) * 16u, to_f16x2(o[8 * i + 0], o[8 * i + 1]), to_f16x2(o[8 * i + 2], o[8 * i + 3]),
+                     to_f16x2(o[8 * i + 4], o[8 * i + 5]), to_f16x2(o[8 * i + 6], o[8 * i + 7]));
+}
+template <>
+__device__ __forceinline__ void store_channels<false>(uint32_t s_act, int R, int row, int c0, const float (&o)[32]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        st_shared_v4(s_act + (uint32_t)((c0 / 4 + i) * R + row) * 16u, to_tf32(o[4 * i + 0]), to_tf32(o[4 * i + 1]), to_tf32(o[4 * i + 2]),
+                     to_tf32(o[4 * i + 3]));
 }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -184,10 +228,11 @@ __device__ __forceinline__ Cell decode_cell(int cell, int n_cells) {
     return c;
 }
 
-template <int NACC>
+template <int NACC, bool F16>
 __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
     k_net_forward(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
-    using G = Geo<NACC>;
+    using G = Geo<NACC, F16>;
+    using O = Op<F16>;
     constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = G::NSLOT;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s_act = smem_u32(smem), s_ring = s_act + G::OFF_RING, s_bar = s_act + G::OFF_BAR;
@@ -230,15 +275,16 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             if (!c.real) continue;
             const int64_t gb = board0 + c.board;
             const float* src = planes + gb * 525 + c.pos;
+            float x[32];  // the planes are 0 / 1: exact in either operand format
 #pragma unroll
-            for (int kc = 0; kc < kInPad / 4; ++kc) {
-                uint32_t w[4];
+            for (int ch = 0; ch < 32; ++ch) x[ch] = (ch < kInPlanes && gb < n) ? __ldg(src + ch * 25) : 0.f;
+            if (F16) {
+                store_channels<F16>(s_act, R, kLead + cell, 0, x);
+            } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int ch = kc * 4 + e;
-                    w[e] = (ch < kInPlanes && gb < n) ? to_tf32(__ldg(src + ch * 25)) : 0u;
-                }
-                st_shared_v4(s_act + (uint32_t)(kc * R + kLead + cell) * 16u, w[0], w[1], w[2], w[3]);
+                for (int kc = 0; kc < O::KCH0; ++kc)
+                    st_shared_v4(s_act + (uint32_t)(kc * R + kLead + cell) * 16u, to_tf32(x[4 * kc]), to_tf32(x[4 * kc + 1]), to_tf32(x[4 * kc + 2]),
+                                 to_tf32(x[4 * kc + 3]));
             }
         }
         fence_proxy_async();
@@ -250,7 +296,7 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             const bool last = l == L - 1;
             if (tid == 0) {
                 // ---- MMA issue: 9 taps x K steps x NACC accumulators
-                const int ksteps = l == 0 ? kInPad / 8 : kHid / 8;
+                const int ksteps = (l == 0 ? O::KCH0 : O::KCH) / 2;
                 const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
                 for (int t = 0; t < 9; ++t) {
                     const uint32_t q = q0 + t, slot = q % NSLOT, use = q / NSLOT;
@@ -258,13 +304,13 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                     tc_fence_after();
                     const int shift = (t / 3 - 1) * 6 + (t % 3 - 1);
                     const uint32_t a0 = s_act + (uint32_t)(kLead + shift) * 16u;
-                    const uint32_t b0 = s_ring + slot * (uint32_t)(kTapFloats * 4);
+                    const uint32_t b0 = s_ring + slot * (uint32_t)O::TAP_BYTES;
                     for (int j = 0; j < ksteps; ++j) {
                         const uint64_t bdesc = smem_desc(b0 + (uint32_t)j * 2048u, 1024u, 128u);
 #pragma unroll
                         for (int a = 0; a < NACC; ++a) {
                             const uint64_t adesc = smem_desc(a0 + (uint32_t)(j * 2 * R + a * 128) * 16u, (uint32_t)R * 16u, 128u);
-                            mma_tf32(dcol + a * 64, adesc, bdesc, (use_s || t > 0 || j > 0) ? 1u : 0u);
+                            mma_ss<F16>(dcol + a * 64, adesc, bdesc, (use_s || t > 0 || j > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
@@ -277,11 +323,11 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                     const uint32_t slot = q_prod % NSLOT, use = q_prod / NSLOT;
                     if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
                     const uint32_t ql = q_prod % (9u * (uint32_t)L), layer = ql / 9u, tap = ql - layer * 9u;
-                    const float* src = net.wconv + (layer == 0 ? (size_t)tap * kTapFloats0
-                                                                : (size_t)9 * kTapFloats0 + ((size_t)(layer - 1) * 9 + tap) * kTapFloats);
-                    const uint32_t bytes = (layer == 0 ? kTapFloats0 : kTapFloats) * 4u;
+                    const uint8_t* src = net.wconv + (layer == 0 ? (size_t)tap * O::TAP_BYTES0
+                                                                  : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
+                    const uint32_t bytes = layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES;
                     mbar_expect_tx(bar_full(slot), bytes);
-                    bulk_g2s(s_ring + slot * (uint32_t)(kTapFloats * 4), src, bytes, bar_full(slot));
+                    bulk_g2s(s_ring + slot * (uint32_t)O::TAP_BYTES, src, bytes, bar_full(slot));
                     ++q_prod;
                 }
             }
@@ -317,12 +363,7 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                         o[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f);
                         o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
                     }
-                    if (!last && c.real) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            st_shared_v4(s_act + (uint32_t)((h * 8 + i) * R + kLead + cell) * 16u, to_tf32(o[4 * i + 0]), to_tf32(o[4 * i + 1]),
-                                         to_tf32(o[4 * i + 2]), to_tf32(o[4 * i + 3]));
-                    }
+                    if (!last && c.real) store_channels<F16>(s_act, R, kLead + cell, h * 32, o);
                     if (preload) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -462,8 +503,11 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
     }
     const double eps = 1e-5;  // nn::BatchNormConfig default of tch 0.10 / torch
     const int L = 1 + 2 * n_blocks;
-    std::vector<float> wconv((size_t)9 * kTapFloats0 + (size_t)(L - 1) * 9 * kTapFloats, 0.f), bias((size_t)(L + 2) * 64, 0.f),
-        head(kHeadFloats, 0.f);
+    const bool f16 = c->net_tf32 == 0;
+    const int cpc = f16 ? Op<true>::CPC : Op<false>::CPC, kch = f16 ? Op<true>::KCH : Op<false>::KCH, kch0 = f16 ? Op<true>::KCH0 : Op<false>::KCH0;
+    const size_t tap_bytes = f16 ? Op<true>::TAP_BYTES : Op<false>::TAP_BYTES, tap_bytes0 = f16 ? Op<true>::TAP_BYTES0 : Op<false>::TAP_BYTES0;
+    std::vector<uint8_t> wconv(9 * tap_bytes0 + (size_t)(L - 1) * 9 * tap_bytes, 0);
+    std::vector<float> bias((size_t)(L + 2) * 64, 0.f), head(kHeadFloats, 0.f);
     for (int l = 0; l < L; ++l) {
         std::string conv, bn;
         if (l == 0) {
@@ -482,17 +526,23 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
         }
         BnFold f;
         if (!fold_bn(ts, conv, bn, kHid, eps, f, err)) return ONB_E_INVALID;
-        const int chunks = l == 0 ? kInPad / 4 : 16;
-        float* dst = wconv.data() + (l == 0 ? 0 : (size_t)9 * kTapFloats0 + (size_t)(l - 1) * 9 * kTapFloats);
-        const size_t tap_floats = l == 0 ? kTapFloats0 : kTapFloats;
+        const int chunks = l == 0 ? kch0 : kch;
+        uint8_t* dst = wconv.data() + (l == 0 ? 0 : 9 * tap_bytes0 + (size_t)(l - 1) * 9 * tap_bytes);
+        const size_t tb = l == 0 ? tap_bytes0 : tap_bytes;
         for (int tap = 0; tap < 9; ++tap)
             for (int kc = 0; kc < chunks; ++kc)
                 for (int co = 0; co < kHid; ++co)
-                    for (int e = 0; e < 4; ++e) {
-                        const int ci = kc * 4 + e;
-                        float x = 0.f;
-                        if (ci < c_in) x = tf32_round_host((float)((double)w->data[((size_t)co * c_in + ci) * 9 + tap] * f.scale[co]));
-                        dst[tap * tap_floats + ((size_t)kc * 64 + co) * 4 + e] = x;
+                    for (int e = 0; e < cpc; ++e) {  // operand layout: [tap][chunk][co][16 bytes of consecutive input channels]
+                        const int ci = kc * cpc + e;
+                        const float x = ci < c_in ? (float)((double)w->data[((size_t)co * c_in + ci) * 9 + tap] * f.scale[co]) : 0.f;
+                        uint8_t* q = dst + tap * tb + ((size_t)kc * 64 + co) * 16;
+                        if (f16) {
+                            const __half hv = __float2half_rn(x);
+                            memcpy(q + e * 2, &hv, 2);
+                        } else {
+                            const float r = tf32_round_host(x);
+                            memcpy(q + e * 4, &r, 4);
+                        }
                     }
         for (int co = 0; co < kHid; ++co) bias[(size_t)l * 64 + co] = (float)f.shift[co];
     }
@@ -525,16 +575,16 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
         }
         head[kV2B] = v2b->data[0];
     }
-    for (float** p : {&c->d_net_w, &c->d_net_bias, &c->d_net_head})
+    for (void** p : {(void**)&c->d_net_w, (void**)&c->d_net_bias, (void**)&c->d_net_head})
         if (*p) {
             cudaFree(*p);
             *p = nullptr;
         }
     c->net_blocks = -1;
-    cudaError_t e = cudaMalloc(&c->d_net_w, wconv.size() * 4);
+    cudaError_t e = cudaMalloc(&c->d_net_w, wconv.size());
     if (e == cudaSuccess) e = cudaMalloc(&c->d_net_bias, bias.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_net_head, head.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_w, wconv.data(), wconv.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_w, wconv.data(), wconv.size(), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -543,39 +593,33 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
         return e == cudaErrorMemoryAllocation ? ONB_E_NOMEM : ONB_E_CUDA;
     }
     c->net_blocks = n_blocks;
+    c->net_f16 = f16 ? 1 : 0;
     return ONB_OK;
 }
 
+template <int NACC, bool F16>
+static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
+    using G = Geo<NACC, F16>;
+    static bool attr = false;  // one device per process (one process per GPU)
+    if (!attr) {
+        const cudaError_t e = cudaFuncSetAttribute(k_net_forward<NACC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * (NACC == 2 ? 2 : 1);
+    k_net_forward<NACC, F16><<<(unsigned)(groups < slots ? groups : slots), 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value) {
-    NetDev nd{c->d_net_w, c->d_net_bias, c->d_net_head, c->net_blocks};
+    const NetDev nd{reinterpret_cast<const uint8_t*>(c->d_net_w), c->d_net_bias, c->d_net_head, c->net_blocks};
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char* wide = getenv("ONB_NET_WIDE");  // exploration knob: 14 boards per CTA, one CTA per SM
-    if (wide && wide[0] == '1') {
-        using G = Geo<4>;
-        static bool attr = false;
-        if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(k_net_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-            if (e != cudaSuccess) return e;
-            attr = true;
-        }
-        const int64_t groups = (c->n + G::NB - 1) / G::NB;
-        const unsigned grid = (unsigned)(groups < sms ? groups : sms);
-        k_net_forward<4><<<grid, 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
-    } else {
-        using G = Geo<2>;
-        static bool attr = false;
-        if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(k_net_forward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-            if (e != cudaSuccess) return e;
-            attr = true;
-        }
-        const int64_t groups = (c->n + G::NB - 1) / G::NB;
-        const unsigned grid = (unsigned)(groups < 2 * sms ? groups : 2 * sms);
-        k_net_forward<2><<<grid, 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
-    }
-    return cudaGetLastError();
+    const bool w = wide && wide[0] == '1';
+    if (c->net_f16) return w ? launch_net_variant<4, true>(c, planes, policy, value, nd, sms) : launch_net_variant<2, true>(c, planes, policy, value, nd, sms);
+    return w ? launch_net_variant<4, false>(c, planes, policy, value, nd, sms) : launch_net_variant<2, false>(c, planes, policy, value, nd, sms);
 }
 
 }  // namespace onb
