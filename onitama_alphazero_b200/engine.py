@@ -161,6 +161,11 @@ class Context:
         with torch.cuda.stream(self.torch_stream()):
             return self.tensor(which).cpu().numpy().view(dtype).reshape(shape)
 
+    def write(self, which, array):
+        """onb_write_buffer: host array -> device buffer (the whole buffer or a prefix of it)"""
+        a = np.ascontiguousarray(array)
+        self._ck(self._lib.onb_write_buffer(self._h, which, L.ptr(a), a.nbytes))
+
     # ------------------------------------------------------------------ perft
     def perft(self, roots, depth):
         r = np.ascontiguousarray(roots, dtype=STATE_DTYPE)

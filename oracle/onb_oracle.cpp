@@ -842,3 +842,108 @@ double orc_bench_perft(const uint8_t* decks5, int64_t n_decks, int depth, int th
 }
 
 }  // extern "C"
+
+// ---- policy/value network (harness restatement of alphazero-training/src/net.rs:9-232, eval mode) -----------------------------
+// Plain f32 tensors, f64 accumulation inside each convolution / linear layer (a checker, not a timed path). Layer by layer as the
+// reference: SmallBlock = conv3x3(pad 1) -> batch_norm (running statistics, eps 1e-5) (net.rs:9-38); ResNetBlock =
+// relu(block2(relu(block1(x))) + x) (net.rs:40-66); value head conv1x1 -> bn -> relu -> linear 25->h -> relu -> linear h->1 -> tanh,
+// policy head conv1x1 (2 channels) -> bn -> relu -> linear 50->50 -> softmax -> [2,25] (net.rs:118-232). Parameters are looked up
+// by their VarStore names ('|' or '.' separators). Parity with the Rust/libtorch original is UNPINNED (no tch here); the restatement
+// is pinned against the PyTorch twin (onitama_alphazero_b200/net.py, which loads the reference's .ot archives) by tests/test_net_cpu.py.
+#include <map>
+#include <string>
+namespace orc {
+struct NetParams {
+    std::map<std::string, std::pair<const float*, int64_t>> t;
+    const float* get(const std::string& name, int64_t numel) const {
+        auto it = t.find(name);
+        if (it == t.end() || it->second.second != numel) return nullptr;
+        return it->second.first;
+    }
+};
+// y[co][5][5] = sum_ci sum_taps w[co][ci][ky][kx] * x[ci][y+ky-1][x+kx-1] + b[co], then batch norm with running statistics
+static bool conv_bn(const NetParams& P, const std::string& conv, const std::string& bn, int c_in, int c_out, int ks, const std::vector<float>& x,
+                    std::vector<float>& y) {
+    const float *w = P.get(conv + ".weight", (int64_t)c_out * c_in * ks * ks), *b = P.get(conv + ".bias", c_out), *g = P.get(bn + ".weight", c_out),
+                *be = P.get(bn + ".bias", c_out), *mu = P.get(bn + ".running_mean", c_out), *var = P.get(bn + ".running_var", c_out);
+    if (!w || !b || !g || !be || !mu || !var) return false;
+    y.assign((size_t)c_out * 25, 0.f);
+    const int r = ks / 2;
+    for (int co = 0; co < c_out; ++co)
+        for (int py = 0; py < 5; ++py)
+            for (int px = 0; px < 5; ++px) {
+                double acc = 0.0;
+                for (int ci = 0; ci < c_in; ++ci)
+                    for (int ky = 0; ky < ks; ++ky)
+                        for (int kx = 0; kx < ks; ++kx) {
+                            const int sy = py + ky - r, sx = px + kx - r;
+                            if (sy < 0 || sy >= 5 || sx < 0 || sx >= 5) continue;
+                            acc += (double)w[(((size_t)co * c_in + ci) * ks + ky) * ks + kx] * (double)x[(size_t)ci * 25 + sy * 5 + sx];
+                        }
+                const float conv_out = (float)(acc + (double)b[co]);
+                y[(size_t)co * 25 + py * 5 + px] = (float)(((double)conv_out - (double)mu[co]) / std::sqrt((double)var[co] + 1e-5) * (double)g[co] + (double)be[co]);
+            }
+    return true;
+}
+static bool linear(const NetParams& P, const std::string& name, int n_in, int n_out, const std::vector<float>& x, std::vector<float>& y) {
+    const float *w = P.get(name + ".weight", (int64_t)n_out * n_in), *b = P.get(name + ".bias", n_out);
+    if (!w || !b) return false;
+    y.assign((size_t)n_out, 0.f);
+    for (int j = 0; j < n_out; ++j) {
+        double acc = (double)b[j];
+        for (int i = 0; i < n_in; ++i) acc += (double)w[(size_t)j * n_in + i] * (double)x[i];
+        y[j] = (float)acc;
+    }
+    return true;
+}
+static void relu(std::vector<float>& v) { for (float& x : v) x = x > 0.f ? x : 0.f; }
+}  // namespace orc
+
+extern "C" {
+// planes [n][21][5][5] -> policy [n][50] (softmax), value [n]. Returns 0, or -1 when a tensor is missing / has the wrong size.
+int orc_net_forward(int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel, const float* planes, int64_t n,
+                    float* policy, float* value) {
+    orc::NetParams P;
+    int hidden = 0;
+    for (int32_t i = 0; i < n_tensors; ++i) {
+        std::string s(names[i]);
+        for (char& ch : s) if (ch == '|') ch = '.';
+        P.t[s] = {data[i], numel[i]};
+        if (s == "bn1.weight") hidden = (int)numel[i];
+    }
+    if (hidden <= 0) return -1;
+    int n_blocks = 0;
+    while (P.t.count("resnet_" + std::to_string(n_blocks) + ".resnet_small_block1.small_block_conv.weight")) ++n_blocks;
+    const int c_in = (int)(P.t.count("conv_init_1.weight") ? P.t["conv_init_1.weight"].second / (9 * hidden) : 0);
+    if (c_in <= 0) return -1;
+    for (int64_t s = 0; s < n; ++s) {
+        std::vector<float> x(planes + s * c_in * 25, planes + (s + 1) * c_in * 25), y, h, t;
+        if (!orc::conv_bn(P, "conv_init_1", "bn1", c_in, hidden, 3, x, y)) return -1;
+        orc::relu(y);
+        for (int b = 0; b < n_blocks; ++b) {
+            const std::string blk = "resnet_" + std::to_string(b) + ".resnet_small_block";
+            if (!orc::conv_bn(P, blk + "1.small_block_conv", blk + "1.small_block_bn", hidden, hidden, 3, y, h)) return -1;
+            orc::relu(h);
+            if (!orc::conv_bn(P, blk + "2.small_block_conv", blk + "2.small_block_bn", hidden, hidden, 3, h, t)) return -1;
+            for (size_t i = 0; i < t.size(); ++i) t[i] += y[i];
+            orc::relu(t);
+            y.swap(t);
+        }
+        std::vector<float> v, v1, v2, p, logits;
+        if (!orc::conv_bn(P, "vh_conv", "vh_bn", hidden, 1, 1, y, v)) return -1;
+        orc::relu(v);
+        if (!orc::linear(P, "vh_linear1", 25, hidden, v, v1)) return -1;
+        orc::relu(v1);
+        if (!orc::linear(P, "vh_linear2", hidden, 1, v1, v2)) return -1;
+        value[s] = (float)std::tanh((double)v2[0]);
+        if (!orc::conv_bn(P, "policy_conv", "policy_bn", hidden, 2, 1, y, p)) return -1;
+        orc::relu(p);
+        if (!orc::linear(P, "ph_linear2", 50, 50, p, logits)) return -1;
+        double m = logits[0], sum = 0.0;
+        for (float l : logits) m = std::max(m, (double)l);
+        for (float l : logits) sum += std::exp((double)l - m);
+        for (int j = 0; j < 50; ++j) policy[s * 50 + j] = (float)(std::exp((double)logits[j] - m) / sum);
+    }
+    return 0;
+}
+}  // extern "C"

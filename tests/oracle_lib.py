@@ -62,6 +62,8 @@ def lib():
                                       C.c_void_p, C.c_int64]
         L.orc_hash_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_mcts_set_noise.argtypes = [C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint64]
+        L.orc_net_forward.restype = C.c_int
+        L.orc_net_forward.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_mcts_search_batch.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_bench_env.restype = C.c_double
@@ -214,6 +216,30 @@ def mcts_search_batch(roots, c_puct, sims, evaluator=0, threads=1):
 def mcts_set_noise(enabled, epsilon=0.25, alpha=0.03, seed=0, game0=0):
     """train-mode root noise for the searches that follow (tree i of a batch uses global tree id game0 + i)"""
     lib().orc_mcts_set_noise(int(bool(enabled)), epsilon, alpha, seed, game0)
+
+
+def net_forward(params, planes):
+    """CPU restatement of ConvResNet::forward (net.rs:215-232): params = {VarStore name: f32 array}; planes [n,21,5,5]."""
+    names, arrays = [], []
+    for k, v in params.items():
+        if k.endswith("num_batches_tracked"):
+            continue
+        if hasattr(v, "detach"):
+            v = v.detach().float().cpu().numpy()
+        names.append(k.encode())
+        arrays.append(np.ascontiguousarray(v, dtype=np.float32))
+    m = len(names)
+    planes = np.ascontiguousarray(planes, dtype=np.float32)
+    n = planes.shape[0]
+    pol = np.zeros((n, 50), dtype=np.float32)
+    val = np.zeros(n, dtype=np.float32)
+    c_names = (C.c_char_p * m)(*names)
+    c_data = (C.c_void_p * m)(*[a.ctypes.data for a in arrays])
+    c_numel = (C.c_int64 * m)(*[a.size for a in arrays])
+    rc = lib().orc_net_forward(m, c_names, c_data, c_numel, _p(planes), n, _p(pol), _p(val))
+    if rc != 0:
+        raise ValueError("orc_net_forward: missing or mis-sized tensor")
+    return pol, val
 
 
 def hash_eval(planes):

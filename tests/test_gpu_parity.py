@@ -880,3 +880,122 @@ def test_table_division_is_ieee_exact(onb):
     rounded quotient over every sqrt(Np)/(n+1), Np and n+1 < 4096, and 2^25 pseudo-random W/n (include/onb.h onb_selftest)."""
     with onb.Context(1, planes=False) as ctx:
         assert ctx.selftest(0) == 0
+
+
+# ------------------------------------------------------------------ the network on the tensor cores (onb_net.cu)
+def _positions(n, seed, plies=9):
+    g = O.new_games(n, seed=seed)
+    for s in range(plies):
+        O.env_step_random(g, seed, s)
+    return g
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tf32", [False, True], ids=["f16", "tf32"])
+@pytest.mark.parametrize("blocks", [0, 1, 3])
+def test_network_kernel_matches_oracle(onb, blocks, tf32):
+    """ConvResNet::forward (net.rs:215-232) as the fused tcgen05 kernel against the CPU restatement (f32 weights, f64 sums).
+    Tolerance: both operand formats round to an 11-bit significand (relative 2^-12 per operand) and accumulate in f32; through
+    1 + 2*blocks convolutions of up to 576 terms that gives |dp| <= 6e-3 on probabilities in [0,1] and |dv| <= 2.5e-2 on tanh
+    outputs for this lively random network (mean |dp| < 1e-4); the same bound holds for torch's own tf32 convolutions."""
+    from test_net_cpu import lively_model
+    model = lively_model(blocks)
+    n = 333  # not a multiple of the 6 / 7 boards a CTA holds
+    g = _positions(n, 11)
+    planes = O.encode(g).reshape(n, 21, 5, 5)
+    want_p, want_v = O.net_forward(model.state_dict(), planes)
+    with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
+        ctx.net_load(model, tf32=tf32)
+        ctx.write(onb.BUF_LEAF_PLANES, planes)
+        ctx.net_forward(onb.BUF_LEAF_PLANES)
+        pol = ctx.read(onb.BUF_POLICY, np.float32, (n, 50))
+        val = ctx.read(onb.BUF_VALUE, np.float32, (n,))
+    assert np.isfinite(pol).all() and np.isfinite(val).all()
+    assert np.abs(pol.sum(1) - 1).max() < 1e-5
+    dp, dv = np.abs(pol - want_p), np.abs(val - want_v)
+    assert dp.max() <= 6e-3 and dp.mean() <= 1e-4, (dp.max(), dp.mean())
+    assert dv.max() <= 2.5e-2 and dv.mean() <= 2e-3, (dv.max(), dv.mean())
+    assert want_p.std(0).max() > 0.01 and want_v.std() > 0.01
+    # a position's result does not depend on where in the batch it sits (needed for search parity below)
+    perm = np.random.default_rng(0).permutation(n)[:50]
+    with onb.Context(50, mcts_max_sims=2, planes=False) as ctx:
+        ctx.net_load(model, tf32=tf32)
+        ctx.write(onb.BUF_LEAF_PLANES, planes[perm])
+        ctx.net_forward(onb.BUF_LEAF_PLANES)
+        pol2 = ctx.read(onb.BUF_POLICY, np.float32, (50, 50))
+        val2 = ctx.read(onb.BUF_VALUE, np.float32, (50,))
+    assert np.array_equal(pol2, pol[perm]) and np.array_equal(val2, val[perm])
+
+
+@pytest.mark.gpu
+def test_network_errors(onb):
+    from test_net_cpu import lively_model
+    with onb.Context(4, mcts_max_sims=2, planes=False) as ctx:
+        with pytest.raises(onb.OnbError):
+            ctx.net_forward(onb.BUF_LEAF_PLANES)          # nothing loaded
+        sd = {k: v for k, v in lively_model(1).state_dict().items() if k != "bn1.running_var"}
+        with pytest.raises(onb.OnbError, match="bn1.running_var"):
+            ctx.net_load(sd)
+        import torch
+        from onitama_alphazero_b200.net import ConvResNet
+        with pytest.raises(onb.OnbError, match="hidden_channels"):
+            ctx.net_load(ConvResNet(32, 21, 1))           # only 64 hidden channels are built
+        ctx.net_load(lively_model(1))
+        with pytest.raises(onb.OnbError):
+            ctx.net_forward(onb.BUF_PLANES)               # env plane buffer not allocated in this context
+        with pytest.raises(onb.OnbError):
+            ctx.net_forward(onb.BUF_MASKS)
+
+
+@pytest.mark.gpu
+def test_search_with_fused_network_bit_exact(onb):
+    """BASELINE config 5 without a host in the loop: onb_mcts_run(ONB_EVAL_NET) = select -> tensor-core network -> expand/backup.
+    The oracle search gets the SAME evaluator through its callback (the kernel, run on a one-position context; results are batch
+    invariant), so trees must be bit-exact: visits, priors, W, pi, best move."""
+    from test_net_cpu import lively_model
+    model = lively_model(3, seed=21)
+    n, sims, c = 8, 48, 2.0
+    roots = _cfg4_roots(16, 5)[[0, 2, 4, 6, 8, 10, 12, 14]]
+    with onb.Context(1, mcts_max_sims=2, planes=False) as one, onb.Context(n, mcts_max_sims=sims, planes=False) as ctx:
+        one.net_load(model)
+        ctx.net_load(model)
+
+        def eval_one(planes525):
+            one.write(onb.BUF_LEAF_PLANES, np.asarray(planes525, dtype=np.float32).reshape(1, 525))
+            one.net_forward(onb.BUF_LEAF_PLANES)
+            return one.read(onb.BUF_POLICY, np.float32, (50,)), float(one.read(onb.BUF_VALUE, np.float32, (1,))[0])
+
+        ctx.set_states(roots)
+        res = ctx.search(c, sims, evaluator=onb.EVAL_NET, fused=True)
+        trees = [ctx.mcts_dump_tree(t) for t in range(n)]
+        ctx.set_states(roots)
+        res2 = ctx.search(c, sims, evaluator=onb.EVAL_NET, fused=False)   # explicit select / onb_mcts_eval / expand_backup
+        assert np.array_equal(res["child_visits"], res2["child_visits"]) and np.array_equal(res["pi"], res2["pi"])
+        checked = 0
+        for t in range(n):
+            if roots["result"][t] != 0:
+                continue
+            want = O.mcts_search(roots[t:t + 1], c, sims, dump=True, callback=eval_one)
+            got = trees[t]
+            assert np.array_equal(got["visits"], want["tree"]["visits"]), t
+            assert np.array_equal(got["prior"], want["tree"]["prior"])
+            assert np.array_equal(got["reward"], want["tree"]["reward"])
+            assert int(res["best"][t]) == want["best"]
+            assert np.array_equal(res["pi"][t], want["pi"])
+            checked += 1
+        assert checked >= 6
+
+
+@pytest.mark.gpu
+def test_selfplay_with_fused_network(onb):
+    """self_play (train.rs:35-98) with the on-device network: no torch module anywhere in the loop"""
+    import torch
+    from test_net_cpu import lively_model
+    n, sims = 64, 24
+    with onb.Context(n, seed=4, mcts_max_sims=sims) as ctx:
+        ctx.net_load(lively_model(3, seed=3))
+        out = onb.self_play(ctx, 2.0, sims, max_plies=8, evaluator=onb.EVAL_NET)
+    m = out["planes"].shape[0]
+    assert 0 < m <= n * 10   # train.rs:74-79: the ply cap is checked after the move, so max_plies + 2 plies are played
+    assert torch.allclose(out["pi"].sum(dim=(1, 2)), torch.ones(m, device=out["pi"].device), atol=1e-5)
+    assert set(out["z"].unique().tolist()) <= {-1.0, 0.0, 1.0}

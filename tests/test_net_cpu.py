@@ -43,3 +43,57 @@ def test_alphaloss_matches_reference_formula():
     assert torch.isclose(pl, -(p.log() * pi).sum() / (6 * 25))   # sum over the card dim, mean over batch x 25 squares
     idx = sample_minibatch(100, 32, generator=g)
     assert idx.shape == (32,) and len(set(idx.tolist())) == 32 and int(idx.max()) < 100
+
+
+def lively_model(blocks=3, seed=7):
+    """ConvResNet with activations of order one in every layer and non-trivial BatchNorm statistics (so that BN folding, the
+    residual path and both heads all matter to the output); deterministic for a given torch version."""
+    from onitama_alphazero_b200.net import ConvResNet
+    torch.manual_seed(seed)
+    model = ConvResNet(64, 21, blocks)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                torch.nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
+                m.bias.normal_(0, 0.1)
+            if isinstance(m, torch.nn.Linear):
+                m.weight.normal_(0, 2.0 / m.in_features ** 0.5)
+                m.bias.normal_(0, 0.3)
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.7, 1.3)
+                m.bias.normal_(0.1, 0.2)
+    return model.eval()
+
+
+@pytest.mark.parametrize("blocks", [0, 1, 3])
+def test_oracle_network_matches_the_pytorch_twin(blocks):
+    """oracle/onb_oracle.cpp orc_net_forward (the checker of the tensor-core kernel) against net.py on real positions"""
+    import numpy as np
+    import oracle_lib as O
+    model = lively_model(blocks)
+    g = O.new_games(24, seed=5)
+    for s in range(9):
+        O.env_step_random(g, 5, s)
+    planes = O.encode(g).reshape(-1, 21, 5, 5)
+    with torch.no_grad():
+        p_ref, v_ref = model(torch.from_numpy(planes))
+    pol, val = O.net_forward(model.state_dict(), planes)
+    assert np.abs(pol - p_ref.reshape(-1, 50).numpy()).max() < 2e-5
+    assert np.abs(val - v_ref.reshape(-1).numpy()).max() < 2e-5
+    assert p_ref.reshape(-1, 50).std(0).max() > 0.01 and v_ref.std() > 0.01   # the outputs do depend on the position
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/model_5e-3_3_resnet.ot"), reason="reference weights not present")
+def test_oracle_network_with_reference_weights():
+    import numpy as np
+    import oracle_lib as O
+    from onitama_alphazero_b200.net import ConvResNet
+    m = ConvResNet(64, 21, 3).load_ot("/root/reference/models/model_5e-3_3_resnet.ot").eval()
+    g = O.new_games(8, seed=1)
+    planes = O.encode(g).reshape(-1, 21, 5, 5)
+    with torch.no_grad():
+        p_ref, v_ref = m(torch.from_numpy(planes))
+    pol, val = O.net_forward(m.state_dict(), planes)
+    assert np.abs(pol - p_ref.reshape(-1, 50).numpy()).max() < 2e-5 and np.abs(val - v_ref.reshape(-1).numpy()).max() < 2e-5
