@@ -47,6 +47,18 @@ def read_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def read_tensor_peak():
+    """dense bf16/f16 tensor peak in TFLOP/s: the sustained figure (the network runs inside a long step)"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)"
+        except Exception:
+            pass
+    return 1590.0, "fallback (B200_PROFILING.md)"
+
+
 def read_traffic(kernel):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
@@ -223,8 +235,8 @@ def workload_config(wl):
                             % (MCTS_SIMS, MCTS_TREES), "trees_per_gpu": MCTS_TREES, "sims": MCTS_SIMS, "c_puct": MCTS_C,
                 "l2": "touched node pools ~2.4 GB/GPU >> 126 MB L2"}
     if wl == "selfplay":
-        return {"workload": "BASELINE config 5: AlphaZero self-play, %d sims/move, 3-block ConvResNet (64 ch, random init, fixed seed) as a torch "
-                            "black box reading the leaf buffer zero-copy, %d concurrent games/GPU, one ply per step, replay samples gathered to GPU 0"
+        return {"workload": "BASELINE config 5: AlphaZero self-play, %d sims/move, 3-block ConvResNet (64 ch, random init, fixed seed) evaluating "
+                            "the leaf buffer in place, %d concurrent games/GPU, one ply per step, replay samples gathered to GPU 0"
                             % (SELFPLAY_SIMS, SELFPLAY_GAMES), "games_per_gpu": SELFPLAY_GAMES, "sims": SELFPLAY_SIMS, "c_puct": MCTS_C,
                 "l2": "node pools + leaf batches >> L2"}
     if wl == "perft":
@@ -244,6 +256,8 @@ def main():
     ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--net", default="fused", choices=["fused", "fused-tf32", "torch"],
+                    help="selfplay workload: the tensor-core network kernel (f16 or tf32 operands) or the PyTorch module as a black box")
     args = ap.parse_args()
     dflt = {"env": (200, 20), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5)}[args.workload]
     if args.impl == "reference":
@@ -544,15 +558,24 @@ def main():
         from onitama_alphazero_b200.net import ConvResNet, make_evaluator
         n, sims = SELFPLAY_GAMES, SELFPLAY_SIMS
         torch.manual_seed(1234)
-        net = make_evaluator(ConvResNet(64, 21, 3).cuda(local_rank))
+        model = ConvResNet(64, 21, 3)
         ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims)
+        fused = args.net != "torch"
+        if fused:
+            ctx.net_load(model, tf32=args.net == "fused-tf32")   # onb_net_load: the network becomes part of the library's search
+            net = None
+        else:
+            net = make_evaluator(model.cuda(local_rank))
         ctx.reset()
         planes_t, pi_t = ctx.tensor(onb.BUF_PLANES), ctx.tensor(onb.BUF_PI)
         got = {"samples": 0}
 
         def one_ply(i):
             ctx.encode(to_host=False)                      # sample planes of the searched position (train.rs:58)
-            ctx.search_device(MCTS_C, sims, net=net, use_graph=True)  # select -> ConvResNet (zero-copy leaf batch) -> expand/backup, x sims
+            if fused:   # onb_mcts_run(ONB_EVAL_NET): select -> tensor-core ConvResNet -> expand/backup, x sims, no host in the loop
+                ctx.search_device(MCTS_C, sims, evaluator=onb.EVAL_NET)
+            else:       # select -> torch module (zero-copy leaf batch, CUDA graph) -> expand/backup, x sims
+                ctx.search_device(MCTS_C, sims, net=net, use_graph=True)
             z = torch.zeros(n, device=planes_t.device)
             out_s = onb.gather_replay(planes_t, pi_t, z, dst=0)   # NCCL gather of the ply's samples to the trainer GPU
             if out_s is not None:
@@ -563,14 +586,27 @@ def main():
         value = world * n * sims * steps / (ms * 1e-3)
         ctx.close()
         per_sim = 1217.0 + 2100 + 204
-        roof = {"bound": "hbm", "achieved": per_sim * n * sims * steps / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": per_sim * n * sims * steps / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_mcts_select + k_mcts_expand_backup",
-                "note": "the step is dominated by the black-box network (library kernels, ~11.7 MFLOP per evaluation), not by these kernels",
-                "peak_source": peak_src}
+        if fused:
+            # the dominant kernel is the network: 7 3x3 convolutions (21->64, 6 x 64->64) on 25 squares + heads = 11.68 MFLOP per evaluation
+            flop = 2.0 * 25 * 64 * 9 * (21 + 6 * 64) + 2.0 * (25 * 64 * 3 + 2500 + 1600 + 64)
+            tpeak, tsrc = read_tensor_peak()
+            ach = flop * n * sims * steps / (ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                    "kernel": "k_net_forward<2,%s>" % ("tf32" if args.net == "fused-tf32" else "f16"), "flop_per_evaluation": flop,
+                    "note": "achieved = useful network FLOPs of the whole ply / ply time (search kernels included in the time); the MMAs also "
+                            "compute the zero-padding cells (25 of 36.6 rows are real squares) and are bound by shared-memory operand reads at "
+                            "N = 64 (6 KB per 128x64x16 MMA); peak = dense bf16/f16 (tf32 runs at half of it)", "peak_source": tsrc}
+        else:
+            roof = {"bound": "hbm", "achieved": per_sim * n * sims * steps / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": per_sim * n * sims * steps / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_mcts_select + k_mcts_expand_backup",
+                    "note": "the step is dominated by the black-box network (library kernels, ~11.7 MFLOP per evaluation), not by these kernels",
+                    "peak_source": peak_src}
         e2e = {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "path": "device-resident self-play ply (search + sample gather + play); nothing crosses PCIe by design"}
-        return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=ms / steps, dtype="u32+f64 (search), f32/tf32 (network)",
-                    roofline=roof, e2e=e2e, gpu_launches=(2 * sims + 4) * steps, clocks=clocks, samples_per_ply=got["samples"])
+        dt = "u32+f64 (search), " + {"fused": "f16 x f16 -> f32 (network)", "fused-tf32": "tf32 x tf32 -> f32 (network)",
+                                     "torch": "f32/tf32 (network, cuDNN)"}[args.net]
+        return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=ms / steps, dtype=dt, network=args.net,
+                    roofline=roof, e2e=e2e, gpu_launches=((3 if fused else 2) * sims + 4) * steps, clocks=clocks, samples_per_ply=got["samples"])
 
     if wl == "env":
         out = bench_env(args.steps, args.warmup)
