@@ -60,7 +60,9 @@ struct Geo {
     static constexpr int NB = NACC == 2 ? (F16 ? 7 : 6) : 14;  // boards per pass (two CTAs per SM when NACC == 2)
     static constexpr int CELLS = NB * kCellsPerBoard;
     static constexpr int R = kLead + CELLS + kTrail;  // rows of the activation matrix
-    static constexpr int NSLOT = F16 ? 4 : (NACC == 2 ? 3 : 4);  // weight ring slots (one tap each)
+    // weight ring slots (one tap each). f16: a whole layer (9 taps) so that the producer runs one layer ahead -- with 4 slots the
+    // MMA thread spent most of its time waiting for weights (L2 -> shared latency of ~1.5k cycles per 8 KB tap vs 256 cycles of MMAs)
+    static constexpr int NSLOT = F16 ? 9 : (NACC == 2 ? 3 : 4);
     static constexpr int ACT_BYTES = R * Op<F16>::KCH * 16;
     static constexpr int OFF_RING = ACT_BYTES;
     static constexpr int RING_BYTES = NSLOT * Op<F16>::TAP_BYTES;
@@ -131,21 +133,28 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
            (1ull << 46);
 }
+// D[tmem] (+)= A[smem] * B[smem]^T. Descriptors are passed as (low word, high word): the high word (stride between 8-row groups,
+// version) is the same for every operand here and the low word (start address | chunk stride << 16) only needs an add per MMA.
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
 template <bool F16>
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
     if (F16)
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(Op<true>::IDESC), "r"(accumulate)
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(Op<true>::IDESC), "r"(accumulate)
             : "memory");
     else
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(Op<false>::IDESC), "r"(accumulate)
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(Op<false>::IDESC), "r"(accumulate)
             : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -296,24 +305,34 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             const bool last = l == L - 1;
             if (tid == 0) {
                 // ---- MMA issue: 9 taps x K steps x NACC accumulators
-                const int ksteps = (l == 0 ? O::KCH0 : O::KCH) / 2;
+                // descriptor low words in 16-byte units: start address | (byte distance between the two K chunks of an MMA) << 16
                 const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
-                for (int t = 0; t < 9; ++t) {
+                const uint32_t a_base = ((s_act >> 4) + (uint32_t)kLead) | ((uint32_t)R << 16);
+                auto issue_tap = [&](int t, int ksteps) {
                     const uint32_t q = q0 + t, slot = q % NSLOT, use = q / NSLOT;
                     mbar_wait(bar_full(slot), use & 1u);
                     tc_fence_after();
-                    const int shift = (t / 3 - 1) * 6 + (t % 3 - 1);
-                    const uint32_t a0 = s_act + (uint32_t)(kLead + shift) * 16u;
-                    const uint32_t b0 = s_ring + slot * (uint32_t)O::TAP_BYTES;
-                    for (int j = 0; j < ksteps; ++j) {
-                        const uint64_t bdesc = smem_desc(b0 + (uint32_t)j * 2048u, 1024u, 128u);
+                    const uint32_t a_t = a_base + (uint32_t)((t / 3 - 1) * 6 + (t % 3 - 1));
+                    const uint32_t b_t = ((s_ring + slot * (uint32_t)O::TAP_BYTES) >> 4) | (64u << 16);
 #pragma unroll
-                        for (int a = 0; a < NACC; ++a) {
-                            const uint64_t adesc = smem_desc(a0 + (uint32_t)(j * 2 * R + a * 128) * 16u, (uint32_t)R * 16u, 128u);
-                            mma_ss<F16>(dcol + a * 64, adesc, bdesc, (use_s || t > 0 || j > 0) ? 1u : 0u);
+                    for (int j = 0; j < O::KCH / 2; ++j) {
+                        if (j < ksteps) {
+#ifndef ONB_NET_DBG_NOMMA
+#pragma unroll
+                            for (int a = 0; a < NACC; ++a)
+                                mma_ss<F16>(dcol + a * 64, a_t + (uint32_t)(j * 2 * R + a * 128), b_t + (uint32_t)j * 128u,
+                                            (use_s || t > 0 || j > 0) ? 1u : 0u);
+#endif
                         }
                     }
                     umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
+                };
+                if (l == 0) {
+#pragma unroll 1
+                    for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH0 / 2);
+                } else {
+#pragma unroll 1
+                    for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH / 2);
                 }
                 umma_commit(bar_acc);
             } else if (tid == 32) {
@@ -340,6 +359,9 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
             const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
             const float4* hw = reinterpret_cast<const float4*>(net.head);
+#ifdef ONB_NET_DBG_NOEPI
+            if (l >= 0 && !last) { fence_proxy_async(); q0 += 9u; continue; }
+#endif
 #pragma unroll
             for (int ai = 0; ai < NACC / 2; ++ai) {
                 const int a = (warp >> 2) + 2 * ai;
