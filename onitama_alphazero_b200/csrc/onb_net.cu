@@ -453,6 +453,257 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
     if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
 }
 
+// ---- version 2: ONE CTA per SM, two independent halves that share one weight stream ---------------------------------------------
+// Measured on version 1 (two CTAs per SM, each streaming its own weights): with MMAs and epilogues disabled the kernel still took
+// 55 % of its time -- 2 341 board groups x 451 KB of weights = 1.06 GB through L2 per call (5.6 TB/s). TMEM (512 columns = accumulators
+// + parked residuals of 14 boards) fixes how many boards an SM can hold, so the only way to halve that traffic is to let both groups
+// of an SM consume the SAME ring. Layout: 16 worker warps = 2 halves x 8 warps, each half exactly the version-1 CTA (its own 7 boards,
+// activation matrix, 256 TMEM columns, MMA-issuing thread, named barrier), running out of phase so one half's MMAs overlap the other
+// half's epilogue; warp 16 is the producer (lane 0 streams taps into a 16-slot ring; a slot is refilled when BOTH halves' MMAs have
+// read it: empty barriers count 2).
+template <bool F16>
+struct Geo2 {
+    static constexpr int NB = 7;  // boards per half
+    static constexpr int CELLS = NB * kCellsPerBoard;
+    static constexpr int R = kLead + CELLS + kTrail;
+    static constexpr int NSLOT = F16 ? 16 : 5;
+    static constexpr int ACT_BYTES = R * Op<F16>::KCH * 16;  // per half
+    static constexpr int OFF_RING = 2 * ACT_BYTES;
+    static constexpr int RING_BYTES = NSLOT * Op<F16>::TAP_BYTES;
+    static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
+    static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;  // per half
+    static constexpr int OFF_BAR = OFF_HEAD + 2 * HEAD_BYTES;
+    static constexpr int SMEM = OFF_BAR + (2 * NSLOT + 2) * 8 + 16;
+    static constexpr int THREADS = 17 * 32;
+    static_assert(CELLS <= 256, "two accumulators of 128 cells per half");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <bool F16>
+__global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
+    k_net_forward2(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
+    using G = Geo2<F16>;
+    using O = Op<F16>;
+    constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = G::NSLOT, NACC = 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t s_base = smem_u32(smem), s_ring = s_base + G::OFF_RING, s_bar = s_base + G::OFF_BAR;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + G::OFF_BAR + (2 * NSLOT + 2) * 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = 1 + 2 * net.n_blocks;
+    const int64_t n_groups = (n + NB - 1) / NB;
+    // iteration i of this CTA: half h works on group (blockIdx.x + i * gridDim.x) * 2 + h (possibly past the end: computed, not stored)
+    const int64_t n_pairs = (n_groups + 1) / 2;
+    if ((int64_t)blockIdx.x >= n_pairs) return;
+    const int64_t my_iters = (n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t total_taps = (uint32_t)my_iters * 9u * (uint32_t)L;
+    auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
+    auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 2);  // both halves' MMAs must have read the slot
+        }
+        mbar_init(s_bar + 2 * NSLOT * 8u, 1);
+        mbar_init(s_bar + (2 * NSLOT + 1) * 8u, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+    for (int i = tid; i < 2 * G::ACT_BYTES / 16; i += G::THREADS) st_shared_v4(s_base + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 16) {
+        // ---- weight producer (one lane): the ring is filled strictly in tap order, as far ahead as it has free slots
+        if (lane == 0) {
+            for (uint32_t q = 0; q < total_taps; ++q) {
+                const uint32_t slot = q % NSLOT, use = q / NSLOT;
+                if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
+                const uint32_t ql = q % (9u * (uint32_t)L), layer = ql / 9u, tap = ql - layer * 9u;
+                const uint8_t* src = net.wconv + (layer == 0 ? (size_t)tap * O::TAP_BYTES0
+                                                              : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
+                const uint32_t bytes = layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES;
+                mbar_expect_tx(bar_full(slot), bytes);
+                bulk_g2s(s_ring + slot * (uint32_t)O::TAP_BYTES, src, bytes, bar_full(slot));
+            }
+        }
+        return;  // the workers only use named barriers from here on
+    }
+
+    const int half = warp >> 3, hwarp = warp & 7, htid = tid & 255;
+    const uint32_t s_act = s_base + (uint32_t)half * G::ACT_BYTES;
+    float* s_head = reinterpret_cast<float*>(smem + G::OFF_HEAD + half * G::HEAD_BYTES);
+    const uint32_t bar_acc = s_bar + (2 * NSLOT + half) * 8u;
+    const uint32_t tmem = *s_tmem + (uint32_t)half * 256u;
+    const uint32_t bar_id = 1u + (uint32_t)half;
+
+    uint32_t q0 = 0, acc_par = 0;
+    for (int64_t gi = 0; gi < my_iters; ++gi) {
+        const int64_t board0 = (((int64_t)blockIdx.x + gi * gridDim.x) * 2 + half) * NB;
+        // ---- input planes -> the first channel chunks of the activation matrix (create_tensor_from_state layout [21][5][5])
+        {
+            const int cell = htid;
+            const Cell c = decode_cell(cell, CELLS);
+            if (c.real) {
+                const int64_t gb = board0 + c.board;
+                const float* src = planes + gb * 525 + c.pos;
+                float x[32];  // the planes are 0 / 1: exact in either operand format
+#pragma unroll
+                for (int ch = 0; ch < 32; ++ch) x[ch] = (ch < kInPlanes && gb < n) ? __ldg(src + ch * 25) : 0.f;
+                if (F16) {
+                    store_channels<F16>(s_act, R, kLead + cell, 0, x);
+                } else {
+#pragma unroll
+                    for (int kc = 0; kc < O::KCH0; ++kc)
+                        st_shared_v4(s_act + (uint32_t)(kc * R + kLead + cell) * 16u, to_tf32(x[4 * kc]), to_tf32(x[4 * kc + 1]),
+                                     to_tf32(x[4 * kc + 2]), to_tf32(x[4 * kc + 3]));
+                }
+            }
+        }
+        fence_proxy_async();
+        for (int l = 0; l < L; ++l) {
+            tc_fence_before();
+            named_bar_sync(bar_id, 256);
+            tc_fence_after();
+            const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
+            const bool last = l == L - 1;
+            if (htid == 0) {
+                // ---- MMA issue: 9 taps x K steps x 2 accumulators; descriptor low words in 16-byte units
+                const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
+                const uint32_t a_base = ((s_act >> 4) + (uint32_t)kLead) | ((uint32_t)R << 16);
+                auto issue_tap = [&](int t, int ksteps) {
+                    const uint32_t q = q0 + t, slot = q % NSLOT, use = q / NSLOT;
+                    mbar_wait(bar_full(slot), use & 1u);
+                    tc_fence_after();
+                    const uint32_t a_t = a_base + (uint32_t)((t / 3 - 1) * 6 + (t % 3 - 1));
+                    const uint32_t b_t = ((s_ring + slot * (uint32_t)O::TAP_BYTES) >> 4) | (64u << 16);
+#pragma unroll
+                    for (int j = 0; j < O::KCH / 2; ++j) {
+                        if (j < ksteps) {
+#ifndef ONB_NET_DBG_NOMMA
+#pragma unroll
+                            for (int a = 0; a < NACC; ++a)
+                                mma_ss<F16>(dcol + a * 64, a_t + (uint32_t)(j * 2 * R + a * 128), b_t + (uint32_t)j * 128u,
+                                            (use_s || t > 0 || j > 0) ? 1u : 0u);
+#endif
+                        }
+                    }
+                    umma_commit(bar_empty(slot));
+                };
+                if (l == 0) {
+#pragma unroll 1
+                    for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH0 / 2);
+                } else {
+#pragma unroll 1
+                    for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH / 2);
+                }
+                umma_commit(bar_acc);
+            }
+            __syncwarp();
+            mbar_wait(bar_acc, acc_par);
+            acc_par ^= 1u;
+            tc_fence_after();
+            // ---- epilogue: this thread owns one cell (TMEM lane) of accumulator hwarp / 4
+            const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
+            const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
+            const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
+            const float4* hw = reinterpret_cast<const float4*>(net.head);
+#ifdef ONB_NET_DBG_NOEPI
+            if (!last) { fence_proxy_async(); q0 += 9u; continue; }
+#endif
+            {
+                const int a = hwarp >> 2;
+                const int cell = a * 128 + (hwarp & 3) * 32 + lane;
+                const Cell c = decode_cell(cell, CELLS);
+                const uint32_t tlane = tmem + ((uint32_t)((hwarp & 3) * 32) << 16);
+                const uint32_t tsrc = tlane + (use_s ? NACC * 64 : 0) + a * 64;
+                const uint32_t tskip = tlane + NACC * 64 + a * 64;
+                float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(tsrc + h * 32, v);
+                    float o[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!use_s) b = __ldg(bias_l + h * 8 + i);
+                        o[4 * i + 0] = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f);
+                        o[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f);
+                        o[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f);
+                        o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
+                    }
+                    if (!last && c.real) store_channels<F16>(s_act, R, kLead + cell, h * 32, o);
+                    if (preload) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b = __ldg(bias_n + h * 8 + i);
+                            v[4 * i + 0] = __float_as_uint(o[4 * i + 0] + b.x);
+                            v[4 * i + 1] = __float_as_uint(o[4 * i + 1] + b.y);
+                            v[4 * i + 2] = __float_as_uint(o[4 * i + 2] + b.z);
+                            v[4 * i + 3] = __float_as_uint(o[4 * i + 3] + b.w);
+                        }
+                        tmem_st32(tskip + h * 32, v);
+                    }
+                    if (last) {  // 1x1 convolutions of both heads (net.rs: policy_conv 64 -> 2, vh_conv 64 -> 1)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 w0 = __ldg(hw + (kHP0 / 4) + h * 8 + i), w1 = __ldg(hw + (kHP1 / 4) + h * 8 + i),
+                                         w2 = __ldg(hw + (kHV / 4) + h * 8 + i);
+                            hp0 = fmaf(o[4 * i + 0], w0.x, fmaf(o[4 * i + 1], w0.y, fmaf(o[4 * i + 2], w0.z, fmaf(o[4 * i + 3], w0.w, hp0))));
+                            hp1 = fmaf(o[4 * i + 0], w1.x, fmaf(o[4 * i + 1], w1.y, fmaf(o[4 * i + 2], w1.z, fmaf(o[4 * i + 3], w1.w, hp1))));
+                            hv = fmaf(o[4 * i + 0], w2.x, fmaf(o[4 * i + 1], w2.y, fmaf(o[4 * i + 2], w2.z, fmaf(o[4 * i + 3], w2.w, hv))));
+                        }
+                    }
+                }
+                if (last && c.real) {
+                    float* hb = s_head + c.board * 75;
+                    hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
+                    hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
+                    hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+                }
+            }
+            if (preload) tmem_wait_st();
+            fence_proxy_async();
+            q0 += 9u;
+        }
+        // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
+        named_bar_sync(bar_id, 256);
+        for (int b = hwarp; b < NB; b += 8) {
+            const int64_t gb = board0 + b;
+            if (gb >= n) continue;
+            const float* hb = s_head + b * 75;
+            const bool two = lane + 32 < 50;
+            float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+            for (int i = 0; i < 50; ++i) {
+                const float x = hb[i];
+                l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
+                if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+            }
+            const float m = warp_max(two ? fmaxf(l0, l1) : l0);
+            const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
+            const float s = warp_sum(e0 + e1);
+            policy[gb * 50 + lane] = e0 / s;
+            if (two) policy[gb * 50 + 32 + lane] = e1 / s;
+            float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+            for (int i = 0; i < 25; ++i) {
+                const float x = hb[50 + i];
+                h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
+                h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+            }
+            float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+            acc = warp_sum(acc);
+            if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+        }
+    }
+    tc_fence_before();
+    named_bar_sync(3, 512);  // both halves are done with TMEM
+    if (warp == 0) tmem_dealloc(*s_tmem, 512);
+}
+
 // ---- host side: fold BatchNorm, round to tf32, lay the weights out as the tensor core reads them ------------------------------
 struct Named {
     std::string name;
@@ -633,11 +884,27 @@ static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy
     return cudaGetLastError();
 }
 
+template <bool F16>
+static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
+    using G = Geo2<F16>;
+    static bool attr = false;
+    if (!attr) {
+        const cudaError_t e = cudaFuncSetAttribute(k_net_forward2<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int64_t pairs = ((c->n + G::NB - 1) / G::NB + 1) / 2;
+    k_net_forward2<F16><<<(unsigned)(pairs < sms ? pairs : sms), G::THREADS, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value) {
     const NetDev nd{reinterpret_cast<const uint8_t*>(c->d_net_w), c->d_net_bias, c->d_net_head, c->net_blocks};
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)
+    if (v2 && v2[0] == '1') return c->net_f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms) : launch_net_v2<false>(c, planes, policy, value, nd, sms);
     const char* wide = getenv("ONB_NET_WIDE");  // exploration knob: 14 boards per CTA, one CTA per SM
     const bool w = wide && wide[0] == '1';
     if (c->net_f16) return w ? launch_net_variant<4, true>(c, planes, policy, value, nd, sms) : launch_net_variant<2, true>(c, planes, policy, value, nd, sms);
