@@ -46,8 +46,9 @@ struct Op {
     static constexpr int KCH = kHid / CPC;             // 8 | 16 chunks per 64 channels
     static constexpr int IN_PAD = F16 ? 32 : 24;       // input planes padded to a multiple of the MMA's K (16 | 8)
     static constexpr int KCH0 = IN_PAD / CPC;          // 4 | 6
-    static constexpr int TAP_BYTES = KCH * 64 * 16;    // one tap of a 64 -> 64 layer: [chunks][64 co][16 B]
-    static constexpr int TAP_BYTES0 = KCH0 * 64 * 16;  // one tap of the first layer
+    static constexpr int KB = KCH / 8;                 // 1 | 2 blocks of 128 bytes (one swizzle row) per matrix row
+    static constexpr int TAP_BYTES = KCH * 64 * 16;    // one tap of a 64 -> 64 layer: [KB][64 co][128 B], swizzled
+    static constexpr int TAP_BYTES0 = (F16 ? 1 : 1) * 64 * 128;  // first layer: its K (32 | 24) fits the first 128-byte block
     // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, A/B format, both K-major, N = 64, M = 128
     static constexpr uint32_t IDESC = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 };
@@ -59,11 +60,11 @@ template <int NACC, bool F16>
 struct Geo {
     static constexpr int NB = NACC == 2 ? (F16 ? 7 : 6) : 14;  // boards per pass (two CTAs per SM when NACC == 2)
     static constexpr int CELLS = NB * kCellsPerBoard;
-    static constexpr int R = kLead + CELLS + kTrail;  // rows of the activation matrix
+    static constexpr int R = (kLead + CELLS + kTrail + 7) / 8 * 8;  // rows of the activation matrix (whole swizzle periods)
     // weight ring slots (one tap each). f16: a whole layer (9 taps) so that the producer runs one layer ahead -- with 4 slots the
     // MMA thread spent most of its time waiting for weights (L2 -> shared latency of ~1.5k cycles per 8 KB tap vs 256 cycles of MMAs)
     static constexpr int NSLOT = F16 ? 9 : (NACC == 2 ? 3 : 4);
-    static constexpr int ACT_BYTES = R * Op<F16>::KCH * 16;
+    static constexpr int ACT_BYTES = R * Op<F16>::KCH * 16;  // a multiple of 1024: the ring stays aligned to the swizzle period
     static constexpr int OFF_RING = ACT_BYTES;
     static constexpr int RING_BYTES = NSLOT * Op<F16>::TAP_BYTES;
     static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
@@ -135,27 +136,72 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 }
 // D[tmem] (+)= A[smem] * B[smem]^T. Descriptors are passed as (low word, high word): the high word (stride between 8-row groups,
 // version) is the same for every operand here and the low word (start address | chunk stride << 16) only needs an add per MMA.
-constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+// Operand layout (both A and B): K-major, 128-byte swizzle. A matrix row is KB blocks of 128 bytes (64 f16 | 32 tf32 channels); block
+// kb of row r lives at base + kb * rows * 128 + r * 128 and its 16-byte chunk c sits at chunk position c ^ (r & 7) (base 1024-aligned).
+// Rows are therefore 128 bytes apart, so a window that starts at ANY row is 128-byte aligned: every 8-row x 32-byte operand fetch of
+// the tensor core touches each bank once. (The first version used the no-swizzle layout with rows 16 bytes apart; windows shifted
+// by a number of rows that is not a multiple of 8 then straddle two 128-byte lines per core matrix and the MMAs ran at ~80 cycles
+// instead of 48.) Descriptor: start address, leading offset 1 (unused for swizzled K-major), 1024 bytes between 8-row groups,
+// version 1, base offset = row phase of the start address (start >> 7) & 7, layout type 2 = SWIZZLE_128B.
+#ifndef ONB_NET_BASEOFF
+#define ONB_NET_BASEOFF 0
+#endif
+__device__ __forceinline__ uint32_t desc_hi(uint32_t start_addr) {
+    return (1024u >> 4) | (1u << 14) | (ONB_NET_BASEOFF ? (((start_addr >> 7) & 7u) << 17) : 0u) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t start_addr) { return ((start_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+// one lane of a converged warp (the issue loops run warp-uniformly so that descriptors stay in uniform registers; only the
+// tcgen05 instructions themselves are issued by the elected lane)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 template <bool F16>
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t accumulate) {
+    const uint32_t a_lo = desc_lo(a_addr), a_hi = desc_hi(a_addr), b_lo = desc_lo(b_addr), b_hi = desc_hi(b_addr);
     if (F16)
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "setp.ne.b32 p, %5, 0;\n\t"
-            "mov.b64 da, {%1, %3};\n\t"
-            "mov.b64 db, {%2, %3};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-            "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(Op<true>::IDESC), "r"(accumulate)
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(Op<true>::IDESC), "r"(accumulate)
             : "memory");
     else
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "setp.ne.b32 p, %5, 0;\n\t"
-            "mov.b64 da, {%1, %3};\n\t"
-            "mov.b64 db, {%2, %3};\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-            "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(Op<false>::IDESC), "r"(accumulate)
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(Op<false>::IDESC), "r"(accumulate)
             : "memory");
+}
+// all MMAs of one tap: K steps of 32 bytes (4 per 128-byte block) x NACC accumulators of 128 rows
+template <bool F16, int NACC>
+__device__ __forceinline__ void issue_tap_mmas(bool elected, uint32_t dcol, uint32_t s_act, int R, int row0, uint32_t b_slot, int ksteps,
+                                               bool accumulate_first) {
+    using O = Op<F16>;
+#pragma unroll
+    for (int j = 0; j < O::KCH / 2; ++j) {
+        if (j < ksteps) {
+            const uint32_t koff = (uint32_t)(j / 4) * 128u;  // block index * rows * 128 is added per operand below
+            const uint32_t b_addr = b_slot + (uint32_t)(j / 4) * (64u * 128u) + (uint32_t)(j % 4) * 32u;
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+                const uint32_t a_addr = s_act + koff * (uint32_t)R + (uint32_t)(row0 + a * 128) * 128u + (uint32_t)(j % 4) * 32u;
+#ifndef ONB_NET_DBG_NOMMA
+                if (elected) mma_ss<F16>(dcol + a * 64, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u);
+#endif
+            }
+        }
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -197,18 +243,22 @@ __device__ __forceinline__ void store_channels(uint32_t s_act, int R, int row, i
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// byte address of 16-byte chunk `chunk` (0 .. KCH-1) of row `row` (see the operand layout above)
+__device__ __forceinline__ uint32_t act_addr(uint32_t s_act, int R, int row, int chunk) {
+    return s_act + (uint32_t)(chunk >> 3) * (uint32_t)R * 128u + (uint32_t)row * 128u + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
+}
 template <>
 __device__ __forceinline__ void store_channels<true>(uint32_t s_act, int R, int row, int c0, const float (&o)[32]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        st_shared_v4(s_act + (uint32_t)((c0 / 8 + i) * R + row) * 16u, to_f16x2(o[8 * i + 0], o[8 * i + 1]), to_f16x2(o[8 * i + 2], o[8 * i + 3]),
+        st_shared_v4(act_addr(s_act, R, row, c0 / 8 + i), to_f16x2(o[8 * i + 0], o[8 * i + 1]), to_f16x2(o[8 * i + 2], o[8 * i + 3]),
                      to_f16x2(o[8 * i + 4], o[8 * i + 5]), to_f16x2(o[8 * i + 6], o[8 * i + 7]));
 }
 template <>
 __device__ __forceinline__ void store_channels<false>(uint32_t s_act, int R, int row, int c0, const float (&o)[32]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-        st_shared_v4(s_act + (uint32_t)((c0 / 4 + i) * R + row) * 16u, to_tf32(o[4 * i + 0]), to_tf32(o[4 * i + 1]), to_tf32(o[4 * i + 2]),
+        st_shared_v4(act_addr(s_act, R, row, c0 / 4 + i), to_tf32(o[4 * i + 0]), to_tf32(o[4 * i + 1]), to_tf32(o[4 * i + 2]),
                      to_tf32(o[4 * i + 3]));
 }
 __device__ __forceinline__ float warp_max(float v) {
@@ -273,6 +323,12 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
 
+#ifdef ONB_NET_PROFILE
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
+#define PF(k) do { const long long now__ = clock64(); pf[k] += now__ - pt; pt = now__; } while (0)
+#else
+#define PF(k) do { } while (0)
+#endif
     uint32_t q0 = 0;      // ring position of the current layer's first tap (all threads)
     uint32_t q_prod = 0;  // taps requested so far (producer thread)
     uint32_t acc_par = 0;
@@ -287,45 +343,30 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             float x[32];  // the planes are 0 / 1: exact in either operand format
 #pragma unroll
             for (int ch = 0; ch < 32; ++ch) x[ch] = (ch < kInPlanes && gb < n) ? __ldg(src + ch * 25) : 0.f;
-            if (F16) {
-                store_channels<F16>(s_act, R, kLead + cell, 0, x);
-            } else {
-#pragma unroll
-                for (int kc = 0; kc < O::KCH0; ++kc)
-                    st_shared_v4(s_act + (uint32_t)(kc * R + kLead + cell) * 16u, to_tf32(x[4 * kc]), to_tf32(x[4 * kc + 1]), to_tf32(x[4 * kc + 2]),
-                                 to_tf32(x[4 * kc + 3]));
-            }
+            store_channels<F16>(s_act, R, kLead + cell, 0, x);  // 32 channels: planes 21..31 are zero
         }
         fence_proxy_async();
+        PF(0);  // input stage
         for (int l = 0; l < L; ++l) {
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
+            PF(1);  // layer-top barrier
             const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
             const bool last = l == L - 1;
-            if (tid == 0) {
-                // ---- MMA issue: 9 taps x K steps x NACC accumulators
-                // descriptor low words in 16-byte units: start address | (byte distance between the two K chunks of an MMA) << 16
-                const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
-                const uint32_t a_base = ((s_act >> 4) + (uint32_t)kLead) | ((uint32_t)R << 16);
+            if (warp == 0) {
+                // ---- MMA issue: 9 taps x K steps x NACC accumulators (the whole warp runs the loop, one lane issues)
+                const bool elected = elect_one();
+                                const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
                 auto issue_tap = [&](int t, int ksteps) {
                     const uint32_t q = q0 + t, slot = q % NSLOT, use = q / NSLOT;
                     mbar_wait(bar_full(slot), use & 1u);
                     tc_fence_after();
-                    const uint32_t a_t = a_base + (uint32_t)((t / 3 - 1) * 6 + (t % 3 - 1));
-                    const uint32_t b_t = ((s_ring + slot * (uint32_t)O::TAP_BYTES) >> 4) | (64u << 16);
-#pragma unroll
-                    for (int j = 0; j < O::KCH / 2; ++j) {
-                        if (j < ksteps) {
-#ifndef ONB_NET_DBG_NOMMA
-#pragma unroll
-                            for (int a = 0; a < NACC; ++a)
-                                mma_ss<F16>(dcol + a * 64, a_t + (uint32_t)(j * 2 * R + a * 128), b_t + (uint32_t)j * 128u,
-                                            (use_s || t > 0 || j > 0) ? 1u : 0u);
-#endif
-                        }
-                    }
-                    umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
+                    PF(2);  // waiting for weights
+                    issue_tap_mmas<F16, NACC>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
+                                              s_ring + slot * (uint32_t)O::TAP_BYTES, ksteps, use_s || t > 0);
+                    if (elected) umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
+                    PF(3);  // issuing MMAs
                 };
                 if (l == 0) {
 #pragma unroll 1
@@ -334,7 +375,7 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
 #pragma unroll 1
                     for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH / 2);
                 }
-                umma_commit(bar_acc);
+                if (elected) umma_commit(bar_acc);
             } else if (tid == 32) {
                 // ---- weight producer: keeps the ring NSLOT taps ahead of the MMAs (weights do not depend on the data)
                 const uint32_t target = min(q0 + 9u + (uint32_t)NSLOT, total_taps);
@@ -345,8 +386,13 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                     const uint8_t* src = net.wconv + (layer == 0 ? (size_t)tap * O::TAP_BYTES0
                                                                   : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
                     const uint32_t bytes = layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES;
+#ifdef ONB_NET_DBG_NOWEIGHTS
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full(slot)) : "memory");
+                    (void)src; (void)bytes;
+#else
                     mbar_expect_tx(bar_full(slot), bytes);
                     bulk_g2s(s_ring + slot * (uint32_t)O::TAP_BYTES, src, bytes, bar_full(slot));
+#endif
                     ++q_prod;
                 }
             }
@@ -354,6 +400,7 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             mbar_wait(bar_acc, acc_par);
             acc_par ^= 1u;
             tc_fence_after();
+            PF(4);  // waiting for the accumulators
             // ---- epilogue: this thread owns one cell (TMEM lane) of accumulator(s) warp/4 (+2)
             const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
             const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
@@ -418,6 +465,7 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             if (preload) tmem_wait_st();
             fence_proxy_async();
             q0 += 9u;
+            PF(5);  // epilogue
         }
         // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
         __syncthreads();
@@ -447,7 +495,13 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             acc = warp_sum(acc);
             if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
         }
+        PF(6);  // heads
     }
+#ifdef ONB_NET_PROFILE
+    if (blockIdx.x == 3 && (tid == 0 || tid == 64))
+        printf("net profile tid %d groups %lld: input %lld barrier %lld weights %lld issue %lld acc %lld epilogue %lld heads %lld\n", tid,
+               (long long)my_groups, pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6]);
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
@@ -465,11 +519,17 @@ template <bool F16>
 struct Geo2 {
     static constexpr int NB = 7;  // boards per half
     static constexpr int CELLS = NB * kCellsPerBoard;
-    static constexpr int R = kLead + CELLS + kTrail;
-    static constexpr int NSLOT = F16 ? 16 : 5;
+    static constexpr int R = (kLead + CELLS + kTrail + 7) / 8 * 8;
+    // ring granularity: f16 keeps two WHOLE LAYERS (9 taps, 72 KB each) -- one full/empty barrier round trip and one bulk copy per layer
+    // instead of per tap (the per-tap try_wait + fence + commit cost ~480 cycles, more than the 8 MMAs between them); tf32 taps are
+    // twice as large, so that variant keeps a 5-slot ring of single taps
+    static constexpr int TPS = F16 ? 9 : 1;   // taps per slot
+    static constexpr int UPL = 9 / TPS;       // slots ("units") per layer
+    static constexpr int NSLOT = F16 ? 2 : 5;
+    static constexpr int SLOT_BYTES = TPS * Op<F16>::TAP_BYTES;
     static constexpr int ACT_BYTES = R * Op<F16>::KCH * 16;  // per half
     static constexpr int OFF_RING = 2 * ACT_BYTES;
-    static constexpr int RING_BYTES = NSLOT * Op<F16>::TAP_BYTES;
+    static constexpr int RING_BYTES = NSLOT * SLOT_BYTES;
     static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
     static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;  // per half
     static constexpr int OFF_BAR = OFF_HEAD + 2 * HEAD_BYTES;
@@ -496,7 +556,8 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
     const int64_t n_pairs = (n_groups + 1) / 2;
     if ((int64_t)blockIdx.x >= n_pairs) return;
     const int64_t my_iters = (n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const uint32_t total_taps = (uint32_t)my_iters * 9u * (uint32_t)L;
+    constexpr int TPS = G::TPS, UPL = G::UPL;
+    const uint32_t total_units = (uint32_t)my_iters * (uint32_t)(UPL * L);
     auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
     auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
 
@@ -519,15 +580,15 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
     if (warp == 16) {
         // ---- weight producer (one lane): the ring is filled strictly in tap order, as far ahead as it has free slots
         if (lane == 0) {
-            for (uint32_t q = 0; q < total_taps; ++q) {
-                const uint32_t slot = q % NSLOT, use = q / NSLOT;
+            for (uint32_t u = 0; u < total_units; ++u) {
+                const uint32_t slot = u % NSLOT, use = u / NSLOT;
                 if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
-                const uint32_t ql = q % (9u * (uint32_t)L), layer = ql / 9u, tap = ql - layer * 9u;
+                const uint32_t ul = u % (uint32_t)(UPL * L), layer = ul / UPL, tap = (ul - layer * UPL) * TPS;
                 const uint8_t* src = net.wconv + (layer == 0 ? (size_t)tap * O::TAP_BYTES0
                                                               : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
-                const uint32_t bytes = layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES;
+                const uint32_t bytes = (uint32_t)TPS * (layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES);
                 mbar_expect_tx(bar_full(slot), bytes);
-                bulk_g2s(s_ring + slot * (uint32_t)O::TAP_BYTES, src, bytes, bar_full(slot));
+                bulk_g2s(s_ring + slot * (uint32_t)G::SLOT_BYTES, src, bytes, bar_full(slot));
             }
         }
         return;  // the workers only use named barriers from here on
@@ -540,6 +601,9 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
     const uint32_t tmem = *s_tmem + (uint32_t)half * 256u;
     const uint32_t bar_id = 1u + (uint32_t)half;
 
+#ifdef ONB_NET_PROFILE
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
+#endif
     uint32_t q0 = 0, acc_par = 0;
     for (int64_t gi = 0; gi < my_iters; ++gi) {
         const int64_t board0 = (((int64_t)blockIdx.x + gi * gridDim.x) * 2 + half) * NB;
@@ -553,66 +617,58 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
                 float x[32];  // the planes are 0 / 1: exact in either operand format
 #pragma unroll
                 for (int ch = 0; ch < 32; ++ch) x[ch] = (ch < kInPlanes && gb < n) ? __ldg(src + ch * 25) : 0.f;
-                if (F16) {
-                    store_channels<F16>(s_act, R, kLead + cell, 0, x);
-                } else {
-#pragma unroll
-                    for (int kc = 0; kc < O::KCH0; ++kc)
-                        st_shared_v4(s_act + (uint32_t)(kc * R + kLead + cell) * 16u, to_tf32(x[4 * kc]), to_tf32(x[4 * kc + 1]),
-                                     to_tf32(x[4 * kc + 2]), to_tf32(x[4 * kc + 3]));
-                }
+                store_channels<F16>(s_act, R, kLead + cell, 0, x);  // 32 channels: planes 21..31 are zero
             }
         }
         fence_proxy_async();
+        PF(0);
         for (int l = 0; l < L; ++l) {
             tc_fence_before();
             named_bar_sync(bar_id, 256);
             tc_fence_after();
+            PF(1);
             const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
             const bool last = l == L - 1;
-            if (htid == 0) {
-                // ---- MMA issue: 9 taps x K steps x 2 accumulators; descriptor low words in 16-byte units
+            if (hwarp == 0) {
+                // ---- MMA issue: 9 taps x K steps x 2 accumulators (the whole warp runs the loop, one lane issues)
+                const bool elected = elect_one();
                 const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
-                const uint32_t a_base = ((s_act >> 4) + (uint32_t)kLead) | ((uint32_t)R << 16);
-                auto issue_tap = [&](int t, int ksteps) {
-                    const uint32_t q = q0 + t, slot = q % NSLOT, use = q / NSLOT;
+                auto issue_unit = [&](int g, int ksteps) {
+                    const uint32_t u = q0 + g, slot = u % NSLOT, use = u / NSLOT;
                     mbar_wait(bar_full(slot), use & 1u);
                     tc_fence_after();
-                    const uint32_t a_t = a_base + (uint32_t)((t / 3 - 1) * 6 + (t % 3 - 1));
-                    const uint32_t b_t = ((s_ring + slot * (uint32_t)O::TAP_BYTES) >> 4) | (64u << 16);
+                    PF(2);
 #pragma unroll
-                    for (int j = 0; j < O::KCH / 2; ++j) {
-                        if (j < ksteps) {
-#ifndef ONB_NET_DBG_NOMMA
-#pragma unroll
-                            for (int a = 0; a < NACC; ++a)
-                                mma_ss<F16>(dcol + a * 64, a_t + (uint32_t)(j * 2 * R + a * 128), b_t + (uint32_t)j * 128u,
-                                            (use_s || t > 0 || j > 0) ? 1u : 0u);
-#endif
-                        }
+                    for (int tt = 0; tt < TPS; ++tt) {
+                        const int t = g * TPS + tt;
+                        issue_tap_mmas<F16, NACC>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
+                                                  s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * O::TAP_BYTES, ksteps, use_s || t > 0);
                     }
-                    umma_commit(bar_empty(slot));
+                    PF(3);
+                    if (elected) umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
+                    PF(7);
                 };
                 if (l == 0) {
 #pragma unroll 1
-                    for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH0 / 2);
+                    for (int g = 0; g < UPL; ++g) issue_unit(g, O::KCH0 / 2);
                 } else {
 #pragma unroll 1
-                    for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH / 2);
+                    for (int g = 0; g < UPL; ++g) issue_unit(g, O::KCH / 2);
                 }
-                umma_commit(bar_acc);
+                if (elected) umma_commit(bar_acc);
             }
             __syncwarp();
             mbar_wait(bar_acc, acc_par);
             acc_par ^= 1u;
             tc_fence_after();
+            PF(4);
             // ---- epilogue: this thread owns one cell (TMEM lane) of accumulator hwarp / 4
             const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
             const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
             const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
             const float4* hw = reinterpret_cast<const float4*>(net.head);
 #ifdef ONB_NET_DBG_NOEPI
-            if (!last) { fence_proxy_async(); q0 += 9u; continue; }
+            if (!last) { fence_proxy_async(); q0 += (uint32_t)UPL; continue; }
 #endif
             {
                 const int a = hwarp >> 2;
@@ -668,7 +724,8 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
             }
             if (preload) tmem_wait_st();
             fence_proxy_async();
-            q0 += 9u;
+            q0 += (uint32_t)UPL;
+            PF(5);
         }
         // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
         named_bar_sync(bar_id, 256);
@@ -678,7 +735,8 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
             const float* hb = s_head + b * 75;
             const bool two = lane + 32 < 50;
             float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
-            for (int i = 0; i < 50; ++i) {
+#pragma unroll 10
+            for (int i = 0; i < 50; ++i) {  // unrolled: ten independent weight loads in flight instead of one
                 const float x = hb[i];
                 l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
                 if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
@@ -689,6 +747,7 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
             policy[gb * 50 + lane] = e0 / s;
             if (two) policy[gb * 50 + 32 + lane] = e1 / s;
             float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+#pragma unroll 5
             for (int i = 0; i < 25; ++i) {
                 const float x = hb[50 + i];
                 h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
@@ -698,7 +757,13 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
             acc = warp_sum(acc);
             if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
         }
+        PF(6);
     }
+#ifdef ONB_NET_PROFILE
+    if (blockIdx.x == 3 && (htid == 0 || htid == 64))
+        printf("net2 profile tid %d iters %lld: input %lld barrier %lld weights %lld issue %lld commit %lld acc %lld epilogue %lld heads %lld\n", tid,
+               (long long)my_iters, pf[0], pf[1], pf[2], pf[3], pf[7], pf[4], pf[5], pf[6]);
+#endif
     tc_fence_before();
     named_bar_sync(3, 512);  // both halves are done with TMEM
     if (warp == 0) tmem_dealloc(*s_tmem, 512);
@@ -799,16 +864,17 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
         }
         BnFold f;
         if (!fold_bn(ts, conv, bn, kHid, eps, f, err)) return ONB_E_INVALID;
-        const int chunks = l == 0 ? kch0 : kch;
+        const int chunks = l == 0 ? 8 : kch;  // the first layer fills one whole 128-byte block (channels beyond 21 are zero)
+        (void)kch0;
         uint8_t* dst = wconv.data() + (l == 0 ? 0 : 9 * tap_bytes0 + (size_t)(l - 1) * 9 * tap_bytes);
         const size_t tb = l == 0 ? tap_bytes0 : tap_bytes;
         for (int tap = 0; tap < 9; ++tap)
             for (int kc = 0; kc < chunks; ++kc)
                 for (int co = 0; co < kHid; ++co)
-                    for (int e = 0; e < cpc; ++e) {  // operand layout: [tap][chunk][co][16 bytes of consecutive input channels]
+                    for (int e = 0; e < cpc; ++e) {  // operand layout: [tap][128-byte block][co][chunk ^ (co & 7)][16 bytes of input channels]
                         const int ci = kc * cpc + e;
                         const float x = ci < c_in ? (float)((double)w->data[((size_t)co * c_in + ci) * 9 + tap] * f.scale[co]) : 0.f;
-                        uint8_t* q = dst + tap * tb + ((size_t)kc * 64 + co) * 16;
+                        uint8_t* q = dst + tap * tb + (size_t)(kc >> 3) * 64 * 128 + (size_t)co * 128 + (size_t)(((kc & 7) ^ (co & 7)) << 4);
                         if (f16) {
                             const __half hv = __float2half_rn(x);
                             memcpy(q + e * 2, &hv, 2);

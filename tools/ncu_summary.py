@@ -12,7 +12,9 @@ KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'smsp__pcsamp_warps_issue_stalled_wait', 'smsp__pcsamp_warps_issue_stalled_math_pipe_throttle',
         'smsp__pcsamp_warps_issue_stalled_not_selected', 'smsp__pcsamp_warps_issue_stalled_selected', 'smsp__pcsamp_warps_issue_stalled_barrier',
         'smsp__pcsamp_warps_issue_stalled_lg_throttle', 'smsp__pcsamp_warps_issue_stalled_branch_resolving',
-        'smsp__pcsamp_warps_issue_stalled_mio_throttle', 'smsp__pcsamp_warps_issue_stalled_no_instructions']
+        'smsp__pcsamp_warps_issue_stalled_mio_throttle', 'smsp__pcsamp_warps_issue_stalled_no_instructions',
+        'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_uniform.sum', 'l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed', 'launch__shared_mem_per_block_dynamic', 'lts__t_bytes.sum', 'launch__occupancy_limit_blocks', 'sm__ctas_launched.sum']
 raw = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
