@@ -63,10 +63,15 @@ struct Geo {
     static constexpr int R = (kLead + CELLS + kTrail + 7) / 8 * 8;  // rows of the activation matrix (whole swizzle periods)
     // weight ring slots (one tap each). f16: a whole layer (9 taps) so that the producer runs one layer ahead -- with 4 slots the
     // MMA thread spent most of its time waiting for weights (L2 -> shared latency of ~1.5k cycles per 8 KB tap vs 256 cycles of MMAs)
-    static constexpr int NSLOT = F16 ? 9 : (NACC == 2 ? 3 : 4);
+    static constexpr int NSLOT = F16 ? 3 : (NACC == 2 ? 3 : 4);
+    // taps per ring slot: one full/empty barrier round trip and one bulk copy per slot. f16: 3 slots x 3 taps = one layer in flight
+    // (per-tap slots cost a try_wait + fence + commit for every 8 MMAs); tf32 taps are twice as large: single taps
+    static constexpr int TPS = F16 ? 3 : 1;
+    static constexpr int UPL = 9 / TPS;  // slots per layer
+    static constexpr int SLOT_BYTES = TPS * Op<F16>::TAP_BYTES;
     static constexpr int ACT_BYTES = R * Op<F16>::KCH * 16;  // a multiple of 1024: the ring stays aligned to the swizzle period
     static constexpr int OFF_RING = ACT_BYTES;
-    static constexpr int RING_BYTES = NSLOT * Op<F16>::TAP_BYTES;
+    static constexpr int RING_BYTES = NSLOT * SLOT_BYTES;
     static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
     static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;
     static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
@@ -302,7 +307,8 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
     const int64_t n_groups = (n + NB - 1) / NB;
     if ((int64_t)blockIdx.x >= n_groups) return;  // whole CTA, before any allocation
     const int64_t my_groups = (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const uint32_t total_taps = (uint32_t)my_groups * 9u * (uint32_t)L;
+    constexpr int TPS = G::TPS, UPL = G::UPL;
+    const uint32_t total_units = (uint32_t)my_groups * (uint32_t)(UPL * L);
     auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
     auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
     const uint32_t bar_acc = s_bar + 2 * NSLOT * 8u;
@@ -358,40 +364,44 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                 // ---- MMA issue: 9 taps x K steps x NACC accumulators (the whole warp runs the loop, one lane issues)
                 const bool elected = elect_one();
                                 const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
-                auto issue_tap = [&](int t, int ksteps) {
-                    const uint32_t q = q0 + t, slot = q % NSLOT, use = q / NSLOT;
+                auto issue_unit = [&](int g, int ksteps) {
+                    const uint32_t u = q0 + g, slot = u % NSLOT, use = u / NSLOT;
                     mbar_wait(bar_full(slot), use & 1u);
                     tc_fence_after();
                     PF(2);  // waiting for weights
-                    issue_tap_mmas<F16, NACC>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
-                                              s_ring + slot * (uint32_t)O::TAP_BYTES, ksteps, use_s || t > 0);
+#pragma unroll
+                    for (int tt = 0; tt < TPS; ++tt) {
+                        const int t = g * TPS + tt;
+                        issue_tap_mmas<F16, NACC>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
+                                                  s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * O::TAP_BYTES, ksteps, use_s || t > 0);
+                    }
                     if (elected) umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
                     PF(3);  // issuing MMAs
                 };
                 if (l == 0) {
 #pragma unroll 1
-                    for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH0 / 2);
+                    for (int g = 0; g < UPL; ++g) issue_unit(g, O::KCH0 / 2);
                 } else {
 #pragma unroll 1
-                    for (int t = 0; t < 9; ++t) issue_tap(t, O::KCH / 2);
+                    for (int g = 0; g < UPL; ++g) issue_unit(g, O::KCH / 2);
                 }
                 if (elected) umma_commit(bar_acc);
             } else if (tid == 32) {
                 // ---- weight producer: keeps the ring NSLOT taps ahead of the MMAs (weights do not depend on the data)
-                const uint32_t target = min(q0 + 9u + (uint32_t)NSLOT, total_taps);
+                const uint32_t target = min(q0 + (uint32_t)(UPL + NSLOT), total_units);
                 while (q_prod < target) {
                     const uint32_t slot = q_prod % NSLOT, use = q_prod / NSLOT;
                     if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
-                    const uint32_t ql = q_prod % (9u * (uint32_t)L), layer = ql / 9u, tap = ql - layer * 9u;
+                    const uint32_t ul = q_prod % (uint32_t)(UPL * L), layer = ul / UPL, tap = (ul - layer * UPL) * TPS;
                     const uint8_t* src = net.wconv + (layer == 0 ? (size_t)tap * O::TAP_BYTES0
                                                                   : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
-                    const uint32_t bytes = layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES;
+                    const uint32_t bytes = (uint32_t)TPS * (layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES);
 #ifdef ONB_NET_DBG_NOWEIGHTS
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full(slot)) : "memory");
                     (void)src; (void)bytes;
 #else
                     mbar_expect_tx(bar_full(slot), bytes);
-                    bulk_g2s(s_ring + slot * (uint32_t)O::TAP_BYTES, src, bytes, bar_full(slot));
+                    bulk_g2s(s_ring + slot * (uint32_t)G::SLOT_BYTES, src, bytes, bar_full(slot));
 #endif
                     ++q_prod;
                 }
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
             const float4* hw = reinterpret_cast<const float4*>(net.head);
 #ifdef ONB_NET_DBG_NOEPI
-            if (l >= 0 && !last) { fence_proxy_async(); q0 += 9u; continue; }
+            if (l >= 0 && !last) { fence_proxy_async(); q0 += (uint32_t)UPL; continue; }
 #endif
 #pragma unroll
             for (int ai = 0; ai < NACC / 2; ++ai) {
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             }
             if (preload) tmem_wait_st();
             fence_proxy_async();
-            q0 += 9u;
+            q0 += (uint32_t)UPL;
             PF(5);  // epilogue
         }
         // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
