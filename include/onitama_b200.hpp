@@ -127,6 +127,20 @@ public:
     Engine& operator=(const Engine&) = delete;
     onb_ctx* ctx() const { return ctx_; }
     int64_t n() const { return n_; }
+    /// Hands the network to the library (the VarStore of train.rs as (name, values) pairs, names as in net.rs:118-213 with '|'
+    /// or '.' separators); agents with device_evaluator = ONB_EVAL_NET then search without a host evaluator in the loop.
+    void load_network(const std::vector<std::pair<std::string, std::vector<float>>>& var_store, bool tf32 = false) {
+        std::vector<const char*> names;
+        std::vector<const float*> data;
+        std::vector<int64_t> numel;
+        for (const auto& kv : var_store) {
+            names.push_back(kv.first.c_str());
+            data.push_back(kv.second.data());
+            numel.push_back((int64_t)kv.second.size());
+        }
+        check(onb_net_precision(ctx_, tf32 ? ONB_NET_TF32 : ONB_NET_F16));
+        check(onb_net_load(ctx_, (int32_t)names.size(), names.data(), data.data(), numel.data()));
+    }
     void check(int32_t rc) const { if (rc != ONB_OK) throw Error(rc, onb_last_error(ctx_)); }
     /// one-game engine shared by the single-state methods of State / the agents (thread local: a context is single threaded)
     static Engine& single(uint32_t min_sims = 0) {

@@ -147,6 +147,68 @@ static void search_and_drivers() {
     CHECK(threw);
 }
 
+// A ConvResNetConfig{64, 21, 1} VarStore with deterministic pseudo-random values (names of net.rs:118-213)
+static std::vector<std::pair<std::string, std::vector<float>>> fake_var_store() {
+    std::vector<std::pair<std::string, std::vector<float>>> vs;
+    uint32_t rng = 12345u;
+    auto uni = [&]() { rng = rng * 1664525u + 1013904223u; return (float)((rng >> 8) & 0xFFFF) / 65536.f - 0.5f; };
+    auto add = [&](const std::string& name, size_t n, float scale, float offset) {
+        std::vector<float> v(n);
+        for (float& x : v) x = uni() * scale + offset;
+        vs.emplace_back(name, std::move(v));
+    };
+    auto conv_bn = [&](const std::string& conv, const std::string& bn, size_t c_out, size_t c_in, size_t k) {
+        add(conv + "|weight", c_out * c_in * k * k, 2.8f / std::sqrt((float)(c_in * k * k)), 0.f);
+        add(conv + "|bias", c_out, 0.2f, 0.f);
+        add(bn + "|weight", c_out, 0.4f, 1.f);
+        add(bn + "|bias", c_out, 0.4f, 0.1f);
+        add(bn + "|running_mean", c_out, 0.4f, 0.f);
+        add(bn + "|running_var", c_out, 0.8f, 1.f);
+    };
+    conv_bn("conv_init_1", "bn1", 64, 21, 3);
+    conv_bn("resnet_0|resnet_small_block1|small_block_conv", "resnet_0|resnet_small_block1|small_block_bn", 64, 64, 3);
+    conv_bn("resnet_0|resnet_small_block2|small_block_conv", "resnet_0|resnet_small_block2|small_block_bn", 64, 64, 3);
+    conv_bn("vh_conv", "vh_bn", 1, 64, 1);
+    conv_bn("policy_conv", "policy_bn", 2, 64, 1);
+    add("vh_linear1|weight", 64 * 25, 0.8f, 0.f); add("vh_linear1|bias", 64, 0.6f, 0.f);
+    add("vh_linear2|weight", 64, 0.5f, 0.f); add("vh_linear2|bias", 1, 0.2f, 0.f);
+    add("ph_linear2|weight", 2500, 0.6f, 0.f); add("ph_linear2|bias", 50, 0.6f, 0.f);
+    return vs;
+}
+
+// TrainingAlphaZeroMcts::generate_move_tensor with the network inside the library (ONB_EVAL_NET) must build the same tree as the
+// split-phase search that gets the same network through the host-evaluator hook (here: the kernel on a second one-game engine).
+static void device_network_search() {
+    const auto vs = fake_var_store();
+    Engine::single(64).load_network(vs);
+    Engine side(1, 2, 0, 0, false);
+    side.load_network(vs);
+    HostEvaluator through_side = [&](const float* planes, int64_t n, float* policy, float* value) {
+        for (int64_t i = 0; i < n; ++i) {
+            side.check(onb_write_buffer(side.ctx(), ONB_BUF_LEAF_PLANES, planes + i * 525, 2100));
+            side.check(onb_net_forward(side.ctx(), ONB_BUF_LEAF_PLANES));
+            side.check(onb_read_buffer(side.ctx(), ONB_BUF_POLICY, policy + i * 50, 200));
+            side.check(onb_read_buffer(side.ctx(), ONB_BUF_VALUE, value + i, 4));
+        }
+    };
+    AlphaZeroMctsConfig cfg;
+    cfg.max_playouts = 48;
+    cfg.exploration_c = 2.0;
+    State s = State::with_deck(Deck({DRAGON, FROG, TIGER, RABBIT, HORSE}));
+    TrainingAlphaZeroMcts on_device{cfg, ONB_EVAL_NET, nullptr}, via_host{cfg, ONB_EVAL_UNIFORM, through_side};
+    auto a = on_device.generate_move_tensor(s, PlayerColor::Red);
+    auto b = via_host.generate_move_tensor(s, PlayerColor::Red);
+    CHECK(a.first.mov.from == b.first.mov.from && a.first.mov.to == b.first.mov.to && a.first.used_card_idx == b.first.used_card_idx);
+    float sum = 0.f;
+    bool same = true;
+    for (int i = 0; i < 50; ++i) { sum += a.second[i]; same = same && a.second[i] == b.second[i]; }
+    CHECK(same);
+    CHECK(std::fabs(sum - 1.f) < 1e-5f);
+    bool threw = false;  // a VarStore of the wrong width is rejected, not silently mis-read
+    try { auto bad = vs; bad[0].second.resize(10); side.load_network(bad); } catch (const Error&) { threw = true; }
+    CHECK(threw);
+}
+
 int main() {
     try {
         create_all_legal_moves_for_red_in_starting_position();
@@ -155,6 +217,7 @@ int main() {
         no_legal_moves();
         expand_order();
         search_and_drivers();
+        device_network_search();
     } catch (const Error& e) {
         std::printf("FAIL exception %d: %s\n", e.code, e.what());
         return 2;
