@@ -151,6 +151,33 @@ def cpu_mcts(n_trees, sims, threads):
     return n_trees * sims / dt, dt
 
 
+def cpu_selfplay(n_trees, sims):
+    """Config 5 the way the reference runs it: the oracle's PUCT arena with the PyTorch module on the CPU as evaluator, one
+    position per forward call (net.rs:217-219 unsqueezes to batch 1), playouts one after the other (mcts_arena.rs:75-102)."""
+    import time
+    import numpy as np
+    import torch
+    from onitama_alphazero_b200.net import ConvResNet
+    O = oracle()
+    torch.manual_seed(1234)
+    model = ConvResNet(64, 21, 3).eval()
+
+    @torch.no_grad()
+    def eval_one(planes525):
+        p, v = model(torch.from_numpy(np.asarray(planes525, dtype=np.float32)).reshape(1, 21, 5, 5))
+        return p.reshape(50).numpy(), float(v.reshape(()))
+
+    roots = cfg4_roots(O, n_trees, SEED)
+    t0 = time.perf_counter()
+    done = 0
+    for t in range(n_trees):
+        if roots["result"][t] == 0:
+            O.mcts_search(roots[t:t + 1], MCTS_C, sims, callback=eval_one)
+            done += sims
+    dt = time.perf_counter() - t0
+    return done / dt, dt, torch.get_num_threads()
+
+
 def all_deals():
     return [[a, b, c, d, e] for a in range(16) for b in range(a + 1, 16) for c in range(16) if c not in (a, b)
             for d in range(c + 1, 16) if d not in (a, b) for e in range(16) if e not in (a, b, c, d)]
@@ -620,10 +647,18 @@ def main():
         out = bench_playout(args.steps, args.warmup)
 
     secondary = None
+    third = None
     if wl == "env" and not args.no_secondary:
         m = bench_mcts(10, 3)
         secondary = {k: m[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches")}
         secondary["config"] = workload_config("mcts")
+        try:  # config 5 with the network on the tensor cores (one ply of 16 384 games x 800 simulations per step)
+            sp = bench_selfplay(2, 3)
+            third = {k: sp[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "network", "roofline", "e2e", "gpu_launches")}
+            third["config"] = workload_config("selfplay")
+            third["steps"], third["warmup"] = 2, 3
+        except Exception as exc:  # never lose the headline over the extra measurement
+            third = {"error": repr(exc)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -644,6 +679,11 @@ def main():
             v1, _ = cpu_mcts(512, MCTS_SIMS, 1)
             cpu_baseline = {"value": v, "unit": "sims/s", "cores": cores, "kind": "port", "single_core_value": v1,
                             "sample": "8192 trees x 400 sims, uniform evaluator (%.1f s wall, %d threads)" % (dt, cores)}
+        elif wl == "selfplay":
+            v, dt, th = cpu_selfplay(4, 100)
+            cpu_baseline = {"value": v, "unit": "sims/s", "cores": th, "kind": "port",
+                            "sample": "4 trees x 100 sims, oracle arena + the PyTorch module on the CPU, one position per forward call as in the "
+                                      "reference (%.1f s wall, %d torch threads)" % (dt, th)}
         elif wl == "perft":
             v, dt = cpu_perft(16 * cores, 5, cores)
             cpu_baseline = {"value": v, "unit": "nodes/s", "cores": cores, "kind": "port",
@@ -659,6 +699,8 @@ def main():
                 "gpu_launches": out["gpu_launches"], "clocks": out["clocks"], "impl": "ours"}
         if secondary is not None:
             line["mcts"] = secondary
+        if third is not None:
+            line["selfplay"] = third
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

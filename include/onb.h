@@ -244,7 +244,9 @@ ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t
  * rounded to an 11-bit significand: ONB_NET_F16 (default) or ONB_NET_TF32, the latter being what libtorch's cuDNN
  * convolutions compute by default on this GPU; heads in f32). This is the evaluator the search would otherwise get
  * from tch as a black box; with it a whole search needs no host round trip.
- * onb_net_precision selects the operand format used by the NEXT onb_net_load.
+ * onb_net_precision selects the operand format used by the NEXT onb_net_load. Two networks can be resident (slots 0 and 1,
+ * slot 0 initially): onb_net_select chooses the one that onb_net_load fills and onb_net_forward / ONB_EVAL_NET evaluate, so
+ * an arena (evaluator.rs:355-399: the new model against the previous one) alternates between them without re-uploading.
  * onb_net_load takes the parameters under the reference's VarStore names (net.rs:118-213, `|` or `.` separators),
  * e.g. "conv_init_1|weight", "bn1|running_var", "resnet_0|resnet_small_block1|small_block_conv|weight",
  * "policy_conv|bias", "ph_linear2|weight", "vh_linear1|weight": host f32 arrays in libtorch layout (OIHW, [out][in]).
@@ -255,6 +257,7 @@ ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t
 #define ONB_NET_F16 0
 #define ONB_NET_TF32 1
 ONB_API int32_t onb_net_precision(onb_ctx* ctx, int32_t mode);
+ONB_API int32_t onb_net_select(onb_ctx* ctx, int32_t slot);
 ONB_API int32_t onb_net_load(onb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel);
 ONB_API int32_t onb_net_forward(onb_ctx* ctx, int32_t planes_buffer);
 

@@ -76,6 +76,7 @@ SYMBOLS = {
     "onb_mcts_tree_info": (C.c_int32, [_P, _P, _P]),
     "onb_selftest": (C.c_int32, [_P, C.c_int32, _P]),
     "onb_net_precision": (C.c_int32, [_P, C.c_int32]),
+    "onb_net_select": (C.c_int32, [_P, C.c_int32]),
     "onb_net_load": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
     "onb_net_forward": (C.c_int32, [_P, C.c_int32]),
 }

@@ -129,7 +129,8 @@ int32_t onb_destroy(onb_ctx* ctx) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_states, c->d_masks, c->d_planes, c->d_actions, c->d_stats, c->d_io_states, c->d_moves, c->d_counts, c->d_nodes,
                     c->d_tree_size, c->d_tree_flags, c->d_roots, c->d_leaf_node, c->d_leaf_state, c->d_leaf_planes, c->d_policy, c->d_value,
-                    c->d_pi, c->d_best, c->d_root_visits, c->d_root_q, c->d_child_visits, c->d_net_w, c->d_net_bias, c->d_net_head};
+                    c->d_pi, c->d_best, c->d_root_visits, c->d_root_q, c->d_child_visits, c->net[0].w, c->net[0].bias, c->net[0].head, c->net[1].w,
+                    c->net[1].bias, c->net[1].head};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->scratch)
@@ -441,7 +442,7 @@ int32_t onb_mcts_eval(onb_ctx* ctx, int32_t evaluator) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (c->mcts_phase != 2) return fail(c, ONB_E_STATE, "onb_mcts_eval: no leaves selected");
     if (evaluator == ONB_EVAL_NET) {
-        if (!c->net_loaded) return fail(c, ONB_E_STATE, "onb_mcts_eval: no network loaded (onb_net_load)");
+        if (!c->net[c->net_cur].loaded) return fail(c, ONB_E_STATE, "onb_mcts_eval: no network loaded (onb_net_load)");
         ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value));
         return ONB_OK;
     }
@@ -467,7 +468,7 @@ int32_t onb_mcts_run(onb_ctx* ctx, int32_t evaluator, uint32_t sims) {
     if (c->sims_done + sims > c->cfg.mcts_max_sims) return fail(c, ONB_E_INVALID, "onb_mcts_run: more simulations than mcts_max_sims");
     if (evaluator == ONB_EVAL_NET) {
         // the network sits between select and expand: three launches per simulation round, all on the context's stream
-        if (!c->net_loaded) return fail(c, ONB_E_STATE, "onb_mcts_run: no network loaded (onb_net_load)");
+        if (!c->net[c->net_cur].loaded) return fail(c, ONB_E_STATE, "onb_mcts_run: no network loaded (onb_net_load)");
         for (uint32_t s = 0; s < sims; ++s) {
             ONB_CUDA(c, launch_mcts_select(c));
             ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value));
@@ -548,11 +549,17 @@ int32_t onb_net_precision(onb_ctx* ctx, int32_t mode) {
     c->net_tf32 = mode == ONB_NET_TF32;
     return ONB_OK;
 }
+int32_t onb_net_select(onb_ctx* ctx, int32_t slot) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (slot != 0 && slot != 1) return fail(c, ONB_E_INVALID, "onb_net_select: slot %d (two networks can be resident: 0, 1)", slot);
+    c->net_cur = slot;
+    return ONB_OK;
+}
 int32_t onb_net_load(onb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (n_tensors <= 0 || !names || !data || !numel) return fail(c, ONB_E_INVALID, "onb_net_load: null argument");
-    c->net_loaded = 0;
     std::string err;
     int32_t rc = ONB_E_INVALID;
     try {
@@ -562,13 +569,12 @@ int32_t onb_net_load(onb_ctx* ctx, int32_t n_tensors, const char* const* names, 
         rc = ONB_E_NOMEM;
     }
     if (rc != ONB_OK) return fail(c, rc, "onb_net_load: %s", err.c_str());
-    c->net_loaded = 1;
     return ONB_OK;
 }
 int32_t onb_net_forward(onb_ctx* ctx, int32_t planes_buffer) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!c->net_loaded) return fail(c, ONB_E_STATE, "onb_net_forward: no network loaded (onb_net_load)");
+    if (!c->net[c->net_cur].loaded) return fail(c, ONB_E_STATE, "onb_net_forward: no network loaded (onb_net_load)");
     const float* planes = planes_buffer == ONB_BUF_LEAF_PLANES ? c->d_leaf_planes : planes_buffer == ONB_BUF_PLANES ? c->d_planes : nullptr;
     if (planes_buffer != ONB_BUF_LEAF_PLANES && planes_buffer != ONB_BUF_PLANES) return fail(c, ONB_E_INVALID, "onb_net_forward: not a plane buffer");
     if (!planes || !c->d_policy) return fail(c, ONB_E_STATE, "onb_net_forward: plane or policy/value buffers were not allocated by onb_create");

@@ -66,13 +66,14 @@ struct Ctx {
     uint32_t sims_target, sims_done;
     int mcts_phase;  // 0 idle, 1 begun/after expand, 2 after select
     // policy/value network (onb_net.cu): weights in tensor-core operand layout, folded biases, head parameters
-    float* d_net_w;
-    float* d_net_bias;
-    float* d_net_head;
-    int net_blocks;
-    int net_loaded;
-    int net_tf32;  // requested operand format for the next onb_net_load: 0 = f16 (default), 1 = tf32
-    int net_f16;   // format of the loaded weights
+    struct NetSlot {
+        float* w;     // conv taps in operand layout
+        float* bias;  // folded biases
+        float* head;  // head parameters
+        int blocks, loaded, f16;
+    } net[2];         // two networks can be resident (an arena pits the new model against the previous one, evaluator.rs:355-399)
+    int net_cur;      // slot used by onb_net_load / onb_net_forward / ONB_EVAL_NET (onb_net_select)
+    int net_tf32;     // requested operand format for the next onb_net_load: 0 = f16 (default), 1 = tf32
     // grow-only device scratch reused across onb_perft calls (counters, cursor, two ping-pong frontiers): repeated
     // cudaMalloc/cudaFree of several hundred MB made the call time vary by +-50 %
     void* scratch[8];

@@ -924,25 +924,28 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
         }
         head[kV2B] = v2b->data[0];
     }
-    for (void** p : {(void**)&c->d_net_w, (void**)&c->d_net_bias, (void**)&c->d_net_head})
+    Ctx::NetSlot& ns = c->net[c->net_cur];
+    cudaStreamSynchronize(c->stream);  // a forward pass with the old weights may still be running
+    for (void** p : {(void**)&ns.w, (void**)&ns.bias, (void**)&ns.head})
         if (*p) {
             cudaFree(*p);
             *p = nullptr;
         }
-    c->net_blocks = -1;
-    cudaError_t e = cudaMalloc(&c->d_net_w, wconv.size());
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_net_bias, bias.size() * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_net_head, head.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_w, wconv.data(), wconv.size(), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_net_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    ns.loaded = 0;
+    cudaError_t e = cudaMalloc(&ns.w, wconv.size());
+    if (e == cudaSuccess) e = cudaMalloc(&ns.bias, bias.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ns.head, head.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ns.w, wconv.data(), wconv.size(), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ns.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ns.head, head.data(), head.size() * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
         err = std::string("CUDA: ") + cudaGetErrorString(e);
         return e == cudaErrorMemoryAllocation ? ONB_E_NOMEM : ONB_E_CUDA;
     }
-    c->net_blocks = n_blocks;
-    c->net_f16 = f16 ? 1 : 0;
+    ns.blocks = n_blocks;
+    ns.f16 = f16 ? 1 : 0;
+    ns.loaded = 1;
     return ONB_OK;
 }
 
@@ -975,15 +978,16 @@ static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, flo
 }
 
 cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value) {
-    const NetDev nd{reinterpret_cast<const uint8_t*>(c->d_net_w), c->d_net_bias, c->d_net_head, c->net_blocks};
+    const Ctx::NetSlot& ns = c->net[c->net_cur];
+    const NetDev nd{reinterpret_cast<const uint8_t*>(ns.w), ns.bias, ns.head, ns.blocks};
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)
-    if (v2 && v2[0] == '1') return c->net_f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms) : launch_net_v2<false>(c, planes, policy, value, nd, sms);
+    if (v2 && v2[0] == '1') return ns.f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms) : launch_net_v2<false>(c, planes, policy, value, nd, sms);
     const char* wide = getenv("ONB_NET_WIDE");  // exploration knob: 14 boards per CTA, one CTA per SM
     const bool w = wide && wide[0] == '1';
-    if (c->net_f16) return w ? launch_net_variant<4, true>(c, planes, policy, value, nd, sms) : launch_net_variant<2, true>(c, planes, policy, value, nd, sms);
+    if (ns.f16) return w ? launch_net_variant<4, true>(c, planes, policy, value, nd, sms) : launch_net_variant<2, true>(c, planes, policy, value, nd, sms);
     return w ? launch_net_variant<4, false>(c, planes, policy, value, nd, sms) : launch_net_variant<2, false>(c, planes, policy, value, nd, sms);
 }
 

@@ -211,6 +211,10 @@ class Context:
     def mcts_play_best(self, out_flags=0):
         self._ck(self._lib.onb_mcts_play_best(self._h, out_flags))
 
+    def net_select(self, slot):
+        """onb_net_select: which of the two resident networks net_load fills and net_forward / EVAL_NET evaluate"""
+        self._ck(self._lib.onb_net_select(self._h, slot))
+
     def net_load(self, params, tf32=False):
         """onb_net_load: params = a torch module / state_dict / dict name -> array with the reference's VarStore names
         (net.rs:118-213; '.' or '|' separators). Folds BatchNorm, lays the weights out for the tensor cores, uploads them.

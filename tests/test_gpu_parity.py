@@ -999,3 +999,45 @@ def test_selfplay_with_fused_network(onb):
     assert 0 < m <= n * 10   # train.rs:74-79: the ply cap is checked after the move, so max_plies + 2 plies are played
     assert torch.allclose(out["pi"].sum(dim=(1, 2)), torch.ones(m, device=out["pi"].device), atol=1e-5)
     assert set(out["z"].unique().tolist()) <= {-1.0, 0.0, 1.0}
+
+
+@pytest.mark.gpu
+def test_arena_between_two_resident_networks(onb):
+    """fight() (evaluator.rs:355-399) with both agents searching through their own network on the tensor cores: the two models stay
+    resident in slots 0 / 1 (onb_net_select). Checks the slot plumbing (slot 1 really evaluates the second model) and that the
+    arena result is reproducible and self-consistent; colours alternate between games."""
+    from test_net_cpu import lively_model
+    n, sims, c = 48, 16, 2.0
+    model_a, model_b = lively_model(1, seed=5), lively_model(3, seed=6)
+    a_is_red = (np.arange(n) % 2) == 0
+    g = _positions(32, 3)
+    planes = O.encode(g).reshape(32, 21, 5, 5)
+    with onb.Context(n, seed=12, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.net_select(0); ctx.net_load(model_a)
+        ctx.net_select(1); ctx.net_load(model_b)
+        for slot, model in ((0, model_a), (1, model_b), (0, model_a)):
+            ctx.net_select(slot)
+            ctx.write(onb.BUF_LEAF_PLANES, planes)
+            ctx.net_forward(onb.BUF_LEAF_PLANES)
+            want_p, want_v = O.net_forward(model.state_dict(), planes)
+            assert np.abs(ctx.read(onb.BUF_POLICY, np.float32, (n, 50))[:32] - want_p).max() <= 6e-3
+            assert np.abs(ctx.read(onb.BUF_VALUE, np.float32, (n,))[:32] - want_v).max() <= 2.5e-2
+        with pytest.raises(onb.OnbError):
+            ctx.net_select(2)
+
+        def agent(slot):
+            def move(cx):
+                cx.net_select(slot)
+                cx.search_device(c, sims, evaluator=onb.EVAL_NET)
+                cx.tensor(onb.BUF_ACTIONS).copy_(cx.tensor(onb.BUF_BEST))
+            return move
+
+        results = []
+        for _ in range(2):
+            ctx.reset()
+            results.append(onb.fight(ctx, agent(0), agent(1), a_is_red, max_plies=40) + (ctx.get_states().tobytes(),))
+    assert results[0] == results[1]                      # deterministic
+    a, b, d = results[0][:3]
+    assert a + b + d == n
+    st = onb.fight_statistics(np.frombuffer(results[0][3], dtype=onb.STATE_DTYPE)["result"], a_is_red)
+    assert st.general == dict(wins=a, loses=b, draws=d)
