@@ -313,6 +313,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner goes to stdout otherwise: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     import onitama_alphazero_b200 as onb
