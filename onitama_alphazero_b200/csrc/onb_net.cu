@@ -1,5 +1,5 @@
 // onb_net.cu -- the policy/value network of the search (ConvResNet, alphazero-training/src/net.rs:118-232) as ONE fused
-// kernel on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, weights streamed by bulk TMA).
+// kernel on the 5th-generation tensor cores (tcgen05.mma kind::f16 / kind::tf32, accumulators in TMEM, weights streamed by bulk TMA).
 //
 // What the reference computes per position (net.rs:215-232, restated in onitama_alphazero_b200/net.py):
 //   y = relu(bn1(conv3x3(x)))                                  21 -> 64 channels on the 5x5 board
@@ -11,16 +11,17 @@
 // Boards are laid out as a continuous sequence of CELLS, 36 per board: one row of 6 zero cells, then 5 rows of (5 squares + 1 zero
 // cell). Every out-of-board neighbour of a square is then one of those zero cells (of this board or the next), so a tap is nothing
 // but a ROW SHIFT of the activation matrix by dy*6+dx cells. The activations live in shared memory in the tensor core's K-major
-// no-swizzle layout with all rows 16 bytes apart (core matrices of 8 rows x 16 B back to back, one 16-byte channel chunk after the
-// other): a shifted window is just a different start address in the shared-memory descriptor -- no im2col copy is ever made.
+// operand layout, one 128-byte swizzled row per cell: a shifted window is just a different start address in the shared-memory
+// descriptor -- no im2col copy is ever made.
 // One CTA keeps NB boards (NACC accumulators of 128 cells x 64 channels in TMEM) on chip through ALL layers; only the input planes
 // are read from and only policy/value are written to global memory. The residual input of a block is parked in TMEM (pre-loaded
 // into the accumulator of the block's second convolution together with that layer's bias), so the skip connection costs nothing.
-// Weights (tf32-rounded, BN folded, already in the operand layout) are streamed tap by tap through a small ring by one producer
-// thread with cp.async.bulk + mbarriers; one thread issues the MMAs; all 8 warps run the epilogues (TMEM -> bias/ReLU -> tf32 ->
-// shared memory). Arithmetic: f32 accumulation of products of operands rounded to an 11-bit significand -- either tf32 (what
-// libtorch's cuDNN convolutions use by default on this GPU) or f16 (same significand, half the shared-memory bytes per MMA, twice
-// the tensor rate; the kernel is bound by the shared-memory reads of the MMA operands, so this is the default). Heads in f32.
+// Weights (rounded, BN folded, already in the swizzled operand layout) are streamed through a small ring by one producer thread
+// with cp.async.bulk + mbarriers; warp 0 runs the MMA issue loop (one elected lane issues); all 8 warps run the epilogues (TMEM ->
+// bias/ReLU -> operand format -> shared memory). Arithmetic: f32 accumulation of products of operands rounded to an 11-bit
+// significand -- either f16 (default) or tf32 (what libtorch's cuDNN convolutions use by default on this GPU; same significand,
+// twice the shared-memory bytes per MMA and half the tensor rate; the kernel is bound by the operand reads). Heads in f32.
+// Measurements, the variants that were tried and the phase timings are in DESIGN.md section 5b.
 #include <cuda_fp16.h>
 
 #include <cmath>
@@ -46,9 +47,8 @@ struct Op {
     static constexpr int KCH = kHid / CPC;             // 8 | 16 chunks per 64 channels
     static constexpr int IN_PAD = F16 ? 32 : 24;       // input planes padded to a multiple of the MMA's K (16 | 8)
     static constexpr int KCH0 = IN_PAD / CPC;          // 4 | 6
-    static constexpr int KB = KCH / 8;                 // 1 | 2 blocks of 128 bytes (one swizzle row) per matrix row
     static constexpr int TAP_BYTES = KCH * 64 * 16;    // one tap of a 64 -> 64 layer: [KB][64 co][128 B], swizzled
-    static constexpr int TAP_BYTES0 = (F16 ? 1 : 1) * 64 * 128;  // first layer: its K (32 | 24) fits the first 128-byte block
+    static constexpr int TAP_BYTES0 = 64 * 128;        // first layer: its K (32 | 24 channels) fits the first 128-byte block
     // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, A/B format, both K-major, N = 64, M = 128
     static constexpr uint32_t IDESC = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 };
@@ -133,14 +133,6 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// shared-memory matrix descriptor, K-major, no swizzle: 8-row x 16-byte core matrices; `lbo` = byte distance between the two
-// 16-byte K chunks one MMA consumes, `sbo` = byte distance between consecutive 8-row groups (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
-           (1ull << 46);
-}
-// D[tmem] (+)= A[smem] * B[smem]^T. Descriptors are passed as (low word, high word): the high word (stride between 8-row groups,
-// version) is the same for every operand here and the low word (start address | chunk stride << 16) only needs an add per MMA.
 // Operand layout (both A and B): K-major, 128-byte swizzle. A matrix row is KB blocks of 128 bytes (64 f16 | 32 tf32 channels); block
 // kb of row r lives at base + kb * rows * 128 + r * 128 and its 16-byte chunk c sits at chunk position c ^ (r & 7) (base 1024-aligned).
 // Rows are therefore 128 bytes apart, so a window that starts at ANY row is 128-byte aligned: every 8-row x 32-byte operand fetch of
