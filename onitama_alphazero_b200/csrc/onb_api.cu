@@ -31,8 +31,10 @@ static int32_t cuda_fail(Ctx* c, cudaError_t e, const char* what) {
         cudaError_t e__ = (call);                           \
         if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); \
     } while (0)
-#define ONB_CHECK_CTX(ctx) \
-    if (!(ctx)) return ONB_E_INVALID
+// every entry point binds the context's device first: one host thread may drive contexts on several GPUs
+#define ONB_CHECK_CTX(ctx)                \
+    if (!(ctx)) return ONB_E_INVALID; \
+    cudaSetDevice(reinterpret_cast<const Ctx*>(ctx)->cfg.device)
 
 template <class T>
 static cudaError_t dalloc(T** p, size_t count) {

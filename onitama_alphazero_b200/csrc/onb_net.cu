@@ -944,11 +944,13 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
 template <int NACC, bool F16>
 static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
     using G = Geo<NACC, F16>;
-    static bool attr = false;  // one device per process (one process per GPU)
-    if (!attr) {
+    static bool attr[64] = {};  // the opt-in is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         const cudaError_t e = cudaFuncSetAttribute(k_net_forward<NACC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) return e;
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * (NACC == 2 ? 2 : 1);
     k_net_forward<NACC, F16><<<(unsigned)(groups < slots ? groups : slots), 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
@@ -958,11 +960,13 @@ static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy
 template <bool F16>
 static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
     using G = Geo2<F16>;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};  // the opt-in is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         const cudaError_t e = cudaFuncSetAttribute(k_net_forward2<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) return e;
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     const int64_t pairs = ((c->n + G::NB - 1) / G::NB + 1) / 2;
     k_net_forward2<F16><<<(unsigned)(pairs < sms ? pairs : sms), G::THREADS, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);

@@ -1041,3 +1041,35 @@ def test_arena_between_two_resident_networks(onb):
     assert a + b + d == n
     st = onb.fight_statistics(np.frombuffer(results[0][3], dtype=onb.STATE_DTYPE)["result"], a_is_red)
     assert st.general == dict(wins=a, loses=b, draws=d)
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process(onb):
+    """One host thread drives contexts on two GPUs (every entry point binds its context's device); results equal the oracle
+    and each other's shard. Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from test_net_cpu import lively_model
+    n, seed = 512, 23
+    model = lively_model(1)
+    with onb.Context(n, seed=seed, device=0, game_id_base=0, mcts_max_sims=32) as a, \
+            onb.Context(n, seed=seed, device=1, game_id_base=n, mcts_max_sims=32) as b:
+        a.reset(); b.reset()
+        a.net_load(model); b.net_load(model)
+        ref = O.new_games(2 * n, seed=seed)
+        for step in range(6):   # interleaved calls on the two devices
+            a.step_random(step, out_flags=onb.OUT_PLANES)
+            b.step_random(step, out_flags=onb.OUT_PLANES)
+            O.env_step_random(ref, seed, step)
+        assert a.get_states().tobytes() == ref[:n].tobytes() and b.get_states().tobytes() == ref[n:].tobytes()
+        ra = a.search(2.0, 32)
+        rb = b.search(2.0, 32)
+        want = O.mcts_search_batch(ref, 2.0, 32, threads=8)
+        live = ref["result"] == 0
+        got = np.concatenate([ra["child_visits"], rb["child_visits"]])
+        assert np.array_equal(got[live], want["child_visits"][live])
+        a.net_forward(onb.BUF_PLANES); b.net_forward(onb.BUF_PLANES)
+        pa, pb = a.read(onb.BUF_POLICY, np.float32, (n, 50)), b.read(onb.BUF_POLICY, np.float32, (n, 50))
+        want_p, _ = O.net_forward(model.state_dict(), O.encode(ref).reshape(-1, 21, 5, 5)[[0, 1, n, n + 1]])
+        assert np.abs(np.stack([pa[0], pa[1], pb[0], pb[1]]) - want_p).max() <= 6e-3
