@@ -947,3 +947,170 @@ int orc_net_forward(int32_t n_tensors, const char* const* names, const float* co
     return 0;
 }
 }  // extern "C"
+
+// ---- plain UCT search with random rollouts (onitama-game/src/ai/mcts/mcts_arena.rs:16-264, the `Mcts` agent of mcts/mod.rs) ----
+// f32 statistics as in the reference: reward sums of +-1 / 0 (exact), winrate = reward / visits, UCT = winrate + c * sqrt(ln(N_parent)
+// / n) with Iterator::max_by(total_cmp) (the LAST maximal child wins; unvisited children score +inf). A node is expanded only once
+// it has been visited more than min_node_visits times (:116-121); every playout ends with a uniformly random rollout from the leaf's
+// position (`simulate`, :190-241, including its pass rule). Project-defined: rand::thread_rng is replaced by the counter RNG -- draw
+// 16 + 2*ply (+1 for the pass slot) of step = playout index; rollouts are cut after 4096 plies (reward 0; the reference loops on);
+// zero-legal-move expansions get two pass pseudo-children as in the PUCT arena (the reference would panic in the next select).
+namespace orc {
+struct UctNode {
+    int64_t parent;
+    std::vector<uint32_t> children;
+    bool has_mov, is_pass;
+    DoneMove mov;
+    uint32_t visits;
+    float reward, winrate;
+    bool is_terminal, is_expanded;
+    int player_color;
+};
+struct UctArena {
+    State root_state;
+    int root_color;
+    uint32_t min_node_visits;
+    float exploration_c;
+    uint64_t seed, game;
+    std::vector<UctNode> arena;
+    uint32_t playouts = 0;
+    bool pass_seen = false;
+    uint64_t rollout_plies = 0;
+
+    static UctNode make_node(int64_t parent, bool has_mov, DoneMove mov, int color) {
+        UctNode n; n.parent = parent; n.has_mov = has_mov; n.is_pass = false; n.mov = mov; n.visits = 0; n.reward = 0.f; n.winrate = 0.f;
+        n.is_terminal = false; n.is_expanded = false; n.player_color = color;
+        return n;
+    }
+    UctArena(const State& s, int color, uint32_t min_visits, float c, uint64_t seed_, uint64_t game_)
+        : root_state(s), root_color(color), min_node_visits(min_visits), exploration_c(c), seed(seed_), game(game_) {
+        arena.push_back(make_node(-1, false, DoneMove{}, color));
+    }
+    static int32_t total_key32(float x) {  // f32::total_cmp as an integer key
+        int32_t b; memcpy(&b, &x, 4);
+        b ^= (int32_t)((uint32_t)(b >> 31) >> 1);
+        return b;
+    }
+    uint32_t select(const UctNode& parent) const {  // :137-160
+        const float lnp = std::log((float)parent.visits);
+        auto uct = [&](const UctNode& child) { return child.winrate + exploration_c * std::sqrt(lnp / (float)child.visits); };
+        uint32_t best = parent.children[0];
+        for (size_t i = 1; i < parent.children.size(); ++i)
+            if (total_key32(uct(arena[parent.children[i]])) >= total_key32(uct(arena[best]))) best = parent.children[i];
+        return best;
+    }
+    void expand(uint32_t parent, const State& st) {  // :167-187
+        const int color = arena[parent].player_color;
+        auto moves = st.generate_all_legal_moves(color);
+        for (auto& cm : moves) {
+            const uint32_t idx = (uint32_t)arena.size();
+            arena.push_back(make_node(parent, true, DoneMove{cm.second, cm.first}, enemy(color)));
+            arena[parent].children.push_back(idx);
+        }
+        if (moves.empty()) {
+            pass_seen = true;
+            const unsigned base = color == RED ? 0u : 2u;
+            for (unsigned s = 0; s < 2; ++s) {
+                const uint32_t idx = (uint32_t)arena.size();
+                UctNode n = make_node(parent, true, DoneMove{Move{0, 0, PAWN}, base + s}, enemy(color));
+                n.is_pass = true;
+                arena.push_back(n);
+                arena[parent].children.push_back(idx);
+            }
+        }
+        arena[parent].is_expanded = true;
+    }
+    float simulate(State st, int color, int reward_color, uint32_t playout) {  // :190-241
+        int move_result = st.current_state();
+        uint32_t ply = 0;
+        while (!is_win(move_result)) {
+            if (ply >= 4096u) return 0.f;
+            auto moves = st.generate_all_legal_moves(color);
+            if (moves.empty()) {
+                const unsigned base = color == RED ? 0u : 2u;
+                st.pass(base + rand_index(rand_u32(seed, game, playout, 16u + 2u * ply + 1u), 2));
+                color = enemy(color);
+                ++ply; ++rollout_plies;
+                continue;
+            }
+            auto& pick = moves[rand_index(rand_u32(seed, game, playout, 16u + 2u * ply), (uint32_t)moves.size())];
+            move_result = st.make_move(pick.second, color, pick.first);
+            color = enemy(color);
+            ++ply; ++rollout_plies;
+        }
+        return (float)reward_fn(move_result, reward_color);
+    }
+    void playout() {  // :87-131
+        State st = root_state;
+        int color = root_color;
+        uint32_t node_idx = 0;
+        while (arena[node_idx].is_expanded && !arena[node_idx].is_terminal) {
+            node_idx = select(arena[node_idx]);
+            const int64_t parent = arena[node_idx].parent;
+            const DoneMove& mv = arena[node_idx].mov;
+            const int r = arena[node_idx].is_pass ? st.pass(mv.used_card_idx) : st.make_move(mv.mov, arena[parent].player_color, mv.used_card_idx);
+            color = enemy(color);
+            if (is_win(r)) arena[node_idx].is_terminal = true;
+        }
+        if (!arena[node_idx].is_expanded && !arena[node_idx].is_terminal && arena[node_idx].visits > min_node_visits) expand(node_idx, st);
+        const int64_t parent = arena[node_idx].parent >= 0 ? arena[node_idx].parent : 0;
+        float reward = simulate(st, color, arena[parent].player_color, playouts);
+        int64_t n = node_idx;  // back_propagate, :243-254
+        for (;;) {
+            UctNode& nd = arena[n];
+            nd.visits += 1; nd.reward += reward; nd.winrate = nd.reward / (float)nd.visits;  // MctsNode::update, :300-304
+            if (nd.parent >= 0) { n = nd.parent; reward = -reward; } else break;
+        }
+    }
+    int64_t search(uint32_t max_playouts) {  // :55-84: the child with the most visits, last maximum wins (max_by_key)
+        while (playouts < max_playouts) { playout(); playouts += 1; }
+        const auto& ch = arena[0].children;
+        if (ch.empty()) return -1;
+        uint32_t best = ch[0];
+        for (size_t i = 1; i < ch.size(); ++i) if (arena[ch[i]].visits >= arena[best].visits) best = ch[i];
+        return best;
+    }
+};
+}  // namespace orc
+
+extern "C" {
+// One search per root (threads > 1: roots in parallel). Outputs per tree: best action (0xFFFF if the root was never expanded),
+// root child visits / reward sums (40 slots, zero padded), node count, winrate of the best child, pass flag.
+void orc_uct_search_batch(const orc_state* roots, int64_t n, float exploration_c, uint32_t min_node_visits, uint32_t sims, uint64_t seed,
+                          uint64_t game0, int threads, uint16_t* best_actions, uint32_t* child_visits40, int32_t* child_rewards40, int64_t* n_nodes,
+                          float* best_winrate, int32_t* pass_seen, uint64_t* rollout_plies) {
+    std::atomic<int64_t> next(0);
+    std::atomic<uint64_t> plies(0);
+    auto work = [&]() {
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            orc::UctArena a(orc::to_state(roots[i]), roots[i].side, min_node_visits, exploration_c, seed, game0 + (uint64_t)i);
+            const int64_t best = a.search(sims);
+            const auto& ch = a.arena[0].children;
+            if (best_actions) {
+                if (best < 0) best_actions[i] = 0xFFFF;
+                else {
+                    const orc::UctNode& b = a.arena[(size_t)best];
+                    best_actions[i] = b.is_pass ? orc::encode_pass(b.mov.used_card_idx) : orc::encode_action(b.mov.used_card_idx, b.mov.mov);
+                }
+            }
+            for (size_t k = 0; k < 40; ++k) {
+                if (child_visits40) child_visits40[i * 40 + k] = k < ch.size() ? a.arena[ch[k]].visits : 0u;
+                if (child_rewards40) child_rewards40[i * 40 + k] = k < ch.size() ? (int32_t)a.arena[ch[k]].reward : 0;
+            }
+            if (n_nodes) n_nodes[i] = (int64_t)a.arena.size();
+            if (best_winrate) best_winrate[i] = best < 0 ? 0.f : a.arena[(size_t)best].winrate;
+            if (pass_seen) pass_seen[i] = a.pass_seen ? 1 : 0;
+            plies.fetch_add(a.rollout_plies);
+        }
+    };
+    if (threads <= 1) work();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    if (rollout_plies) *rollout_plies = plies.load();
+}
+}  // extern "C"

@@ -62,6 +62,7 @@ def lib():
                                       C.c_void_p, C.c_int64]
         L.orc_hash_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_mcts_set_noise.argtypes = [C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint64]
+        L.orc_uct_search_batch.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int] + [C.c_void_p] * 7
         L.orc_net_forward.restype = C.c_int
         L.orc_net_forward.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_mcts_search_batch.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
@@ -216,6 +217,21 @@ def mcts_search_batch(roots, c_puct, sims, evaluator=0, threads=1):
 def mcts_set_noise(enabled, epsilon=0.25, alpha=0.03, seed=0, game0=0):
     """train-mode root noise for the searches that follow (tree i of a batch uses global tree id game0 + i)"""
     lib().orc_mcts_set_noise(int(bool(enabled)), epsilon, alpha, seed, game0)
+
+
+def uct_search_batch(roots, exploration_c, min_node_visits, sims, seed=0, game0=0, threads=1):
+    """Plain UCT with random rollouts (onitama-game/src/ai/mcts/mcts_arena.rs), one tree per root."""
+    n = len(roots)
+    best = np.zeros(n, dtype=np.uint16)
+    cv = np.zeros((n, 40), dtype=np.uint32)
+    cr = np.zeros((n, 40), dtype=np.int32)
+    nn = np.zeros(n, dtype=np.int64)
+    wr = np.zeros(n, dtype=np.float32)
+    ps = np.zeros(n, dtype=np.int32)
+    plies = np.zeros(1, dtype=np.uint64)
+    lib().orc_uct_search_batch(_p(roots), n, exploration_c, min_node_visits, sims, seed, game0, threads, _p(best), _p(cv), _p(cr), _p(nn), _p(wr),
+                               _p(ps), _p(plies))
+    return dict(best=best, child_visits=cv, child_rewards=cr, n_nodes=nn, best_winrate=wr, pass_seen=ps, rollout_plies=int(plies[0]))
 
 
 def net_forward(params, planes):

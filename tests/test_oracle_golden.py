@@ -249,3 +249,58 @@ def test_pass_nodes_defined():
     t = r["tree"]
     assert t["n_child"][0] == 2 and (t["flags"][1:3] & 4).all()
     assert O.decode_action(r["best"])["is_pass"] == 1
+
+
+# ------------------------------------------------------------------ plain UCT with rollouts (ai/mcts/mcts_arena.rs)
+def _bb(r, c):
+    return 0x80000000 >> (r * 5 + c)
+
+
+# the reference's own known-answer tests for the `Mcts` agent (ai/mcts/mcts_arena.rs:459-554): position, parameters, expected move
+PLAIN_MCTS_CASES = [
+    dict(cite="mcts_arena.rs:459-486 test_best_move_win", deck=[3, 2, 0, 1, 11], side=1, min_visits=5, c=math.sqrt(2.0),
+         set={"kings0": _bb(1, 3)}, expect=dict(frm=1, to=8, piece=0, card_idx=3)),
+    dict(cite="mcts_arena.rs:488-521 test_no_way_to_hide_for_blue", deck=[12, 8, 3, 11, 1], side=1, min_visits=5, c=2.0,
+         set={"kings1": _bb(0, 4), "pawns1": 0, "pawns0": _bb(0, 3) | _bb(1, 4)}, expect=dict(frm=4, to=2, piece=1, card_idx=2)),
+    dict(cite="mcts_arena.rs:523-553 test_worst_case_capture_blue", deck=[8, 7, 6, 9, 11], side=1, min_visits=1, c=1.0,
+         set={"kings1": _bb(1, 2), "pawns0": _bb(2, 3) | _bb(3, 2)}, expect=dict(frm=7, to=2, piece=1, card_idx=3)),
+]
+
+
+def plain_mcts_root(case):
+    g = O.new_games(1, deck=case["deck"])
+    for k, v in case["set"].items():
+        g[k[:-1]][0][int(k[-1])] = v
+    g["side"][0] = case["side"]
+    return g
+
+
+@pytest.mark.parametrize("case", PLAIN_MCTS_CASES, ids=lambda c: c["cite"].split()[-1])
+def test_plain_mcts_reference_known_answers(case):
+    """5000 playouts as in the reference's tests; the expected move must come out for every RNG stream tried (the reference's
+    thread_rng is unseeded, so its tests assert exactly this robustness)."""
+    g = plain_mcts_root(case)
+    for seed in (1, 2, 3):
+        r = O.uct_search_batch(g, case["c"], case["min_visits"], 5000, seed=seed)
+        d = O.decode_action(int(r["best"][0]))
+        assert {k: d[k] for k in ("frm", "to", "piece", "card_idx")} == case["expect"], (seed, d)
+        assert int(r["child_visits"][0].sum()) <= 5000 and r["pass_seen"][0] == 0
+
+
+def test_plain_mcts_structure():
+    """min_node_visits gates expansion (mcts_arena.rs:116-121): the root is expanded DURING playout min + 2 (which still rolls out
+    from the root itself), so the children share playouts - (min + 2) visits; unvisited children score +inf and the LAST one wins
+    the tie, so the first visits run from the last child back."""
+    g = O.new_games(1, deck=[1, 2, 0, 3, 11])
+    for min_v, sims in ((5, 7), (5, 12), (0, 5), (5, 400)):
+        r = O.uct_search_batch(g, math.sqrt(2.0), min_v, sims, seed=9)
+        v = r["child_visits"][0][:10]
+        assert int(v.sum()) == max(0, sims - (min_v + 2))
+        k = int(v.sum())
+        if 0 < k <= 10:
+            assert v.tolist() == [0] * (10 - k) + [1] * k
+    two = np.concatenate([g, g])
+    a = O.uct_search_batch(two, 1.4, 5, 300, seed=4, game0=10)
+    assert not np.array_equal(a["child_visits"][0], a["child_visits"][1])     # different game ids -> different rollouts
+    b = O.uct_search_batch(two[1:], 1.4, 5, 300, seed=4, game0=11)
+    assert np.array_equal(a["child_visits"][1], b["child_visits"][0])           # keyed by the global game id
