@@ -238,6 +238,15 @@ ONB_API int32_t onb_mcts_dump_tree(onb_ctx* ctx, int64_t tree, int64_t cap, onb_
  * reference is undefined for that tree, bit1: node pool overflow) */
 ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_host);
 
+/* ---- plain UCT with random rollouts: the `Mcts` agent (onitama-game/src/ai/mcts/{mod.rs,mcts_arena.rs}) ---------------
+ * The evaluation opponent of the reference's arena (evaluator.rs), one tree per game, rooted like the PUCT search:
+ * onb_mcts_begin (its c_puct is ignored); onb_uct_run(ctx, exploration_c, min_node_visits, playouts);
+ * onb_mcts_finish (best = the root child with most visits, last maximum wins = max_by_key of mcts_arena.rs:64-67; pi =
+ * visit shares) / onb_mcts_play_best / onb_mcts_dump_tree (reward = the f32 reward sum, exactly). Defaults of the
+ * reference: exploration_c = sqrt(2), min_node_visits = 5, 5000 playouts (mod.rs:21-30; its 1 s wall-clock limit is
+ * not reproduced). The rollouts draw from the counter RNG keyed by (seed, global game id, playout, ply). */
+ONB_API int32_t onb_uct_run(onb_ctx* ctx, float exploration_c, uint32_t min_node_visits, uint32_t playouts);
+
 /* ---- policy/value network on the device ---------------------------------------------------------------------
  * ConvResNet::forward (alphazero-training/src/net.rs:215-232) for every position of a plane buffer, as one fused
  * tensor-core kernel (BatchNorm in eval mode folded into the convolutions; f32 accumulation of products of operands

@@ -1,5 +1,6 @@
 // onb_api.cu -- the extern "C" boundary of libonb.so (include/onb.h): context lifecycle, host<->device
 // staging and error mapping. No torch types, no C++ exceptions, no CPU fallback.
+#include <cmath>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -132,7 +133,7 @@ int32_t onb_destroy(onb_ctx* ctx) {
     void* ptrs[] = {c->d_states, c->d_masks, c->d_planes, c->d_actions, c->d_stats, c->d_io_states, c->d_moves, c->d_counts, c->d_nodes,
                     c->d_tree_size, c->d_tree_flags, c->d_roots, c->d_leaf_node, c->d_leaf_state, c->d_leaf_planes, c->d_policy, c->d_value,
                     c->d_pi, c->d_best, c->d_root_visits, c->d_root_q, c->d_child_visits, c->net[0].w, c->net[0].bias, c->net[0].head, c->net[1].w,
-                    c->net[1].bias, c->net[1].head};
+                    c->net[1].bias, c->net[1].head, c->d_ln_table};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->scratch)
@@ -481,6 +482,31 @@ int32_t onb_mcts_run(onb_ctx* ctx, int32_t evaluator, uint32_t sims) {
     }
     ONB_CUDA(c, launch_mcts_run(c, evaluator, sims));
     c->sims_done += sims;
+    return ONB_OK;
+}
+int32_t onb_uct_run(onb_ctx* ctx, float exploration_c, uint32_t min_node_visits, uint32_t playouts) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (c->mcts_phase != 1) return fail(c, ONB_E_STATE, "onb_uct_run: call onb_mcts_begin first");
+    if (c->sims_done + playouts > c->cfg.mcts_max_sims) return fail(c, ONB_E_INVALID, "onb_uct_run: more playouts than mcts_max_sims");
+    const uint32_t need = c->sims_done + playouts + 2;
+    if (c->ln_cap < need) {  // ln(parent visits) as the reference computes it: f32 logf on the host
+        ONB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->d_ln_table) cudaFree(c->d_ln_table);
+        c->d_ln_table = nullptr;
+        c->ln_cap = 0;
+        const uint32_t cap = need < c->cfg.mcts_max_sims + 2 ? c->cfg.mcts_max_sims + 2 : need;
+        float* host = static_cast<float*>(malloc((size_t)cap * 4));
+        if (!host) return fail(c, ONB_E_NOMEM, "onb_uct_run: out of host memory");
+        for (uint32_t i = 0; i < cap; ++i) host[i] = logf((float)i);
+        cudaError_t e = cudaMalloc(&c->d_ln_table, (size_t)cap * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(c->d_ln_table, host, (size_t)cap * 4, cudaMemcpyHostToDevice);
+        free(host);
+        ONB_CUDA(c, e);
+        c->ln_cap = cap;
+    }
+    ONB_CUDA(c, launch_uct_run(c, exploration_c, min_node_visits, playouts));
+    c->sims_done += playouts;
     return ONB_OK;
 }
 int32_t onb_mcts_finish(onb_ctx* ctx, onb_action* best_host, float* pi_host, uint32_t* root_visits_host, double* root_q_host, uint32_t* child_visits_host) {

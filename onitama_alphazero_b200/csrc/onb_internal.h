@@ -65,6 +65,8 @@ struct Ctx {
     uint64_t noise_seed;
     uint32_t sims_target, sims_done;
     int mcts_phase;  // 0 idle, 1 begun/after expand, 2 after select
+    float* d_ln_table;  // logf(i) for the plain UCT search (filled by the host: the libm call behind Rust's f32::ln)
+    uint32_t ln_cap;
     // policy/value network (onb_net.cu): weights in tensor-core operand layout, folded biases, head parameters
     struct NetSlot {
         float* w;     // conv taps in operand layout
@@ -97,6 +99,7 @@ cudaError_t launch_mcts_select(Ctx* c);
 cudaError_t launch_mcts_expand_backup(Ctx* c);
 cudaError_t launch_mcts_eval(Ctx* c, int evaluator);
 cudaError_t launch_mcts_run(Ctx* c, int evaluator, uint32_t sims);
+cudaError_t launch_uct_run(Ctx* c, float exploration_c, uint32_t min_node_visits, uint32_t sims);
 cudaError_t launch_mcts_finish(Ctx* c);
 cudaError_t launch_mcts_play_best(Ctx* c, uint32_t out_flags);
 

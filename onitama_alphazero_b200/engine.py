@@ -195,6 +195,12 @@ class Context:
     def mcts_run(self, evaluator, sims):
         self._ck(self._lib.onb_mcts_run(self._h, evaluator, sims))
 
+    def uct_search(self, exploration_c=2.0 ** 0.5, min_node_visits=5, playouts=5000, to_host=True):
+        """The reference's `Mcts` agent for every game at once: plain UCT with random rollouts (ai/mcts/mcts_arena.rs)."""
+        self.mcts_begin(0.0, playouts)
+        self._ck(self._lib.onb_uct_run(self._h, exploration_c, min_node_visits, playouts))
+        return self.mcts_finish(to_host=to_host)
+
     def mcts_finish(self, to_host=True, out=None):
         """out: optional dict of preallocated arrays (e.g. views of pinned memory) with the keys below; reused across calls."""
         if not to_host:

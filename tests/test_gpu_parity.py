@@ -1073,3 +1073,74 @@ def test_two_devices_in_one_process(onb):
         pa, pb = a.read(onb.BUF_POLICY, np.float32, (n, 50)), b.read(onb.BUF_POLICY, np.float32, (n, 50))
         want_p, _ = O.net_forward(model.state_dict(), O.encode(ref).reshape(-1, 21, 5, 5)[[0, 1, n, n + 1]])
         assert np.abs(np.stack([pa[0], pa[1], pb[0], pb[1]]) - want_p).max() <= 6e-3
+
+
+# ------------------------------------------------------------------ plain UCT with rollouts (the `Mcts` agent)
+@pytest.mark.gpu
+@pytest.mark.parametrize("min_visits,c,sims", [(5, math.sqrt(2.0), 600), (1, 1.0, 400), (0, 2.0, 300)])
+def test_plain_uct_bit_exact_vs_oracle(onb, min_visits, c, sims):
+    """onb_uct_run against the restatement of ai/mcts/mcts_arena.rs on the config-4 roots: every root child's visit count and
+    reward sum, the node count and the chosen move must be identical (f32 UCT scores, logf table, shared counter RNG for the rollouts)."""
+    seed, base = 77, 1000
+    roots = _cfg4_roots(48, 5)
+    n = len(roots)
+    with onb.Context(n, seed=seed, game_id_base=base, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.set_states(roots)
+        res = ctx.uct_search(c, min_visits, sims)
+        nn, fl = ctx.mcts_tree_info()
+        trees = [ctx.mcts_dump_tree(t) for t in range(0, n, 7)]
+    want = O.uct_search_batch(roots, c, min_visits, sims, seed=seed, game0=base, threads=8)
+    live = roots["result"] == 0
+    assert live.sum() >= 40
+    assert np.array_equal(res["child_visits"][live], want["child_visits"][live])
+    assert np.array_equal(res["best"][live], want["best"][live])
+    assert np.array_equal(nn[live].astype(np.int64), want["n_nodes"][live])
+    for i, t in enumerate(range(0, n, 7)):
+        if not live[t]:
+            continue
+        tr = trees[i]
+        k = int(tr["n_child"][0])
+        fc = int(tr["first_child"][0])
+        assert np.array_equal(tr["reward"][fc:fc + k].astype(np.int32), want["child_rewards"][t][:k])
+        assert int(tr["visits"][0]) == sims
+    assert not (fl[live] & 2).any()
+
+
+@pytest.mark.gpu
+def test_plain_uct_reference_known_answers_on_gpu(onb):
+    """ai/mcts/mcts_arena.rs:459-554 through the C ABI: 5000 playouts, the expected move for each position"""
+    from test_oracle_golden import PLAIN_MCTS_CASES, plain_mcts_root
+    for case in PLAIN_MCTS_CASES:
+        g = plain_mcts_root(case)
+        roots = np.concatenate([g] * 4)                      # four independent RNG streams (global game ids 0..3)
+        with onb.Context(4, seed=11, mcts_max_sims=5000, planes=False) as ctx:
+            ctx.set_states(roots)
+            res = ctx.uct_search(case["c"], case["min_visits"], 5000)
+        for a in res["best"]:
+            d = O.decode_action(int(a))
+            assert {k: d[k] for k in ("frm", "to", "piece", "card_idx")} == case["expect"], (case["cite"], d)
+        want = O.uct_search_batch(roots, case["c"], case["min_visits"], 5000, seed=11, threads=4)
+        assert np.array_equal(res["child_visits"], want["child_visits"])
+
+
+@pytest.mark.gpu
+def test_arena_network_search_against_plain_uct(onb):
+    """evaluator.rs pits AlphaZero against the `Mcts` agent: both searches on the device, colours alternating."""
+    from test_net_cpu import lively_model
+    n = 32
+    a_is_red = (np.arange(n) % 2) == 0
+    with onb.Context(n, seed=5, mcts_max_sims=200, planes=False) as ctx:
+        ctx.net_load(lively_model(1, seed=2))
+        ctx.reset()
+
+        def alphazero(cx):
+            cx.search_device(2.0, 32, evaluator=onb.EVAL_NET)
+            cx.tensor(onb.BUF_ACTIONS).copy_(cx.tensor(onb.BUF_BEST))
+
+        def plain(cx):
+            cx.uct_search(math.sqrt(2.0), 5, 200, to_host=False)
+            cx.tensor(onb.BUF_ACTIONS).copy_(cx.tensor(onb.BUF_BEST))
+
+        a, b, d = onb.fight(ctx, alphazero, plain, a_is_red, max_plies=60)
+    assert a + b + d == n
+    assert b > a      # 200 rollouts beat a random-weight network with 32 simulations
