@@ -266,6 +266,10 @@ def workload_config(wl):
                             "the leaf buffer in place, %d concurrent games/GPU, one ply per step, replay samples gathered to GPU 0"
                             % (SELFPLAY_SIMS, SELFPLAY_GAMES), "games_per_gpu": SELFPLAY_GAMES, "sims": SELFPLAY_SIMS, "c_puct": MCTS_C,
                 "l2": "node pools + leaf batches >> L2"}
+    if wl == "uct":
+        return {"workload": "plain UCT with random rollouts (the reference's Mcts agent, evaluator.rs opponent): %d playouts/move, %d concurrent "
+                            "trees/GPU, config-4 roots, c = sqrt(2), min_node_visits = 5" % (MCTS_SIMS, MCTS_TREES), "trees_per_gpu": MCTS_TREES,
+                "playouts": MCTS_SIMS, "l2": "node pools >> L2"}
     if wl == "perft":
         return {"workload": "BASELINE config 2: perft-style legal-move enumeration depth 6 from the standard opening over all 131040 canonical "
                             "card deals, 1 GPU", "deals": 131040, "depth": 6, "l2": "DFS phase is register resident (~0 B/node); L2 flushed between iterations"}
@@ -280,13 +284,13 @@ def main():
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default per workload: env 200, mcts 20, perft 5, selfplay 3, playout 50)")
     ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default per workload, >= 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay"])
+    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay", "uct"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--net", default="fused", choices=["fused", "fused-tf32", "torch"],
                     help="selfplay workload: the tensor-core network kernel (f16 or tf32 operands) or the PyTorch module as a black box")
     args = ap.parse_args()
-    dflt = {"env": (200, 20), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5)}[args.workload]
+    dflt = {"env": (200, 20), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3)}[args.workload]
     if args.impl == "reference":
         dflt = (3, 1)
     args.steps = dflt[0] if args.steps is None else args.steps
@@ -581,6 +585,38 @@ def main():
         return dict(metric="perft_nodes_per_sec", value=value, unit="nodes/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
                     gpu_launches=5 * steps, clocks=clocks)
 
+    # ---------------------------------------------------------------- plain UCT with random rollouts (the reference's Mcts agent)
+    def bench_uct(steps, warmup):
+        n, sims = MCTS_TREES, MCTS_SIMS
+        ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims, planes=False)
+        ctx.reset()
+        base = ctx.get_states()
+        cur = base.copy()
+        for step in range(16):   # the config-4 roots: positions after (id mod 16) random plies
+            ctx.step_random(step)
+            nxt = ctx.get_states()
+            live = (np.arange(n) % 16) > step
+            cur[live] = nxt[live]
+            ctx.set_states(cur)
+        dead = cur["result"] != 0
+        cur[dead] = base[dead]
+        ctx.set_states(cur)
+
+        def one(i):
+            ctx.uct_search(2.0 ** 0.5, 5, sims, to_host=False)
+
+        ms, clocks = timed(one, warmup, steps)
+        nn, fl = ctx.mcts_tree_info()
+        assert int((fl & 2).sum()) == 0, "node pool overflow"
+        value = world * n * sims * steps / (ms * 1e-3)
+        ctx.close()
+        roof = {"bound": "hbm", "achieved": 0.0, "peak": peak, "unit": "GB/s", "frac": 0.0, "traffic": None, "kernel": "k_uct_run",
+                "note": "a playout is a short tree descent plus a random game of ~35 plies played in registers by the 8 lanes of the tree's "
+                        "group: issue-bound, ~0 algorithmic bytes per ply", "mean_nodes_per_tree": float(nn.mean()), "peak_source": peak_src}
+        e2e = {"value": value, "unit": "playouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "path": "device-resident"}
+        return dict(metric="uct_playouts_per_sec", value=value, unit="playouts/s", ms_per_step=ms / steps, dtype="u32+f32", roofline=roof, e2e=e2e,
+                    gpu_launches=3 * steps, clocks=clocks)
+
     # ---------------------------------------------------------------- self-play with the network (config 5)
     def bench_selfplay(steps, warmup):
         from onitama_alphazero_b200.net import ConvResNet, make_evaluator
@@ -640,6 +676,8 @@ def main():
         out = bench_env(args.steps, args.warmup)
     elif wl == "selfplay":
         out = bench_selfplay(args.steps, args.warmup)
+    elif wl == "uct":
+        out = bench_uct(args.steps, args.warmup)
     elif wl == "perft":
         out = bench_perft(args.steps, args.warmup)
     elif wl == "mcts":
@@ -685,6 +723,16 @@ def main():
             cpu_baseline = {"value": v, "unit": "sims/s", "cores": th, "kind": "port",
                             "sample": "4 trees x 100 sims, oracle arena + the PyTorch module on the CPU, one position per forward call as in the "
                                       "reference (%.1f s wall, %d torch threads)" % (dt, th)}
+        elif wl == "uct":
+            O = oracle()
+            import time as _t
+            roots = cfg4_roots(O, 1024, SEED)
+            t0 = _t.perf_counter()
+            r = O.uct_search_batch(roots, 2.0 ** 0.5, 5, MCTS_SIMS, seed=SEED, threads=cores)
+            dt = _t.perf_counter() - t0
+            cpu_baseline = {"value": 1024 * MCTS_SIMS / dt, "unit": "playouts/s", "cores": cores, "kind": "port",
+                            "sample": "1024 trees x 400 playouts (%.1f s wall, %d threads, %.1f rollout plies per playout)"
+                                      % (dt, cores, r["rollout_plies"] / (1024.0 * MCTS_SIMS))}
         elif wl == "perft":
             v, dt = cpu_perft(16 * cores, 5, cores)
             cpu_baseline = {"value": v, "unit": "nodes/s", "cores": cores, "kind": "port",

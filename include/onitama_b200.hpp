@@ -158,6 +158,7 @@ private:
 constexpr uint32_t RED_KING_SP = 0x00000200u, BLUE_KING_SP = 0x20000000u, BLUE_PAWNS_SP = 0xD8000000u, RED_PAWNS_SP = 0x00000D80u;  // state.rs:24-45
 constexpr size_t BLUE_TEMPLE = 2, RED_TEMPLE = 22;                                                                                  // state.rs:48-49
 inline uint32_t get_bit(uint32_t x, size_t n) { return (x >> (31 - n)) & 1u; }  // common/mod.rs:2-4
+inline uint32_t from_2d_to_bitboard(uint32_t row, uint32_t col) { return 0x80000000u >> (row * 5 + col); }  // common/mod.rs:10-16
 
 struct State {
     Deck deck;
@@ -292,6 +293,45 @@ struct Random : Agent {
     const char* name() const override { return "Random AI"; }
     std::unique_ptr<Agent> clone_dyn() const override { return std::make_unique<Random>(*this); }
     uint64_t id() const override { return seed; }
+};
+
+/// ai/mcts/mod.rs:13-68: plain UCT with random rollouts (mcts_arena.rs). The 1 s wall-clock limit of the reference is not
+/// reproduced: a search always runs max_playouts playouts. Rollout draws come from the counter RNG keyed by (seed, game = 0).
+struct Mcts : Agent {
+    double search_time_ms = 1000.;  // ignored
+    uint32_t min_node_visits = 5;
+    float exploration_c = 1.41421356f;
+    uint32_t max_playouts = 5000;
+    uint64_t seed = 0;
+    std::pair<DoneMove, double> generate_move(const GameState& gs) override {
+        thread_local std::unique_ptr<Engine> e;
+        thread_local uint64_t e_seed = ~0ull;
+        thread_local uint32_t e_sims = 0;
+        if (!e || e_seed != seed || e_sims < max_playouts) { e.reset(); e = std::make_unique<Engine>(1, max_playouts, seed, 0, false); e_seed = seed; e_sims = max_playouts; }
+        onb_state o = gs.state.to_onb(gs.curr_player_color);
+        e->check(onb_env_set_states(e->ctx(), &o, 0, 1));
+        e->check(onb_mcts_begin(e->ctx(), 0., max_playouts));
+        e->check(onb_uct_run(e->ctx(), exploration_c, min_node_visits, max_playouts));
+        onb_action best = 0;
+        uint32_t visits[40], root_visits = 0;
+        e->check(onb_mcts_finish(e->ctx(), &best, nullptr, &root_visits, nullptr, visits));
+        if (best == ONB_ACTION_NONE) throw Error(ONB_E_STATE, "Must find the best child");  // mcts_arena.rs:67
+        // the reference returns the winrate of the chosen child (mcts_arena.rs:78-83)
+        const size_t cap = 1 + 40 * (size_t)max_playouts + 2;
+        std::vector<uint32_t> v(cap), fc(cap), nc(cap);
+        std::vector<double> rew(cap);
+        std::vector<uint16_t> act(cap);
+        onb_tree_dump d{v.data(), rew.data(), nullptr, act.data(), nullptr, fc.data(), nc.data(), nullptr};
+        int64_t n_nodes = 0;
+        e->check(onb_mcts_dump_tree(e->ctx(), 0, (int64_t)cap, &d, &n_nodes));
+        double winrate = 0.;
+        for (uint32_t k = 0; k < nc[0]; ++k)
+            if (act[fc[0] + k] == best && v[fc[0] + k]) winrate = (double)((float)rew[fc[0] + k] / (float)v[fc[0] + k]);
+        return {from_action(best), winrate};
+    }
+    const char* name() const override { return "MCTS AI"; }
+    std::unique_ptr<Agent> clone_dyn() const override { return std::make_unique<Mcts>(*this); }
+    uint64_t id() const override { return (uint64_t)search_time_ms * 1000000ull + (uint64_t)exploration_c + max_playouts + min_node_visits; }
 };
 
 struct AlphaZeroMctsConfig {  // alphazero_mcts/mod.rs:26-43

@@ -209,6 +209,39 @@ static void device_network_search() {
     CHECK(threw);
 }
 
+// ai/mcts/mcts_arena.rs:459-554: the reference's known-answer searches for the `Mcts` agent, through the mirror
+static void plain_mcts_reference_tests() {
+    {   // test_best_move_win: Blue must take the Red king with the Dragon card
+        Deck deck({RABBIT, FROG, TIGER, DRAGON, HORSE});
+        GameState gs = GameState::with_deck(deck);
+        gs.state.kings[0] = from_2d_to_bitboard(1, 3);
+        gs.curr_player_color = PlayerColor::Blue;
+        Mcts m;  // defaults of mod.rs:21-30: sqrt(2), 5 visits, 5000 playouts
+        auto r = m.generate_move(gs);
+        CHECK((r.first == DoneMove{Move{1, 8, PieceKind::Pawn}, 3}));
+        CHECK(r.second > 0.9);
+    }
+    {   // test_no_way_to_hide_for_blue: the only move that does not lose is Rabbit e5-c5
+        Deck deck({OX, MONKEY, RABBIT, HORSE, DRAGON});
+        GameState gs = GameState::with_deck(deck);
+        gs.state.kings[1] = from_2d_to_bitboard(0, 4);
+        gs.state.pawns[1] = 0;
+        gs.state.pawns[0] = from_2d_to_bitboard(0, 3) | from_2d_to_bitboard(1, 4);
+        gs.curr_player_color = PlayerColor::Blue;
+        Mcts m; m.exploration_c = 2.0f;
+        CHECK((m.generate_move(gs).first == DoneMove{Move{4, 2, PieceKind::King}, 2}));
+    }
+    {   // test_worst_case_capture_blue
+        Deck deck({MONKEY, ROOSTER, GOOSE, MANTIS, HORSE});
+        GameState gs = GameState::with_deck(deck);
+        gs.state.kings[1] = from_2d_to_bitboard(1, 2);
+        gs.state.pawns[0] = from_2d_to_bitboard(2, 3) | from_2d_to_bitboard(3, 2);
+        gs.curr_player_color = PlayerColor::Blue;
+        Mcts m; m.exploration_c = 1.0f; m.min_node_visits = 1;
+        CHECK((m.generate_move(gs).first == DoneMove{Move{7, 2, PieceKind::King}, 3}));
+    }
+}
+
 int main() {
     try {
         create_all_legal_moves_for_red_in_starting_position();
@@ -218,6 +251,7 @@ int main() {
         expand_order();
         search_and_drivers();
         device_network_search();
+        plain_mcts_reference_tests();
     } catch (const Error& e) {
         std::printf("FAIL exception %d: %s\n", e.code, e.what());
         return 2;
