@@ -287,6 +287,8 @@ def main():
     ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay", "uct"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-mode", action="store_true",
+                    help="selfplay workload: search without the root exploration noise (self_play of train.rs searches in train mode)")
     ap.add_argument("--net", default="fused", choices=["fused", "fused-tf32", "torch"],
                     help="selfplay workload: the tensor-core network kernel (f16 or tf32 operands) or the PyTorch module as a black box")
     args = ap.parse_args()
@@ -631,6 +633,8 @@ def main():
         else:
             net = make_evaluator(model.cuda(local_rank))
         ctx.reset()
+        if not args.eval_mode:   # TrainingAlphaZeroMcts of self_play: Dirichlet-style noise at the root (mcts_arena.rs:186-202)
+            ctx.mcts_set_noise(True, 0.25, 0.03, SEED)
         planes_t, pi_t = ctx.tensor(onb.BUF_PLANES), ctx.tensor(onb.BUF_PI)
         got = {"samples": 0}
 
@@ -669,6 +673,7 @@ def main():
                "path": "device-resident self-play ply (search + sample gather + play); nothing crosses PCIe by design"}
         dt = "u32+f64 (search), " + {"fused": "f16 x f16 -> f32 (network)", "fused-tf32": "tf32 x tf32 -> f32 (network)",
                                      "torch": "f32/tf32 (network, cuDNN)"}[args.net]
+        roof["search_mode"] = "eval (no root noise)" if args.eval_mode else "train (root exploration noise, epsilon 0.25, alpha 0.03)"
         return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=ms / steps, dtype=dt, network=args.net,
                     roofline=roof, e2e=e2e, gpu_launches=((3 if fused else 2) * sims + 4) * steps, clocks=clocks, samples_per_ply=got["samples"])
 
