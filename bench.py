@@ -211,11 +211,19 @@ def run_reference(args, rank):
     vals = []
     if wl == "env":
         n, s = 1 << 18, 12
-        sample = "%d games x %d lockstep steps per timed step (same kernel contents: move gen, random action, apply, reset, mask, planes)" % (n, s)
+        budget = 150.0  # seconds for the whole --steps/--warmup run: the per-step sample shrinks if the first step says it would not fit
         for i in range(args.warmup + args.steps):
             v, dt = cpu_env(n, s, cores)
             if i >= args.warmup:
                 vals.append((v, dt))
+            if i == 0 and dt * (args.warmup + args.steps) > budget:
+                shrink = dt * (args.warmup + args.steps) / budget
+                if s / shrink >= 1.0:
+                    s = max(1, int(s / shrink))
+                else:
+                    n = max(4096, int(n * s / shrink))
+                    s = 1
+        sample = "%d games x %d lockstep steps per timed step (same kernel contents: move gen, random action, apply, reset, mask, planes)" % (n, s)
         unit, metric = "env_steps/s", "env_steps_per_sec"
     elif wl == "mcts":
         n = 1024
@@ -233,6 +241,26 @@ def run_reference(args, rank):
             if i >= args.warmup:
                 vals.append((v, dt))
         unit, metric = "nodes/s", "perft_nodes_per_sec"
+    elif wl == "uct":
+        import time as _t
+        O = oracle()
+        n = 512
+        roots = cfg4_roots(O, n, SEED)
+        sample = "%d trees x %d playouts per timed step, plain UCT with random rollouts" % (n, MCTS_SIMS)
+        for i in range(args.warmup + args.steps):
+            t0 = _t.perf_counter()
+            O.uct_search_batch(roots, 2.0 ** 0.5, 5, MCTS_SIMS, seed=SEED, threads=cores)
+            dt = _t.perf_counter() - t0
+            if i >= args.warmup:
+                vals.append((n * MCTS_SIMS / dt, dt))
+        unit, metric = "playouts/s", "uct_playouts_per_sec"
+    elif wl == "selfplay":
+        sample = "2 trees x 100 sims per timed step, oracle arena + the PyTorch module on the CPU, one position per forward call as in the reference"
+        for i in range(args.warmup + args.steps):
+            v, dt, cores = cpu_selfplay(2, 100)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        unit, metric = "sims/s", "mcts_sims_per_sec"
     else:
         sample = "%d games to terminal, single thread" % PLAYOUT_GAMES
         cores = 1
