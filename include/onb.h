@@ -154,6 +154,11 @@ ONB_API int32_t onb_attack_maps(uint32_t out800[800]);
 /* (re)start every game. n_decks = 0: deal from the RNG with `epoch`; 1: the same deck for all games;
  * n_games: one deck per game. Replaces State::with_deck / GameState::with_deck (train.rs:44-49). */
 ONB_API int32_t onb_env_reset(onb_ctx* ctx, const uint8_t* decks5_host, int64_t n_decks, uint32_t epoch);
+/* Re-deals selected games in place (start position, cards from the counter RNG at `epoch`, or the fixed deck of the last
+ * onb_env_reset): mask_host[i] != 0 selects game i; mask_host == NULL selects every game that is over. *n_reset (optional)
+ * receives the number of games restarted. This is what keeps every slot of a lockstep self-play busy: a worker of the
+ * reference starts its next game as soon as one ends (train.rs:44-98 inside the per-thread loop of :218-245). */
+ONB_API int32_t onb_env_reset_games(onb_ctx* ctx, const uint8_t* mask_host, uint32_t epoch, int64_t* n_reset);
 ONB_API int32_t onb_env_set_states(onb_ctx* ctx, const onb_state* states_host, int64_t first, int64_t n);
 ONB_API int32_t onb_env_get_states(onb_ctx* ctx, onb_state* states_host, int64_t first, int64_t n);
 /* State::generate_all_legal_moves (state.rs:301-378) for the side to move of every game.

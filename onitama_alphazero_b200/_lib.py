@@ -52,6 +52,7 @@ SYMBOLS = {
     "onb_deal": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32, _P]),
     "onb_attack_maps": (C.c_int32, [_P]),
     "onb_env_reset": (C.c_int32, [_P, _P, C.c_int64, C.c_uint32]),
+    "onb_env_reset_games": (C.c_int32, [_P, _P, C.c_uint32, _P]),
     "onb_env_set_states": (C.c_int32, [_P, _P, C.c_int64, C.c_int64]),
     "onb_env_get_states": (C.c_int32, [_P, _P, C.c_int64, C.c_int64]),
     "onb_env_legal_moves": (C.c_int32, [_P, _P, _P]),

@@ -273,6 +273,25 @@ int32_t onb_env_reset(onb_ctx* ctx, const uint8_t* decks5_host, int64_t n_decks,
     return ONB_OK;
 }
 
+int32_t onb_env_reset_games(onb_ctx* ctx, const uint8_t* mask_host, uint32_t epoch, int64_t* n_reset) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    uint8_t* d = nullptr;
+    const size_t mask_bytes = ((size_t)c->n + 7) & ~(size_t)7;  // layout: [n mask bytes, padded to 8][8-byte counter]
+    ONB_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&d), mask_bytes + 8));
+    unsigned long long* d_count = reinterpret_cast<unsigned long long*>(d + mask_bytes);
+    cudaError_t e = cudaMemsetAsync(d_count, 0, 8, c->stream);
+    if (e == cudaSuccess && mask_host) e = cudaMemcpyAsync(d, mask_host, (size_t)c->n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_env_reset_where(c, mask_host ? d : nullptr, epoch, d_count);
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_count, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(c, e, "onb_env_reset_games");
+    if (n_reset) *n_reset = (int64_t)h;
+    return ONB_OK;
+}
+
 int32_t onb_env_set_states(onb_ctx* ctx, const onb_state* states_host, int64_t first, int64_t n) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);

@@ -28,6 +28,19 @@ __global__ void __launch_bounds__(256) k_env_reset(uint4* __restrict__ states, i
     states[i] = pack(start_game(cards));
 }
 
+// re-deal selected games in place: mask[i] != 0, or (mask == nullptr) every game that is over
+__global__ void __launch_bounds__(256) k_env_reset_where(uint4* __restrict__ states, int64_t n, const uint8_t* __restrict__ mask, int32_t fixed_cards,
+                                                         uint64_t seed, uint64_t game0, uint32_t epoch, unsigned long long* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (i < n) {
+        hit = mask ? mask[i] != 0 : unpack(states[i]).result != 0;
+        if (hit) states[i] = pack(start_game(fixed_cards >= 0 ? (uint32_t)fixed_cards : deal_cards(game_key(seed, game0 + (uint64_t)i), epoch)));
+    }
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, hit);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, (unsigned long long)__popc(b));
+}
+
 // ------------------------------------------------------------------------------------------ boundary conversion
 __global__ void __launch_bounds__(256) k_states_export(const uint4* __restrict__ states, uint32_t* __restrict__ out6, int64_t first, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,6 +303,11 @@ static cudaError_t launch_step_mode(Ctx* c, uint32_t step, int auto_reset, int32
 
 cudaError_t launch_env_reset(Ctx* c, const uint8_t* d_decks5, int64_t n_decks, uint32_t epoch) {
     k_env_reset<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_states, c->n, d_decks5, n_decks, c->cfg.seed, c->cfg.game_id_base, epoch);
+    return cudaGetLastError();
+}
+cudaError_t launch_env_reset_where(Ctx* c, const uint8_t* d_mask, uint32_t epoch, unsigned long long* d_count) {
+    k_env_reset_where<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->d_states, c->n, d_mask, c->fixed_cards, c->cfg.seed, c->cfg.game_id_base,
+                                                                             epoch, d_count);
     return cudaGetLastError();
 }
 cudaError_t launch_states_export(Ctx* c, onb_state* d_out, int64_t first, int64_t n) {

@@ -85,6 +85,7 @@ struct Ctx {
 
 // env (onb_env.cu)
 cudaError_t launch_env_reset(Ctx* c, const uint8_t* d_decks5, int64_t n_decks, uint32_t epoch);
+cudaError_t launch_env_reset_where(Ctx* c, const uint8_t* d_mask, uint32_t epoch, unsigned long long* d_count);
 cudaError_t launch_states_export(Ctx* c, onb_state* d_out, int64_t first, int64_t n);
 cudaError_t launch_states_import(Ctx* c, const onb_state* d_in, int64_t first, int64_t n);
 cudaError_t launch_legal_moves(Ctx* c);

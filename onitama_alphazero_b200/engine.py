@@ -101,6 +101,13 @@ class Context:
         d = np.ascontiguousarray(decks, dtype=np.uint8).reshape(-1, 5)
         self._ck(self._lib.onb_env_reset(self._h, L.ptr(d), len(d), epoch))
 
+    def reset_games(self, mask=None, epoch=0):
+        """onb_env_reset_games: restart the games selected by mask (uint8/bool [n]); None restarts every finished game. Returns the count."""
+        cnt = C.c_int64(0)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._ck(self._lib.onb_env_reset_games(self._h, None if m is None else L.ptr(m), epoch, C.byref(cnt)))
+        return int(cnt.value)
+
     def set_states(self, states, first=0):
         s = np.ascontiguousarray(states, dtype=STATE_DTYPE)
         self._ck(self._lib.onb_env_set_states(self._h, L.ptr(s), first, len(s)))

@@ -107,6 +107,62 @@ def _self_play(ctx, c_puct, sims, max_plies, evaluator, net, decks):
     return dict(planes=planes, pi=pi, z=z, color=color, game=game)
 
 
+def self_play_continuous(ctx, c_puct, sims, n_games, max_plies=150, evaluator=L.EVAL_UNIFORM, net=None, train=False, noise_seed=0):
+    """self_play for at least n_games games with every slot of the context kept busy: a slot whose game ends (or hits the ply cap)
+    is re-dealt at once (onb_env_reset_games), the way a worker thread of the reference starts its next game as soon as one is over
+    (train.rs:218-245 around :44-98). Lockstep self_play instead searches finished slots until the longest game ends -- with game
+    lengths between ~10 and 152 plies that wastes most of the work. Only completed games are returned; sample order is ply-major.
+    Extra keys: `serial` [m] (slot + n * generation: samples with the same serial belong to one game), `games` (completed games)."""
+    with torch.cuda.stream(ctx.torch_stream()):
+        n = ctx.n
+        dev = "cuda:%d" % ctx.device
+        ctx.reset()
+        ctx.mcts_set_noise(bool(train), 0.25, 0.03, noise_seed)
+        states_t = ctx.tensor(L.BUF_STATES)
+        generation = torch.zeros(n, dtype=torch.int64, device=dev)   # games already finished in this slot
+        plies = torch.zeros(n, dtype=torch.int64, device=dev)        # plies played in the slot's current game
+        slots = torch.arange(n, device=dev)
+        rec = {"planes": [], "pi": [], "color": [], "serial": []}
+        winners = {}   # serial -> 0 draw (ply cap), 1 Red, 2 Blue
+        done, tick = 0, 0
+        while done < n_games:
+            st = states_t.clone()
+            ctx.encode(to_host=False)                       # create_tensor_from_state of the searched position (train.rs:58)
+            ctx.search_device(c_puct, sims, evaluator=evaluator, net=net)
+            rec["planes"].append(ctx.tensor(L.BUF_PLANES).clone())
+            rec["pi"].append(ctx.tensor(L.BUF_PI).clone())
+            rec["color"].append(((st[:, 1] >> 30) & 1).to(torch.int8))
+            rec["serial"].append(slots + n * generation)
+            ctx.mcts_play_best()
+            plies += 1
+            result = (states_t.clone()[:, 2] >> 29) & 3
+            # train.rs:74-79: the cap is checked after the move with max_plies counting down from 150 -> a game has at most max_plies + 2 plies
+            over = (result != 0) | (plies >= max_plies + 2)
+            if bool(over.any()):
+                idx = over.nonzero(as_tuple=True)[0]
+                ser = (idx + n * generation[idx]).tolist()
+                for s_, r_ in zip(ser, result[idx].tolist()):
+                    winners[s_] = r_
+                done += len(ser)
+                tick += 1
+                ctx.reset_games(over.to(torch.uint8).cpu().numpy(), epoch=tick)
+                generation[idx] += 1
+                plies[idx] = 0
+        planes = torch.cat(rec["planes"])
+        pi = torch.cat(rec["pi"])
+        color = torch.cat(rec["color"])
+        serial = torch.cat(rec["serial"])
+        table = torch.full((int(serial.max()) + 1,), -1, dtype=torch.int64, device=dev)
+        keys = torch.tensor(list(winners.keys()), dtype=torch.int64, device=dev)
+        table[keys] = torch.tensor(list(winners.values()), dtype=torch.int64, device=dev)
+        r = table[serial]
+        keep = r >= 0                                         # games still running when the quota was reached are dropped
+        r, color_k = r[keep], color[keep]
+        z = torch.where(r == 0, 0.0, torch.where((r - 1) == color_k.to(r.dtype), 1.0, -1.0)).to(torch.float32)
+        ctx.mcts_set_noise(False)
+        return dict(planes=planes[keep], pi=pi[keep], z=z, color=color_k, serial=serial[keep], games=done)
+
+
 def fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies=150):
     with torch.cuda.stream(ctx.torch_stream()):
         return _fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies)

@@ -1144,3 +1144,49 @@ def test_arena_network_search_against_plain_uct(onb):
         a, b, d = onb.fight(ctx, alphazero, plain, a_is_red, max_plies=60)
     assert a + b + d == n
     assert b > a      # 200 rollouts beat a random-weight network with 32 simulations
+
+
+@pytest.mark.gpu
+def test_self_play_continuous_keeps_slots_busy(onb):
+    """self_play_continuous re-deals a slot as soon as its game is over (onb_env_reset_games). Its first-generation games are the very
+    games lockstep self_play produces (same seeds, deterministic eval-mode search), sample for sample; later generations are new deals."""
+    import torch
+    n, sims, c = 48, 16, 2.0
+    with onb.Context(n, seed=31, mcts_max_sims=sims) as ctx:
+        lock = onb.self_play(ctx, c, sims, max_plies=150)
+        cont = onb.self_play_continuous(ctx, c, sims, n_games=3 * n, max_plies=150)
+        # reset_games: explicit mask and "finished only"
+        ctx.reset()
+        before = ctx.get_states()
+        mask = np.zeros(n, np.uint8); mask[[3, 7]] = 1
+        assert ctx.reset_games(mask, epoch=9) == 2
+        after = ctx.get_states()
+        changed = [i for i in range(n) if after[i].tobytes() != before[i].tobytes()]
+        assert set(changed) <= {3, 7} and len(changed) >= 1          # a new deal almost surely differs
+        assert ctx.reset_games(None, epoch=10) == 0                    # nothing is over yet
+    assert cont["games"] >= 3 * n
+    serial = cont["serial"].cpu().numpy()
+    assert len(np.unique(serial)) == cont["games"]
+    assert (serial >= n).any()                                         # slots were reused
+    m = cont["planes"].shape[0]
+    assert torch.allclose(cont["pi"].sum(dim=(1, 2)), torch.ones(m, device=cont["pi"].device), atol=1e-5)
+    assert set(cont["z"].unique().tolist()) <= {-1.0, 0.0, 1.0}
+    # side-to-move plane matches the recorded colour
+    assert torch.equal(cont["planes"][:, 20, 0, 0] > 0.5, cont["color"] == 1)
+    # within a game z flips with the colour to move
+    zc = cont["z"] * (1 - 2 * cont["color"].to(torch.float32))
+    for s in np.unique(serial)[:40]:
+        v = zc[torch.from_numpy(serial == s).to(zc.device)]
+        assert float(v.max() - v.min()) == 0.0
+    # generation 0 == lockstep self_play
+    lock_game = lock["game"].cpu().numpy()
+    checked = 0
+    for s in range(n):
+        a = torch.from_numpy(serial == s).to(zc.device)
+        if not bool(a.any()):
+            continue                                                   # still running when the quota was reached
+        b = torch.from_numpy(lock_game == s).to(zc.device)
+        assert torch.equal(cont["planes"][a], lock["planes"][b]) and torch.equal(cont["pi"][a], lock["pi"][b])
+        assert torch.equal(cont["z"][a], lock["z"][b])
+        checked += 1
+    assert checked >= n // 2
