@@ -863,15 +863,18 @@ def test_reference_tactical_positions(onb):
 
 
 def test_example_training_iteration_runs(onb):
-    """examples/selfplay_train_loop.py: self-play (train mode, network) -> replay ring -> alphaloss SGD -> arena vs Random."""
+    """examples/selfplay_train_loop.py: continuous self-play (train mode, network) -> replay ring -> alphaloss SGD -> arenas vs Random / Mcts."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("selfplay_train_loop", os.path.join(ROOT, "examples", "selfplay_train_loop.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    log = mod.main(["--games", "48", "--sims", "16", "--iters", "1", "--max-plies", "12", "--batch", "64", "--sgd-steps", "3",
-                    "--eval-games", "16"])
-    assert len(log) == 1 and log[0]["samples"] > 0 and log[0]["wins"] + log[0]["losses"] + log[0]["draws"] == 16
-    assert np.isfinite(log[0]["value_loss"]) and np.isfinite(log[0]["policy_loss"])
+    for extra in ([], ["--torch-net"]):   # the network inside the library (onb_net_load) and as a PyTorch black box
+        log = mod.main(["--slots", "48", "--games", "64", "--sims", "16", "--iters", "1", "--max-plies", "12", "--batch", "64", "--sgd-steps", "3",
+                        "--eval-games", "16", "--mcts-playouts", "60"] + extra)
+        assert len(log) == 1 and log[0]["samples"] > 0 and log[0]["games"] >= 64
+        assert log[0]["wins"] + log[0]["losses"] + log[0]["draws"] == 16
+        assert sum(log[0]["vs_mcts"][k] for k in ("wins", "losses", "draws")) == 16
+        assert np.isfinite(log[0]["value_loss"]) and np.isfinite(log[0]["policy_loss"])
 
 
 @pytest.mark.gpu
