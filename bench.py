@@ -687,7 +687,7 @@ def main():
             flop = 2.0 * 25 * 64 * 9 * (21 + 6 * 64) + 2.0 * (25 * 64 * 3 + 2500 + 1600 + 64)
             tpeak, tsrc = read_tensor_peak()
             ach = flop * n * sims * steps / (ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+            roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": read_traffic("k_net_forward"),
                     "kernel": "k_net_forward<2,%s>" % ("tf32" if args.net == "fused-tf32" else "f16"), "flop_per_evaluation": flop,
                     "note": "achieved = useful network FLOPs of the whole ply / ply time (search kernels included in the time); the MMAs also "
                             "compute the zero-padding cells (25 of 36.6 rows are real squares) and are bound by shared-memory operand reads at "
