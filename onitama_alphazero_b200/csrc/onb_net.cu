@@ -358,17 +358,22 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                                 const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
                 auto issue_unit = [&](int g, int ksteps) {
                     const uint32_t u = q0 + g, slot = u % NSLOT, use = u / NSLOT;
+#ifdef ONB_NET_PROFILE
+                    if (!mbar_try(bar_full(slot), use & 1u)) pf[7] += 1;  // weights not there yet
+#endif
                     mbar_wait(bar_full(slot), use & 1u);
-                    tc_fence_after();
                     PF(2);  // waiting for weights
+                    tc_fence_after();
+                    PF(0);  // (profile build: the fence is booked on the input-stage counter)
 #pragma unroll
                     for (int tt = 0; tt < TPS; ++tt) {
                         const int t = g * TPS + tt;
                         issue_tap_mmas<F16, NACC>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
                                                   s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * O::TAP_BYTES, ksteps, use_s || t > 0);
                     }
-                    if (elected) umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
                     PF(3);  // issuing MMAs
+                    if (elected) umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
+                    PF(1);  // (profile build: the commit is booked on the barrier counter)
                 };
                 if (l == 0) {
 #pragma unroll 1
@@ -501,8 +506,8 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
     }
 #ifdef ONB_NET_PROFILE
     if (blockIdx.x == 3 && (tid == 0 || tid == 64))
-        printf("net profile tid %d groups %lld: input %lld barrier %lld weights %lld issue %lld acc %lld epilogue %lld heads %lld\n", tid,
-               (long long)my_groups, pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6]);
+        printf("net profile tid %d groups %lld: input+fence %lld barrier+commit %lld weights %lld (late %lld) issue %lld acc %lld epilogue %lld heads %lld\n",
+               tid, (long long)my_groups, pf[0], pf[1], pf[2], pf[7], pf[3], pf[4], pf[5], pf[6]);
 #endif
     tc_fence_before();
     __syncthreads();
@@ -952,7 +957,8 @@ static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
-    const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * (NACC == 2 ? 2 : 1);
+    const char* one = getenv("ONB_NET_ONE_CTA");  // experiment: a single CTA per SM (is the MMA issue time contention or a per-thread limit?)
+    const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * ((NACC == 2 && !(one && one[0] == '1')) ? 2 : 1);
     k_net_forward<NACC, F16><<<(unsigned)(groups < slots ? groups : slots), 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
     return cudaGetLastError();
 }
