@@ -133,7 +133,7 @@ int32_t onb_destroy(onb_ctx* ctx) {
     void* ptrs[] = {c->d_states, c->d_masks, c->d_planes, c->d_actions, c->d_stats, c->d_io_states, c->d_moves, c->d_counts, c->d_nodes,
                     c->d_tree_size, c->d_tree_flags, c->d_roots, c->d_leaf_node, c->d_leaf_state, c->d_leaf_planes, c->d_policy, c->d_value,
                     c->d_pi, c->d_best, c->d_root_visits, c->d_root_q, c->d_child_visits, c->net[0].w, c->net[0].bias, c->net[0].head, c->net[1].w,
-                    c->net[1].bias, c->net[1].head, c->d_ln_table};
+                    c->net[1].bias, c->net[1].head, c->d_ln_table, c->d_net_scratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->scratch)

@@ -74,6 +74,8 @@ struct Ctx {
         float* head;  // head parameters
         int blocks, loaded, f16;
     } net[2];         // two networks can be resident (an arena pits the new model against the previous one, evaluator.rs:355-399)
+    void* d_net_scratch;       // residual scratch of the three-CTAs-per-SM network kernel
+    size_t net_scratch_bytes;
     int net_cur;      // slot used by onb_net_load / onb_net_forward / ONB_EVAL_NET (onb_net_select)
     int net_tf32;     // requested operand format for the next onb_net_load: 0 = f16 (default), 1 = tf32
     // grow-only device scratch reused across onb_perft calls (counters, cursor, two ping-pong frontiers): repeated

@@ -776,6 +776,213 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
     if (warp == 0) tmem_dealloc(*s_tmem, 512);
 }
 
+// ---- version 3: three CTAs per SM ---------------------------------------------------------------------------------------------
+// The phase timers of version 1 show ~4.2 k cycles per layer and CTA with no MMA in flight against 4.8 k of MMA issue, and TMEM (two
+// accumulators + two parked residuals = 256 columns per CTA) is what limits an SM to two CTAs. Here the residual lives in an
+// L2-resident global scratch instead (f32, written by the epilogue that produces a block input, read back by the epilogue of the
+// block's second convolution -- 64 KB per CTA, coalesced 16-byte accesses), a CTA needs only its two accumulators (128 columns),
+// the weight ring holds single taps (4 x 8 KB), and the epilogue works on 16 channels at a time to fit 80 registers: three CTAs of
+// 7 boards per SM, so that a third group's MMAs fill the gaps of the other two. f16 operands only.
+struct Geo3 {
+    static constexpr int NB = 7, CELLS = NB * kCellsPerBoard, R = (kLead + CELLS + kTrail + 7) / 8 * 8;
+    static constexpr int NSLOT = 4;
+    static constexpr int ACT_BYTES = R * 128;
+    static constexpr int OFF_RING = ACT_BYTES;
+    static constexpr int RING_BYTES = NSLOT * Op<true>::TAP_BYTES;
+    static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
+    static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;
+    static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
+    static constexpr int SMEM = OFF_BAR + (2 * NSLOT + 1) * 8 + 16;
+    static constexpr int TMEM_COLS = 128;
+    static constexpr int SCRATCH_FLOAT4 = 16 * 256;  // residual scratch per CTA: [16 chunks of 4 channels][256 cells]
+    static_assert(SMEM * 3 <= 227 * 1024, "three CTAs per SM");
+};
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(256, 3)
+    k_net_forward3(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net,
+                   float4* __restrict__ scratch) {
+    using G = Geo3;
+    using O = Op<true>;
+    constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = G::NSLOT, NACC = 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t s_act = smem_u32(smem), s_ring = s_act + G::OFF_RING, s_bar = s_act + G::OFF_BAR;
+    float* s_head = reinterpret_cast<float*>(smem + G::OFF_HEAD);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + G::OFF_BAR + (2 * NSLOT + 1) * 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = 1 + 2 * net.n_blocks;
+    const int64_t n_groups = (n + NB - 1) / NB;
+    if ((int64_t)blockIdx.x >= n_groups) return;  // whole CTA, before any allocation
+    const int64_t my_groups = (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t total_taps = (uint32_t)my_groups * 9u * (uint32_t)L;
+    auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
+    auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
+    const uint32_t bar_acc = s_bar + 2 * NSLOT * 8u;
+    float4* skip = scratch + (size_t)blockIdx.x * G::SCRATCH_FLOAT4 + tid;  // + chunk * 256
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
+    for (int i = tid; i < G::ACT_BYTES / 16; i += 256) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero for good
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+
+    uint32_t q0 = 0, q_prod = 0, acc_par = 0;
+    const int a = warp >> 2;                               // this thread's accumulator and cell
+    const int cell = a * 128 + (warp & 3) * 32 + lane;
+    const Cell c = decode_cell(cell, CELLS);
+    const uint32_t tsrc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + a * 64;
+    for (int64_t gi = 0; gi < my_groups; ++gi) {
+        const int64_t board0 = ((int64_t)blockIdx.x + gi * gridDim.x) * NB;
+        // ---- input planes -> the first channel chunks of the activation matrix
+        if (c.real) {
+            const int64_t gb = board0 + c.board;
+            const float* src = planes + gb * 525 + c.pos;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {  // 32 channels (planes 21..31 are zero), 16 at a time
+                float x[16];
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch) x[ch] = (q * 16 + ch < kInPlanes && gb < n) ? __ldg(src + (q * 16 + ch) * 25) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    st_shared_v4(act_addr(s_act, R, kLead + cell, q * 2 + i), to_f16x2(x[8 * i + 0], x[8 * i + 1]), to_f16x2(x[8 * i + 2], x[8 * i + 3]),
+                                 to_f16x2(x[8 * i + 4], x[8 * i + 5]), to_f16x2(x[8 * i + 6], x[8 * i + 7]));
+            }
+        }
+        fence_proxy_async();
+        for (int l = 0; l < L; ++l) {
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            const bool second = l >= 2 && (l & 1) == 0;  // second convolution of a block: the residual is added in the epilogue
+            const bool last = l == L - 1;
+            if (warp == 0) {
+                // ---- MMA issue (the whole warp runs the loop, one lane issues)
+                const bool elected = elect_one();
+                const int ksteps = (l == 0 ? O::KCH0 : O::KCH) / 2;
+#pragma unroll 1
+                for (int t = 0; t < 9; ++t) {
+                    const uint32_t q = q0 + t, slot = q % NSLOT, use = q / NSLOT;
+                    mbar_wait(bar_full(slot), use & 1u);
+                    tc_fence_after();
+                    issue_tap_mmas<true, NACC>(elected, tmem, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1), s_ring + slot * (uint32_t)O::TAP_BYTES,
+                                               ksteps, t > 0);
+                    if (elected) umma_commit(bar_empty(slot));
+                }
+                if (elected) umma_commit(bar_acc);
+            } else if (tid == 32) {
+                // ---- weight producer: keeps the ring NSLOT taps ahead of the MMAs
+                const uint32_t target = min(q0 + 9u + (uint32_t)NSLOT, total_taps);
+                while (q_prod < target) {
+                    const uint32_t slot = q_prod % NSLOT, use = q_prod / NSLOT;
+                    if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
+                    const uint32_t ql = q_prod % (9u * (uint32_t)L);
+                    mbar_expect_tx(bar_full(slot), O::TAP_BYTES);
+                    bulk_g2s(s_ring + slot * (uint32_t)O::TAP_BYTES, net.wconv + (size_t)ql * O::TAP_BYTES, O::TAP_BYTES, bar_full(slot));
+                    ++q_prod;
+                }
+            }
+            __syncwarp();
+            mbar_wait(bar_acc, acc_par);
+            acc_par ^= 1u;
+            tc_fence_after();
+            // ---- epilogue: 16 channels at a time
+            const bool park = (l & 1) == 0 && !last;  // this layer's output is a block input: keep it for the residual add
+            const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
+            const float4* hw = reinterpret_cast<const float4*>(net.head);
+            float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+#pragma unroll 1
+            for (int h = 0; h < 4; ++h) {
+                uint32_t v[16];
+                tmem_ld16(tsrc + h * 16, v);
+                float o[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b = __ldg(bias_l + h * 4 + i);
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (second) r = __ldcg(skip + (h * 4 + i) * 256);
+                    o[4 * i + 0] = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x + r.x, 0.f);
+                    o[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y + r.y, 0.f);
+                    o[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z + r.z, 0.f);
+                    o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w + r.w, 0.f);
+                    if (park) __stcg(skip + (h * 4 + i) * 256, make_float4(o[4 * i + 0], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+                }
+                if (!last && c.real) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        st_shared_v4(act_addr(s_act, R, kLead + cell, h * 2 + i), to_f16x2(o[8 * i + 0], o[8 * i + 1]), to_f16x2(o[8 * i + 2], o[8 * i + 3]),
+                                     to_f16x2(o[8 * i + 4], o[8 * i + 5]), to_f16x2(o[8 * i + 6], o[8 * i + 7]));
+                }
+                if (last) {  // 1x1 convolutions of both heads
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 w0 = __ldg(hw + (kHP0 / 4) + h * 4 + i), w1 = __ldg(hw + (kHP1 / 4) + h * 4 + i), w2 = __ldg(hw + (kHV / 4) + h * 4 + i);
+                        hp0 = fmaf(o[4 * i + 0], w0.x, fmaf(o[4 * i + 1], w0.y, fmaf(o[4 * i + 2], w0.z, fmaf(o[4 * i + 3], w0.w, hp0))));
+                        hp1 = fmaf(o[4 * i + 0], w1.x, fmaf(o[4 * i + 1], w1.y, fmaf(o[4 * i + 2], w1.z, fmaf(o[4 * i + 3], w1.w, hp1))));
+                        hv = fmaf(o[4 * i + 0], w2.x, fmaf(o[4 * i + 1], w2.y, fmaf(o[4 * i + 2], w2.z, fmaf(o[4 * i + 3], w2.w, hv))));
+                    }
+                }
+            }
+            if (last && c.real) {
+                float* hb = s_head + c.board * 75;
+                hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
+                hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
+                hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+            }
+            fence_proxy_async();
+            q0 += 9u;
+        }
+        // ---- heads: one warp per board
+        __syncthreads();
+        for (int b = warp; b < NB; b += 8) {
+            const int64_t gb = board0 + b;
+            if (gb >= n) continue;
+            const float* hb = s_head + b * 75;
+            const bool two = lane + 32 < 50;
+            float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+            for (int i = 0; i < 50; ++i) {
+                const float x = hb[i];
+                l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
+                if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+            }
+            const float m = warp_max(two ? fmaxf(l0, l1) : l0);
+            const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
+            const float s = warp_sum(e0 + e1);
+            policy[gb * 50 + lane] = e0 / s;
+            if (two) policy[gb * 50 + 32 + lane] = e1 / s;
+            float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+            for (int i = 0; i < 25; ++i) {
+                const float x = hb[50 + i];
+                h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
+                h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+            }
+            float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+            acc = warp_sum(acc);
+            if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
+}
+
 // ---- host side: fold BatchNorm, round to tf32, lay the weights out as the tensor core reads them ------------------------------
 struct Named {
     std::string name;
@@ -979,12 +1186,40 @@ static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, flo
     return cudaGetLastError();
 }
 
+static cudaError_t launch_net_v3(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
+    using G = Geo3;
+    static bool attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(k_net_forward3, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+    const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * 3;
+    const unsigned grid = (unsigned)(groups < slots ? groups : slots);
+    const size_t need = (size_t)grid * G::SCRATCH_FLOAT4 * sizeof(float4);
+    if (c->net_scratch_bytes < need) {
+        cudaStreamSynchronize(c->stream);
+        if (c->d_net_scratch) cudaFree(c->d_net_scratch);
+        c->d_net_scratch = nullptr;
+        c->net_scratch_bytes = 0;
+        const cudaError_t e = cudaMalloc(&c->d_net_scratch, need);
+        if (e != cudaSuccess) return e;
+        c->net_scratch_bytes = need;
+    }
+    k_net_forward3<<<grid, 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd, reinterpret_cast<float4*>(c->d_net_scratch));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value) {
     const Ctx::NetSlot& ns = c->net[c->net_cur];
     const NetDev nd{reinterpret_cast<const uint8_t*>(ns.w), ns.bias, ns.head, ns.blocks};
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* v3 = getenv("ONB_NET_V3");  // three CTAs per SM, residual in an L2-resident scratch (f16 operands only)
+    if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms);
     const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)
     if (v2 && v2[0] == '1') return ns.f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms) : launch_net_v2<false>(c, planes, policy, value, nd, sms);
     const char* wide = getenv("ONB_NET_WIDE");  // exploration knob: 14 boards per CTA, one CTA per SM
