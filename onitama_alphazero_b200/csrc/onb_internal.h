@@ -80,8 +80,8 @@ struct Ctx {
     int net_tf32;     // requested operand format for the next onb_net_load: 0 = f16 (default), 1 = tf32
     // grow-only device scratch reused across onb_perft calls (counters, cursor, two ping-pong frontiers): repeated
     // cudaMalloc/cudaFree of several hundred MB made the call time vary by +-50 %
-    void* scratch[8];
-    size_t scratch_cap[8];
+    void* scratch[16];
+    size_t scratch_cap[16];
     char err[512];
 };
 

@@ -65,11 +65,25 @@ __global__ void __launch_bounds__(128) k_perft_expand(const uint4* __restrict__ 
     unsigned long long base = 0;
     if (lane == 31 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
     base = __shfl_sync(0xFFFFFFFFu, base, 31);
-    if (!live) return;
     if (COUNT_ONLY) return;
-    atomicAdd(&nodes[(int64_t)root * depth_total + level], (unsigned long long)total);
-    if (nwin) atomicAdd(&wins[(int64_t)root * depth_total + level], (unsigned long long)nwin);
-    if (total == 0) atomicAdd(&zero[(int64_t)root * depth_total + level], 1ull);
+    {   // counters: one set of atomics per warp when every lane works for the same root (siblings sit together in the frontier)
+        const unsigned full = 0xFFFFFFFFu;
+        const uint32_t r0 = __shfl_sync(full, live ? root : 0xFFFFFFFFu, 0);
+        const bool same = __all_sync(full, (live ? root : 0xFFFFFFFFu) == r0);
+        if (same) {
+            const uint32_t T = __reduce_add_sync(full, total), W = __reduce_add_sync(full, nwin), Z = __reduce_add_sync(full, live && total == 0 ? 1u : 0u);
+            if (lane == 0 && live) {
+                if (T) atomicAdd(&nodes[(int64_t)root * depth_total + level], (unsigned long long)T);
+                if (W) atomicAdd(&wins[(int64_t)root * depth_total + level], (unsigned long long)W);
+                if (Z) atomicAdd(&zero[(int64_t)root * depth_total + level], (unsigned long long)Z);
+            }
+        } else if (live) {
+            atomicAdd(&nodes[(int64_t)root * depth_total + level], (unsigned long long)total);
+            if (nwin) atomicAdd(&wins[(int64_t)root * depth_total + level], (unsigned long long)nwin);
+            if (total == 0) atomicAdd(&zero[(int64_t)root * depth_total + level], 1ull);
+        }
+    }
+    if (!live) return;
     unsigned long long pos = base + (incl - n_children);
     for (uint32_t s = 0; s < 2; ++s) {
         const uint32_t idx = side * 2u + s;
@@ -304,6 +318,128 @@ static cudaError_t launch_dfs(Ctx* c, const uint4* st, const uint32_t* rt, int64
     return cudaGetLastError();
 }
 
+// ---- phase 2b: the last two levels of one frontier node per thread -----------------------------------------------------------
+// With the frontier two plies above the horizon a thread generates the node's children and bulk-counts each child's moves: the
+// opponent's hand is the same for all children (the mover's card goes to the neutral slot), so both attack-table rows are hoisted
+// and a child costs ~10 table reads and popcounts. Work per thread is small and similar across a warp (the flat DFS above runs
+// 16 of 32 lanes on average), and the counters are added per warp when all lanes share a root (frontier order keeps siblings together).
+__global__ void __launch_bounds__(256) k_perft_leaf2(const uint4* __restrict__ states, const uint32_t* __restrict__ roots, int64_t n_items,
+                                                     unsigned long long* __restrict__ nodes, unsigned long long* __restrict__ wins,
+                                                     unsigned long long* __restrict__ zero, int depth_total, int level) {
+    // the attack table is read from its global-memory mirror (L1 resident): ~20 reads per thread do not pay for staging it in shared
+    // memory per CTA; the rows of the children's mover are read once per node and kept in registers
+    const uint32_t* T = g_attack.t;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n_items;
+    uint32_t root = 0xFFFFFFFFu, t0 = 0, w0 = 0, z0 = 0, t1 = 0, w1 = 0, z1 = 0;
+    if (live) {
+        const Game g = unpack(states[i]);
+        root = roots[i];
+        const uint32_t side = g.side;
+        const uint32_t own_p = side ? g.pawn_b : g.pawn_r, own_k = side ? g.king_b : g.king_r;
+        const uint32_t en_p = side ? g.pawn_r : g.pawn_b, en_k = side ? g.king_r : g.king_b;
+        const uint32_t own = own_p | own_k;
+        const uint32_t win_t = en_k & ~en_p;
+        const uint32_t temple = 1u << (side ? kRedTemple : kBlueTemple);
+        const uint32_t temple2 = 1u << (side ? kBlueTemple : kRedTemple);  // the children's side moves towards the other temple
+        const uint32_t* U0 = T + ((side ^ 1u) * 16u + card_at(g.cards, (side ^ 1u) * 2u)) * 25u;
+        const uint32_t* U1 = T + ((side ^ 1u) * 16u + card_at(g.cards, (side ^ 1u) * 2u + 1u)) * 25u;
+        // the opponent's pieces (the children's movers): square bit, both cards' masks, temple bit if it is the king
+        constexpr int MAXP = 5;
+        uint32_t pb[MAXP], m0[MAXP], m1[MAXP], tk[MAXP];
+        const uint32_t en = en_p | en_k;
+        const bool small = __popc(en) <= MAXP;  // always true for positions reachable by play; fabricated ones take the generic loop
+        {
+            uint32_t r = en;
+#pragma unroll
+            for (int j = 0; j < MAXP; ++j) {
+                pb[j] = 0; m0[j] = 0; m1[j] = 0; tk[j] = 0;
+                if (r) {
+                    const int f2 = __ffs(r) - 1;
+                    r &= r - 1;
+                    pb[j] = 1u << f2;
+                    m0[j] = __ldg(U0 + f2);
+                    m1[j] = __ldg(U1 + f2);
+                    tk[j] = ((en_p >> f2) & 1u) ? 0u : temple2;
+                }
+            }
+        }
+#pragma unroll 1
+        for (uint32_t s = 0; s < 2; ++s) {
+            const uint32_t* Ts = T + (side * 16u + card_at(g.cards, side * 2u + s)) * 25u;
+            uint32_t rem = own;
+#pragma unroll 1
+            while (rem) {
+                const int f = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const uint32_t king = ((own_p >> f) & 1u) ^ 1u;
+                const uint32_t a = __ldg(Ts + f) & ~own;
+                const uint32_t wm = a & (win_t | (king ? temple : 0u));
+                t0 += __popc(a);
+                w0 += __popc(wm);
+                uint32_t b = a & ~wm;  // wins end the line
+#pragma unroll 1
+                while (b) {
+                    const uint32_t tb = b & (0u - b);
+                    b &= b - 1;
+                    // the child position from its mover's (the opponent's) point of view
+                    const uint32_t c_own_p = en_p & ~tb, c_own = c_own_p | en_k;  // a pawn on `to` is captured
+                    const uint32_t c_en_k = king ? tb : own_k;                     // win target: the king that just moved or stayed
+                    uint32_t ct = 0, cw = 0;
+                    if (small) {
+#pragma unroll
+                        for (int j = 0; j < MAXP; ++j) {
+                            const uint32_t alive = (pb[j] & c_own) ? ~c_own : 0u;  // a captured pawn (or an empty slot) has no moves
+                            const uint32_t a0 = m0[j] & alive, a1 = m1[j] & alive;
+                            const uint32_t tw = c_en_k | tk[j];
+                            ct += __popc(a0) + __popc(a1);
+                            cw += __popc(a0 & tw) + __popc(a1 & tw);
+                        }
+                    } else {
+                        uint32_t r2 = c_own;
+                        while (r2) {
+                            const int f2 = __ffs(r2) - 1;
+                            r2 &= r2 - 1;
+                            const uint32_t tw = c_en_k | (((c_own_p >> f2) & 1u) ? 0u : temple2);
+                            const uint32_t a0 = __ldg(U0 + f2) & ~c_own, a1 = __ldg(U1 + f2) & ~c_own;
+                            ct += __popc(a0) + __popc(a1);
+                            cw += __popc(a0 & tw) + __popc(a1 & tw);
+                        }
+                    }
+                    t1 += ct;
+                    w1 += cw;
+                    z1 += ct == 0;
+                }
+            }
+        }
+        z0 = t0 == 0;
+    }
+    // counters: one set of atomics per warp when every lane works for the same root
+    const unsigned full = 0xFFFFFFFFu;
+    const bool same = __all_sync(full, root == __shfl_sync(full, root, 0));
+    const int64_t row = (int64_t)root * depth_total + level;
+    if (same) {
+        if (root == 0xFFFFFFFFu) return;  // a warp beyond the end
+        const uint32_t T0 = __reduce_add_sync(full, t0), W0 = __reduce_add_sync(full, w0), Z0 = __reduce_add_sync(full, z0);
+        const uint32_t T1 = __reduce_add_sync(full, t1), W1 = __reduce_add_sync(full, w1), Z1 = __reduce_add_sync(full, z1);
+        if ((threadIdx.x & 31) == 0) {
+            if (T0) atomicAdd(&nodes[row], (unsigned long long)T0);
+            if (W0) atomicAdd(&wins[row], (unsigned long long)W0);
+            if (Z0) atomicAdd(&zero[row], (unsigned long long)Z0);
+            if (T1) atomicAdd(&nodes[row + 1], (unsigned long long)T1);
+            if (W1) atomicAdd(&wins[row + 1], (unsigned long long)W1);
+            if (Z1) atomicAdd(&zero[row + 1], (unsigned long long)Z1);
+        }
+    } else if (live) {
+        if (t0) atomicAdd(&nodes[row], (unsigned long long)t0);
+        if (w0) atomicAdd(&wins[row], (unsigned long long)w0);
+        if (z0) atomicAdd(&zero[row], (unsigned long long)z0);
+        if (t1) atomicAdd(&nodes[row + 1], (unsigned long long)t1);
+        if (w1) atomicAdd(&wins[row + 1], (unsigned long long)w1);
+        if (z1) atomicAdd(&zero[row + 1], (unsigned long long)z1);
+    }
+}
+
 static int32_t perft_fail(Ctx* c, cudaError_t e, const char* what) {
     snprintf(c->err, sizeof(c->err), "onb_perft: %s: %s", what, cudaGetErrorString(e));
     return e == cudaErrorMemoryAllocation ? ONB_E_NOMEM : ONB_E_CUDA;
@@ -323,6 +459,42 @@ static cudaError_t scratch_get(Ctx* c, int slot, size_t bytes, void** out) {
         c->scratch_cap[slot] = want;
     }
     *out = c->scratch[slot];
+    return cudaSuccess;
+}
+
+// Frontier -> counters for the `rem` plies that remain, in bounded memory: while more than two plies remain the frontier is expanded
+// chunk by chunk into a per-level scratch pair and each chunk is finished recursively; two plies above the horizon k_perft_leaf2
+// takes over. `slot` = first scratch slot of this recursion level (two slots per level).
+static cudaError_t perft_finish(Ctx* c, const uint4* st, const uint32_t* rt, int64_t n_items, unsigned long long* nodes, unsigned long long* wins,
+                                unsigned long long* zero, unsigned long long* d_cursor, int depth, int level, int slot) {
+    const int rem = depth - level;
+    if (n_items <= 0 || rem <= 0) return cudaSuccess;
+    if (rem == 1) return launch_dfs<1>(c, st, rt, n_items, nodes, wins, zero, depth);
+    if (rem == 2) {
+        k_perft_leaf2<<<(unsigned)((n_items + 255) / 256), 256, 0, c->stream>>>(st, rt, n_items, nodes, wins, zero, depth, level);
+        return cudaGetLastError();
+    }
+    if (slot + 1 >= 16) return cudaErrorInvalidValue;
+    const int64_t chunk = 8 << 20;  // parents per chunk: at most 40 children each -> the child frontier stays below 6.7 GB
+    for (int64_t off = 0; off < n_items; off += chunk) {
+        const int64_t m = n_items - off < chunk ? n_items - off : chunk;
+        unsigned long long total = 0;
+        cudaError_t e = cudaMemsetAsync(d_cursor, 0, 8, c->stream);
+        if (e != cudaSuccess) return e;
+        k_perft_expand<true><<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(st + off, rt + off, m, nullptr, nullptr, d_cursor, nodes, wins, zero, depth,
+                                                                                level);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(&total, d_cursor, 8, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
+        uint4* ns = nullptr;
+        uint32_t* nr = nullptr;
+        if ((e = scratch_get(c, slot, (size_t)total * 16, (void**)&ns)) != cudaSuccess) return e;
+        if ((e = scratch_get(c, slot + 1, (size_t)total * 4, (void**)&nr)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(d_cursor, 0, 8, c->stream)) != cudaSuccess) return e;
+        k_perft_expand<false><<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(st + off, rt + off, m, ns, nr, d_cursor, nodes, wins, zero, depth, level);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = perft_finish(c, ns, nr, (int64_t)total, nodes, wins, zero, d_cursor, depth, level + 1, slot + 2)) != cudaSuccess) return e;
+    }
     return cudaSuccess;
 }
 
@@ -366,7 +538,9 @@ int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uin
             PF(cudaStreamSynchronize(c->stream), "sync");
             int level = 0;
             // breadth-first while the frontier is too small to fill 148 SMs or the remaining depth exceeds the DFS template range
-            while (n_cur > 0 && ((depth - level) > kMaxDfs || ((depth - level) > 1 && n_cur < (int64_t)(1 << 21)))) {
+            int64_t bfs_nodes = 1 << 21;
+            if (const char* env = getenv("ONB_PERFT_BFS_NODES")) bfs_nodes = atoll(env);  // experiment: deeper frontier, shallower DFS
+            while (n_cur > 0 && ((depth - level) > kMaxDfs || ((depth - level) > 1 && n_cur < bfs_nodes))) {
                 unsigned long long total = 0;
                 PF(cudaMemsetAsync(d_cursor, 0, 8, c->stream), "memset");
                 k_perft_expand<true><<<(unsigned)((n_cur + 127) / 128), 128, 0, c->stream>>>(cur_s, cur_r, n_cur, nullptr, nullptr, d_cursor, d_nodes, d_wins,
@@ -389,7 +563,10 @@ int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uin
                 ++level;
             }
             const int rem = depth - level;
-            if (n_cur > 0 && rem > 0) {
+            const char* dfs_env = getenv("ONB_PERFT_DFS");  // exploration knob: finish with the flat DFS instead of expand + two-ply kernel
+            if (!(dfs_env && dfs_env[0] == '1')) {
+                PF(perft_finish(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, d_cursor, depth, level, 8), "finish");
+            } else if (n_cur > 0 && rem > 0) {
                 switch (rem) {
                     case 1: PF(launch_dfs<1>(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, depth), "dfs"); break;
                     case 2: PF(launch_dfs<2>(c, cur_s, cur_r, n_cur, d_nodes, d_wins, d_zero, depth), "dfs"); break;
