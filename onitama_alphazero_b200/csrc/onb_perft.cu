@@ -364,6 +364,15 @@ __global__ void __launch_bounds__(256) k_perft_leaf2(const uint4* __restrict__ s
                 }
             }
         }
+        // replies of the opponent when none of its pieces is captured: masks, their number, and the winning ones if this side's king stays
+        uint32_t f0[MAXP], f1[MAXP], base_ct = 0, base_cw = 0;
+#pragma unroll
+        for (int j = 0; j < MAXP; ++j) {
+            f0[j] = m0[j] & ~en;
+            f1[j] = m1[j] & ~en;
+            base_ct += __popc(f0[j]) + __popc(f1[j]);
+            base_cw += __popc(f0[j] & (own_k | tk[j])) + __popc(f1[j] & (own_k | tk[j]));
+        }
 #pragma unroll 1
         for (uint32_t s = 0; s < 2; ++s) {
             const uint32_t* Ts = T + (side * 16u + card_at(g.cards, side * 2u + s)) * 25u;
@@ -378,6 +387,32 @@ __global__ void __launch_bounds__(256) k_perft_leaf2(const uint4* __restrict__ s
                 t0 += __popc(a);
                 w0 += __popc(wm);
                 uint32_t b = a & ~wm;  // wins end the line
+                if (small) {
+                    // The reply count of a child depends only on the opponent's own pieces, its winning replies only on where this
+                    // side's king stands: a quiet pawn move changes neither -> counted in bulk; a quiet king move changes the target
+                    // square only; captures (the opponent loses a pawn) take the per-child loop below.
+                    const uint32_t quiet = b & ~en_p;
+                    if (!king) {
+                        const uint32_t nq = __popc(quiet);
+                        t1 += nq * base_ct;
+                        w1 += nq * base_cw;
+                        z1 += base_ct == 0 ? nq : 0u;
+                        b &= en_p;
+                    } else {
+                        uint32_t q = quiet;
+                        while (q) {
+                            const uint32_t tb = q & (0u - q);
+                            q &= q - 1;
+                            uint32_t cw = 0;
+#pragma unroll
+                            for (int j = 0; j < MAXP; ++j) cw += __popc(f0[j] & (tb | tk[j])) + __popc(f1[j] & (tb | tk[j]));
+                            t1 += base_ct;
+                            w1 += cw;
+                            z1 += base_ct == 0;
+                        }
+                        b &= en_p;
+                    }
+                }
 #pragma unroll 1
                 while (b) {
                     const uint32_t tb = b & (0u - b);
