@@ -243,6 +243,38 @@ ONB_API int32_t onb_mcts_dump_tree(onb_ctx* ctx, int64_t tree, int64_t cap, onb_
  * reference is undefined for that tree, bit1: node pool overflow) */
 ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_host);
 
+/* ---- self_play (alphazero-training/src/train.rs:35-98) for all games of the context, natively -------------------------------
+ * Plays until at least n_games games are complete: per ply { planes of every slot (train.rs:58); search (evaluator = ONB_EVAL_*,
+ * ONB_EVAL_NET for the loaded network; train != 0: root exploration noise, epsilon 0.25 / alpha 0.03); record (planes, pi,
+ * colour); play the best move; finished games (a win, or max_plies + 2 plies: the ply cap of train.rs:74-79) get their z =
+ * reward(result, sample colour) and their slot is re-dealt at once }. Nothing but one 8-byte counter per ply crosses PCIe.
+ * The result points at device buffers owned by the context (valid until the next onb_self_play / onb_destroy): sample
+ * i = ply * n_games_of_ctx + slot; valid_idx[0 .. n_valid) lists, ascending, the samples that belong to completed games (the
+ * games still running when the quota was reached are not listed). serial = slot + n * (games finished before in that slot).
+ * sample_cap bounds the buffers (samples; >= one ply); truncated = 1 if it was reached before n_games were complete.
+ * Requires onb_config.alloc_planes and mcts_max_sims >= sims. Every game is dealt from the counter RNG (epoch = ply + 1). */
+typedef struct onb_selfplay_config {
+    double c_puct;
+    uint32_t sims;
+    int32_t evaluator;
+    int64_t n_games;
+    uint32_t max_plies; /* train.rs: 150 */
+    int32_t train;
+    uint64_t noise_seed;
+    int64_t sample_cap;
+} onb_selfplay_config;
+typedef struct onb_selfplay_result {
+    int64_t n_samples, n_valid, n_games, plies_run;
+    int32_t truncated, reserved;
+    float* planes;      /* [n_samples][21][5][5] */
+    float* pi;          /* [n_samples][2][25] */
+    float* z;           /* [n_samples] */
+    uint8_t* color;     /* [n_samples] side to move */
+    int64_t* serial;    /* [n_samples] */
+    int64_t* valid_idx; /* [n_valid] */
+} onb_selfplay_result;
+ONB_API int32_t onb_self_play(onb_ctx* ctx, const onb_selfplay_config* cfg, onb_selfplay_result* out);
+
 /* ---- plain UCT with random rollouts: the `Mcts` agent (onitama-game/src/ai/mcts/{mod.rs,mcts_arena.rs}) ---------------
  * The evaluation opponent of the reference's arena (evaluator.rs), one tree per game, rooted like the PUCT search:
  * onb_mcts_begin (its c_puct is ignored); onb_uct_run(ctx, exploration_c, min_node_visits, playouts);

@@ -76,12 +76,24 @@ SYMBOLS = {
     "onb_mcts_dump_tree": (C.c_int32, [_P, C.c_int64, C.c_int64, C.POINTER(TreeDump), C.POINTER(C.c_int64)]),
     "onb_mcts_tree_info": (C.c_int32, [_P, _P, _P]),
     "onb_selftest": (C.c_int32, [_P, C.c_int32, _P]),
+    "onb_self_play": (C.c_int32, [_P, _P, _P]),
     "onb_uct_run": (C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32]),
     "onb_net_precision": (C.c_int32, [_P, C.c_int32]),
     "onb_net_select": (C.c_int32, [_P, C.c_int32]),
     "onb_net_load": (C.c_int32, [_P, C.c_int32, _P, _P, _P]),
     "onb_net_forward": (C.c_int32, [_P, C.c_int32]),
 }
+
+class SelfPlayConfig(C.Structure):
+    _fields_ = [("c_puct", C.c_double), ("sims", C.c_uint32), ("evaluator", C.c_int32), ("n_games", C.c_int64), ("max_plies", C.c_uint32),
+                ("train", C.c_int32), ("noise_seed", C.c_uint64), ("sample_cap", C.c_int64)]
+
+
+class SelfPlayResult(C.Structure):
+    _fields_ = [("n_samples", C.c_int64), ("n_valid", C.c_int64), ("n_games", C.c_int64), ("plies_run", C.c_int64), ("truncated", C.c_int32),
+                ("reserved", C.c_int32), ("planes", C.c_void_p), ("pi", C.c_void_p), ("z", C.c_void_p), ("color", C.c_void_p),
+                ("serial", C.c_void_p), ("valid_idx", C.c_void_p)]
+
 
 _lib = None
 

@@ -134,6 +134,8 @@ int32_t onb_destroy(onb_ctx* ctx) {
                     c->d_tree_size, c->d_tree_flags, c->d_roots, c->d_leaf_node, c->d_leaf_state, c->d_leaf_planes, c->d_policy, c->d_value,
                     c->d_pi, c->d_best, c->d_root_visits, c->d_root_q, c->d_child_visits, c->net[0].w, c->net[0].bias, c->net[0].head, c->net[1].w,
                     c->net[1].bias, c->net[1].head, c->d_ln_table, c->d_net_scratch};
+    for (void* p : c->sp_buf)
+        if (p) cudaFree(p);
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->scratch)
@@ -501,6 +503,35 @@ int32_t onb_mcts_run(onb_ctx* ctx, int32_t evaluator, uint32_t sims) {
     }
     ONB_CUDA(c, launch_mcts_run(c, evaluator, sims));
     c->sims_done += sims;
+    return ONB_OK;
+}
+static int32_t self_play_search(Ctx* c, const onb_selfplay_config* cfg) {
+    onb_ctx* x = reinterpret_cast<onb_ctx*>(c);
+    int32_t rc = onb_mcts_begin(x, cfg->c_puct, cfg->sims);
+    if (rc == ONB_OK) rc = onb_mcts_run(x, cfg->evaluator, cfg->sims);
+    if (rc == ONB_OK) rc = onb_mcts_finish(x, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return rc;
+}
+int32_t onb_self_play(onb_ctx* ctx, const onb_selfplay_config* cfg, onb_selfplay_result* out) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!cfg || !out) return fail(c, ONB_E_INVALID, "onb_self_play: null argument");
+    if (!c->d_planes || !c->d_nodes) return fail(c, ONB_E_STATE, "onb_self_play: the context needs alloc_planes and mcts_max_sims > 0");
+    if (cfg->sims == 0 || cfg->sims > c->cfg.mcts_max_sims) return fail(c, ONB_E_INVALID, "onb_self_play: sims %u not in 1..mcts_max_sims", cfg->sims);
+    if (cfg->n_games <= 0) return fail(c, ONB_E_INVALID, "onb_self_play: n_games must be positive");
+    memset(out, 0, sizeof(*out));
+    int32_t rc = onb_mcts_set_noise(ctx, cfg->train ? 1 : 0, 0.25, 0.03, cfg->noise_seed);
+    if (rc != ONB_OK) return rc;
+    char err[400];
+    err[0] = 0;
+    try {
+        rc = run_self_play(c, cfg, out, self_play_search, err, sizeof(err));
+    } catch (const std::exception& ex) {
+        snprintf(err, sizeof(err), "onb_self_play: %s", ex.what());
+        rc = ONB_E_NOMEM;
+    }
+    onb_mcts_set_noise(ctx, 0, 0.25, 0.03, 0);
+    if (rc != ONB_OK) return fail(c, rc, "%s", err);
     return ONB_OK;
 }
 int32_t onb_uct_run(onb_ctx* ctx, float exploration_c, uint32_t min_node_visits, uint32_t playouts) {

@@ -74,6 +74,8 @@ struct Ctx {
         float* head;  // head parameters
         int blocks, loaded, f16;
     } net[2];         // two networks can be resident (an arena pits the new model against the previous one, evaluator.rs:355-399)
+    void* sp_buf[10];          // grow-only buffers of onb_self_play (samples, per-slot bookkeeping)
+    size_t sp_cap[10];
     void* d_net_scratch;       // residual scratch of the three-CTAs-per-SM network kernel
     size_t net_scratch_bytes;
     int net_cur;      // slot used by onb_net_load / onb_net_forward / ONB_EVAL_NET (onb_net_select)
@@ -109,6 +111,10 @@ cudaError_t launch_mcts_play_best(Ctx* c, uint32_t out_flags);
 // network (onb_net.cu)
 int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel, std::string& err);
 cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value);
+
+// native self-play driver (onb_selfplay.cu)
+int32_t run_self_play(Ctx* c, const onb_selfplay_config* cfg, onb_selfplay_result* out, int32_t (*search)(Ctx*, const onb_selfplay_config*), char* err,
+                      size_t err_len);
 
 constexpr int kModeActions = 2;  // env step modes: 0 = ONB_POLICY_UNIFORM, 1 = ONB_POLICY_AGENT, 2 = explicit actions
 

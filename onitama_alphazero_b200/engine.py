@@ -202,6 +202,31 @@ class Context:
     def mcts_run(self, evaluator, sims):
         self._ck(self._lib.onb_mcts_run(self._h, evaluator, sims))
 
+    def self_play_native(self, c_puct, sims, n_games, max_plies=150, evaluator=L.EVAL_UNIFORM, train=False, noise_seed=0, sample_cap=None):
+        """onb_self_play: the whole self-play loop inside the library (search, recording, moves, z, restart of finished slots).
+        Returns torch tensors of the completed games' samples (gathered from the context's device buffers) like
+        selfplay.self_play_continuous."""
+        import torch
+        if sample_cap is None:
+            sample_cap = self.n * (max_plies + 2) * max(2, 2 * (n_games + self.n - 1) // self.n)
+        cfg = L.SelfPlayConfig(c_puct, sims, evaluator, n_games, max_plies, int(bool(train)), noise_seed, sample_cap)
+        res = L.SelfPlayResult()
+        self._ck(self._lib.onb_self_play(self._h, C.byref(cfg), C.byref(res)))
+        with torch.cuda.stream(self.torch_stream()):
+            m = int(res.n_samples)
+
+            def view(ptr, shape, typestr, dtype):
+                if m == 0 or not ptr:
+                    return torch.zeros(shape, dtype=dtype, device="cuda:%d" % self.device)
+                return torch.as_tensor(_DevBuf(ptr, shape, typestr), device="cuda:%d" % self.device)
+
+            idx = view(res.valid_idx, (int(res.n_valid),), "<i8", torch.int64)
+            out = dict(planes=view(res.planes, (m, 21, 5, 5), "<f4", torch.float32)[idx], pi=view(res.pi, (m, 2, 25), "<f4", torch.float32)[idx],
+                       z=view(res.z, (m,), "<f4", torch.float32)[idx], color=view(res.color, (m,), "|u1", torch.uint8)[idx].to(torch.int8),
+                       serial=view(res.serial, (m,), "<i8", torch.int64)[idx], games=int(res.n_games), plies_run=int(res.plies_run),
+                       truncated=bool(res.truncated))
+        return out
+
     def uct_search(self, exploration_c=2.0 ** 0.5, min_node_visits=5, playouts=5000, to_host=True):
         """The reference's `Mcts` agent for every game at once: plain UCT with random rollouts (ai/mcts/mcts_arena.rs)."""
         self.mcts_begin(0.0, playouts)

@@ -124,7 +124,7 @@ def self_play_continuous(ctx, c_puct, sims, n_games, max_plies=150, evaluator=L.
         slots = torch.arange(n, device=dev)
         rec = {"planes": [], "pi": [], "color": [], "serial": []}
         winners = {}   # serial -> 0 draw (ply cap), 1 Red, 2 Blue
-        done, tick = 0, 0
+        done, tick = 0, 0   # tick = plies played so far; a slot restarted after ply `tick` is dealt at epoch tick + 1 (as onb_self_play does)
         while done < n_games:
             st = states_t.clone()
             ctx.encode(to_host=False)                       # create_tensor_from_state of the searched position (train.rs:58)
@@ -144,10 +144,10 @@ def self_play_continuous(ctx, c_puct, sims, n_games, max_plies=150, evaluator=L.
                 for s_, r_ in zip(ser, result[idx].tolist()):
                     winners[s_] = r_
                 done += len(ser)
-                tick += 1
-                ctx.reset_games(over.to(torch.uint8).cpu().numpy(), epoch=tick)
+                ctx.reset_games(over.to(torch.uint8).cpu().numpy(), epoch=tick + 1)
                 generation[idx] += 1
                 plies[idx] = 0
+            tick += 1
         planes = torch.cat(rec["planes"])
         pi = torch.cat(rec["pi"])
         color = torch.cat(rec["color"])

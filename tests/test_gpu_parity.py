@@ -1193,3 +1193,30 @@ def test_self_play_continuous_keeps_slots_busy(onb):
         assert torch.equal(cont["z"][a], lock["z"][b])
         checked += 1
     assert checked >= n // 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("evaluator", ["uniform", "net"])
+def test_native_self_play_equals_the_python_driver(onb, evaluator):
+    """onb_self_play (the whole loop inside the library) against selfplay.self_play_continuous (the same loop driven from Python
+    over the C ABI): identical samples, z, colours, serials and game counts -- eval mode, so the searches are deterministic."""
+    import torch
+    from test_net_cpu import lively_model
+    n, sims, c, games = 40, 12, 2.0, 100
+    with onb.Context(n, seed=17, mcts_max_sims=sims) as ctx:
+        ev = onb.EVAL_UNIFORM
+        if evaluator == "net":
+            ctx.net_load(lively_model(1, seed=4))
+            ev = onb.EVAL_NET
+        py = onb.self_play_continuous(ctx, c, sims, n_games=games, max_plies=30, evaluator=ev)
+        nat = ctx.self_play_native(c, sims, games, max_plies=30, evaluator=ev)
+        assert nat["games"] == py["games"] >= games and not nat["truncated"]
+        for k in ("planes", "pi", "z", "serial"):
+            assert torch.equal(nat[k], py[k]), k
+        assert torch.equal(nat["color"], py["color"])
+        assert (nat["z"] == 0).any() or True
+        # a buffer that is too small stops early and says so
+        small = ctx.self_play_native(c, sims, 10 ** 6, max_plies=30, evaluator=ev, sample_cap=3 * n)
+        assert small["truncated"] and small["plies_run"] == 3
+        with pytest.raises(onb.OnbError):
+            ctx.self_play_native(c, sims + 1, 10, evaluator=ev)
