@@ -274,6 +274,8 @@ typedef struct onb_selfplay_result {
     int64_t* valid_idx; /* [n_valid] */
 } onb_selfplay_result;
 ONB_API int32_t onb_self_play(onb_ctx* ctx, const onb_selfplay_config* cfg, onb_selfplay_result* out);
+/* host copy of a borrowed device pointer (onb_buffer, onb_selfplay_result), ordered after the work queued on the context's stream */
+ONB_API int32_t onb_copy_to_host(onb_ctx* ctx, void* host, const void* device, int64_t bytes);
 
 /* ---- plain UCT with random rollouts: the `Mcts` agent (onitama-game/src/ai/mcts/{mod.rs,mcts_arena.rs}) ---------------
  * The evaluation opponent of the reference's arena (evaluator.rs), one tree per game, rooted like the PUCT search:

@@ -479,6 +479,44 @@ inline std::vector<SelfPlayData> self_play(const TrainingAlphaZeroMcts& mcts, co
     return out;
 }
 
+/// self_play for a training run: `slots` games in flight on one engine, every slot restarted the moment its game is over, until
+/// config.self_play_game_amnt games are complete (onb_self_play: the loop runs inside the library, the samples are copied to the
+/// host once at the end). Needs a device evaluator: mcts.device_evaluator = ONB_EVAL_NET after Engine::load_network, or
+/// ONB_EVAL_UNIFORM / ONB_EVAL_HASH. Samples come ply-major; games still running when the quota is reached are dropped.
+inline std::vector<SelfPlayData> self_play_continuous(Engine& e, const TrainingAlphaZeroMcts& mcts, const TrainConfig& config) {
+    if (mcts.model) throw Error(ONB_E_INVALID, "self_play_continuous: a host evaluator cannot run inside the library; load the network instead");
+    onb_selfplay_config cfg{};
+    cfg.c_puct = mcts.config.exploration_c; cfg.sims = mcts.config.max_playouts; cfg.evaluator = mcts.device_evaluator;
+    cfg.n_games = (int64_t)config.self_play_game_amnt; cfg.max_plies = (uint32_t)config.max_plies; cfg.train = mcts.config.train ? 1 : 0;
+    cfg.noise_seed = mcts.config.noise_seed;
+    const int64_t generations = 2 + 2 * ((int64_t)config.self_play_game_amnt + e.n() - 1) / e.n();
+    cfg.sample_cap = e.n() * (config.max_plies + 2) * generations;
+    onb_selfplay_result r{};
+    e.check(onb_self_play(e.ctx(), &cfg, &r));
+    std::vector<int64_t> idx((size_t)r.n_valid);
+    std::vector<float> planes((size_t)r.n_samples * 525), pi((size_t)r.n_samples * 50), z((size_t)r.n_samples);
+    std::vector<uint8_t> color((size_t)r.n_samples);
+    e.check(onb_sync(e.ctx()));
+    if (r.n_samples) {
+        if (!idx.empty()) e.check(onb_copy_to_host(e.ctx(), idx.data(), r.valid_idx, (int64_t)idx.size() * 8));
+        e.check(onb_copy_to_host(e.ctx(), planes.data(), r.planes, (int64_t)planes.size() * 4));
+        e.check(onb_copy_to_host(e.ctx(), pi.data(), r.pi, (int64_t)pi.size() * 4));
+        e.check(onb_copy_to_host(e.ctx(), z.data(), r.z, (int64_t)z.size() * 4));
+        e.check(onb_copy_to_host(e.ctx(), color.data(), r.color, (int64_t)color.size()));
+    }
+    std::vector<SelfPlayData> out;
+    out.reserve(idx.size());
+    for (int64_t i : idx) {
+        SelfPlayData d;
+        std::memcpy(d.pi.data(), &pi[(size_t)i * 50], 200);
+        std::memcpy(d.state.data(), &planes[(size_t)i * 525], 2100);
+        d.z = z[(size_t)i];
+        d.player_color = (PlayerColor)color[(size_t)i];
+        out.push_back(d);
+    }
+    return out;
+}
+
 // ---------------------------------------------------------------------------------------------- fight (evaluator.rs:355-399)
 struct EvaluatorConfig {
     size_t game_amnt = 20;

@@ -77,6 +77,7 @@ SYMBOLS = {
     "onb_mcts_tree_info": (C.c_int32, [_P, _P, _P]),
     "onb_selftest": (C.c_int32, [_P, C.c_int32, _P]),
     "onb_self_play": (C.c_int32, [_P, _P, _P]),
+    "onb_copy_to_host": (C.c_int32, [_P, _P, _P, C.c_int64]),
     "onb_uct_run": (C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32]),
     "onb_net_precision": (C.c_int32, [_P, C.c_int32]),
     "onb_net_select": (C.c_int32, [_P, C.c_int32]),

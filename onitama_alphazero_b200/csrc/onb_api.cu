@@ -534,6 +534,15 @@ int32_t onb_self_play(onb_ctx* ctx, const onb_selfplay_config* cfg, onb_selfplay
     if (rc != ONB_OK) return fail(c, rc, "%s", err);
     return ONB_OK;
 }
+int32_t onb_copy_to_host(onb_ctx* ctx, void* host, const void* device, int64_t bytes) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!host || !device || bytes < 0) return fail(c, ONB_E_INVALID, "onb_copy_to_host: bad arguments");
+    if (bytes == 0) return ONB_OK;
+    ONB_CUDA(c, cudaMemcpyAsync(host, device, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    ONB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ONB_OK;
+}
 int32_t onb_uct_run(onb_ctx* ctx, float exploration_c, uint32_t min_node_visits, uint32_t playouts) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);

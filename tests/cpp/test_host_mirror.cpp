@@ -242,6 +242,32 @@ static void plain_mcts_reference_tests() {
     }
 }
 
+// self_play_continuous: the loop inside the library; sample invariants of train.rs:55-88 and the quota
+static void native_self_play() {
+    Engine e(16, 24, 5);
+    TrainingAlphaZeroMcts sp;
+    sp.config.max_playouts = 24;
+    sp.config.exploration_c = 2.0;
+    TrainConfig tc;
+    tc.self_play_game_amnt = 40;
+    tc.max_plies = 20;
+    auto data = self_play_continuous(e, sp, tc);
+    CHECK(!data.empty() && data.size() <= 16u * 22u * 8u);
+    size_t decided = 0;
+    for (auto& d : data) {
+        float ps = 0.f; for (float p : d.pi) ps += p;
+        CHECK(std::fabs(ps - 1.f) < 1e-5f);
+        CHECK(d.z == 0.f || d.z == 1.f || d.z == -1.f);
+        decided += d.z != 0.f;
+        CHECK(d.state[20 * 25] == (d.player_color == PlayerColor::Blue ? 1.f : 0.f));
+    }
+    CHECK(decided > 0);
+    bool threw = false;  // a host evaluator cannot run inside the library
+    sp.model = [](const float*, int64_t, float*, float*) {};
+    try { self_play_continuous(e, sp, tc); } catch (const Error&) { threw = true; }
+    CHECK(threw);
+}
+
 int main() {
     try {
         create_all_legal_moves_for_red_in_starting_position();
@@ -252,6 +278,7 @@ int main() {
         search_and_drivers();
         device_network_search();
         plain_mcts_reference_tests();
+        native_self_play();
     } catch (const Error& e) {
         std::printf("FAIL exception %d: %s\n", e.code, e.what());
         return 2;
