@@ -21,6 +21,14 @@ with onb.Context(n, seed=1, mcts_max_sims=sims) as ctx:
     b = onb.self_play_continuous(ctx, 2.0, sims, n_games=factor * n, evaluator=onb.EVAL_NET)
     torch.cuda.synchronize()
     tb = time.perf_counter() - t0
+    ctx.self_play_native(2.0, sims, n // 4, evaluator=onb.EVAL_NET)            # warm-up (buffer allocation)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cnat = ctx.self_play_native(2.0, sims, factor * n, evaluator=onb.EVAL_NET)
+    torch.cuda.synchronize()
+    tc = time.perf_counter() - t0
 ma, mb = a["planes"].shape[0], b["planes"].shape[0]
 print("lockstep   : %d games, %d samples (%.1f plies/game) in %.2f s -> %.0f games/s, %.0f samples/s" % (n, ma, ma / n, ta, n / ta, ma / ta))
 print("continuous : %d games, %d samples (%.1f plies/game) in %.2f s -> %.0f games/s, %.0f samples/s" % (b["games"], mb, mb / b["games"], tb, b["games"] / tb, mb / tb))
+mc = cnat["planes"].shape[0]
+print("native     : %d games, %d samples (%.1f plies/game) in %.2f s -> %.0f games/s, %.0f samples/s" % (cnat["games"], mc, mc / cnat["games"], tc, cnat["games"] / tc, mc / tc))
