@@ -53,8 +53,12 @@ def main(argv=None):
         # ---- self-play (train.rs:218-245): train-mode root noise, the current network as evaluator, finished slots restart at once
         with onb.Context(args.slots, seed=args.seed + it, mcts_max_sims=args.sims) as ctx:
             ev, net = evaluator_for(ctx)
-            data = onb.self_play_continuous(ctx, 2.0, args.sims, n_games=args.games, max_plies=args.max_plies, evaluator=ev, net=net,
-                                            train=True, noise_seed=args.seed + 1000 * it)
+            if net is None:   # the whole loop inside the library (onb_self_play)
+                data = ctx.self_play_native(2.0, args.sims, args.games, max_plies=args.max_plies, evaluator=ev, train=True,
+                                            noise_seed=args.seed + 1000 * it)
+            else:             # the same loop driven from Python, the PyTorch module between select and expand
+                data = onb.self_play_continuous(ctx, 2.0, args.sims, n_games=args.games, max_plies=args.max_plies, evaluator=ev, net=net,
+                                                train=True, noise_seed=args.seed + 1000 * it)
         replay.add(data["planes"], data["pi"], data["z"])
         # ---- training (train.rs:264-339)
         model.train()
