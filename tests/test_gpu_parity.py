@@ -1220,3 +1220,23 @@ def test_native_self_play_equals_the_python_driver(onb, evaluator):
         assert small["truncated"] and small["plies_run"] == 3
         with pytest.raises(onb.OnbError):
             ctx.self_play_native(c, sims + 1, 10, evaluator=ev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tf32", [False, True], ids=["f16", "tf32"])
+def test_network_kernel_on_the_reference_trained_weights(onb, tf32):
+    """The tensor-core kernel with the reference's shipped 3-block weights (tests/golden/net_golden.npz) against the outputs of
+    the PyTorch twin recorded in the fixture. Same tolerance as for the random networks (11-bit operands, f32 accumulation)."""
+    from test_net_cpu import load_net_golden
+    weights, planes, pol, val = load_net_golden()
+    n = len(planes)
+    with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
+        ctx.net_load(weights, tf32=tf32)
+        ctx.write(onb.BUF_LEAF_PLANES, planes)
+        ctx.net_forward(onb.BUF_LEAF_PLANES)
+        got_p = ctx.read(onb.BUF_POLICY, np.float32, (n, 50))
+        got_v = ctx.read(onb.BUF_VALUE, np.float32, (n,))
+    dp, dv = np.abs(got_p - pol), np.abs(got_v - val)
+    assert dp.max() <= 6e-3 and dp.mean() <= 1e-4, (dp.max(), dp.mean())
+    assert dv.max() <= 2.5e-2, dv.max()
+    assert (got_p.argmax(1) == pol.argmax(1)).mean() >= 0.95   # the preferred move survives the operand rounding

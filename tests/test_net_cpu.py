@@ -97,3 +97,29 @@ def test_oracle_network_with_reference_weights():
         p_ref, v_ref = m(torch.from_numpy(planes))
     pol, val = O.net_forward(m.state_dict(), planes)
     assert np.abs(pol - p_ref.reshape(-1, 50).numpy()).max() < 2e-5 and np.abs(val - v_ref.reshape(-1).numpy()).max() < 2e-5
+
+
+def load_net_golden():
+    """tests/golden/net_golden.npz (made by tests/golden/gen_net_golden.py from the reference's shipped 3-block weights)"""
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "net_golden.npz"))
+    weights = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+    return weights, z["planes"], z["policy"], z["value"]
+
+
+def test_oracle_network_on_the_reference_trained_weights_fixture():
+    """The committed fixture (reference weights + outputs of the PyTorch twin) is available on the GPU box too; the oracle must
+    reproduce it, and the fixture must be what the twin computes today."""
+    import numpy as np
+    import oracle_lib as O
+    from onitama_alphazero_b200.net import ConvResNet
+    weights, planes, pol, val = load_net_golden()
+    assert len(weights) == 60 and planes.shape[1:] == (21, 5, 5)
+    p, v = O.net_forward(weights, planes)
+    assert np.abs(p - pol).max() < 2e-5 and np.abs(v - val).max() < 2e-5
+    m = ConvResNet(64, 21, 3)
+    m.load_state_dict({k: torch.from_numpy(w) for k, w in weights.items()}, strict=False)
+    with torch.no_grad():
+        p2, v2 = m.eval()(torch.from_numpy(planes))
+    assert np.abs(p2.reshape(-1, 50).numpy() - pol).max() < 1e-6 and np.abs(v2.reshape(-1).numpy() - val).max() < 1e-6
+    assert pol.std(0).max() > 0.01          # the trained policy head does depend on the position
