@@ -277,7 +277,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "note": "C++ restatement of the reference CPU path (oracle/onb_oracle.cpp); the Rust reference cannot be built in this image"}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def workload_config(wl):
@@ -306,6 +306,29 @@ def workload_config(wl):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else that libraries print there (NCCL's version banner, ...) is sent to
+    stderr by pointing fd 1 at fd 2 for the rest of the run; emit_line() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,6 +343,7 @@ def main():
     ap.add_argument("--net", default="fused", choices=["fused", "fused-tf32", "torch"],
                     help="selfplay workload: the tensor-core network kernel (f16 or tf32 operands) or the PyTorch module as a black box")
     args = ap.parse_args()
+    claim_stdout()
     dflt = {"env": (200, 20), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3)}[args.workload]
     if args.impl == "reference":
         dflt = (3, 1)
@@ -785,7 +809,7 @@ def main():
             line["mcts"] = secondary
         if third is not None:
             line["selfplay"] = third
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
