@@ -100,8 +100,15 @@ __global__ void __launch_bounds__(128) k_perft_expand(const uint4* __restrict__ 
                 a &= a - 1;
                 Game ch = g;
                 apply_move(ch, make_action(idx, (uint32_t)f, to, king));
-                out_states[pos] = pack(ch);
-                out_root[pos] = root;
+                if (out_root) {
+                    out_states[pos] = pack(ch);
+                    out_root[pos] = root;
+                } else {
+                    // leaf format (the level k_perft_leaf2 reads): one 16-byte entry with the root id inside; both kings are on the
+                    // board (a king capture ends the line), so a square index replaces each one-hot king board
+                    out_states[pos] = make_uint4(ch.pawn_r | ((uint32_t)(__ffs(ch.king_r) - 1) << 25),
+                                                 ch.pawn_b | ((uint32_t)(__ffs(ch.king_b) - 1) << 25) | (ch.side << 30), ch.cards, root);
+                }
                 ++pos;
             }
         }
@@ -333,8 +340,17 @@ __global__ void __launch_bounds__(256) k_perft_leaf2(const uint4* __restrict__ s
     const bool live = i < n_items;
     uint32_t root = 0xFFFFFFFFu, t0 = 0, w0 = 0, z0 = 0, t1 = 0, w1 = 0, z1 = 0;
     if (live) {
-        const Game g = unpack(states[i]);
-        root = roots[i];
+        Game g;
+        if (roots) {
+            g = unpack(states[i]);
+            root = roots[i];
+        } else {  // leaf format written by k_perft_expand (see there)
+            const uint4 e = states[i];
+            g.pawn_r = e.x & 0x1FFFFFFu; g.king_r = 1u << ((e.x >> 25) & 31u);
+            g.pawn_b = e.y & 0x1FFFFFFu; g.king_b = 1u << ((e.y >> 25) & 31u);
+            g.side = (e.y >> 30) & 1u; g.cards = e.z; g.result = 0; g.passed = 0;
+            root = e.w;
+        }
         const uint32_t side = g.side;
         const uint32_t own_p = side ? g.pawn_b : g.pawn_r, own_k = side ? g.king_b : g.king_r;
         const uint32_t en_p = side ? g.pawn_r : g.pawn_b, en_k = side ? g.king_r : g.king_b;
@@ -523,8 +539,9 @@ static cudaError_t perft_finish(Ctx* c, const uint4* st, const uint32_t* rt, int
         if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
         uint4* ns = nullptr;
         uint32_t* nr = nullptr;
+        const bool leaf_next = depth - (level + 1) == 2;  // the children go straight to k_perft_leaf2: 16-byte entries with the root inside
         if ((e = scratch_get(c, slot, (size_t)total * 16, (void**)&ns)) != cudaSuccess) return e;
-        if ((e = scratch_get(c, slot + 1, (size_t)total * 4, (void**)&nr)) != cudaSuccess) return e;
+        if (!leaf_next && (e = scratch_get(c, slot + 1, (size_t)total * 4, (void**)&nr)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(d_cursor, 0, 8, c->stream)) != cudaSuccess) return e;
         k_perft_expand<false><<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(st + off, rt + off, m, ns, nr, d_cursor, nodes, wins, zero, depth, level);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
