@@ -294,6 +294,10 @@ def workload_config(wl):
                             "the leaf buffer in place, %d concurrent games/GPU, one ply per step, replay samples gathered to GPU 0"
                             % (SELFPLAY_SIMS, SELFPLAY_GAMES), "games_per_gpu": SELFPLAY_GAMES, "sims": SELFPLAY_SIMS, "c_puct": MCTS_C,
                 "l2": "node pools + leaf batches >> L2"}
+    if wl == "games":
+        return {"workload": "whole self-play games inside the library (onb_self_play): %d slots/GPU, %d sims/move, 3-block ConvResNet on the tensor "
+                            "cores, finished slots restart at once, train-mode root noise" % (SELFPLAY_GAMES, SELFPLAY_SIMS),
+                "slots_per_gpu": SELFPLAY_GAMES, "sims": SELFPLAY_SIMS, "l2": "node pools + sample buffers >> L2"}
     if wl == "uct":
         return {"workload": "plain UCT with random rollouts (the reference's Mcts agent, evaluator.rs opponent): %d playouts/move, %d concurrent "
                             "trees/GPU, config-4 roots, c = sqrt(2), min_node_visits = 5" % (MCTS_SIMS, MCTS_TREES), "trees_per_gpu": MCTS_TREES,
@@ -335,7 +339,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default per workload: env 200, mcts 20, perft 5, selfplay 3, playout 50)")
     ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default per workload, >= 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay", "uct"])
+    ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay", "uct", "games"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-mode", action="store_true",
@@ -344,7 +348,7 @@ def main():
                     help="selfplay workload: the tensor-core network kernel (f16 or tf32 operands) or the PyTorch module as a black box")
     args = ap.parse_args()
     claim_stdout()
-    dflt = {"env": (200, 20), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3)}[args.workload]
+    dflt = {"env": (200, 20), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3), "games": (2, 3)}[args.workload]
     if args.impl == "reference":
         dflt = (3, 1)
     args.steps = dflt[0] if args.steps is None else args.steps
@@ -673,6 +677,42 @@ def main():
         return dict(metric="uct_playouts_per_sec", value=value, unit="playouts/s", ms_per_step=ms / steps, dtype="u32+f32", roofline=roof, e2e=e2e,
                     gpu_launches=3 * steps, clocks=clocks)
 
+    # ---------------------------------------------------------------- whole self-play games, natively (onb_self_play)
+    def bench_games(steps, warmup):
+        from onitama_alphazero_b200.net import ConvResNet
+        n, sims = SELFPLAY_GAMES, SELFPLAY_SIMS
+        torch.manual_seed(1234)
+        ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims)
+        ctx.net_load(ConvResNet(64, 21, 3), tf32=args.net == "fused-tf32")
+        quota = n // 4          # a step = self-play until a quarter of the slots' worth of games is complete
+        cap = n * 64            # plies of sample buffer: far more than a step needs
+        tot = {"games": 0, "samples": 0, "plies": 0}
+
+        def one(i):
+            r = ctx.self_play_native(MCTS_C, sims, quota, evaluator=onb.EVAL_NET, train=not args.eval_mode, noise_seed=SEED + i, sample_cap=cap)
+            if i >= warmup:
+                tot["games"] += r["games"]; tot["samples"] += int(r["planes"].shape[0]); tot["plies"] += r["plies_run"]
+
+        ms, clocks = timed(one, warmup, steps)
+        ctx.close()
+        g = torch.tensor([tot["games"], tot["samples"], tot["plies"]], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(g)
+        games, samples, plies = [float(x) for x in g.tolist()]
+        value = games / (ms * 1e-3)
+        flop = 2.0 * 25 * 64 * 9 * (21 + 6 * 64) + 2.0 * (25 * 64 * 3 + 2500 + 1600 + 64)
+        tpeak, tsrc = read_tensor_peak()
+        ach = flop * n * sims * (plies / world) / (ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": read_traffic("k_net_forward"),
+                "kernel": "k_net_forward<2,%s>" % ("tf32" if args.net == "fused-tf32" else "f16"), "peak_source": tsrc,
+                "samples_per_sec": samples / (ms * 1e-3), "plies_per_step": plies / world / max(1, steps),
+                "note": "every ply searches all slots (16 384 x 800 network evaluations); finished slots restart at once; a step ends when n/4 games are complete"}
+        e2e = {"value": value, "unit": "games/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * plies / world / max(1, steps),
+               "path": "onb_self_play: one 8-byte counter per ply crosses PCIe; samples stay in device buffers for the trainer"}
+        return dict(metric="selfplay_games_per_sec", value=value, unit="games/s", ms_per_step=ms / steps,
+                    dtype="u32+f64 (search), f16 x f16 -> f32 (network)", roofline=roof, e2e=e2e, gpu_launches=int(plies / world) * (3 * sims + 12),
+                    clocks=clocks)
+
     # ---------------------------------------------------------------- self-play with the network (config 5)
     def bench_selfplay(steps, warmup):
         from onitama_alphazero_b200.net import ConvResNet, make_evaluator
@@ -737,6 +777,8 @@ def main():
         out = bench_selfplay(args.steps, args.warmup)
     elif wl == "uct":
         out = bench_uct(args.steps, args.warmup)
+    elif wl == "games":
+        out = bench_games(args.steps, args.warmup)
     elif wl == "perft":
         out = bench_perft(args.steps, args.warmup)
     elif wl == "mcts":
@@ -782,6 +824,11 @@ def main():
             cpu_baseline = {"value": v, "unit": "sims/s", "cores": th, "kind": "port",
                             "sample": "4 trees x 100 sims, oracle arena + the PyTorch module on the CPU, one position per forward call as in the "
                                       "reference (%.1f s wall, %d torch threads)" % (dt, th)}
+        elif wl == "games":
+            v, dt, th = cpu_selfplay(2, 100)
+            cpu_baseline = {"value": v / (SELFPLAY_SIMS * 27.5), "unit": "games/s", "cores": th, "kind": "port",
+                            "sample": "derived: %.1f sims/s of the oracle arena + PyTorch module on the CPU (2 trees x 100 sims, %.1f s) / (%d sims x 27.5 "
+                                      "plies per game)" % (v, dt, SELFPLAY_SIMS)}
         elif wl == "uct":
             O = oracle()
             import time as _t
