@@ -61,11 +61,10 @@ struct Geo {
     static constexpr int NB = NACC == 2 ? (F16 ? 7 : 6) : 14;  // boards per pass (two CTAs per SM when NACC == 2)
     static constexpr int CELLS = NB * kCellsPerBoard;
     static constexpr int R = (kLead + CELLS + kTrail + 7) / 8 * 8;  // rows of the activation matrix (whole swizzle periods)
-    // weight ring slots (one tap each). f16: a whole layer (9 taps) so that the producer runs one layer ahead -- with 4 slots the
-    // MMA thread spent most of its time waiting for weights (L2 -> shared latency of ~1.5k cycles per 8 KB tap vs 256 cycles of MMAs)
+    // weight ring: NSLOT slots of TPS taps, one full/empty barrier round trip and one bulk copy per slot. f16: 3 slots x 3 taps =
+    // one whole layer in flight, so the producer runs a layer ahead of the MMAs (with 4 single-tap slots the MMA thread waited for
+    // weights, and per-tap slots cost a try_wait + fence + commit for every 8 MMAs); tf32 taps are twice as large: single taps
     static constexpr int NSLOT = F16 ? 3 : (NACC == 2 ? 3 : 4);
-    // taps per ring slot: one full/empty barrier round trip and one bulk copy per slot. f16: 3 slots x 3 taps = one layer in flight
-    // (per-tap slots cost a try_wait + fence + commit for every 8 MMAs); tf32 taps are twice as large: single taps
     static constexpr int TPS = F16 ? 3 : 1;
     static constexpr int UPL = 9 / TPS;  // slots per layer
     static constexpr int SLOT_BYTES = TPS * Op<F16>::TAP_BYTES;
