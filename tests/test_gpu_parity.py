@@ -1240,3 +1240,27 @@ def test_network_kernel_on_the_reference_trained_weights(onb, tf32):
     assert dp.max() <= 6e-3 and dp.mean() <= 1e-4, (dp.max(), dp.mean())
     assert dv.max() <= 2.5e-2, dv.max()
     assert (got_p.argmax(1) == pol.argmax(1)).mean() >= 0.95   # the preferred move survives the operand rounding
+
+
+@pytest.mark.gpu
+def test_config5_full_size_properties(onb):
+    """BASELINE config 5 at full size (16 384 games, 800 simulations per move, 3-block network on the tensor cores, train-mode root
+    noise) for two plies through onb_self_play: size-independent properties of the search output and of the bookkeeping."""
+    import torch
+    from test_net_cpu import lively_model
+    n, sims = 16384, 800
+    with onb.Context(n, seed=8, mcts_max_sims=sims) as ctx:
+        ctx.net_load(lively_model(3, seed=12))
+        r = ctx.self_play_native(2.0, sims, 10 ** 9, evaluator=onb.EVAL_NET, train=True, noise_seed=3, sample_cap=2 * n)
+        assert r["truncated"] and r["plies_run"] == 2          # the quota cannot be met in two plies: the buffer bound stops the run
+        nn, fl = ctx.mcts_tree_info()                            # the trees of the last search are still in place
+        pi = ctx.read(onb.BUF_PI, np.float32, (n, 50))
+        trees = [ctx.mcts_dump_tree(t) for t in range(0, n, 1024)]
+    assert not (fl & 2).any()                                    # no node pool overflow
+    assert np.abs(pi.sum(1) - 1).max() < 1e-5
+    assert (nn > 1000).all() and (nn <= 1 + 40 * sims).all()
+    for tr in trees:
+        k, fc = int(tr["n_child"][0]), int(tr["first_child"][0])
+        assert int(tr["visits"][0]) == sims
+        assert int(tr["visits"][fc:fc + k].sum()) == sims - 1    # every playout but the first one descends into exactly one root child
+        assert int(tr["visits"][fc:fc + k].max()) >= (sims - 1) / 40
