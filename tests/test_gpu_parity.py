@@ -1264,3 +1264,45 @@ def test_config5_full_size_properties(onb):
         assert int(tr["visits"][0]) == sims
         assert int(tr["visits"][fc:fc + k].sum()) == sims - 1    # every playout but the first one descends into exactly one root child
         assert int(tr["visits"][fc:fc + k].max()) >= (sims - 1) / 40
+
+
+@pytest.mark.gpu
+def test_full_size_properties_of_plain_uct_and_network(onb):
+    """Size-independent properties at benchmark sizes: 16 384 plain-UCT trees x 400 playouts (visit bookkeeping of
+    mcts_arena.rs:87-131) and the network over 262 144 positions (its outputs do not depend on the batch around a position)."""
+    from test_net_cpu import lively_model
+    n, playouts, min_v = 16384, 400, 5
+    with onb.Context(n, seed=19, mcts_max_sims=playouts) as ctx:
+        ctx.reset()
+        for s in range(5):
+            ctx.step_random(s)
+        live = ctx.get_states()["result"] == 0
+        res = ctx.uct_search(2.0 ** 0.5, min_v, playouts)
+        nn, fl = ctx.mcts_tree_info()
+    assert not (fl & 2).any()
+    assert (res["root_visits"][live] == playouts).all()
+    # the root is expanded during playout min + 2, which still rolls out from the root itself
+    assert (res["child_visits"][live].astype(np.int64).sum(1) == playouts - (min_v + 2)).all()
+    assert np.abs(res["pi"][live].reshape(-1, 50).sum(1) - 1).max() < 1e-5
+    assert (nn[live] <= 1 + 40 * playouts).all()
+    big = 262144
+    model = lively_model(3, seed=31)
+    with onb.Context(big, seed=2, mcts_max_sims=1) as ctx:
+        ctx.reset()
+        for s in range(6):
+            ctx.step_random(s, auto_reset=True, out_flags=onb.OUT_PLANES)
+        ctx.net_load(model)
+        ctx.net_forward(onb.BUF_PLANES)
+        pol = ctx.read(onb.BUF_POLICY, np.float32, (big, 50))
+        val = ctx.read(onb.BUF_VALUE, np.float32, (big,))
+        planes = ctx.read(onb.BUF_PLANES, np.float32, (big, 21, 5, 5))
+    assert np.isfinite(pol).all() and np.abs(pol.sum(1) - 1).max() < 1e-5 and (np.abs(val) <= 1).all()
+    pick = np.random.default_rng(1).choice(big, 96, replace=False)
+    with onb.Context(96, mcts_max_sims=1, planes=False) as ctx:
+        ctx.net_load(model)
+        ctx.write(onb.BUF_LEAF_PLANES, planes[pick])
+        ctx.net_forward(onb.BUF_LEAF_PLANES)
+        assert np.array_equal(ctx.read(onb.BUF_POLICY, np.float32, (96, 50)), pol[pick])
+        assert np.array_equal(ctx.read(onb.BUF_VALUE, np.float32, (96,)), val[pick])
+    want_p, want_v = O.net_forward(model.state_dict(), planes[pick[:24]])
+    assert np.abs(pol[pick[:24]] - want_p).max() <= 6e-3 and np.abs(val[pick[:24]] - want_v).max() <= 2.5e-2
