@@ -183,6 +183,21 @@ struct State {
         pawns[0] = o.pawns[0]; pawns[1] = o.pawns[1]; kings[0] = o.kings[0]; kings[1] = o.kings[1];
         for (int i = 0; i < 5; ++i) deck.cards[i] = Card{o.cards[i]};
     }
+    /// state.rs:75-108: the board as text, row 5 (Blue's home row) first
+    std::string display() const {
+        const std::string border = "---+---+---+---+---+---+\n";
+        std::string r = border;
+        for (size_t i = 0; i < 25; ++i) {
+            if (i % 5 == 0) r += " " + std::to_string(5 - i / 5) + " ";
+            if (get_bit(pawns[0], i)) r += "| r ";
+            else if (get_bit(pawns[1], i)) r += "| b ";
+            else if (get_bit(kings[0], i)) r += "| R ";
+            else if (get_bit(kings[1], i)) r += "| B ";
+            else r += "| . ";
+            if ((i + 1) % 5 == 0) { r += "|\n"; r += border; }
+        }
+        return r + "   | a | b | c | d | e |";
+    }
     bool is_terminal() const {  // state.rs:111-117
         return kings[0] == 0 || kings[1] == 0 || kings[0] == BLUE_KING_SP || kings[1] == RED_KING_SP;
     }

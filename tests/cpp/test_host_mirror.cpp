@@ -268,8 +268,18 @@ static void native_self_play() {
     CHECK(threw);
 }
 
+// state.rs:397-416 correct_display (host-only code)
+static void correct_display() {
+    const std::string expected =
+        "\n---+---+---+---+---+---+\n 5 | b | b | B | b | b |\n---+---+---+---+---+---+\n 4 | . | . | . | . | . |\n---+---+---+---+---+---+\n"
+        " 3 | . | . | . | . | . |\n---+---+---+---+---+---+\n 2 | . | . | . | . | . |\n---+---+---+---+---+---+\n 1 | r | r | R | r | r |\n"
+        "---+---+---+---+---+---+\n   | a | b | c | d | e |\n";
+    CHECK("\n" + State::with_deck(Deck()).display() + "\n" == expected);
+}
+
 int main() {
     try {
+        correct_display();
         create_all_legal_moves_for_red_in_starting_position();
         create_all_legal_moves_for_blue_in_starting_position();
         make_move_tests();
