@@ -277,6 +277,33 @@ ONB_API int32_t onb_self_play(onb_ctx* ctx, const onb_selfplay_config* cfg, onb_
 /* host copy of a borrowed device pointer (onb_buffer, onb_selfplay_result), ordered after the work queued on the context's stream */
 ONB_API int32_t onb_copy_to_host(onb_ctx* ctx, void* host, const void* device, int64_t bytes);
 
+/* ---- fight (alphazero-training/src/evaluator.rs:355-399) for all games of the context in lockstep -----------------------------
+ * Two agents, each game played from its current position (call onb_env_reset first) until it is decided or max_plies + 2 plies
+ * were played (the ply cap of evaluator.rs:386-392; such games count as draws). a_is_red_host[i] != 0: agent A plays Red in game
+ * i (the reference swaps colours every game). Agents: ONB_AGENT_RANDOM = the `Random` agent (ai/random.rs, draws keyed by the
+ * ply); ONB_AGENT_PUCT = AlphaZeroMcts (evaluator = ONB_EVAL_*, for ONB_EVAL_NET the resident network net_slot, sims, c);
+ * ONB_AGENT_UCT = `Mcts` (sims playouts, c, min_node_visits). results (device, [n]: 0 undecided, 1 Red won, 2 Blue won) stays
+ * valid until the next driver call; results_host (optional) receives a copy. The Elo update of evaluator.rs:58-110 is a fold over
+ * these per-game results in game order (host bookkeeping: selfplay.fight_statistics / FightStatistics of the C++ mirror). */
+#define ONB_AGENT_RANDOM 0
+#define ONB_AGENT_PUCT 1
+#define ONB_AGENT_UCT 2
+typedef struct onb_agent {
+    int32_t kind;
+    int32_t evaluator;
+    int32_t net_slot;
+    uint32_t sims;
+    double c;
+    uint32_t min_node_visits;
+    uint32_t reserved;
+} onb_agent;
+typedef struct onb_fight_result {
+    int64_t a_wins, b_wins, draws, plies_run;
+    uint8_t* results;
+} onb_fight_result;
+ONB_API int32_t onb_fight(onb_ctx* ctx, const onb_agent* a, const onb_agent* b, const uint8_t* a_is_red_host, uint32_t max_plies,
+                          onb_fight_result* out, uint8_t* results_host);
+
 /* ---- plain UCT with random rollouts: the `Mcts` agent (onitama-game/src/ai/mcts/{mod.rs,mcts_arena.rs}) ---------------
  * The evaluation opponent of the reference's arena (evaluator.rs), one tree per game, rooted like the PUCT search:
  * onb_mcts_begin (its c_puct is ignored); onb_uct_run(ctx, exploration_c, min_node_visits, playouts);

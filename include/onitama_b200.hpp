@@ -571,4 +571,29 @@ inline FightStatistics fight(const EvaluatorConfig& config, std::unique_ptr<Agen
     return statistics;
 }
 
+/// fight() for config.game_amnt games at once on one engine (onb_fight: the arena loop runs inside the library). Agent A plays Red
+/// in games 0, 2, 4, ... like the colour swap of evaluator.rs:393-397; the statistics are folded in game order.
+/// Agents are described by onb_agent (ONB_AGENT_RANDOM / ONB_AGENT_PUCT / ONB_AGENT_UCT); the engine must have been created
+/// with n_games == config.game_amnt and enough mcts_max_sims.
+inline FightStatistics fight_device(Engine& e, const EvaluatorConfig& config, const onb_agent& agent, const onb_agent& opponent) {
+    if ((size_t)e.n() != config.game_amnt) throw Error(ONB_E_INVALID, "fight_device: the engine must hold game_amnt games");
+    if (config.deck) {
+        uint8_t d[5];
+        for (int i = 0; i < 5; ++i) d[i] = (uint8_t)config.deck->cards[i].index;
+        e.check(onb_env_reset(e.ctx(), d, 1, 0));
+    } else {
+        e.check(onb_env_reset(e.ctx(), nullptr, 0, 0));
+    }
+    std::vector<uint8_t> a_is_red(config.game_amnt), results(config.game_amnt);
+    for (size_t g = 0; g < config.game_amnt; ++g) a_is_red[g] = g % 2 == 0;
+    onb_fight_result r{};
+    e.check(onb_fight(e.ctx(), &agent, &opponent, a_is_red.data(), (uint32_t)config.max_plies, &r, results.data()));
+    FightStatistics statistics;
+    for (size_t g = 0; g < config.game_amnt; ++g) {
+        const MoveResult progress = results[g] == 1 ? MoveResult::RedWin : results[g] == 2 ? MoveResult::BlueWin : MoveResult::InProgress;
+        statistics.update(progress, a_is_red[g] ? PlayerColor::Red : PlayerColor::Blue);
+    }
+    return statistics;
+}
+
 }  // namespace onitama

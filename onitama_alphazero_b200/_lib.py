@@ -78,6 +78,7 @@ SYMBOLS = {
     "onb_selftest": (C.c_int32, [_P, C.c_int32, _P]),
     "onb_self_play": (C.c_int32, [_P, _P, _P]),
     "onb_copy_to_host": (C.c_int32, [_P, _P, _P, C.c_int64]),
+    "onb_fight": (C.c_int32, [_P, _P, _P, _P, C.c_uint32, _P, _P]),
     "onb_uct_run": (C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32]),
     "onb_net_precision": (C.c_int32, [_P, C.c_int32]),
     "onb_net_select": (C.c_int32, [_P, C.c_int32]),
@@ -88,6 +89,19 @@ SYMBOLS = {
 class SelfPlayConfig(C.Structure):
     _fields_ = [("c_puct", C.c_double), ("sims", C.c_uint32), ("evaluator", C.c_int32), ("n_games", C.c_int64), ("max_plies", C.c_uint32),
                 ("train", C.c_int32), ("noise_seed", C.c_uint64), ("sample_cap", C.c_int64)]
+
+
+AGENT_RANDOM, AGENT_PUCT, AGENT_UCT = 0, 1, 2
+
+
+class Agent(C.Structure):
+    """onb_agent: kind, evaluator (PUCT), net_slot (ONB_EVAL_NET), sims / playouts, exploration constant, min_node_visits (UCT)"""
+    _fields_ = [("kind", C.c_int32), ("evaluator", C.c_int32), ("net_slot", C.c_int32), ("sims", C.c_uint32), ("c", C.c_double),
+                ("min_node_visits", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class FightResult(C.Structure):
+    _fields_ = [("a_wins", C.c_int64), ("b_wins", C.c_int64), ("draws", C.c_int64), ("plies_run", C.c_int64), ("results", C.c_void_p)]
 
 
 class SelfPlayResult(C.Structure):

@@ -534,6 +534,48 @@ int32_t onb_self_play(onb_ctx* ctx, const onb_selfplay_config* cfg, onb_selfplay
     if (rc != ONB_OK) return fail(c, rc, "%s", err);
     return ONB_OK;
 }
+static int32_t fight_move(Ctx* c, const onb_agent* ag, uint32_t ply) {
+    onb_ctx* x = reinterpret_cast<onb_ctx*>(c);
+    if (ag->kind == ONB_AGENT_RANDOM) return onb_env_choose_random(x, ply, ONB_POLICY_AGENT);
+    int32_t rc = onb_mcts_begin(x, ag->c, ag->sims);
+    if (rc != ONB_OK) return rc;
+    if (ag->kind == ONB_AGENT_PUCT) {
+        if (ag->evaluator == ONB_EVAL_NET && (rc = onb_net_select(x, ag->net_slot)) != ONB_OK) return rc;
+        rc = onb_mcts_run(x, ag->evaluator, ag->sims);
+    } else {
+        rc = onb_uct_run(x, (float)ag->c, ag->min_node_visits, ag->sims);
+    }
+    if (rc == ONB_OK) rc = onb_mcts_finish(x, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc != ONB_OK) return rc;
+    // the chosen moves become the agent's actions (ONB_ACTION_NONE for decided roots)
+    cudaError_t e = cudaMemcpyAsync(c->d_actions, c->d_best, (size_t)c->n * 2, cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(c, e, "onb_fight");
+    return ONB_OK;
+}
+int32_t onb_fight(onb_ctx* ctx, const onb_agent* a, const onb_agent* b, const uint8_t* a_is_red_host, uint32_t max_plies, onb_fight_result* out,
+                  uint8_t* results_host) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!a || !b || !a_is_red_host || !out) return fail(c, ONB_E_INVALID, "onb_fight: null argument");
+    for (const onb_agent* ag : {a, b}) {
+        if (ag->kind != ONB_AGENT_RANDOM && ag->kind != ONB_AGENT_PUCT && ag->kind != ONB_AGENT_UCT)
+            return fail(c, ONB_E_INVALID, "onb_fight: unknown agent kind %d", ag->kind);
+        if (ag->kind != ONB_AGENT_RANDOM && (!c->d_nodes || ag->sims == 0 || ag->sims > c->cfg.mcts_max_sims))
+            return fail(c, ONB_E_INVALID, "onb_fight: a searching agent needs 1 <= sims <= mcts_max_sims");
+    }
+    memset(out, 0, sizeof(*out));
+    int32_t rc = onb_mcts_set_noise(ctx, 0, 0.25, 0.03, 0);  // arenas search in eval mode (AlphaZeroMcts, not TrainingAlphaZeroMcts)
+    if (rc != ONB_OK) return rc;
+    char err[400];
+    err[0] = 0;
+    rc = run_fight(c, a, b, a_is_red_host, max_plies, out, fight_move, err, sizeof(err));
+    if (rc != ONB_OK) return fail(c, rc, "%s", err);
+    if (results_host) {
+        ONB_CUDA(c, cudaMemcpyAsync(results_host, out->results, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+        ONB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return ONB_OK;
+}
 int32_t onb_copy_to_host(onb_ctx* ctx, void* host, const void* device, int64_t bytes) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);

@@ -116,6 +116,9 @@ cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float
 int32_t run_self_play(Ctx* c, const onb_selfplay_config* cfg, onb_selfplay_result* out, int32_t (*search)(Ctx*, const onb_selfplay_config*), char* err,
                       size_t err_len);
 
+int32_t run_fight(Ctx* c, const onb_agent* a, const onb_agent* b, const uint8_t* a_is_red_host, uint32_t max_plies, onb_fight_result* out,
+                  int32_t (*move)(Ctx*, const onb_agent*, uint32_t), char* err, size_t err_len);
+
 constexpr int kModeActions = 2;  // env step modes: 0 = ONB_POLICY_UNIFORM, 1 = ONB_POLICY_AGENT, 2 = explicit actions
 
 }  // namespace onb

@@ -54,6 +54,31 @@ __global__ void __launch_bounds__(256) k_sp_close(uint4* __restrict__ states, in
     atomicAdd(done, 1ull);
 }
 
+// arena: pick agent A's or agent B's action per game (agent A moves when the side to move is the colour it plays in that game)
+__global__ void __launch_bounds__(256) k_fight_merge(const uint4* __restrict__ states, int64_t n, const uint8_t* __restrict__ a_is_red,
+                                                     const uint16_t* __restrict__ act_a, const uint16_t* __restrict__ act_b, uint16_t* __restrict__ actions) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Game g = unpack(states[i]);
+    const bool a_to_move = (g.side == 0u) == (a_is_red[i] != 0);
+    actions[i] = g.result == 0 ? (a_to_move ? act_a[i] : act_b[i]) : (uint16_t)0xFFFFu;
+}
+__global__ void __launch_bounds__(256) k_count_live(const uint4* __restrict__ states, int64_t n, unsigned long long* __restrict__ live) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool alive = i < n && unpack(states[i]).result == 0;
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, alive);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(live, (unsigned long long)__popc(b));
+}
+__global__ void __launch_bounds__(256) k_fight_tally(const uint4* __restrict__ states, int64_t n, const uint8_t* __restrict__ a_is_red,
+                                                     uint8_t* __restrict__ results, unsigned long long* __restrict__ tally) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = unpack(states[i]).result;
+    results[i] = (uint8_t)r;
+    if (r == 0) atomicAdd(&tally[2], 1ull);                                             // draw: the ply cap ended the game
+    else atomicAdd(&tally[((r == 1u) == (a_is_red[i] != 0)) ? 0 : 1], 1ull);            // agent A wins when its colour won
+}
+
 cudaError_t grow(Ctx* c, int slot, size_t bytes, void** out) {
     if (bytes == 0) bytes = 16;
     if (c->sp_cap[slot] < bytes) {
@@ -158,6 +183,68 @@ int32_t run_self_play(Ctx* c, const onb_selfplay_config* cfg, onb_selfplay_resul
     out->color = color;
     out->serial = serial;
     out->valid_idx = idx;
+    c->mcts_phase = 0;
+    return ONB_OK;
+}
+
+// fight (evaluator.rs:355-399) for all games of the context in lockstep: `move` leaves an agent's actions for every game in
+// d_actions; the per-game choice, the step and the end-of-game test stay on the device (one 8-byte counter per ply is read back).
+int32_t run_fight(Ctx* c, const onb_agent* a, const onb_agent* b, const uint8_t* a_is_red_host, uint32_t max_plies, onb_fight_result* out,
+                  int32_t (*move)(Ctx*, const onb_agent*, uint32_t), char* err, size_t err_len) {
+    const int64_t n = c->n;
+    uint8_t *mask = nullptr, *results = nullptr;
+    uint16_t *act_a = nullptr, *act_b = nullptr;
+    unsigned long long* counters = nullptr;  // [0] live games of the current ply, [1..3] tally
+    cudaError_t e;
+#define FT(call)                                                                    \
+    do {                                                                            \
+        e = (call);                                                                 \
+        if (e != cudaSuccess) {                                                     \
+            snprintf(err, err_len, "onb_fight: %s: %s", #call, cudaGetErrorString(e)); \
+            return e == cudaErrorMemoryAllocation ? ONB_E_NOMEM : ONB_E_CUDA;       \
+        }                                                                           \
+    } while (0)
+    FT(grow(c, 3, (size_t)n, (void**)&mask));       // the arena reuses the self-play scratch slots (a context runs one driver at a time)
+    FT(grow(c, 4, (size_t)n, (void**)&results));
+    FT(grow(c, 6, (size_t)n * 2, (void**)&act_a));
+    FT(grow(c, 7, (size_t)n * 2, (void**)&act_b));
+    FT(grow(c, 8, 32, (void**)&counters));
+    FT(cudaMemcpyAsync(mask, a_is_red_host, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    int64_t plies_left = (int64_t)max_plies, tick = 0;
+    for (;;) {
+        unsigned long long live = 0;
+        FT(cudaMemsetAsync(counters, 0, 8, c->stream));
+        k_count_live<<<grid, 256, 0, c->stream>>>(c->d_states, n, counters);
+        FT(cudaGetLastError());
+        FT(cudaMemcpyAsync(&live, counters, 8, cudaMemcpyDeviceToHost, c->stream));
+        FT(cudaStreamSynchronize(c->stream));
+        if (live == 0) break;                       // evaluator.rs:366: every game is decided
+        int32_t rc = move(c, a, (uint32_t)tick);
+        if (rc != ONB_OK) { snprintf(err, err_len, "%s", c->err); return rc; }
+        FT(cudaMemcpyAsync(act_a, c->d_actions, (size_t)n * 2, cudaMemcpyDeviceToDevice, c->stream));
+        rc = move(c, b, (uint32_t)tick);
+        if (rc != ONB_OK) { snprintf(err, err_len, "%s", c->err); return rc; }
+        FT(cudaMemcpyAsync(act_b, c->d_actions, (size_t)n * 2, cudaMemcpyDeviceToDevice, c->stream));
+        k_fight_merge<<<grid, 256, 0, c->stream>>>(c->d_states, n, mask, act_a, act_b, c->d_actions);
+        FT(cudaGetLastError());
+        FT(launch_env_step(c, kModeActions, 0, 0, 0));
+        ++tick;
+        if (plies_left < 0) break;                  // evaluator.rs:386-392: checked after the move, then decremented (max_plies + 2 plies)
+        plies_left -= 1;
+    }
+    FT(cudaMemsetAsync(counters + 1, 0, 24, c->stream));
+    k_fight_tally<<<grid, 256, 0, c->stream>>>(c->d_states, n, mask, results, counters + 1);
+    FT(cudaGetLastError());
+    unsigned long long tally[3] = {0, 0, 0};
+    FT(cudaMemcpyAsync(tally, counters + 1, 24, cudaMemcpyDeviceToHost, c->stream));
+    FT(cudaStreamSynchronize(c->stream));
+#undef FT
+    out->a_wins = (int64_t)tally[0];
+    out->b_wins = (int64_t)tally[1];
+    out->draws = (int64_t)tally[2];
+    out->plies_run = tick;
+    out->results = results;
     c->mcts_phase = 0;
     return ONB_OK;
 }

@@ -227,6 +227,27 @@ class Context:
                        truncated=bool(res.truncated))
         return out
 
+    @staticmethod
+    def agent_random():
+        return L.Agent(L.AGENT_RANDOM, 0, 0, 0, 0.0, 0, 0)
+
+    @staticmethod
+    def agent_puct(sims, c_puct=2.0, evaluator=L.EVAL_UNIFORM, net_slot=0):
+        return L.Agent(L.AGENT_PUCT, evaluator, net_slot, sims, c_puct, 0, 0)
+
+    @staticmethod
+    def agent_uct(playouts, exploration_c=2.0 ** 0.5, min_node_visits=5):
+        return L.Agent(L.AGENT_UCT, 0, 0, playouts, exploration_c, min_node_visits, 0)
+
+    def fight_native(self, agent_a, agent_b, a_is_red, max_plies=150):
+        """onb_fight: the arena loop inside the library. Returns (a_wins, b_wins, draws, per-game results [n] uint8)."""
+        mask = np.ascontiguousarray(np.asarray(a_is_red), dtype=np.uint8)
+        res = L.FightResult()
+        results = np.zeros(self.n, dtype=np.uint8)
+        self._ck(self._lib.onb_fight(self._h, C.byref(agent_a), C.byref(agent_b), L.ptr(mask), max_plies, C.byref(res), L.ptr(results)))
+        self.last_fight_results = results
+        return int(res.a_wins), int(res.b_wins), int(res.draws), results
+
     def uct_search(self, exploration_c=2.0 ** 0.5, min_node_visits=5, playouts=5000, to_host=True):
         """The reference's `Mcts` agent for every game at once: plain UCT with random rollouts (ai/mcts/mcts_arena.rs)."""
         self.mcts_begin(0.0, playouts)

@@ -277,6 +277,23 @@ static void correct_display() {
     CHECK("\n" + State::with_deck(Deck()).display() + "\n" == expected);
 }
 
+// fight_device: the arena inside the library; PUCT (uniform evaluator) must beat the Random agent, plain UCT must beat it too
+static void native_fight() {
+    Engine e(24, 200, 9, 0, false);
+    EvaluatorConfig ec;
+    ec.game_amnt = 24;
+    onb_agent puct{ONB_AGENT_PUCT, ONB_EVAL_UNIFORM, 0, 64, 2.0, 0, 0}, rnd{ONB_AGENT_RANDOM, 0, 0, 0, 0., 0, 0}, uct{ONB_AGENT_UCT, 0, 0, 200, 1.41421356, 5, 0};
+    FightStatistics a = fight_device(e, ec, puct, rnd);
+    CHECK(a.wins + a.losses + a.draws == 24 && a.games_red == 12 && a.games_blue == 12);
+    CHECK(a.wins > a.losses);
+    FightStatistics b = fight_device(e, ec, uct, rnd);
+    CHECK(b.wins + b.losses + b.draws == 24 && b.wins > b.losses);
+    bool threw = false;
+    onb_agent bad = puct; bad.sims = 100000;   // more simulations than the engine was created for
+    try { fight_device(e, ec, bad, rnd); } catch (const Error&) { threw = true; }
+    CHECK(threw);
+}
+
 int main() {
     try {
         correct_display();
@@ -289,6 +306,7 @@ int main() {
         device_network_search();
         plain_mcts_reference_tests();
         native_self_play();
+        native_fight();
     } catch (const Error& e) {
         std::printf("FAIL exception %d: %s\n", e.code, e.what());
         return 2;

@@ -1306,3 +1306,50 @@ def test_full_size_properties_of_plain_uct_and_network(onb):
         assert np.array_equal(ctx.read(onb.BUF_VALUE, np.float32, (96,)), val[pick])
     want_p, want_v = O.net_forward(model.state_dict(), planes[pick[:24]])
     assert np.abs(pol[pick[:24]] - want_p).max() <= 6e-3 and np.abs(val[pick[:24]] - want_v).max() <= 2.5e-2
+
+
+@pytest.mark.gpu
+def test_native_fight_equals_the_python_driver(onb):
+    """onb_fight (the arena loop inside the library) against selfplay.fight (the same loop driven from Python): identical final
+    positions, per-game results and W/L/D for PUCT vs Random, PUCT(network) vs plain UCT, and the ply cap."""
+    import torch
+    from test_net_cpu import lively_model
+    n, sims = 40, 24
+    a_is_red = (np.arange(n) % 2) == 0
+    with onb.Context(n, seed=21, mcts_max_sims=120, planes=False) as ctx:
+        ctx.net_load(lively_model(1, seed=8))
+
+        def py_puct(ev):
+            def f(cx):
+                cx.search_device(2.0, sims, evaluator=ev)
+                cx.tensor(onb.BUF_ACTIONS).copy_(cx.tensor(onb.BUF_BEST))
+            return f
+
+        def py_uct(cx):
+            cx.uct_search(2.0 ** 0.5, 5, 120, to_host=False)
+            cx.tensor(onb.BUF_ACTIONS).copy_(cx.tensor(onb.BUF_BEST))
+
+        for name, py_a, py_b, nat_a, nat_b, cap in (
+                ("puct-vs-random", py_puct(onb.EVAL_UNIFORM), None, ctx.agent_puct(sims, 2.0), ctx.agent_random(), 150),
+                ("net-vs-uct", py_puct(onb.EVAL_NET), py_uct, ctx.agent_puct(sims, 2.0, onb.EVAL_NET, 0), ctx.agent_uct(120), 150),
+                ("ply-cap", py_puct(onb.EVAL_UNIFORM), None, ctx.agent_puct(sims, 2.0), ctx.agent_random(), 3)):
+            counter = {"i": 0}
+
+            def py_random(cx):
+                cx.choose_random(counter["i"], policy=onb.POLICY_AGENT)
+                counter["i"] += 1
+
+            ctx.reset()
+            want = onb.fight(ctx, py_a, py_b or py_random, a_is_red, max_plies=cap)
+            want_states = ctx.get_states().tobytes()
+            want_results = ctx.last_fight_results.copy()
+            ctx.reset()
+            a, b, d, results = ctx.fight_native(nat_a, nat_b, a_is_red, max_plies=cap)
+            assert (a, b, d) == want, name
+            assert ctx.get_states().tobytes() == want_states, name
+            assert np.array_equal(results, want_results), name
+            assert a + b + d == n
+            if cap == 3:
+                assert d > 0          # five plies are not enough to finish every game
+        with pytest.raises(onb.OnbError):
+            ctx.fight_native(ctx.agent_puct(10 ** 6), ctx.agent_random(), a_is_red)
