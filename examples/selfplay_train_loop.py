@@ -91,9 +91,12 @@ def main(argv=None):
                 cx.uct_search(2.0 ** 0.5, 5, args.mcts_playouts, to_host=False)
                 cx.tensor(onb.BUF_ACTIONS).copy_(cx.tensor(onb.BUF_BEST))
 
-            for name, opponent in (("random", rnd), ("mcts", plain_mcts)):
+            for name, opponent, native in (("random", rnd, ctx.agent_random()), ("mcts", plain_mcts, ctx.agent_uct(args.mcts_playouts))):
                 ctx.reset()
-                w, l, d = onb.fight(ctx, az, opponent, a_is_red, max_plies=150)
+                if net is None:   # the arena loop inside the library (onb_fight)
+                    w, l, d, _ = ctx.fight_native(ctx.agent_puct(args.sims, 2.0, ev, 0), native, a_is_red, max_plies=150)
+                else:
+                    w, l, d = onb.fight(ctx, az, opponent, a_is_red, max_plies=150)
                 stats = onb.fight_statistics(ctx.last_fight_results, a_is_red)
                 results[name] = dict(wins=w, losses=l, draws=d, elo=stats.rating_a)
         log.append(dict(iteration=it, games=int(data["games"]), samples=int(data["planes"].shape[0]), replay=replay.size,
