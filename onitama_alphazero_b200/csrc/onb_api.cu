@@ -32,10 +32,21 @@ static int32_t cuda_fail(Ctx* c, cudaError_t e, const char* what) {
         cudaError_t e__ = (call);                           \
         if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); \
     } while (0)
-// every entry point binds the context's device first: one host thread may drive contexts on several GPUs
-#define ONB_CHECK_CTX(ctx)                \
+// every entry point binds the context's device for the duration of the call (and puts the caller's device back): one host thread
+// may drive contexts on several GPUs, and a drop-in library must not change the caller's current device behind its back
+struct DeviceGuard {
+    int prev = -1, mine;
+    explicit DeviceGuard(int dev) : mine(dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != mine) cudaSetDevice(mine);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != mine) cudaSetDevice(prev);
+    }
+};
+#define ONB_CHECK_CTX(ctx)            \
     if (!(ctx)) return ONB_E_INVALID; \
-    cudaSetDevice(reinterpret_cast<const Ctx*>(ctx)->cfg.device)
+    DeviceGuard onb_device_guard__(reinterpret_cast<const Ctx*>(ctx)->cfg.device)
 
 template <class T>
 static cudaError_t dalloc(T** p, size_t count) {
@@ -86,6 +97,7 @@ int32_t onb_create(const onb_config* cfg, onb_ctx** out) {
             return e__ == cudaErrorMemoryAllocation ? ONB_E_NOMEM : ONB_E_CUDA;                     \
         }                                                                                           \
     } while (0)
+    DeviceGuard onb_device_guard__(cfg->device);
     ONB_CREATE_CUDA(cudaSetDevice(cfg->device));
     if (cfg->stream) {
         c->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
