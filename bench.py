@@ -336,7 +336,7 @@ def emit_line(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="timed steps (default per workload: env 200, mcts 20, perft 5, selfplay 3, playout 50)")
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default per workload: env 1000, mcts 20, perft 5, selfplay 3, playout 50)")
     ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default per workload, >= 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay", "uct", "games"])
@@ -348,7 +348,7 @@ def main():
                     help="selfplay workload: the tensor-core network kernel (f16 or tf32 operands) or the PyTorch module as a black box")
     args = ap.parse_args()
     claim_stdout()
-    dflt = {"env": (200, 20), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3), "games": (2, 3)}[args.workload]
+    dflt = {"env": (1000, 50), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3), "games": (2, 3)}[args.workload]
     if args.impl == "reference":
         dflt = (3, 1)
     args.steps = dflt[0] if args.steps is None else args.steps
