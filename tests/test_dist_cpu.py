@@ -70,3 +70,21 @@ def test_gather_replay_gloo_world2():
         want_planes = (torch.rand((m, 21, 5, 5), generator=g) > 0.5).float().numpy()
         want_pi = torch.rand((m, 2, 25), generator=g).numpy()
         assert np.array_equal(planes[sl], want_planes) and np.array_equal(pi[sl], want_pi)
+
+
+def test_reference_arm_under_torchrun_prints_one_json_line():
+    """bench.py --impl reference launched the way the driver launches N > 1: rank 0 alone measures and prints, the other
+    rank exits 0 without work, stdout carries exactly one JSON line."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29593", os.path.join(root, "bench.py"), "--gpus", "2", "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] == "env_steps_per_sec"
