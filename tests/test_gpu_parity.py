@@ -1208,13 +1208,17 @@ def test_native_self_play_equals_the_python_driver(onb, evaluator):
         if evaluator == "net":
             ctx.net_load(lively_model(1, seed=4))
             ev = onb.EVAL_NET
-        py = onb.self_play_continuous(ctx, c, sims, n_games=games, max_plies=30, evaluator=ev)
-        nat = ctx.self_play_native(c, sims, games, max_plies=30, evaluator=ev)
-        assert nat["games"] == py["games"] >= games and not nat["truncated"]
-        for k in ("planes", "pi", "z", "serial"):
-            assert torch.equal(nat[k], py[k]), k
-        assert torch.equal(nat["color"], py["color"])
-        assert (nat["z"] == 0).any() or True
+        for train in (False, True):   # train mode: the root noise comes from the counter RNG, so both drivers still agree exactly
+            py = onb.self_play_continuous(ctx, c, sims, n_games=games, max_plies=30, evaluator=ev, train=train, noise_seed=5)
+            nat = ctx.self_play_native(c, sims, games, max_plies=30, evaluator=ev, train=train, noise_seed=5)
+            assert nat["games"] == py["games"] >= games and not nat["truncated"]
+            for k in ("planes", "pi", "z", "serial"):
+                assert torch.equal(nat[k], py[k]), (k, train)
+            assert torch.equal(nat["color"], py["color"])
+            if train:
+                assert not torch.equal(nat["pi"], eval_pi)    # the noise does change the searches
+            else:
+                eval_pi = nat["pi"]
         # a buffer that is too small stops early and says so
         small = ctx.self_play_native(c, sims, 10 ** 6, max_plies=30, evaluator=ev, sample_cap=3 * n)
         assert small["truncated"] and small["plies_run"] == 3
