@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay", "uct", "games"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true", help="skip the config-5 section of the default env run (12 000 launches: too many for an ncu launch list)")
     ap.add_argument("--eval-mode", action="store_true",
                     help="selfplay workload: search without the root exploration noise (self_play of train.rs searches in train mode)")
     ap.add_argument("--net", default="fused", choices=["fused", "fused-tf32", "torch"],
@@ -793,6 +794,8 @@ def main():
         secondary = {k: m[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches")}
         secondary["config"] = workload_config("mcts")
         try:  # config 5 with the network on the tensor cores (one ply of 16 384 games x 800 simulations per step)
+            if args.no_selfplay:
+                raise RuntimeError("skipped (--no-selfplay)")
             sp = bench_selfplay(2, 3)
             third = {k: sp[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "network", "roofline", "e2e", "gpu_launches")}
             third["config"] = workload_config("selfplay")
