@@ -70,49 +70,63 @@ def read_traffic(kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons read IN PROCESS through NVML: one sample immediately before the timed region, one immediately
+    after, and as many as fit while the host waits for the region to drain (sample() is called from the wait loop), so even a
+    6 ms region is covered. Falls back to one `nvidia-smi` query per sample() if pynvml is missing."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("hw_power_brake_slowdown", 0x80))
 
-    def __init__(self, index):
-        self.rows = []
-        self.proc = None
-        self.index = index
-
-    def start(self):
+    def __init__(self, index, uuid=None):
+        self.rows, self.h, self.nv, self.index = [], None, None, index
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)) if uuid and not str(uuid).startswith("GPU-") else str(uuid))
             except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm), "window": "warm-up + timed region"}
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = index
+                if vis:
+                    try:
+                        phys = int(vis.split(",")[index])
+                    except Exception:
+                        phys = index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def sample(self, tag="during"):
+        try:
+            if self.h is not None:
+                nv = self.nv
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((tag, mhz, self.max_mhz, mask))
+            else:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.rows.append((tag, float(out[0]), float(out[1]), int(out[2].strip(), 16)))
+        except Exception:
+            pass
+
+    def result(self, window):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0, "window": window}
+        sm = sorted(r[1] for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, bit in self.REASONS:
+                if r[3] & bit:
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in self.rows), "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_min": sm[0], "sm_mhz_first_last": [self.rows[0][1], self.rows[-1][1]], "source": "nvml (in process)" if self.h is not None else "nvidia-smi",
+                "window": window}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -122,11 +136,24 @@ def oracle():
     return oracle_lib
 
 
+class CpuEnv:
+    """The CPU arm of config 3 on a game array that lives across timed steps (like the GPU context's): `n` games, every call
+    steps all of them `steps` times (random action, apply, auto-reset, legal mask, 21x5x5 planes), all host threads."""
+
+    def __init__(self, n_games, threads):
+        self.O = oracle()
+        self.n, self.threads, self.step = n_games, threads, 0
+        self.g = self.O.new_games(n_games, seed=SEED)
+
+    def run(self, steps):
+        sink = ctypes.c_double()
+        dt = self.O.lib().orc_bench_env_steps(self.g.ctypes.data, self.n, 0, self.step, steps, SEED, self.threads, 1, ctypes.byref(sink))
+        self.step += steps
+        return self.n * steps / dt, dt
+
+
 def cpu_env(n_games, steps, threads):
-    O = oracle()
-    sink = ctypes.c_double()
-    dt = O.lib().orc_bench_env(n_games, steps, SEED, threads, 1, ctypes.byref(sink))
-    return n_games * steps / dt, dt
+    return CpuEnv(n_games, threads).run(steps)
 
 
 def cfg4_roots(O, n, seed):
@@ -210,20 +237,14 @@ def run_reference(args, rank):
     wl = args.workload
     vals = []
     if wl == "env":
-        n, s = 1 << 18, 12
-        budget = 150.0  # seconds for the whole --steps/--warmup run: the per-step sample shrinks if the first step says it would not fit
+        # the config the line prints: the same 1 048 576 games, ONE lockstep step of all of them per timed step, game array kept
+        # across steps (so the positions are the mid-game mix the GPU arm sees, not 1 M opening moves)
+        env = CpuEnv(ENV_GAMES, cores)
         for i in range(args.warmup + args.steps):
-            v, dt = cpu_env(n, s, cores)
+            v, dt = env.run(1)
             if i >= args.warmup:
                 vals.append((v, dt))
-            if i == 0 and dt * (args.warmup + args.steps) > budget:
-                shrink = dt * (args.warmup + args.steps) / budget
-                if s / shrink >= 1.0:
-                    s = max(1, int(s / shrink))
-                else:
-                    n = max(4096, int(n * s / shrink))
-                    s = 1
-        sample = "%d games x %d lockstep steps per timed step (same kernel contents: move gen, random action, apply, reset, mask, planes)" % (n, s)
+        sample = "%d games x 1 lockstep step per timed step, %d threads (same step contents: move gen, random action, apply, reset, mask, planes)" % (ENV_GAMES, cores)
         unit, metric = "env_steps/s", "env_steps_per_sec"
     elif wl == "mcts":
         n = 1024
@@ -340,6 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default per workload, >= 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay", "uct", "games"])
+    ap.add_argument("--subbatches", type=int, default=4, help="env e2e: sub-batches in flight inside onb_actor (>= 4 hides the copies under three kernels)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the config-5 section of the default env run (12 000 launches: too many for an ncu launch list)")
@@ -352,6 +374,7 @@ def main():
     dflt = {"env": (1000, 50), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3), "games": (2, 3)}[args.workload]
     if args.impl == "reference":
         dflt = (3, 1)
+    args.steps_given = args.steps is not None
     args.steps = dflt[0] if args.steps is None else args.steps
     args.warmup = dflt[1] if args.warmup is None else args.warmup
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -399,12 +422,24 @@ def main():
             return float(t.item())
         return ms
 
+    try:
+        dev_uuid = torch.cuda.get_device_properties(local_rank).uuid
+    except Exception:
+        dev_uuid = None
+    sampler_box = {}
+
+    def new_sampler():
+        # NVML handle is created once (nvmlInit + lookup take milliseconds); every timed region gets its own row list
+        if "s" not in sampler_box:
+            sampler_box["s"] = ClockSampler(local_rank, dev_uuid)
+        sampler_box["s"].rows = []
+        return sampler_box["s"]
+
     def timed(fn, warmup, steps, between=None):
-        # the clock sampler (nvidia-smi, 100 ms period) runs from the first warm-up step to the end of the timed region:
-        # the timed region alone can be shorter than one sampling period
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        """W untimed warm-up steps, then exactly K steps between two CUDA events on the launch stream, barrier + synchronize on both
+        sides, max over ranks. Clocks: NVML is read immediately before the first event, while the host waits for the second one
+        (every rank samples its own GPU; rank 0's samples are reported), and immediately after."""
+        sampler = new_sampler()
         for i in range(warmup):
             fn(i)
             if between:
@@ -412,23 +447,30 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if between is None:
+            sampler.sample("before")
             e0.record(stream)
             for i in range(steps):
                 fn(warmup + i)
             e1.record(stream)
+            while not e1.query():
+                sampler.sample("during")
+            sampler.sample("after")
             barrier()
             ms = e0.elapsed_time(e1)
         else:  # L2 flush between iterations: time each iteration on its own
             ms = 0.0
             for i in range(steps):
                 between()
+                sampler.sample("before")
                 e0.record(stream)
                 fn(warmup + i)
                 e1.record(stream)
-                e1.synchronize()
+                while not e1.query():
+                    sampler.sample("during")
                 ms += e0.elapsed_time(e1)
+            sampler.sample("after")
             barrier()
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.result("immediately before / during / immediately after the timed region") if rank == 0 else None
         return max_over_ranks(ms), clocks
 
     out = {}
@@ -448,64 +490,78 @@ def main():
         achieved = ENV_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic("k_env_step"),
                 "kernel": "k_env_step<uniform,planes>", "algorithmic_bytes_per_launch": ENV_BYTES_PER_STEP * n, "peak_source": peak_src}
-        # e2e: recorded actions replayed from PINNED HOST memory through onb_env_step (H2D inside), masks + stats read back (D2H)
-        # every step. The batch is split into two half-size contexts on two streams, as a host actor would do: while the host
-        # waits for (and consumes) the masks of one half, the other half is stepping, so PCIe copies overlap with compute.
+        # e2e: the reference-facing call with HOST buffers. A host actor feeds every game's action from pinned host memory and gets
+        # back what a self-play driver consumes per step -- which games were decided and by whom (2 bits/game) plus the counters --
+        # through onb_actor_submit / onb_actor_wait: the context's games as N_SUB sub-batches, each on its own stream inside the
+        # library (H2D actions -> step kernel incl. masks + planes in HBM -> D2H results -> event), the host blocking on ONE event per
+        # sub-batch. Actions are a recorded trajectory (so every step is a legal, mid-game step exactly like the device-timed run).
+        from onitama_alphazero_b200.engine import Actor
+        HL = onb._lib
+        n_sub = args.subbatches
+        e_steps = min(steps, 300)
+        k_all = warmup + e_steps
+        host_actions = torch.empty((k_all, n), dtype=torch.int16).pin_memory()
+        ctx.reset()
+        acts_dev = ctx.tensor(onb.BUF_ACTIONS)
+        for i in range(k_all):
+            ctx.step_random(i, auto_reset=True, out_flags=onb.OUT_ACTIONS)
+            host_actions[i].copy_(acts_dev, non_blocking=True)
+        want_tail = ctx.get_states(n - 4096, 4096).tobytes()   # the replayed games must end where the recorded ones did
+        trace_ptr = host_actions.data_ptr()
+
+        def e2e_run(host_flags, native):
+            ctx.reset()
+            ctx.stats(clear=True)
+            with Actor(ctx, n_sub=n_sub, out_flags=flags, host_flags=host_flags) as act:
+                firsts = [v["first"] for v in act.views]
+
+                def run(i0, k):
+                    if native:   # the same ring driven inside the library (no host think time, no Python in the loop)
+                        act.replay((trace_ptr + 2 * n * i0, n, k), step0=i0, auto_reset=True)
+                        return
+                    for i in range(i0, i0 + k):
+                        row = trace_ptr + 2 * n * i
+                        for j in range(n_sub):
+                            act.wait(j)   # the host now holds the results of step i-1 of this sub-batch and decides its next actions
+                            act.submit(j, row + 2 * firsts[j], step=i, auto_reset=True)
+                    for j in range(n_sub):
+                        act.wait(j)
+
+                run(0, warmup)
+                act.join()
+                barrier()
+                sampler = new_sampler()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                sampler.sample("before")
+                e0.record(stream)
+                run(warmup, e_steps)
+                act.join()
+                e1.record(stream)
+                sampler.sample("after")
+                barrier()
+                ems = max_over_ranks(e0.elapsed_time(e1))
+                st2 = ctx.stats()
+                assert int(st2[onb.STAT_STEPS]) == n * k_all and int(st2[HL.STAT_BAD_ACTIONS]) == 0
+                if host_flags & HL.HOST_STATS:
+                    assert int(act.views[-1]["stats"][onb.STAT_STEPS]) <= n * k_all
+                assert ctx.get_states(n - 4096, 4096).tobytes() == want_tail, "replayed trajectory diverged"
+            d2h = (8 * n if host_flags & HL.HOST_MASKS else 0) + (n // 4 if host_flags & HL.HOST_DONE else 0) + (64 * n_sub if host_flags & HL.HOST_STATS else 0)
+            return world * n * e_steps / (ems * 1e-3), ems / e_steps, d2h, sampler.result("before / after the e2e region") if rank == 0 else None
+
+        v_done, ms_done, d2h_done, e_clocks = e2e_run(HL.HOST_DONE | HL.HOST_STATS, False)
+        v_native, ms_native, _, _ = e2e_run(HL.HOST_DONE | HL.HOST_STATS, True)
+        v_masks, ms_masks, d2h_masks, _ = e2e_run(HL.HOST_MASKS | HL.HOST_DONE | HL.HOST_STATS, False)
+        e2e = {"value": v_done, "unit": "env_steps/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": d2h_done, "ms_per_step": ms_done,
+               "steps": e_steps, "sub_batches": n_sub, "clocks": e_clocks,
+               "path": "onb_actor_submit/onb_actor_wait from the host loop: actions of every game from pinned host memory (H2D), step kernel "
+                       "incl. legal masks + planes written to HBM for the network, D2H of the per-game decided/winner bits (2 bits/game) and "
+                       "the counters every step; %d sub-batches in flight on the library's own streams" % n_sub,
+               "variants": {"native_ring": {"value": v_native, "ms_per_step": ms_native,
+                                            "path": "onb_actor_replay: the same ring driven inside the library, no host think time"},
+                            "masks_to_host": {"value": v_masks, "ms_per_step": ms_masks, "d2h_bytes_per_step": d2h_masks,
+                                              "path": "as the headline plus the 8 B/game legal masks copied to the host every step (round 1's e2e bytes)"}}}
         ctx.close()
-        k_all = warmup + steps
-        half = n // 2
-        hstreams = [torch.cuda.Stream(device=local_rank) for _ in range(2)]
-        hctx = [onb.Context(half, seed=SEED, device=local_rank, game_id_base=rank * n + h * half, stream=hstreams[h].cuda_stream) for h in range(2)]
-        host_actions = [torch.empty((k_all, half), dtype=torch.int16).pin_memory() for _ in range(2)]
-        host_masks = [torch.empty((half, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
-        host_stats = [torch.empty((onb._lib.STAT_COUNT,), dtype=torch.int64).pin_memory() for _ in range(2)]
-        masks_dev = [c.tensor(onb.BUF_MASKS) for c in hctx]
-        stats_dev = [c.tensor(onb.BUF_STATS) for c in hctx]
-        for h in range(2):
-            with torch.cuda.stream(hstreams[h]):
-                hctx[h].reset()
-                acts_dev = hctx[h].tensor(onb.BUF_ACTIONS)
-                for i in range(k_all):
-                    hctx[h].step_random(i, auto_reset=True, out_flags=onb.OUT_ACTIONS)
-                    host_actions[h][i].copy_(acts_dev)
-                hstreams[h].synchronize()
-                hctx[h].reset()
-                hctx[h].stats(clear=True)
-
-        def issue(h, i):
-            with torch.cuda.stream(hstreams[h]):
-                hctx[h].step_from_host_ptr(host_actions[h][i].data_ptr(), step=i, auto_reset=True, out_flags=flags)
-                host_masks[h].copy_(masks_dev[h], non_blocking=True)
-                host_stats[h].copy_(stats_dev[h], non_blocking=True)
-
-        def run(i0, k):
-            for h in range(2):
-                issue(h, i0)
-            for i in range(i0 + 1, i0 + k):
-                for h in range(2):
-                    hstreams[h].synchronize()  # the host actor has the masks of step i-1 of this half and picks its next actions
-                    issue(h, i)
-            for h in range(2):
-                hstreams[h].synchronize()
-
-        run(0, warmup)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for h in range(2):
-            hstreams[h].wait_stream(stream)
-        run(warmup, steps)
-        for h in range(2):
-            stream.wait_stream(hstreams[h])
-        e1.record(stream)
-        barrier()
-        ems = max_over_ranks(e0.elapsed_time(e1))
-        assert int(host_stats[0][onb.STAT_STEPS]) + int(host_stats[1][onb.STAT_STEPS]) == n * k_all
-        e2e = {"value": world * n * steps / (ems * 1e-3), "unit": "env_steps/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 8 * n + 128,
-               "ms_per_step": ems / steps, "path": "onb_env_step(host actions in pinned memory) + D2H of legal masks and stats every step, two half-batches "
-                                                   "pipelined on two streams; planes stay in HBM for the network"}
-        for c in hctx:
-            c.close()
+        del host_actions
         return dict(metric="env_steps_per_sec", value=value, unit="env_steps/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
                     gpu_launches=steps, clocks=clocks)
 
@@ -790,16 +846,22 @@ def main():
     secondary = None
     third = None
     if wl == "env" and not args.no_secondary:
-        m = bench_mcts(10, 3)
-        secondary = {k: m[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches")}
+        # the config-4 and config-5 sections obey --steps/--warmup too (their own defaults when the flags are absent; config 5 is
+        # capped at 30 plies of 0.3 s so that an env-sized --steps cannot turn the run into minutes) and carry their own clocks
+        m_steps, m_warm = (args.steps, args.warmup) if args.steps_given else (20, 5)
+        m_steps = min(m_steps, 200)
+        m = bench_mcts(m_steps, max(3, m_warm))
+        secondary = {k: m[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e", "gpu_launches", "clocks")}
         secondary["config"] = workload_config("mcts")
+        secondary["steps"], secondary["warmup"] = m_steps, max(3, m_warm)
         try:  # config 5 with the network on the tensor cores (one ply of 16 384 games x 800 simulations per step)
             if args.no_selfplay:
                 raise RuntimeError("skipped (--no-selfplay)")
-            sp = bench_selfplay(2, 3)
-            third = {k: sp[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "network", "roofline", "e2e", "gpu_launches")}
+            s_steps, s_warm = (min(args.steps, 30), min(max(3, args.warmup), 5)) if args.steps_given else (3, 3)
+            sp = bench_selfplay(s_steps, s_warm)
+            third = {k: sp[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "network", "roofline", "e2e", "gpu_launches", "clocks")}
             third["config"] = workload_config("selfplay")
-            third["steps"], third["warmup"] = 2, 3
+            third["steps"], third["warmup"] = s_steps, s_warm
         except Exception as exc:  # never lose the headline over the extra measurement
             third = {"error": repr(exc)}
 
@@ -807,9 +869,12 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         if wl == "env":
-            v, dt = cpu_env(1 << 18, 32, cores)
+            env = CpuEnv(ENV_GAMES, cores)
+            env.run(8)   # leave the opening positions behind (untimed)
+            v, dt = env.run(24)
             cpu_baseline = {"value": v, "unit": "env_steps/s", "cores": cores, "kind": "port",
-                            "sample": "262144 games x 32 lockstep steps incl. mask + plane encode (%.1f s wall, %d threads)" % (dt, cores)}
+                            "sample": "the same %d games x 24 lockstep steps incl. mask + plane encode, after 8 untimed steps (%.1f s wall, %d threads)"
+                                      % (ENV_GAMES, dt, cores)}
             v1, dt1 = cpu_env(1 << 15, 32, 1)
             cpu_baseline["single_core_value"] = v1
             if secondary is not None:

@@ -102,6 +102,7 @@ typedef struct onb_state {
 #define ONB_STAT_BLUE_WINS 2
 #define ONB_STAT_PASSES 3
 #define ONB_STAT_RESETS 4
+#define ONB_STAT_BAD_ACTIONS 5 /* host actions rejected by onb_env_step / onb_actor_submit (from or to square > 24) */
 #define ONB_STAT_COUNT 8
 
 typedef struct onb_ctx onb_ctx;
@@ -145,7 +146,7 @@ ONB_API int32_t onb_start_states(const uint8_t* decks5, int64_t n, onb_state* ou
 ONB_API uint32_t onb_rand_u32(uint64_t seed, uint64_t game, uint32_t step, uint32_t draw);
 /* random deal = first 5 of a shuffle of the 16 cards (replaces Deck::default, deck.rs:139-151) */
 ONB_API int32_t onb_deal(uint64_t seed, uint64_t game, uint32_t epoch, uint8_t out5[5]);
-/* ATTACK_MAPS[2][16][25] in the reference layout (card.rs:476) as held in __constant__ memory */
+/* ATTACK_MAPS[2][16][25] in the reference layout (card.rs:476): the table the kernels stage into shared memory */
 ONB_API int32_t onb_attack_maps(uint32_t out800[800]);
 
 /* ------------------------------------------------------------------------------------------------
@@ -171,7 +172,8 @@ ONB_API int32_t onb_env_legal_masks(onb_ctx* ctx, uint32_t* masks_host);
 ONB_API int32_t onb_env_encode(onb_ctx* ctx, float* planes_host);
 /* State::make_move / State::pass + side switch (state.rs:139-202, game_state.rs:65-80) with the given
  * actions. actions_host NULL = use ONB_BUF_ACTIONS as already filled on the device. Finished games and games
- * whose action is ONB_ACTION_NONE are left untouched. auto_reset: a game that ends is replaced by a fresh deal (RNG epoch step+1; `step` is only
+ * whose action is ONB_ACTION_NONE are left untouched; so is a game whose action names a from or to square above 24 (the reference
+ * would index out of its 25-square board: such actions are counted in ONB_STAT_BAD_ACTIONS instead of corrupting the packed state). auto_reset: a game that ends is replaced by a fresh deal (RNG epoch step+1; `step` is only
  * used for that). out_flags selects which observation buffers of the new state are written. */
 ONB_API int32_t onb_env_step(onb_ctx* ctx, const onb_action* actions_host, uint32_t step, int32_t auto_reset,
                              uint32_t out_flags);
@@ -191,6 +193,49 @@ ONB_API int32_t onb_env_run_random(onb_ctx* ctx, uint32_t step0, uint32_t n_step
 ONB_API int32_t onb_env_playout(onb_ctx* ctx, uint32_t step0, uint32_t max_plies, int32_t policy, uint32_t* plies_host,
                         uint64_t* trace_host);
 ONB_API int32_t onb_env_stats(onb_ctx* ctx, uint64_t stats_host[ONB_STAT_COUNT], int32_t clear);
+
+/* ---- host-acted stepping, pipelined inside the library ------------------------------------------------------------------
+ * The env loop of a self-play driver whose policy lives on the HOST (train.rs:55-80 with generate_move on the Rust side): per
+ * step the actions go in and "what happened" comes out. The context's games are cut into n_sub contiguous sub-batches
+ * (boundaries on multiples of 64 games); each has its own stream, pinned host staging and completion event, so while the host
+ * consumes sub-batch j the other n_sub - 1 are copying or stepping and PCIe never idles behind a kernel (4 is a good n_sub).
+ *   onb_actor_create(ctx, n_sub, out_flags, host_flags, &actor)
+ *       out_flags  = ONB_OUT_* observation buffers written ON THE DEVICE every step (planes stay in HBM for the network);
+ *       host_flags = what is copied back to pinned host memory every step:
+ *         ONB_HOST_MASKS  uint32[count][2]     policy-shaped legal masks of the new states (8 B / game)
+ *         ONB_HOST_DONE   uint32[count/32][2]  per 32 games one word pair: bit j of [w][0] = game first+32w+j was WON BY RED in this
+ *                                              step, bit j of [w][1] = won by Blue (2 bits / game: all a z back-fill needs)
+ *         ONB_HOST_STATS  uint64[ONB_STAT_COUNT] the context's counters as of this sub-batch's step
+ *   onb_actor_get_view(actor, j, &view)    the sub-batch's range and its pinned host buffers (library-owned, valid until destroy)
+ *   onb_actor_submit(actor, j, actions_host, step, auto_reset)
+ *       asynchronous: H2D of the sub-batch's `count` actions (actions_host, or view.actions when NULL; pinned memory keeps the
+ *       copy asynchronous) -> onb_env_step semantics on the slice -> D2H of the host_flags outputs -> event. actions_host must
+ *       stay untouched until onb_actor_wait.
+ *   onb_actor_wait(actor, j)               blocks on that ONE event; afterwards view.masks / done / stats hold the step's outputs
+ *   onb_actor_replay(actor, trace, stride, step0, n_steps, auto_reset)
+ *       the same ring driven by the library: action of game g at step t = trace[t * stride + g] (replay of recorded games)
+ *   onb_actor_join(actor)                  orders the context's own stream after everything submitted (no host block); the next
+ *                                          submit re-forks. Other context calls must not overlap with sub-batches in flight.
+ * Results equal onb_env_step on the whole context (tests/test_gpu_parity.py::test_actor_pipeline_*). */
+#define ONB_HOST_MASKS 1u
+#define ONB_HOST_DONE 2u
+#define ONB_HOST_STATS 4u
+typedef struct onb_actor onb_actor;
+typedef struct onb_actor_view {
+    int64_t first, count;
+    onb_action* actions; /* [count]        pinned staging the host may fill (optional: submit accepts any host pointer) */
+    uint32_t* masks;     /* [count][2]     NULL unless ONB_HOST_MASKS */
+    uint32_t* done;      /* [count/32][2]  NULL unless ONB_HOST_DONE */
+    uint64_t* stats;     /* [ONB_STAT_COUNT] NULL unless ONB_HOST_STATS */
+} onb_actor_view;
+ONB_API int32_t onb_actor_create(onb_ctx* ctx, int32_t n_sub, uint32_t out_flags, uint32_t host_flags, onb_actor** out);
+ONB_API int32_t onb_actor_destroy(onb_actor* actor);
+ONB_API int32_t onb_actor_get_view(onb_actor* actor, int32_t sub, onb_actor_view* view);
+ONB_API int32_t onb_actor_submit(onb_actor* actor, int32_t sub, const onb_action* actions_host, uint32_t step, int32_t auto_reset);
+ONB_API int32_t onb_actor_wait(onb_actor* actor, int32_t sub);
+ONB_API int32_t onb_actor_join(onb_actor* actor);
+ONB_API int32_t onb_actor_replay(onb_actor* actor, const onb_action* trace_host, int64_t stride, uint32_t step0, uint32_t n_steps,
+                                 int32_t auto_reset);
 
 /* ------------------------------------------------------------------------------------------------
  * perft-style enumeration (BASELINE config 2)

@@ -15,7 +15,8 @@ OUT_MASKS, OUT_PLANES, OUT_ACTIONS = 1, 2, 4
 EVAL_UNIFORM, EVAL_HASH, EVAL_NET = 0, 1, 2
 (BUF_STATES, BUF_MASKS, BUF_PLANES, BUF_ACTIONS, BUF_LEAF_PLANES, BUF_POLICY, BUF_VALUE, BUF_PI, BUF_BEST,
  BUF_STATS) = range(10)
-STAT_STEPS, STAT_RED_WINS, STAT_BLUE_WINS, STAT_PASSES, STAT_RESETS, STAT_COUNT = 0, 1, 2, 3, 4, 8
+STAT_STEPS, STAT_RED_WINS, STAT_BLUE_WINS, STAT_PASSES, STAT_RESETS, STAT_BAD_ACTIONS, STAT_COUNT = 0, 1, 2, 3, 4, 5, 8
+HOST_MASKS, HOST_DONE, HOST_STATS = 1, 2, 4
 ACTION_NONE = 0xFFFF
 
 # onb_state (24 bytes)
@@ -33,6 +34,11 @@ class Config(C.Structure):
 class TreeDump(C.Structure):
     _fields_ = [("visits", C.c_void_p), ("reward", C.c_void_p), ("prior", C.c_void_p), ("action", C.c_void_p),
                 ("parent", C.c_void_p), ("first_child", C.c_void_p), ("n_child", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class ActorView(C.Structure):
+    _fields_ = [("first", C.c_int64), ("count", C.c_int64), ("actions", C.c_void_p), ("masks", C.c_void_p), ("done", C.c_void_p),
+                ("stats", C.c_void_p)]
 
 
 # every symbol include/onb.h declares: name -> (restype, argtypes)
@@ -64,6 +70,13 @@ SYMBOLS = {
     "onb_env_run_random": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]),
     "onb_env_playout": (C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_int32, _P, _P]),
     "onb_env_stats": (C.c_int32, [_P, _P, C.c_int32]),
+    "onb_actor_create": (C.c_int32, [_P, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+    "onb_actor_destroy": (C.c_int32, [_P]),
+    "onb_actor_get_view": (C.c_int32, [_P, C.c_int32, C.POINTER(ActorView)]),
+    "onb_actor_submit": (C.c_int32, [_P, C.c_int32, _P, C.c_uint32, C.c_int32]),
+    "onb_actor_wait": (C.c_int32, [_P, C.c_int32]),
+    "onb_actor_join": (C.c_int32, [_P]),
+    "onb_actor_replay": (C.c_int32, [_P, _P, C.c_int64, C.c_uint32, C.c_uint32, C.c_int32]),
     "onb_perft": (C.c_int32, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P]),
     "onb_mcts_begin": (C.c_int32, [_P, C.c_double, C.c_uint32]),
     "onb_mcts_set_noise": (C.c_int32, [_P, C.c_int32, C.c_double, C.c_double, C.c_uint64]),

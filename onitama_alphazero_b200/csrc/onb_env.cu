@@ -136,12 +136,13 @@ template <int MODE, bool PLANES, int GAMES, int THREADS>
 __global__ void __launch_bounds__(THREADS, (PLANES ? ONB_ENV_MINB : 1)) k_env_step(uint4* __restrict__ states, int64_t n, uint16_t* __restrict__ actions,
                                                        uint32_t* __restrict__ masks, float* __restrict__ planes,
                                                        unsigned long long* __restrict__ stats, uint64_t seed, uint64_t game0, uint32_t step,
-                                                       int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
+                                                       int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only,
+                                                       uint2* __restrict__ done_bits) {
     __shared__ __align__(16) uint32_t s_att[800];
     __shared__ uint32_t s_pl[PLANES ? GAMES * kPlanes + 1 : 1];
-    __shared__ uint32_t s_stat[4];
+    __shared__ uint32_t s_stat[5];
     load_attack_table_to_smem(s_att);
-    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0;
+    if (threadIdx.x < 5) s_stat[threadIdx.x] = 0;
     __syncthreads();
 
     const int64_t n_tiles = (n + GAMES - 1) / GAMES;
@@ -155,7 +156,15 @@ __global__ void __launch_bounds__(THREADS, (PLANES ? ONB_ENV_MINB : 1)) k_env_st
             if (live) {
                 g = unpack(states[i]);
                 uint32_t a = 0xFFFFu;
-                if (MODE == 2) a = actions[i];
+                if (MODE == 2) {
+                    a = actions[i];
+                    // a host action naming a square above 24 would shift into the card / side / result bits of the packed state
+                    // (the reference's layout only sets its 7 padding bits there): rejected, counted, game untouched
+                    if (a != 0xFFFFu && !(a & kPassBit) && ((a & 31u) > 24u || ((a >> 5) & 31u) > 24u)) {
+                        a = 0xFFFFu;
+                        atomicAdd(&s_stat[4], 1u);
+                    }
+                }
                 // explicit actions: ONB_ACTION_NONE leaves the game untouched (e.g. the best move of a tree whose root was decided)
                 if (MODE != 3 && g.result == 0 && !(MODE == 2 && a == 0xFFFFu)) {
                     const uint64_t key = game_key(seed, game0 + (uint64_t)i);
@@ -182,6 +191,8 @@ __global__ void __launch_bounds__(THREADS, (PLANES ? ONB_ENV_MINB : 1)) k_env_st
                 const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, stepped), b1 = __ballot_sync(0xFFFFFFFFu, res == 1),
                                b2 = __ballot_sync(0xFFFFFFFFu, res == 2), b3 = __ballot_sync(0xFFFFFFFFu, passed);
                 if ((threadIdx.x & 31) == 0) {
+                    // ONB_HOST_DONE: which of these 32 games were decided by this step (2 bits per game instead of a state read-back)
+                    if (done_bits && tile * GAMES + threadIdx.x < n) done_bits[(tile * GAMES + threadIdx.x) >> 5] = make_uint2(b1, b2);
                     if (b0) atomicAdd(&s_stat[0], __popc(b0));
                     if (b1) atomicAdd(&s_stat[1], __popc(b1));
                     if (b2) atomicAdd(&s_stat[2], __popc(b2));
@@ -226,8 +237,9 @@ __global__ void __launch_bounds__(THREADS, (PLANES ? ONB_ENV_MINB : 1)) k_env_st
     }
     if (MODE != 3) {
         __syncthreads();
-        if (threadIdx.x < 4 && s_stat[threadIdx.x]) {
-            const int slot = threadIdx.x == 0 ? ONB_STAT_STEPS : threadIdx.x == 1 ? ONB_STAT_RED_WINS : threadIdx.x == 2 ? ONB_STAT_BLUE_WINS : ONB_STAT_PASSES;
+        if (threadIdx.x < 5 && s_stat[threadIdx.x]) {
+            const int slot = threadIdx.x == 0 ? ONB_STAT_STEPS : threadIdx.x == 1 ? ONB_STAT_RED_WINS : threadIdx.x == 2 ? ONB_STAT_BLUE_WINS
+                           : threadIdx.x == 3 ? ONB_STAT_PASSES : ONB_STAT_BAD_ACTIONS;
             atomicAdd(&stats[slot], (unsigned long long)s_stat[threadIdx.x]);
             if (auto_reset && (threadIdx.x == 1 || threadIdx.x == 2)) atomicAdd(&stats[ONB_STAT_RESETS], (unsigned long long)s_stat[threadIdx.x]);
         }
@@ -281,24 +293,35 @@ __global__ void __launch_bounds__(kTile) k_env_playout(uint4* __restrict__ state
 }
 
 // ------------------------------------------------------------------------------------------ launchers
+// A slice [first, first + count) of the context's games on a stream of the caller's choice (onb_actor_*: sub-batches of one context
+// stepped on their own streams); first must be a multiple of 64 so that the plane tiles stay 16-byte aligned and warps map to whole
+// words of the done bits. The whole context on its own stream is the slice {0, n, c->stream, nullptr}.
+struct StepSlice {
+    int64_t first, count;
+    cudaStream_t stream;
+    uint2* done_bits;  // [count / 32] or nullptr
+};
 template <int MODE, bool PLANES, int GAMES, int THREADS>
-static cudaError_t launch_step_shape(Ctx* c, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
+static cudaError_t launch_step_shape(Ctx* c, const StepSlice& sl, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags,
+                                     int choose_only) {
     // one tile per CTA (hardware block scheduling balances the load); grid-strided only for absurdly large n
-    const int64_t tiles = (c->n + GAMES - 1) / GAMES;
+    const int64_t tiles = (sl.count + GAMES - 1) / GAMES;
     const int64_t cap = (int64_t)1 << 30;
     const int grid = (int)(tiles < cap ? tiles : cap);
-    k_env_step<MODE, PLANES, GAMES, THREADS><<<grid, THREADS, 0, c->stream>>>(c->d_states, c->n, c->d_actions, c->d_masks, c->d_planes, c->d_stats,
-                                                                             c->cfg.seed, c->cfg.game_id_base, step, auto_reset, fixed_cards,
-                                                                             out_flags, choose_only);
+    if (grid == 0) return cudaSuccess;
+    k_env_step<MODE, PLANES, GAMES, THREADS><<<grid, THREADS, 0, sl.stream>>>(
+        c->d_states + sl.first, sl.count, c->d_actions + sl.first, c->d_masks + 2 * sl.first, c->d_planes ? c->d_planes + 525 * sl.first : nullptr,
+        c->d_stats, c->cfg.seed, c->cfg.game_id_base + (uint64_t)sl.first, step, auto_reset, fixed_cards, out_flags, choose_only, sl.done_bits);
     return cudaGetLastError();
 }
 template <int MODE>
-static cudaError_t launch_step_mode(Ctx* c, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags, int choose_only) {
+static cudaError_t launch_step_mode(Ctx* c, const StepSlice& sl, uint32_t step, int auto_reset, int32_t fixed_cards, uint32_t out_flags,
+                                    int choose_only) {
     // rules-only variants: 128 games on 128 threads. With planes: 64 games stepped by 2 warps, then all threads of the CTA drain
     // the 134 KB tile (measured on B200, 1 Mi games: 128g/128t 347 us, 32g/256t 318 us, 64g/256t 321 us, 64g/512t 313 us,
     // 128g/512t 319 us, 64g/640t 311 us; a pure fill of the same buffer takes 295 us).
-    if (!(out_flags & ONB_OUT_PLANES)) return launch_step_shape<MODE, false, 128, 128>(c, step, auto_reset, fixed_cards, out_flags, choose_only);
-    return launch_step_shape<MODE, true, 64, ONB_ENV_THREADS>(c, step, auto_reset, fixed_cards, out_flags, choose_only);
+    if (!(out_flags & ONB_OUT_PLANES)) return launch_step_shape<MODE, false, 128, 128>(c, sl, step, auto_reset, fixed_cards, out_flags, choose_only);
+    return launch_step_shape<MODE, true, 64, ONB_ENV_THREADS>(c, sl, step, auto_reset, fixed_cards, out_flags, choose_only);
 }
 
 cudaError_t launch_env_reset(Ctx* c, const uint8_t* d_decks5, int64_t n_decks, uint32_t epoch) {
@@ -323,16 +346,23 @@ cudaError_t launch_legal_moves(Ctx* c) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_env_step(Ctx* c, int mode, uint32_t step, int auto_reset, uint32_t out_flags) {
+static cudaError_t launch_env_step_on(Ctx* c, const StepSlice& sl, int mode, uint32_t step, int auto_reset, uint32_t out_flags) {
     const int32_t fixed = c->fixed_cards;
     switch (mode) {
-        case 0: return launch_step_mode<0>(c, step, auto_reset, fixed, out_flags, 0);
-        case 1: return launch_step_mode<1>(c, step, auto_reset, fixed, out_flags, 0);
-        case 2: return launch_step_mode<2>(c, step, auto_reset, fixed, out_flags, 0);
-        case 4: return launch_step_mode<0>(c, step, 0, fixed, 0, 1);
-        case 5: return launch_step_mode<1>(c, step, 0, fixed, 0, 1);
-        default: return launch_step_mode<3>(c, step, 0, fixed, out_flags, 0);
+        case 0: return launch_step_mode<0>(c, sl, step, auto_reset, fixed, out_flags, 0);
+        case 1: return launch_step_mode<1>(c, sl, step, auto_reset, fixed, out_flags, 0);
+        case 2: return launch_step_mode<2>(c, sl, step, auto_reset, fixed, out_flags, 0);
+        case 4: return launch_step_mode<0>(c, sl, step, 0, fixed, 0, 1);
+        case 5: return launch_step_mode<1>(c, sl, step, 0, fixed, 0, 1);
+        default: return launch_step_mode<3>(c, sl, step, 0, fixed, out_flags, 0);
     }
+}
+cudaError_t launch_env_step(Ctx* c, int mode, uint32_t step, int auto_reset, uint32_t out_flags) {
+    return launch_env_step_on(c, StepSlice{0, c->n, c->stream, nullptr}, mode, step, auto_reset, out_flags);
+}
+cudaError_t launch_env_step_slice(Ctx* c, int mode, uint32_t step, int auto_reset, uint32_t out_flags, int64_t first, int64_t count,
+                                  cudaStream_t stream, uint32_t* done_bits) {
+    return launch_env_step_on(c, StepSlice{first, count, stream, reinterpret_cast<uint2*>(done_bits)}, mode, step, auto_reset, out_flags);
 }
 cudaError_t launch_observe(Ctx* c, uint32_t out_flags) { return launch_env_step(c, 3, 0, 0, out_flags); }
 

@@ -95,6 +95,9 @@ cudaError_t launch_states_import(Ctx* c, const onb_state* d_in, int64_t first, i
 cudaError_t launch_legal_moves(Ctx* c);
 cudaError_t launch_observe(Ctx* c, uint32_t out_flags);
 cudaError_t launch_env_step(Ctx* c, int mode, uint32_t step, int auto_reset, uint32_t out_flags);
+// the same on games [first, first + count) and a stream of the caller's choice (first % 64 == 0); done_bits: [count/32][2] or nullptr
+cudaError_t launch_env_step_slice(Ctx* c, int mode, uint32_t step, int auto_reset, uint32_t out_flags, int64_t first, int64_t count,
+                                  cudaStream_t stream, uint32_t* done_bits);
 // perft (onb_perft.cu)
 int32_t run_perft(Ctx* c, const onb_state* roots_host, int64_t n, int depth, uint64_t* nodes, uint64_t* wins, uint64_t* zero);
 // mcts (onb_mcts.cu)

@@ -66,12 +66,9 @@ constexpr AttackTable make_attack_table() {
     return a;
 }
 constexpr AttackTable kAttackHost = make_attack_table();
-// The 16-card move table in __constant__ memory (3 200 B). Kernels whose lanes index it divergently
-// stage it into shared memory once per CTA (load_attack_table_to_smem).
-static __constant__ AttackTable c_attack = make_attack_table();
-
-// Global-memory mirror for the staging copy: lanes read consecutive words (coalesced, L1/L2 resident), whereas
-// lane-divergent reads of __constant__ memory serialise in the constant cache.
+// The 16-card move table (3 200 B) lives in device memory and is staged into shared memory once per CTA
+// (load_attack_table_to_smem): lanes index it divergently (one `from` square per lane), which would serialise in the
+// constant cache, whereas the staging copy reads consecutive words (coalesced, L1/L2 resident).
 static __device__ AttackTable g_attack = make_attack_table();
 
 __device__ __forceinline__ void load_attack_table_to_smem(uint32_t* s_att) {

@@ -345,6 +345,76 @@ class Context:
         return self.mcts_finish()
 
 
+class Actor:
+    """onb_actor_*: host-acted stepping of a context, pipelined over `n_sub` sub-batches inside the library (own streams, pinned host
+    staging, one event per sub-batch). views[j] holds numpy views of the library's pinned buffers: actions [count] u16 (optional staging
+    for the host's actions), masks [count, 2] u32, done [count/32, 2] u32 (bit j of [w, 0] / [w, 1]: game first+32w+j was won by Red / Blue
+    in the step), stats [STAT_COUNT] u64 -- valid after wait(j)."""
+
+    def __init__(self, ctx, n_sub=4, out_flags=0, host_flags=L.HOST_DONE):
+        self.ctx, self._lib, self.n_sub = ctx, ctx._lib, n_sub
+        h = C.c_void_p()
+        ctx._ck(self._lib.onb_actor_create(ctx._h, n_sub, out_flags, host_flags, C.byref(h)))
+        self._h = h
+        self.views = []
+        for j in range(n_sub):
+            v = L.ActorView()
+            ctx._ck(self._lib.onb_actor_get_view(self._h, j, C.byref(v)))
+            cnt = int(v.count)
+
+            def arr(ptr, ctype, shape, dtype):
+                if not ptr or cnt == 0:
+                    return None
+                n = int(np.prod(shape))
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).view(dtype).reshape(shape)
+
+            self.views.append(dict(first=int(v.first), count=cnt, actions=arr(v.actions, C.c_uint16, (cnt,), np.uint16),
+                                   masks=arr(v.masks, C.c_uint32, (cnt, 2), np.uint32), done=arr(v.done, C.c_uint32, ((cnt + 31) // 32, 2), np.uint32),
+                                   stats=arr(v.stats, C.c_uint64, (L.STAT_COUNT,), np.uint64)))
+
+    def submit(self, sub, actions=None, step=0, auto_reset=False):
+        """actions: None (the sub-batch's pinned staging, views[sub]['actions']), a raw host address (int), or a uint16 array of the
+        sub-batch's `count` actions -- it must stay alive and untouched until wait(sub)."""
+        if actions is None or isinstance(actions, int):
+            p = C.c_void_p(actions) if actions else None
+        else:
+            assert actions.dtype == np.uint16 and actions.flags["C_CONTIGUOUS"] and actions.size == self.views[sub]["count"]
+            p = L.ptr(actions)
+        self.ctx._ck(self._lib.onb_actor_submit(self._h, sub, p, step, int(auto_reset)))
+
+    def wait(self, sub):
+        self.ctx._ck(self._lib.onb_actor_wait(self._h, sub))
+
+    def join(self):
+        self.ctx._ck(self._lib.onb_actor_join(self._h))
+
+    def replay(self, trace, step0=0, auto_reset=False):
+        """trace: uint16 [n_steps, stride >= n] array or (address, stride, n_steps) of pinned host memory"""
+        if isinstance(trace, tuple):
+            addr, stride, steps = trace
+        else:
+            assert trace.dtype == np.uint16 and trace.ndim == 2 and trace.flags["C_CONTIGUOUS"]
+            addr, stride, steps = trace.ctypes.data, trace.shape[1], trace.shape[0]
+        self.ctx._ck(self._lib.onb_actor_replay(self._h, C.c_void_p(addr), stride, step0, steps, int(auto_reset)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.onb_actor_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _search_device(self, c_puct, sims, evaluator=L.EVAL_UNIFORM, net=None, use_graph=False):
     """Context.search without copying the results to the host (PI / BEST stay in their device buffers).
     use_graph: capture one simulation round (select -> network -> expand/backup) in a CUDA graph on the context's stream and

@@ -773,20 +773,22 @@ void orc_mcts_search_batch(const orc_state* roots, int64_t n, double c_puct, uin
 // ---- timed CPU baselines (ref-shaped code paths above), multi-threaded over games ----
 // cfg 3: n games, `steps` lockstep random steps with auto-reset + legal mask + plane encode per step.
 // Returns seconds. `sink` receives a checksum so the work cannot be optimised away.
-double orc_bench_env(int64_t n, uint32_t steps, uint64_t seed, int threads, int with_encode, double* sink) {
-    std::vector<orc_state> g((size_t)n);
-    orc_new_games(g.data(), n, 0, seed, 0, nullptr);
+// cfg 3 on a game array the caller keeps between calls: `steps` lockstep steps (step ids step0, step0+1, ...) of games
+// [0, n) with global ids game0 + i: random action, apply, auto-reset, legal mask and (with_encode) the 21x5x5 planes.
+// Returns seconds. This is what bench.py times per step for the CPU arm: the same 1 048 576 games, one step per timed step.
+double orc_bench_env_steps(orc_state* g, int64_t n, uint64_t game0, uint32_t step0, uint32_t steps, uint64_t seed, int threads, int with_encode,
+                           double* sink) {
     std::vector<double> sums((size_t)std::max(threads, 1), 0.);
     auto t0 = std::chrono::steady_clock::now();
     auto work = [&](int tid, int64_t lo, int64_t hi) {
         std::vector<float> planes(525);
         uint32_t mask[2];
         double acc = 0.;
-        for (uint32_t s = 0; s < steps; ++s)
+        for (uint32_t s = step0; s < step0 + steps; ++s)
             for (int64_t i = lo; i < hi; ++i) {
-                uint16_t a = orc::choose_random_action(orc::to_state(g[i]), g[i].side, 0, seed, (uint64_t)i, s);
+                uint16_t a = orc::choose_random_action(orc::to_state(g[i]), g[i].side, 0, seed, game0 + (uint64_t)i, s);
                 orc::apply_action(g[i], a);
-                if (g[i].result != 0) orc::new_game(g[i], seed, (uint64_t)i, s + 1, nullptr);
+                if (g[i].result != 0) orc::new_game(g[i], seed, game0 + (uint64_t)i, s + 1, nullptr);
                 orc::legal_mask(orc::to_state(g[i]), g[i].side, mask);
                 acc += mask[0] ^ mask[1];
                 if (with_encode) { orc::encode_planes(orc::to_state(g[i]), g[i].side, planes.data()); acc += planes[(s * 7 + i) % 525]; }
@@ -802,6 +804,11 @@ double orc_bench_env(int64_t n, uint32_t steps, uint64_t seed, int threads, int 
     double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (sink) { double s = 0; for (double v : sums) s += v; *sink = s; }
     return dt;
+}
+double orc_bench_env(int64_t n, uint32_t steps, uint64_t seed, int threads, int with_encode, double* sink) {
+    std::vector<orc_state> g((size_t)n);
+    orc_new_games(g.data(), n, 0, seed, 0, nullptr);
+    return orc_bench_env_steps(g.data(), n, 0, 0, steps, seed, threads, with_encode, sink);
 }
 
 // cfg 4: n trees (roots given), `sims` playouts each, uniform evaluator. Returns seconds.

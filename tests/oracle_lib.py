@@ -69,6 +69,8 @@ def lib():
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_bench_env.restype = C.c_double
         L.orc_bench_env.argtypes = [C.c_int64, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        L.orc_bench_env_steps.restype = C.c_double
+        L.orc_bench_env_steps.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
         L.orc_bench_mcts.restype = C.c_double
         L.orc_bench_mcts.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_uint32, C.c_int, C.c_void_p]
         L.orc_bench_perft.restype = C.c_double

@@ -1357,3 +1357,104 @@ def test_native_fight_equals_the_python_driver(onb):
                 assert d > 0          # five plies are not enough to finish every game
         with pytest.raises(onb.OnbError):
             ctx.fight_native(ctx.agent_puct(10 ** 6), ctx.agent_random(), a_is_red)
+
+
+# ------------------------------------------------------------------ host-acted stepping pipelined inside the library (onb_actor_*)
+def _done_bits(view_done, count):
+    """unpack ONB_HOST_DONE words -> per-game result code of the step (0 undecided, 1 Red won, 2 Blue won)"""
+    red = np.unpackbits(view_done[:, 0].copy().view(np.uint8), bitorder="little")[:count]
+    blue = np.unpackbits(view_done[:, 1].copy().view(np.uint8), bitorder="little")[:count]
+    return red.astype(np.uint8) + 2 * blue.astype(np.uint8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,n_sub", [(3000, 4), (1, 1), (65, 3), (130, 7), (4096, 4)])
+def test_actor_pipeline_equals_whole_batch_stepping(onb, n, n_sub):
+    """onb_actor_submit/wait on sub-batches (own streams, pinned staging) == onb_env_step on the whole context == the oracle,
+    incl. the 2-bit-per-game done words, the masks copied to the host, planes on the device and auto-reset."""
+    from onitama_alphazero_b200.engine import Actor
+    L = onb._lib
+    seed, base = 77 + n, 1 << 20
+    with onb.Context(n, seed=seed, game_id_base=base) as ctx:
+        ctx.reset()
+        ref = O.new_games(n, seed=seed, game0=base)
+        with Actor(ctx, n_sub=n_sub, out_flags=onb.OUT_PLANES, host_flags=L.HOST_MASKS | L.HOST_DONE | L.HOST_STATS) as act:
+            assert sum(v["count"] for v in act.views) == n and all(v["first"] % 64 == 0 for v in act.views)
+            for step in range(45):
+                shadow = ref.copy()
+                acts = O.env_step_random(shadow, seed, step, policy=0, auto_reset=False, game0=base)   # the host's policy: the oracle's
+                before = ref.copy()
+                O.env_step(ref, acts)
+                want_res = np.where(before["result"] == 0, ref["result"], 0).astype(np.uint8)
+                for i in np.nonzero(ref["result"] != 0)[0]:   # auto-reset: a decided game is re-dealt at epoch step + 1
+                    ref[i] = O.new_games(1, seed=seed, game0=base + int(i), epoch=step + 1)[0]
+                for j, v in enumerate(act.views):       # host fills the pinned staging of sub-batch j and submits it
+                    if v["count"]:
+                        v["actions"][:] = acts[v["first"]:v["first"] + v["count"]]
+                    act.submit(j, None, step=step, auto_reset=True)
+                for j, v in enumerate(act.views):
+                    act.wait(j)
+                    if v["count"] == 0:
+                        continue
+                    sl = slice(v["first"], v["first"] + v["count"])
+                    assert np.array_equal(v["masks"], O.legal_masks(ref[sl])), "host masks differ at step %d" % step
+                    assert np.array_equal(_done_bits(v["done"], v["count"]), want_res[sl]), "done bits differ at step %d" % step
+            act.join()
+            assert ctx.get_states().tobytes() == ref.tobytes()
+            assert np.array_equal(ctx.read(onb.BUF_PLANES, np.float32, (n, 21, 5, 5)), O.encode(ref))
+            st = ctx.stats()
+            assert int(act.views[-1]["stats"][onb.STAT_STEPS]) <= int(st[onb.STAT_STEPS])
+            assert st[onb.STAT_RESETS] == st[onb.STAT_RED_WINS] + st[onb.STAT_BLUE_WINS]
+
+
+@pytest.mark.gpu
+def test_actor_replay_and_submit_from_caller_memory(onb):
+    """onb_actor_replay (the ring driven by the library from a recorded trace) and submit() from the caller's own host array give
+    the games the whole-batch random stepping recorded."""
+    from onitama_alphazero_b200.engine import Actor
+    n, seed, steps = 5000, 11, 30
+    with onb.Context(n, seed=seed, planes=False) as ctx:
+        ctx.reset()
+        trace = np.zeros((steps, n), dtype=np.uint16)
+        for t in range(steps):
+            ctx.step_random(t, auto_reset=True, out_flags=onb.OUT_ACTIONS)
+            trace[t] = ctx.read(onb.BUF_ACTIONS, np.uint16, (n,))
+        want = ctx.get_states()
+        st0 = ctx.stats(clear=True)
+        ctx.reset()
+        with Actor(ctx, n_sub=4, host_flags=onb._lib.HOST_DONE) as act:
+            act.replay(trace, step0=0, auto_reset=True)
+            act.join()
+            assert ctx.get_states().tobytes() == want.tobytes()
+            st1 = ctx.stats(clear=True)
+            assert np.array_equal(st0[:5], st1[:5])
+            ctx.reset()
+            for t in range(steps):
+                for j, v in enumerate(act.views):
+                    act.wait(j)
+                    act.submit(j, np.ascontiguousarray(trace[t, v["first"]:v["first"] + v["count"]]), step=t, auto_reset=True)
+                    act.wait(j)   # the temporary slice must outlive the copy
+            act.join()
+            assert ctx.get_states().tobytes() == want.tobytes()
+            with pytest.raises(onb.OnbError) as e:
+                act.submit(0, None, step=0)
+                act.submit(0, None, step=1)
+            assert e.value.code == -4
+            act.wait(0)
+
+
+@pytest.mark.gpu
+def test_bad_host_actions_are_rejected_not_applied(onb):
+    """from / to squares above 24 would shift into the card and side bits of the packed state: such host actions leave the game untouched
+    and are counted (ONB_STAT_BAD_ACTIONS)"""
+    n = 96
+    with onb.Context(n, seed=4) as ctx:
+        ctx.reset()
+        before = ctx.get_states()
+        acts = np.full(n, 0xFFFF, dtype=np.uint16)
+        acts[0] = 25 | (3 << 5)            # to = 25
+        acts[1] = 3 | (31 << 5) | (1 << 12)  # from = 31
+        acts[2] = 31 | (31 << 5) | (3 << 10)
+        ctx.step(acts)
+        assert ctx.get_states().tobytes() == before.tobytes()
+        assert int(ctx.stats()[onb._lib.STAT_BAD_ACTIONS]) == 3
