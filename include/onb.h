@@ -360,9 +360,10 @@ ONB_API int32_t onb_uct_run(onb_ctx* ctx, float exploration_c, uint32_t min_node
 
 /* ---- policy/value network on the device ---------------------------------------------------------------------
  * ConvResNet::forward (alphazero-training/src/net.rs:215-232) for every position of a plane buffer, as one fused
- * tensor-core kernel (BatchNorm in eval mode folded into the convolutions; f32 accumulation of products of operands
- * rounded to an 11-bit significand: ONB_NET_F16 (default) or ONB_NET_TF32, the latter being what libtorch's cuDNN
- * convolutions compute by default on this GPU; heads in f32). This is the evaluator the search would otherwise get
+ * tensor-core kernel (BatchNorm in eval mode folded into the convolutions; f32 accumulation; heads in f32). Arithmetic of the
+ * convolutions: ONB_NET_F32 reproduces the reference's f32 results (split operands, see below); ONB_NET_F16 (default, the fast
+ * mode) and ONB_NET_TF32 round the operands to an 11-bit significand -- TF32 is what libtorch's cuDNN convolutions compute by
+ * default on this GPU. f16-based modes reject a network whose folded weights exceed f16's range (ONB_E_INVALID: use TF32). This is the evaluator the search would otherwise get
  * from tch as a black box; with it a whole search needs no host round trip.
  * onb_net_precision selects the operand format used by the NEXT onb_net_load. Two networks can be resident (slots 0 and 1,
  * slot 0 initially): onb_net_select chooses the one that onb_net_load fills and onb_net_forward / ONB_EVAL_NET evaluate, so
@@ -374,8 +375,11 @@ ONB_API int32_t onb_uct_run(onb_ctx* ctx, float exploration_c, uint32_t min_node
  * (ConvResNetConfig of train.rs) -- anything else is rejected with ONB_E_INVALID.
  * onb_net_forward reads planes_buffer (ONB_BUF_LEAF_PLANES or ONB_BUF_PLANES, [n][21][5][5] f32) and writes
  * ONB_BUF_POLICY [n][2][25] (softmax over 50) and ONB_BUF_VALUE [n]. onb_mcts_eval / onb_mcts_run accept ONB_EVAL_NET. */
-#define ONB_NET_F16 0
-#define ONB_NET_TF32 1
+#define ONB_NET_F16 0  /* fast mode: operands rounded to f16 (11-bit significand), f32 accumulation */
+#define ONB_NET_TF32 1 /* operands rounded to tf32 (11-bit significand, f32 exponent range) */
+#define ONB_NET_F32 2  /* f32-faithful: every operand split as x = x1 + 2^-11 x2 (two f16 parts, >= 22 significand bits), three
+                          tensor-core products per multiply-accumulate, f32 accumulation: max |dp|, |dv| <= 1e-5 against the f32
+                          reference arithmetic of net.rs:215-232 (libtorch on Device::Cpu, train.rs:163-164); ~3x the time of F16 */
 ONB_API int32_t onb_net_precision(onb_ctx* ctx, int32_t mode);
 ONB_API int32_t onb_net_select(onb_ctx* ctx, int32_t slot);
 ONB_API int32_t onb_net_load(onb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel);

@@ -17,6 +17,7 @@ EVAL_UNIFORM, EVAL_HASH, EVAL_NET = 0, 1, 2
  BUF_STATS) = range(10)
 STAT_STEPS, STAT_RED_WINS, STAT_BLUE_WINS, STAT_PASSES, STAT_RESETS, STAT_BAD_ACTIONS, STAT_COUNT = 0, 1, 2, 3, 4, 5, 8
 HOST_MASKS, HOST_DONE, HOST_STATS = 1, 2, 4
+NET_F16, NET_TF32, NET_F32 = 0, 1, 2
 ACTION_NONE = 0xFFFF
 
 # onb_state (24 bytes)

@@ -686,8 +686,8 @@ int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_
 int32_t onb_net_precision(onb_ctx* ctx, int32_t mode) {
     ONB_CHECK_CTX(ctx);
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (mode != ONB_NET_F16 && mode != ONB_NET_TF32) return fail(c, ONB_E_INVALID, "onb_net_precision: unknown mode %d", mode);
-    c->net_tf32 = mode == ONB_NET_TF32;
+    if (mode != ONB_NET_F16 && mode != ONB_NET_TF32 && mode != ONB_NET_F32) return fail(c, ONB_E_INVALID, "onb_net_precision: unknown mode %d", mode);
+    c->net_tf32 = mode;
     return ONB_OK;
 }
 int32_t onb_net_select(onb_ctx* ctx, int32_t slot) {

@@ -72,14 +72,14 @@ struct Ctx {
         float* w;     // conv taps in operand layout
         float* bias;  // folded biases
         float* head;  // head parameters
-        int blocks, loaded, f16;
+        int blocks, loaded, f16, x3;  // f16: f16 operands (else tf32); x3: split-operand f32-faithful mode (ONB_NET_F32)
     } net[2];         // two networks can be resident (an arena pits the new model against the previous one, evaluator.rs:355-399)
     void* sp_buf[10];          // grow-only buffers of onb_self_play (samples, per-slot bookkeeping)
     size_t sp_cap[10];
     void* d_net_scratch;       // residual scratch of the three-CTAs-per-SM network kernel
     size_t net_scratch_bytes;
     int net_cur;      // slot used by onb_net_load / onb_net_forward / ONB_EVAL_NET (onb_net_select)
-    int net_tf32;     // requested operand format for the next onb_net_load: 0 = f16 (default), 1 = tf32
+    int net_tf32;     // requested arithmetic for the next onb_net_load: ONB_NET_F16 (default) | ONB_NET_TF32 | ONB_NET_F32
     // grow-only device scratch reused across onb_perft calls (counters, cursor, two ping-pong frontiers): repeated
     // cudaMalloc/cudaFree of several hundred MB made the call time vary by +-50 %
     void* scratch[16];

@@ -56,8 +56,16 @@ struct Op {
 constexpr int kHP0 = 0, kHP1 = 64, kHV = 128, kHB = 192, kPhW = 196, kPhB = 2696, kV1W = 2748, kV1B = 4348, kV2W = 4412, kV2B = 4476,
               kHeadFloats = 4480;
 
-template <int NACC, bool F16>
+// X3 (ONB_NET_F32, f16 operands only): every f32 operand x is split as x = x1 + 2^-11 x2 with x1 = f16(x), x2 = f16((x - x1) 2^11)
+// (22+ significand bits; the scaling keeps x2 in f16's normal range however small x is). A product a b is then
+// a1 b1 + 2^-11 (a1 b2 + a2 b1) up to 2^-23 relative: three MMAs per step, the first into accumulator D1, the other two into a
+// second accumulator D2 that the epilogue adds as D1 + 2^-11 D2. Two activation matrices (a1, a2), weights streamed as (b1, b2)
+// pairs per tap, TMEM = {D1, D2} x {plain, residual-preloaded} x NACC x 64 columns = 512: one CTA per SM.
+constexpr float kX3Scale = 2048.f, kX3InvScale = 1.f / 2048.f;
+template <int NACC, bool F16, bool X3 = false>
 struct Geo {
+    static_assert(!X3 || (F16 && NACC == 2), "the split-operand mode is built on the f16 operand path with two accumulators");
+    static constexpr int NMAT = X3 ? 2 : 1;                    // activation matrices / weight copies per tap
     static constexpr int NB = NACC == 2 ? (F16 ? 7 : 6) : 14;  // boards per pass (two CTAs per SM when NACC == 2)
     static constexpr int CELLS = NB * kCellsPerBoard;
     static constexpr int R = (kLead + CELLS + kTrail + 7) / 8 * 8;  // rows of the activation matrix (whole swizzle periods)
@@ -67,9 +75,10 @@ struct Geo {
     static constexpr int NSLOT = F16 ? 3 : (NACC == 2 ? 3 : 4);
     static constexpr int TPS = F16 ? 3 : 1;
     static constexpr int UPL = 9 / TPS;  // slots per layer
-    static constexpr int SLOT_BYTES = TPS * Op<F16>::TAP_BYTES;
+    static constexpr int TAP_STRIDE = NMAT * Op<F16>::TAP_BYTES;  // X3: [b1 tap][b2 tap]
+    static constexpr int SLOT_BYTES = TPS * TAP_STRIDE;
     static constexpr int ACT_BYTES = R * Op<F16>::KCH * 16;  // a multiple of 1024: the ring stays aligned to the swizzle period
-    static constexpr int OFF_RING = ACT_BYTES;
+    static constexpr int OFF_RING = NMAT * ACT_BYTES;
     static constexpr int RING_BYTES = NSLOT * SLOT_BYTES;
     static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
     static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;
@@ -77,7 +86,9 @@ struct Geo {
     static constexpr int SMEM_USED = OFF_BAR + (2 * NSLOT + 1) * 8 + 16;
     // TMEM holds two CTAs of 256 columns: ask for enough shared memory that a third CTA can never become resident and block in tcgen05.alloc
     static constexpr int SMEM = NACC == 2 && SMEM_USED < 78 * 1024 ? 78 * 1024 : SMEM_USED;
-    static constexpr int TMEM_COLS = NACC * 128;  // NACC accumulators + NACC residual accumulators of 64 columns
+    static constexpr int SET_COLS = NMAT * NACC * 64;  // one accumulator set: D1 (and D2) of NACC x 64 columns
+    static constexpr int TMEM_COLS = 2 * SET_COLS;     // the plain set + the residual-preloaded set
+    static_assert(SMEM_USED <= 227 * 1024, "shared memory");
     static_assert(CELLS <= NACC * 128, "cells must fit the accumulators");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "power of two");
 };
@@ -180,9 +191,11 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_addr, uint32_
             : "memory");
 }
 // all MMAs of one tap: K steps of 32 bytes (4 per 128-byte block) x NACC accumulators of 128 rows
-template <bool F16, int NACC>
+// X3: a2_off / b2_off = byte distance of the second activation matrix / the tap's second weight copy (0 otherwise); D2 sits
+// NACC * 64 columns after D1 and starts from zero at the layer's first step (accumulate_second = false) whatever D1 was preloaded with.
+template <bool F16, int NACC, bool X3 = false>
 __device__ __forceinline__ void issue_tap_mmas(bool elected, uint32_t dcol, uint32_t s_act, int R, int row0, uint32_t b_slot, int ksteps,
-                                               bool accumulate_first) {
+                                               bool accumulate_first, uint32_t a2_off = 0, uint32_t b2_off = 0, bool accumulate_second = true) {
     using O = Op<F16>;
 #pragma unroll
     for (int j = 0; j < O::KCH / 2; ++j) {
@@ -193,7 +206,13 @@ __device__ __forceinline__ void issue_tap_mmas(bool elected, uint32_t dcol, uint
             for (int a = 0; a < NACC; ++a) {
                 const uint32_t a_addr = s_act + koff * (uint32_t)R + (uint32_t)(row0 + a * 128) * 128u + (uint32_t)(j % 4) * 32u;
 #ifndef ONB_NET_DBG_NOMMA
-                if (elected) mma_ss<F16>(dcol + a * 64, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u);
+                if (elected) {
+                    mma_ss<F16>(dcol + a * 64, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u);
+                    if (X3) {
+                        mma_ss<F16>(dcol + (NACC + a) * 64, a_addr, b_addr + b2_off, (accumulate_second || j > 0) ? 1u : 0u);  // a1 b2
+                        mma_ss<F16>(dcol + (NACC + a) * 64, a_addr + a2_off, b_addr, 1u);                                       // a2 b1
+                    }
+                }
 #endif
             }
         }
@@ -257,6 +276,25 @@ __device__ __forceinline__ void store_channels<false>(uint32_t s_act, int R, int
         st_shared_v4(act_addr(s_act, R, row, c0 / 4 + i), to_tf32(o[4 * i + 0]), to_tf32(o[4 * i + 1]), to_tf32(o[4 * i + 2]),
                      to_tf32(o[4 * i + 3]));
 }
+// split-operand store: x1 = f16(x) into the first activation matrix, x2 = f16((x - x1) 2^11) into the second (x - x1 is exact in f32)
+__device__ __forceinline__ void store_channels_x3(uint32_t s_act, uint32_t a2_off, int R, int row, int c0, const float (&o)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float x0 = fminf(o[8 * i + 2 * q], 65504.f), x1 = fminf(o[8 * i + 2 * q + 1], 65504.f);
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
+            hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const uint32_t addr = act_addr(s_act, R, row, c0 / 8 + i);
+        st_shared_v4(addr, hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(addr + a2_off, lo[0], lo[1], lo[2], lo[3]);
+    }
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
@@ -283,10 +321,10 @@ __device__ __forceinline__ Cell decode_cell(int cell, int n_cells) {
     return c;
 }
 
-template <int NACC, bool F16>
-__global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
+template <int NACC, bool F16, bool X3 = false>
+__global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
     k_net_forward(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
-    using G = Geo<NACC, F16>;
+    using G = Geo<NACC, F16, X3>;
     using O = Op<F16>;
     constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = G::NSLOT;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -313,12 +351,14 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
-    for (int i = tid; i < G::ACT_BYTES / 16; i += 256) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero for good
+    for (int i = tid; i < G::NMAT * G::ACT_BYTES / 16; i += 256) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero for good
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
+    constexpr uint32_t A2 = X3 ? (uint32_t)G::ACT_BYTES : 0u, B2 = X3 ? (uint32_t)O::TAP_BYTES : 0u;  // second activation matrix / weight copy
+    constexpr uint32_t SET = (uint32_t)G::SET_COLS;  // TMEM columns of one accumulator set (D1 [+ D2])
 
 #ifdef ONB_NET_PROFILE
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
@@ -340,7 +380,8 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             float x[32];  // the planes are 0 / 1: exact in either operand format
 #pragma unroll
             for (int ch = 0; ch < 32; ++ch) x[ch] = (ch < kInPlanes && gb < n) ? __ldg(src + ch * 25) : 0.f;
-            store_channels<F16>(s_act, R, kLead + cell, 0, x);  // 32 channels: planes 21..31 are zero
+            if (X3) store_channels_x3(s_act, A2, R, kLead + cell, 0, x);
+            else store_channels<F16>(s_act, R, kLead + cell, 0, x);  // 32 channels: planes 21..31 are zero
         }
         fence_proxy_async();
         PF(0);  // input stage
@@ -354,7 +395,7 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
             if (warp == 0) {
                 // ---- MMA issue: 9 taps x K steps x NACC accumulators (the whole warp runs the loop, one lane issues)
                 const bool elected = elect_one();
-                                const uint32_t dcol = tmem + (use_s ? NACC * 64 : 0);
+                const uint32_t dcol = tmem + (use_s ? SET : 0u);
                 auto issue_unit = [&](int g, int ksteps) {
                     const uint32_t u = q0 + g, slot = u % NSLOT, use = u / NSLOT;
 #ifdef ONB_NET_PROFILE
@@ -367,8 +408,9 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
 #pragma unroll
                     for (int tt = 0; tt < TPS; ++tt) {
                         const int t = g * TPS + tt;
-                        issue_tap_mmas<F16, NACC>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
-                                                  s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * O::TAP_BYTES, ksteps, use_s || t > 0);
+                        issue_tap_mmas<F16, NACC, X3>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
+                                                      s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
+                                                      use_s || t > 0, A2, B2, t > 0);
                     }
                     PF(3);  // issuing MMAs
                     if (elected) umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
@@ -389,9 +431,9 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                     const uint32_t slot = q_prod % NSLOT, use = q_prod / NSLOT;
                     if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
                     const uint32_t ul = q_prod % (uint32_t)(UPL * L), layer = ul / UPL, tap = (ul - layer * UPL) * TPS;
-                    const uint8_t* src = net.wconv + (layer == 0 ? (size_t)tap * O::TAP_BYTES0
+                    const uint8_t* src = net.wconv + (size_t)G::NMAT * (layer == 0 ? (size_t)tap * O::TAP_BYTES0
                                                                   : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
-                    const uint32_t bytes = (uint32_t)TPS * (layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES);
+                    const uint32_t bytes = (uint32_t)(TPS * G::NMAT) * (layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES);
 #ifdef ONB_NET_DBG_NOWEIGHTS
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full(slot)) : "memory");
                     (void)src; (void)bytes;
@@ -421,13 +463,19 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                 const int cell = a * 128 + (warp & 3) * 32 + lane;
                 const Cell c = decode_cell(cell, CELLS);
                 const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-                const uint32_t tsrc = tlane + (use_s ? NACC * 64 : 0) + a * 64;
-                const uint32_t tskip = tlane + NACC * 64 + a * 64;
+                const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * 64;
+                const uint32_t tskip = tlane + SET + a * 64;
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t v[32];
                     tmem_ld32(tsrc + h * 32, v);
+                    if (X3) {  // D1 + 2^-11 D2
+                        uint32_t v2[32];
+                        tmem_ld32(tsrc + NACC * 64 + h * 32, v2);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v2[i]), kX3InvScale, __uint_as_float(v[i])));
+                    }
                     float o[32];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -438,7 +486,10 @@ __global__ void __launch_bounds__(256, NACC == 2 ? 2 : 1)
                         o[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f);
                         o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
                     }
-                    if (!last && c.real) store_channels<F16>(s_act, R, kLead + cell, h * 32, o);
+                    if (!last && c.real) {
+                        if (X3) store_channels_x3(s_act, A2, R, kLead + cell, h * 32, o);
+                        else store_channels<F16>(s_act, R, kLead + cell, h * 32, o);
+                    }
                     if (preload) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -1054,11 +1105,14 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
     }
     const double eps = 1e-5;  // nn::BatchNormConfig default of tch 0.10 / torch
     const int L = 1 + 2 * n_blocks;
-    const bool f16 = c->net_tf32 == 0;
-    const int cpc = f16 ? Op<true>::CPC : Op<false>::CPC, kch = f16 ? Op<true>::KCH : Op<false>::KCH, kch0 = f16 ? Op<true>::KCH0 : Op<false>::KCH0;
+    const int mode = c->net_tf32;  // ONB_NET_F16 | ONB_NET_TF32 | ONB_NET_F32 (f16 operands split in two, see Geo)
+    const bool f16 = mode != ONB_NET_TF32, x3 = mode == ONB_NET_F32;
+    const int nmat = x3 ? 2 : 1;
+    const int cpc = f16 ? Op<true>::CPC : Op<false>::CPC, kch = f16 ? Op<true>::KCH : Op<false>::KCH;
     const size_t tap_bytes = f16 ? Op<true>::TAP_BYTES : Op<false>::TAP_BYTES, tap_bytes0 = f16 ? Op<true>::TAP_BYTES0 : Op<false>::TAP_BYTES0;
-    std::vector<uint8_t> wconv(9 * tap_bytes0 + (size_t)(L - 1) * 9 * tap_bytes, 0);
+    std::vector<uint8_t> wconv((size_t)nmat * (9 * tap_bytes0 + (size_t)(L - 1) * 9 * tap_bytes), 0);
     std::vector<float> bias((size_t)(L + 2) * 64, 0.f), head(kHeadFloats, 0.f);
+    double w_absmax = 0.0;
     for (int l = 0; l < L; ++l) {
         std::string conv, bn;
         if (l == 0) {
@@ -1078,19 +1132,24 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
         BnFold f;
         if (!fold_bn(ts, conv, bn, kHid, eps, f, err)) return ONB_E_INVALID;
         const int chunks = l == 0 ? 8 : kch;  // the first layer fills one whole 128-byte block (channels beyond 21 are zero)
-        (void)kch0;
-        uint8_t* dst = wconv.data() + (l == 0 ? 0 : 9 * tap_bytes0 + (size_t)(l - 1) * 9 * tap_bytes);
         const size_t tb = l == 0 ? tap_bytes0 : tap_bytes;
+        uint8_t* dst = wconv.data() + (size_t)nmat * (l == 0 ? 0 : 9 * tap_bytes0 + (size_t)(l - 1) * 9 * tap_bytes);
         for (int tap = 0; tap < 9; ++tap)
             for (int kc = 0; kc < chunks; ++kc)
                 for (int co = 0; co < kHid; ++co)
-                    for (int e = 0; e < cpc; ++e) {  // operand layout: [tap][128-byte block][co][chunk ^ (co & 7)][16 bytes of input channels]
+                    for (int e = 0; e < cpc; ++e) {  // operand layout: [tap][copy][128-byte block][co][chunk ^ (co & 7)][16 bytes of input channels]
                         const int ci = kc * cpc + e;
-                        const float x = ci < c_in ? (float)((double)w->data[((size_t)co * c_in + ci) * 9 + tap] * f.scale[co]) : 0.f;
-                        uint8_t* q = dst + tap * tb + (size_t)(kc >> 3) * 64 * 128 + (size_t)co * 128 + (size_t)(((kc & 7) ^ (co & 7)) << 4);
+                        const double xd = ci < c_in ? (double)w->data[((size_t)co * c_in + ci) * 9 + tap] * f.scale[co] : 0.0;
+                        const float x = (float)xd;
+                        if (std::fabs(xd) > w_absmax) w_absmax = std::fabs(xd);
+                        uint8_t* q = dst + (size_t)tap * nmat * tb + (size_t)(kc >> 3) * 64 * 128 + (size_t)co * 128 + (size_t)(((kc & 7) ^ (co & 7)) << 4);
                         if (f16) {
                             const __half hv = __float2half_rn(x);
                             memcpy(q + e * 2, &hv, 2);
+                            if (x3) {  // w = w1 + 2^-11 w2 (the remainder is taken from the f64 folded weight)
+                                const __half lv = __float2half_rn((float)((xd - (double)__half2float(hv)) * (double)kX3Scale));
+                                memcpy(q + tb + e * 2, &lv, 2);
+                            }
                         } else {
                             const float r = tf32_round_host(x);
                             memcpy(q + e * 4, &r, 4);
@@ -1127,6 +1186,12 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
         }
         head[kV2B] = v2b->data[0];
     }
+    // f16 operands: a folded weight beyond f16's largest finite value would become inf (the small end is harmless in the split mode and
+    // costs significand bits below 6.1e-5 in the plain f16 mode -- see onb.h); such a network has to be loaded with ONB_NET_TF32
+    if (f16 && w_absmax > 65504.0) {
+        err = "a BatchNorm-folded convolution weight has magnitude " + std::to_string(w_absmax) + " > 65504 (f16 range): load this network with ONB_NET_TF32";
+        return ONB_E_INVALID;
+    }
     Ctx::NetSlot& ns = c->net[c->net_cur];
     cudaStreamSynchronize(c->stream);  // a forward pass with the old weights may still be running
     for (void** p : {(void**)&ns.w, (void**)&ns.bias, (void**)&ns.head})
@@ -1148,24 +1213,25 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
     }
     ns.blocks = n_blocks;
     ns.f16 = f16 ? 1 : 0;
+    ns.x3 = x3 ? 1 : 0;
     ns.loaded = 1;
     return ONB_OK;
 }
 
-template <int NACC, bool F16>
+template <int NACC, bool F16, bool X3 = false>
 static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
-    using G = Geo<NACC, F16>;
+    using G = Geo<NACC, F16, X3>;
     static bool attr[64] = {};  // the opt-in is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr[dev]) {
-        const cudaError_t e = cudaFuncSetAttribute(k_net_forward<NACC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        const cudaError_t e = cudaFuncSetAttribute(k_net_forward<NACC, F16, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     const char* one = getenv("ONB_NET_ONE_CTA");  // experiment: a single CTA per SM (is the MMA issue time contention or a per-thread limit?)
-    const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * ((NACC == 2 && !(one && one[0] == '1')) ? 2 : 1);
-    k_net_forward<NACC, F16><<<(unsigned)(groups < slots ? groups : slots), 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
+    const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * ((NACC == 2 && !X3 && !(one && one[0] == '1')) ? 2 : 1);
+    k_net_forward<NACC, F16, X3><<<(unsigned)(groups < slots ? groups : slots), 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
     return cudaGetLastError();
 }
 
@@ -1217,6 +1283,7 @@ cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (ns.x3) return launch_net_variant<2, true, true>(c, planes, policy, value, nd, sms);  // ONB_NET_F32: split operands, f32-faithful
     const char* v3 = getenv("ONB_NET_V3");  // three CTAs per SM, residual in an L2-resident scratch (f16 operands only)
     if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms);
     const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)

@@ -274,11 +274,14 @@ class Context:
         """onb_net_select: which of the two resident networks net_load fills and net_forward / EVAL_NET evaluate"""
         self._ck(self._lib.onb_net_select(self._h, slot))
 
-    def net_load(self, params, tf32=False):
+    def net_load(self, params, tf32=False, precision=None):
         """onb_net_load: params = a torch module / state_dict / dict name -> array with the reference's VarStore names
         (net.rs:118-213; '.' or '|' separators). Folds BatchNorm, lays the weights out for the tensor cores, uploads them.
-        tf32: tf32 operands (cuDNN's default conv arithmetic) instead of f16 (same 11-bit significand, twice as fast)."""
-        self._ck(self._lib.onb_net_precision(self._h, 1 if tf32 else 0))
+        precision: "f32" = f32-faithful split-operand arithmetic (ONB_NET_F32: |dp|, |dv| <= 1e-5 vs the reference's f32 CPU
+        forward), "f16" (default) = the fast mode, operands rounded to f16's 11-bit significand, "tf32" = tf32 operands (cuDNN's
+        default conv arithmetic); tf32=True is the older spelling of precision="tf32"."""
+        mode = {"f16": L.NET_F16, "tf32": L.NET_TF32, "f32": L.NET_F32}[precision or ("tf32" if tf32 else "f16")]
+        self._ck(self._lib.onb_net_precision(self._h, mode))
         if hasattr(params, "state_dict"):
             params = params.state_dict()
         names, arrays = [], []

@@ -45,9 +45,10 @@ def test_alphaloss_matches_reference_formula():
     assert idx.shape == (32,) and len(set(idx.tolist())) == 32 and int(idx.max()) < 100
 
 
-def lively_model(blocks=3, seed=7):
+def lively_model(blocks=3, seed=7, res_gain=None):
     """ConvResNet with activations of order one in every layer and non-trivial BatchNorm statistics (so that BN folding, the
-    residual path and both heads all matter to the output); deterministic for a given torch version."""
+    residual path and both heads all matter to the output); deterministic for a given torch version. res_gain scales the second
+    convolution of every residual block (default: 1 up to 3 blocks, 0.5 beyond -- deeper towers would otherwise saturate tanh)."""
     from onitama_alphazero_b200.net import ConvResNet
     torch.manual_seed(seed)
     model = ConvResNet(64, 21, blocks)
@@ -64,6 +65,14 @@ def lively_model(blocks=3, seed=7):
                 m.running_var.uniform_(0.5, 1.5)
                 m.weight.uniform_(0.7, 1.3)
                 m.bias.normal_(0.1, 0.2)
+        gain = res_gain if res_gain is not None else (1.0 if blocks <= 3 else 0.5)
+        if gain != 1.0:
+            for name, p in model.named_parameters():
+                if "small_block2.small_block_conv.weight" in name:
+                    p.mul_(gain)
+        if blocks > 3:  # the trunk's activations grow with depth: keep tanh and softmax out of saturation
+            model.vh_conv.weight.mul_(0.02)
+            model.policy_conv.weight.mul_(0.2)
     return model.eval()
 
 

@@ -9,7 +9,8 @@ from onitama_alphazero_b200.net import ConvResNet
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 blocks = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-tf32 = len(sys.argv) > 3 and sys.argv[3] == "tf32"
+prec = sys.argv[3] if len(sys.argv) > 3 else "f16"   # f16 | tf32 | f32 (split operands, f32-faithful)
+tf32 = prec == "tf32"
 torch.manual_seed(7)
 model = ConvResNet(64, 21, blocks)
 with torch.no_grad():  # lively activations and non-trivial BatchNorm statistics so that every path is exercised
@@ -33,7 +34,7 @@ with onb.Context(n, seed=3, mcts_max_sims=4) as ctx:
     for s in range(7):
         ctx.step_random(s, auto_reset=True, out_flags=onb.OUT_PLANES)
     planes = ctx.tensor(L.BUF_PLANES).clone()
-    ctx.net_load(model, tf32=tf32)
+    ctx.net_load(model, precision=prec)
     ctx.net_forward(L.BUF_PLANES)
     ctx.sync()
     pol = ctx.tensor(L.BUF_POLICY).clone().cpu().numpy().reshape(n, 50)
@@ -42,7 +43,7 @@ with onb.Context(n, seed=3, mcts_max_sims=4) as ctx:
         p_ref, v_ref = model.cuda()(planes.reshape(n, 21, 5, 5))
     p_ref = p_ref.reshape(n, 50).cpu().numpy(); v_ref = v_ref.reshape(n).cpu().numpy()
     dp = np.abs(pol - p_ref); dv = np.abs(val - v_ref)
-    print("tf32" if tf32 else "f16", "n", n, "blocks", blocks, "max|dp|", dp.max(), "mean|dp|", dp.mean(), "max|dv|", dv.max(), "mean|dv|", dv.mean())
+    print(prec, "n", n, "blocks", blocks, "max|dp|", dp.max(), "mean|dp|", dp.mean(), "max|dv|", dv.max(), "mean|dv|", dv.mean())
     print("policy sums", pol.sum(1).min(), pol.sum(1).max(), "ref p range", p_ref.min(), p_ref.max(), "v range", v_ref.min(), v_ref.max())
     print("variation across boards: policy std max %.4f, value std %.4f" % (p_ref.std(0).max(), v_ref.std()))
     bad = np.argwhere(dp > 5e-3)
