@@ -33,6 +33,10 @@ PLAYOUT_GAMES = 4096
 SELFPLAY_GAMES = 16384
 SELFPLAY_SIMS = 800
 SEED = 20240607
+NET_PRECISION = {"fused-f32": "f32", "fused": "f16", "fused-tf32": "tf32", "torch": "torch"}
+NET_DTYPE = {"fused-f32": "f32-faithful network: split f16 operands (x = x1 + 2^-11 x2), 3 products per multiply-add, f32 accumulate",
+             "fused": "f16 x f16 -> f32 network (FAST MODE: operands rounded to 11 bits, not the reference's f32 arithmetic)",
+             "fused-tf32": "tf32 x tf32 -> f32 network (operands rounded to 11 bits)", "torch": "f32/tf32 (network, cuDNN)"}
 # algorithmic bytes per unit of work
 ENV_BYTES_PER_STEP = 16 + 16 + 8 + 2100  # state read, state write, legal mask, planes
 
@@ -367,8 +371,9 @@ def main():
     ap.add_argument("--no-selfplay", action="store_true", help="skip the config-5 section of the default env run (12 000 launches: too many for an ncu launch list)")
     ap.add_argument("--eval-mode", action="store_true",
                     help="selfplay workload: search without the root exploration noise (self_play of train.rs searches in train mode)")
-    ap.add_argument("--net", default="fused", choices=["fused", "fused-tf32", "torch"],
-                    help="selfplay workload: the tensor-core network kernel (f16 or tf32 operands) or the PyTorch module as a black box")
+    ap.add_argument("--net", default="fused-f32", choices=["fused-f32", "fused", "fused-tf32", "torch"],
+                    help="selfplay workload: the tensor-core network kernel -- fused-f32 = f32-faithful split-operand arithmetic (the headline: "
+                         "the reference computes in f32), fused = the f16 fast mode, fused-tf32 = tf32 operands -- or the PyTorch module as a black box")
     args = ap.parse_args()
     claim_stdout()
     dflt = {"env": (1000, 50), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3), "games": (2, 3)}[args.workload]
@@ -740,7 +745,7 @@ def main():
         n, sims = SELFPLAY_GAMES, SELFPLAY_SIMS
         torch.manual_seed(1234)
         ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims)
-        ctx.net_load(ConvResNet(64, 21, 3), tf32=args.net == "fused-tf32")
+        ctx.net_load(ConvResNet(64, 21, 3), precision=NET_PRECISION[args.net])
         quota = n // 4          # a step = self-play until a quarter of the slots' worth of games is complete
         cap = n * 64            # plies of sample buffer: far more than a step needs
         tot = {"games": 0, "samples": 0, "plies": 0}
@@ -761,25 +766,26 @@ def main():
         tpeak, tsrc = read_tensor_peak()
         ach = flop * n * sims * (plies / world) / (ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": read_traffic("k_net_forward"),
-                "kernel": "k_net_forward<2,%s>" % ("tf32" if args.net == "fused-tf32" else "f16"), "peak_source": tsrc,
+                "kernel": "k_net_forward<2,%s>" % NET_PRECISION[args.net], "peak_source": tsrc,
                 "samples_per_sec": samples / (ms * 1e-3), "plies_per_step": plies / world / max(1, steps),
                 "note": "every ply searches all slots (16 384 x 800 network evaluations); finished slots restart at once; a step ends when n/4 games are complete"}
         e2e = {"value": value, "unit": "games/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * plies / world / max(1, steps),
                "path": "onb_self_play: one 8-byte counter per ply crosses PCIe; samples stay in device buffers for the trainer"}
         return dict(metric="selfplay_games_per_sec", value=value, unit="games/s", ms_per_step=ms / steps,
-                    dtype="u32+f64 (search), f16 x f16 -> f32 (network)", roofline=roof, e2e=e2e, gpu_launches=int(plies / world) * (3 * sims + 12),
+                    dtype="u32+f64 (search), " + NET_DTYPE[args.net], roofline=roof, e2e=e2e, gpu_launches=int(plies / world) * (3 * sims + 12),
                     clocks=clocks)
 
     # ---------------------------------------------------------------- self-play with the network (config 5)
-    def bench_selfplay(steps, warmup):
+    def bench_selfplay(steps, warmup, net_mode=None):
         from onitama_alphazero_b200.net import ConvResNet, make_evaluator
+        net_mode = net_mode or args.net
         n, sims = SELFPLAY_GAMES, SELFPLAY_SIMS
         torch.manual_seed(1234)
         model = ConvResNet(64, 21, 3)
         ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims)
-        fused = args.net != "torch"
+        fused = net_mode != "torch"
         if fused:
-            ctx.net_load(model, tf32=args.net == "fused-tf32")   # onb_net_load: the network becomes part of the library's search
+            ctx.net_load(model, precision=NET_PRECISION[net_mode])   # onb_net_load: the network becomes part of the library's search
             net = None
         else:
             net = make_evaluator(model.cuda(local_rank))
@@ -811,10 +817,12 @@ def main():
             tpeak, tsrc = read_tensor_peak()
             ach = flop * n * sims * steps / (ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": read_traffic("k_net_forward"),
-                    "kernel": "k_net_forward<2,%s>" % ("tf32" if args.net == "fused-tf32" else "f16"), "flop_per_evaluation": flop,
-                    "note": "achieved = useful network FLOPs of the whole ply / ply time (search kernels included in the time); the MMAs also "
-                            "compute the zero-padding cells (25 of 36.6 rows are real squares) and are bound by shared-memory operand reads at "
-                            "N = 64 (6 KB per 128x64x16 MMA); peak = dense bf16/f16 (tf32 runs at half of it)", "peak_source": tsrc}
+                    "kernel": "k_net_forward<2,%s>" % NET_PRECISION[net_mode], "flop_per_evaluation": flop,
+                    "note": "achieved = USEFUL network FLOPs (one f32 multiply-add per weight and square, as the reference computes) of the whole "
+                            "ply / ply time, search kernels included in the time; the f32-faithful mode spends three f16 tensor-core products per "
+                            "useful multiply-add (split operands), so its tensor pipe does 3x this figure; the MMAs also compute the zero-padding "
+                            "cells (25 of 36.6 rows are real squares) and are bound by shared-memory operand reads at N = 64; peak = dense bf16/f16",
+                    "peak_source": tsrc}
         else:
             roof = {"bound": "hbm", "achieved": per_sim * n * sims * steps / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": per_sim * n * sims * steps / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_mcts_select + k_mcts_expand_backup",
@@ -822,11 +830,10 @@ def main():
                     "peak_source": peak_src}
         e2e = {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "path": "device-resident self-play ply (search + sample gather + play); nothing crosses PCIe by design"}
-        dt = "u32+f64 (search), " + {"fused": "f16 x f16 -> f32 (network)", "fused-tf32": "tf32 x tf32 -> f32 (network)",
-                                     "torch": "f32/tf32 (network, cuDNN)"}[args.net]
         roof["search_mode"] = "eval (no root noise)" if args.eval_mode else "train (root exploration noise, epsilon 0.25, alpha 0.03)"
-        return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=ms / steps, dtype=dt, network=args.net,
-                    roofline=roof, e2e=e2e, gpu_launches=((3 if fused else 2) * sims + 4) * steps, clocks=clocks, samples_per_ply=got["samples"])
+        return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=ms / steps, dtype="u32+f64 (search), " + NET_DTYPE[net_mode],
+                    network=net_mode, roofline=roof, e2e=e2e, gpu_launches=((3 if fused else 2) * sims + 4) * steps, clocks=clocks,
+                    samples_per_ply=got["samples"])
 
     if wl == "env":
         out = bench_env(args.steps, args.warmup)
@@ -857,11 +864,14 @@ def main():
         try:  # config 5 with the network on the tensor cores (one ply of 16 384 games x 800 simulations per step)
             if args.no_selfplay:
                 raise RuntimeError("skipped (--no-selfplay)")
-            s_steps, s_warm = (min(args.steps, 30), min(max(3, args.warmup), 5)) if args.steps_given else (3, 3)
-            sp = bench_selfplay(s_steps, s_warm)
+            s_steps, s_warm = (min(args.steps, 10), min(max(3, args.warmup), 5)) if args.steps_given else (3, 3)
+            sp = bench_selfplay(s_steps, s_warm, "fused-f32")   # headline: the reference's f32 arithmetic
             third = {k: sp[k] for k in ("metric", "value", "unit", "ms_per_step", "dtype", "network", "roofline", "e2e", "gpu_launches", "clocks")}
             third["config"] = workload_config("selfplay")
             third["steps"], third["warmup"] = s_steps, s_warm
+            fast = bench_selfplay(s_steps, s_warm, "fused")     # explicitly labelled fast mode (f16 operands)
+            third["fast_mode_f16"] = {k: fast[k] for k in ("value", "unit", "ms_per_step", "dtype", "network", "gpu_launches")}
+            third["fast_mode_f16"]["roofline_frac"] = fast["roofline"]["frac"]
         except Exception as exc:  # never lose the headline over the extra measurement
             third = {"error": repr(exc)}
 

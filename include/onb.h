@@ -289,14 +289,17 @@ ONB_API int32_t onb_mcts_dump_tree(onb_ctx* ctx, int64_t tree, int64_t cap, onb_
 ONB_API int32_t onb_mcts_tree_info(onb_ctx* ctx, uint32_t* n_nodes_host, uint8_t* flags_host);
 
 /* ---- self_play (alphazero-training/src/train.rs:35-98) for all games of the context, natively -------------------------------
- * Plays until at least n_games games are complete: per ply { planes of every slot (train.rs:58); search (evaluator = ONB_EVAL_*,
- * ONB_EVAL_NET for the loaded network; train != 0: root exploration noise, epsilon 0.25 / alpha 0.03); record (planes, pi,
- * colour); play the best move; finished games (a win, or max_plies + 2 plies: the ply cap of train.rs:74-79) get their z =
- * reward(result, sample colour) and their slot is re-dealt at once }. Nothing but one 8-byte counter per ply crosses PCIe.
+ * Plays exactly max(n_games, slots) games, every one of them TO ITS END: per ply { planes of every slot (train.rs:58); search of
+ * the slots with a game in progress (evaluator = ONB_EVAL_*, ONB_EVAL_NET for the loaded network; train != 0: root exploration
+ * noise, epsilon 0.25 / alpha 0.03); record (planes, pi, colour); play the best move; finished games (a win, or max_plies + 2
+ * plies: the ply cap of train.rs:74-79) get their z = reward(result, sample colour); their slots -- in slot order -- start the
+ * next game at once while games remain to be started and go idle afterwards }. No game is abandoned when the quota is reached
+ * (dropping the games still running would drop the LONG ones and bias z / pi; a worker of the reference plays its
+ * self_play_game_amnt games to completion). Two 8-byte counters per ply cross PCIe.
  * The result points at device buffers owned by the context (valid until the next onb_self_play / onb_destroy): sample
- * i = ply * n_games_of_ctx + slot; valid_idx[0 .. n_valid) lists, ascending, the samples that belong to completed games (the
- * games still running when the quota was reached are not listed). serial = slot + n * (games finished before in that slot).
- * sample_cap bounds the buffers (samples; >= one ply); truncated = 1 if it was reached before n_games were complete.
+ * i = ply * n_games_of_ctx + slot; valid_idx[0 .. n_valid) lists, ascending, the samples of the completed games (all games
+ * unless truncated). serial = slot + n * (games finished before in that slot).
+ * sample_cap bounds the buffers (samples; >= one ply); truncated = 1 if it was reached first (running games are then dropped).
  * Requires onb_config.alloc_planes and mcts_max_sims >= sims. Every game is dealt from the counter RNG (epoch = ply + 1). */
 typedef struct onb_selfplay_config {
     double c_puct;
@@ -328,8 +331,8 @@ ONB_API int32_t onb_copy_to_host(onb_ctx* ctx, void* host, const void* device, i
  * i (the reference swaps colours every game). Agents: ONB_AGENT_RANDOM = the `Random` agent (ai/random.rs, draws keyed by the
  * ply); ONB_AGENT_PUCT = AlphaZeroMcts (evaluator = ONB_EVAL_*, for ONB_EVAL_NET the resident network net_slot, sims, c);
  * ONB_AGENT_UCT = `Mcts` (sims playouts, c, min_node_visits). results (device, [n]: 0 undecided, 1 Red won, 2 Blue won) stays
- * valid until the next driver call; results_host (optional) receives a copy. The Elo update of evaluator.rs:58-110 is a fold over
- * these per-game results in game order (host bookkeeping: selfplay.fight_statistics / FightStatistics of the C++ mirror). */
+ * valid until the next onb_fight; results_host (optional) receives a copy. The Elo update of evaluator.rs:58-110 is a fold over
+ * these per-game results in game order: onb_fight_stats below. */
 #define ONB_AGENT_RANDOM 0
 #define ONB_AGENT_PUCT 1
 #define ONB_AGENT_UCT 2
@@ -345,9 +348,54 @@ typedef struct onb_agent {
 typedef struct onb_fight_result {
     int64_t a_wins, b_wins, draws, plies_run;
     uint8_t* results;
+    int64_t moves_chosen; /* (game, ply) pairs an agent had to choose a move for: each ply an agent searches ONLY the undecided games in
+                             which it is to move (evaluator.rs:379), never the opponent's */
 } onb_fight_result;
 ONB_API int32_t onb_fight(onb_ctx* ctx, const onb_agent* a, const onb_agent* b, const uint8_t* a_is_red_host, uint32_t max_plies,
                           onb_fight_result* out, uint8_t* results_host);
+/* FightStatistics of the last onb_fight (evaluator.rs:38-110), folded ON THE DEVICE over the per-game results in game order:
+ * W/L/D of agent A in total and per colour it played, win rates, and the sequential Elo updates of EloRating::elo_change
+ * (elo_rating.rs:53-70, K = 32) starting from (rating_a, rating_b). history_host (optional): [n][4] doubles = before_a, after_a,
+ * before_b, after_b per game (RatingChange). color index 0 = games A played as Red, 1 = as Blue. */
+typedef struct onb_fight_statistics {
+    int64_t n_games, wins, loses, draws;
+    int64_t color_wins[2], color_loses[2], color_draws[2];
+    double winrate, color_winrate[2];
+    double rating_a, rating_b;
+} onb_fight_statistics;
+ONB_API int32_t onb_fight_stats(onb_ctx* ctx, double rating_a, double rating_b, onb_fight_statistics* out, double* history_host);
+
+/* ---- the one collective of the path: replay samples to the trainer GPU (replaces the join + extend over the worker
+ * threads of train.rs:241-245) ------------------------------------------------------------------------------------------------
+ * Games shard over GPUs with no data-path collective; at the end of a self-play iteration every rank ships its samples (planes
+ * [m][21][5][5], pi [m][2][25], z [m], all f32: 2 304 B per sample) to the trainer rank over NVLink / NVSwitch. NCCL is bound at
+ * run time (dlopen of the libnccl.so.2 already mapped in the process, else the system one): without NCCL these calls return
+ * ONB_E_STATE and everything else keeps working.
+ *   onb_comm_unique_id(id)                      rank 0 makes an id and hands it to the other ranks (any host channel)
+ *   onb_comm_create(ctx, n_ranks, rank, id, existing, &comm)
+ *                                               one communicator per context (ncclCommInitRank on the context's device); or pass
+ *                                               existing = an ncclComm_t the host already owns (id may then be NULL)
+ *   onb_selfplay_pack(ctx, &result, &planes, &pi, &z, &m)
+ *                                               the valid samples of an onb_self_play result as contiguous device arrays
+ *   onb_gather_counts(ctx, comm, m_local, counts_host, &total)
+ *                                               collective: every rank learns every rank's sample count (to size the buffers)
+ *   onb_gather_samples(ctx, comm, dst_rank, planes, pi, z, m_local, out_planes, out_pi, out_z, out_cap, counts_host, &total)
+ *                                               collective over all ranks of comm, on the context's stream: counts and the
+ *                                               destination's capacity are exchanged (one 16-byte all-gather + host read), then
+ *                                               rank dst_rank receives every rank's samples concatenated in rank order into its
+ *                                               out_* DEVICE buffers (capacity out_cap samples; ignored on other ranks);
+ *                                               counts_host [n_ranks] and total are filled on every rank. If the total exceeds
+ *                                               the destination's capacity EVERY rank returns ONB_E_OVERFLOW and nothing is sent.
+ *                                               The data transfer itself is asynchronous on the stream. */
+typedef struct onb_comm onb_comm;
+ONB_API int32_t onb_comm_unique_id(uint8_t id_out[128]);
+ONB_API int32_t onb_comm_create(onb_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t id[128], void* existing_nccl_comm, onb_comm** out);
+ONB_API int32_t onb_comm_destroy(onb_comm* comm);
+ONB_API int32_t onb_selfplay_pack(onb_ctx* ctx, const onb_selfplay_result* res, float** planes, float** pi, float** z, int64_t* m_out);
+ONB_API int32_t onb_gather_counts(onb_ctx* ctx, onb_comm* comm, int64_t m_local, int64_t* counts_host, int64_t* total);
+ONB_API int32_t onb_gather_samples(onb_ctx* ctx, onb_comm* comm, int32_t dst_rank, const float* planes, const float* pi, const float* z,
+                                   int64_t m_local, float* out_planes, float* out_pi, float* out_z, int64_t out_cap, int64_t* counts_host,
+                                   int64_t* total);
 
 /* ---- plain UCT with random rollouts: the `Mcts` agent (onitama-game/src/ai/mcts/{mod.rs,mcts_arena.rs}) ---------------
  * The evaluation opponent of the reference's arena (evaluator.rs), one tree per game, rooted like the PUCT search:

@@ -20,6 +20,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -27,6 +28,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -129,7 +131,8 @@ public:
     int64_t n() const { return n_; }
     /// Hands the network to the library (the VarStore of train.rs as (name, values) pairs, names as in net.rs:118-213 with '|'
     /// or '.' separators); agents with device_evaluator = ONB_EVAL_NET then search without a host evaluator in the loop.
-    void load_network(const std::vector<std::pair<std::string, std::vector<float>>>& var_store, bool tf32 = false) {
+    /// precision: ONB_NET_F32 = the reference's f32 arithmetic (split operands), ONB_NET_F16 = fast mode, ONB_NET_TF32
+    void load_network(const std::vector<std::pair<std::string, std::vector<float>>>& var_store, int precision = ONB_NET_F32) {
         std::vector<const char*> names;
         std::vector<const float*> data;
         std::vector<int64_t> numel;
@@ -138,10 +141,11 @@ public:
             data.push_back(kv.second.data());
             numel.push_back((int64_t)kv.second.size());
         }
-        check(onb_net_precision(ctx_, tf32 ? ONB_NET_TF32 : ONB_NET_F16));
+        check(onb_net_precision(ctx_, precision));
         check(onb_net_load(ctx_, (int32_t)names.size(), names.data(), data.data(), numel.data()));
     }
     void check(int32_t rc) const { if (rc != ONB_OK) throw Error(rc, onb_last_error(ctx_)); }
+    std::vector<uint8_t> last_fight_results;  ///< per-game MoveResult codes of the last fight_device (0 undecided, 1 RedWin, 2 BlueWin)
     /// one-game engine shared by the single-state methods of State / the agents (thread local: a context is single threaded)
     static Engine& single(uint32_t min_sims = 0) {
         thread_local std::unique_ptr<Engine> e;
@@ -494,10 +498,11 @@ inline std::vector<SelfPlayData> self_play(const TrainingAlphaZeroMcts& mcts, co
     return out;
 }
 
-/// self_play for a training run: `slots` games in flight on one engine, every slot restarted the moment its game is over, until
-/// config.self_play_game_amnt games are complete (onb_self_play: the loop runs inside the library, the samples are copied to the
-/// host once at the end). Needs a device evaluator: mcts.device_evaluator = ONB_EVAL_NET after Engine::load_network, or
-/// ONB_EVAL_UNIFORM / ONB_EVAL_HASH. Samples come ply-major; games still running when the quota is reached are dropped.
+/// self_play for a training run: `slots` games in flight on one engine; a slot starts its next game the moment one is over while
+/// games remain to be started, and EVERY started game is played to its end: exactly max(config.self_play_game_amnt, slots) complete
+/// games come back (onb_self_play: the loop runs inside the library, the samples are copied to the host once at the end). Needs a
+/// device evaluator: mcts.device_evaluator = ONB_EVAL_NET after Engine::load_network, or ONB_EVAL_UNIFORM / ONB_EVAL_HASH. Samples
+/// come ply-major.
 inline std::vector<SelfPlayData> self_play_continuous(Engine& e, const TrainingAlphaZeroMcts& mcts, const TrainConfig& config) {
     if (mcts.model) throw Error(ONB_E_INVALID, "self_play_continuous: a host evaluator cannot run inside the library; load the network instead");
     onb_selfplay_config cfg{};
@@ -539,14 +544,39 @@ struct EvaluatorConfig {
     std::optional<Deck> deck;
     uint64_t seed = 0;
 };
-struct FightStatistics {  // the counters of evaluator.rs:38-56
+/// EloRating::elo_change (elo_rating.rs:53-70): K = 32, scale 1/400
+struct EloRating {
+    static std::pair<double, double> elo_change(double ra, double rb, bool is_a_win) {
+        const double ea = 1. / (1. + std::pow(10.0, 2.5e-3 * (rb - ra))), eb = 1. / (1. + std::pow(10.0, 2.5e-3 * (ra - rb)));
+        const double sa = is_a_win ? 1. : 0., sb = 1. - sa;
+        return {ra + 32. * (sa - ea), rb + 32. * (sb - eb)};
+    }
+};
+struct RatingChange {
+    double before_a, after_a, before_b, after_b;
+};
+struct FightStatistics {  // evaluator.rs:38-110: W/L/D in total and per colour of the agent, win rates, sequential Elo updates
     size_t wins = 0, losses = 0, draws = 0, wins_red = 0, wins_blue = 0, games_red = 0, games_blue = 0;
+    double winrate = 0., color_winrate[2] = {0., 0.};
+    double rating_a = 800., rating_b = 800.;  // Rating::default (elo_rating.rs:17-21)
+    std::vector<RatingChange> rating_change_history;
+    FightStatistics() = default;
+    FightStatistics(double ra, double rb) : rating_a(ra), rating_b(rb) {}
     void update(MoveResult progress, PlayerColor agent_color) {
         (agent_color == PlayerColor::Red ? games_red : games_blue) += 1;
-        if (!is_win(progress)) { draws += 1; return; }
-        const bool agent_won = (progress == MoveResult::RedWin) == (agent_color == PlayerColor::Red);
-        if (agent_won) { wins += 1; (agent_color == PlayerColor::Red ? wins_red : wins_blue) += 1; }
-        else losses += 1;
+        const double ba = rating_a, bb = rating_b;
+        if (!is_win(progress)) {
+            draws += 1;
+        } else {
+            const bool agent_won = (progress == MoveResult::RedWin) == (agent_color == PlayerColor::Red);
+            std::tie(rating_a, rating_b) = EloRating::elo_change(rating_a, rating_b, agent_won);
+            if (agent_won) { wins += 1; (agent_color == PlayerColor::Red ? wins_red : wins_blue) += 1; }
+            else losses += 1;
+        }
+        rating_change_history.push_back({ba, rating_a, bb, rating_b});
+        winrate = (double)wins / (double)(wins + losses + draws);
+        color_winrate[0] = (double)wins_red / (double)games_red;
+        color_winrate[1] = (double)wins_blue / (double)games_blue;
     }
 };
 inline FightStatistics fight(const EvaluatorConfig& config, std::unique_ptr<Agent> agent, std::unique_ptr<Agent> opponent) {
@@ -571,11 +601,13 @@ inline FightStatistics fight(const EvaluatorConfig& config, std::unique_ptr<Agen
     return statistics;
 }
 
-/// fight() for config.game_amnt games at once on one engine (onb_fight: the arena loop runs inside the library). Agent A plays Red
-/// in games 0, 2, 4, ... like the colour swap of evaluator.rs:393-397; the statistics are folded in game order.
+/// fight() for config.game_amnt games at once on one engine (onb_fight: the arena loop runs inside the library; each ply an agent
+/// searches only the games in which it is to move). Agent A plays Red in games 0, 2, 4, ... like the colour swap of
+/// evaluator.rs:393-397; the statistics incl. the Elo updates are folded in game order ON THE DEVICE (onb_fight_stats).
 /// Agents are described by onb_agent (ONB_AGENT_RANDOM / ONB_AGENT_PUCT / ONB_AGENT_UCT); the engine must have been created
 /// with n_games == config.game_amnt and enough mcts_max_sims.
-inline FightStatistics fight_device(Engine& e, const EvaluatorConfig& config, const onb_agent& agent, const onb_agent& opponent) {
+inline FightStatistics fight_device(Engine& e, const EvaluatorConfig& config, const onb_agent& agent, const onb_agent& opponent, double rating_a = 800.,
+                                    double rating_b = 800.) {
     if ((size_t)e.n() != config.game_amnt) throw Error(ONB_E_INVALID, "fight_device: the engine must hold game_amnt games");
     if (config.deck) {
         uint8_t d[5];
@@ -588,11 +620,19 @@ inline FightStatistics fight_device(Engine& e, const EvaluatorConfig& config, co
     for (size_t g = 0; g < config.game_amnt; ++g) a_is_red[g] = g % 2 == 0;
     onb_fight_result r{};
     e.check(onb_fight(e.ctx(), &agent, &opponent, a_is_red.data(), (uint32_t)config.max_plies, &r, results.data()));
-    FightStatistics statistics;
-    for (size_t g = 0; g < config.game_amnt; ++g) {
-        const MoveResult progress = results[g] == 1 ? MoveResult::RedWin : results[g] == 2 ? MoveResult::BlueWin : MoveResult::InProgress;
-        statistics.update(progress, a_is_red[g] ? PlayerColor::Red : PlayerColor::Blue);
-    }
+    onb_fight_statistics st{};
+    std::vector<double> history(config.game_amnt * 4);
+    e.check(onb_fight_stats(e.ctx(), rating_a, rating_b, &st, history.data()));
+    FightStatistics statistics(rating_a, rating_b);
+    statistics.wins = (size_t)st.wins; statistics.losses = (size_t)st.loses; statistics.draws = (size_t)st.draws;
+    statistics.wins_red = (size_t)st.color_wins[0]; statistics.wins_blue = (size_t)st.color_wins[1];
+    statistics.games_red = (size_t)(st.color_wins[0] + st.color_loses[0] + st.color_draws[0]);
+    statistics.games_blue = (size_t)(st.color_wins[1] + st.color_loses[1] + st.color_draws[1]);
+    statistics.winrate = st.winrate; statistics.color_winrate[0] = st.color_winrate[0]; statistics.color_winrate[1] = st.color_winrate[1];
+    statistics.rating_a = st.rating_a; statistics.rating_b = st.rating_b;
+    for (size_t g = 0; g < config.game_amnt; ++g)
+        statistics.rating_change_history.push_back({history[4 * g], history[4 * g + 1], history[4 * g + 2], history[4 * g + 3]});
+    e.last_fight_results = results;
     return statistics;
 }
 

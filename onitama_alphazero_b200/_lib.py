@@ -93,6 +93,13 @@ SYMBOLS = {
     "onb_self_play": (C.c_int32, [_P, _P, _P]),
     "onb_copy_to_host": (C.c_int32, [_P, _P, _P, C.c_int64]),
     "onb_fight": (C.c_int32, [_P, _P, _P, _P, C.c_uint32, _P, _P]),
+    "onb_fight_stats": (C.c_int32, [_P, C.c_double, C.c_double, _P, _P]),
+    "onb_comm_unique_id": (C.c_int32, [_P]),
+    "onb_comm_create": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P, C.POINTER(_P)]),
+    "onb_comm_destroy": (C.c_int32, [_P]),
+    "onb_selfplay_pack": (C.c_int32, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "onb_gather_counts": (C.c_int32, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    "onb_gather_samples": (C.c_int32, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     "onb_uct_run": (C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32]),
     "onb_net_precision": (C.c_int32, [_P, C.c_int32]),
     "onb_net_select": (C.c_int32, [_P, C.c_int32]),
@@ -115,7 +122,15 @@ class Agent(C.Structure):
 
 
 class FightResult(C.Structure):
-    _fields_ = [("a_wins", C.c_int64), ("b_wins", C.c_int64), ("draws", C.c_int64), ("plies_run", C.c_int64), ("results", C.c_void_p)]
+    _fields_ = [("a_wins", C.c_int64), ("b_wins", C.c_int64), ("draws", C.c_int64), ("plies_run", C.c_int64), ("results", C.c_void_p),
+                ("moves_chosen", C.c_int64)]
+
+
+class FightStats(C.Structure):
+    """onb_fight_statistics (FightStatistics of evaluator.rs:38-110, folded on the device)"""
+    _fields_ = [("n_games", C.c_int64), ("wins", C.c_int64), ("loses", C.c_int64), ("draws", C.c_int64), ("color_wins", C.c_int64 * 2),
+                ("color_loses", C.c_int64 * 2), ("color_draws", C.c_int64 * 2), ("winrate", C.c_double), ("color_winrate", C.c_double * 2),
+                ("rating_a", C.c_double), ("rating_b", C.c_double)]
 
 
 class SelfPlayResult(C.Structure):

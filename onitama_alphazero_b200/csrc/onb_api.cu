@@ -451,6 +451,8 @@ int32_t onb_mcts_begin(onb_ctx* ctx, double c_puct, uint32_t sims) {
     c->c_puct = c_puct;
     c->sims_target = sims;
     c->sims_done = 0;
+    c->n_act = 0;  // the public search covers every game of the context
+    c->d_tree_game = nullptr;
     ONB_CUDA(c, launch_mcts_begin(c));
     c->mcts_phase = 1;
     return ONB_OK;
@@ -479,7 +481,7 @@ int32_t onb_mcts_eval(onb_ctx* ctx, int32_t evaluator) {
     if (c->mcts_phase != 2) return fail(c, ONB_E_STATE, "onb_mcts_eval: no leaves selected");
     if (evaluator == ONB_EVAL_NET) {
         if (!c->net[c->net_cur].loaded) return fail(c, ONB_E_STATE, "onb_mcts_eval: no network loaded (onb_net_load)");
-        ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value));
+        ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value, trees(c)));
         return ONB_OK;
     }
     if (evaluator != ONB_EVAL_UNIFORM && evaluator != ONB_EVAL_HASH) return fail(c, ONB_E_INVALID, "onb_mcts_eval: unknown evaluator %d", evaluator);
@@ -507,7 +509,7 @@ int32_t onb_mcts_run(onb_ctx* ctx, int32_t evaluator, uint32_t sims) {
         if (!c->net[c->net_cur].loaded) return fail(c, ONB_E_STATE, "onb_mcts_run: no network loaded (onb_net_load)");
         for (uint32_t s = 0; s < sims; ++s) {
             ONB_CUDA(c, launch_mcts_select(c));
-            ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value));
+            ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value, trees(c)));
             ONB_CUDA(c, launch_mcts_expand_backup(c));
         }
         c->sims_done += sims;
@@ -517,9 +519,25 @@ int32_t onb_mcts_run(onb_ctx* ctx, int32_t evaluator, uint32_t sims) {
     c->sims_done += sims;
     return ONB_OK;
 }
-static int32_t self_play_search(Ctx* c, const onb_selfplay_config* cfg) {
+// onb_mcts_begin for a SUBSET of the games: tree t searches game d_games[t] (device list, ascending), t < m. d_games == nullptr: all games.
+static int32_t mcts_begin_subset(Ctx* c, double c_puct, uint32_t sims, const int32_t* d_games, int64_t m) {
     onb_ctx* x = reinterpret_cast<onb_ctx*>(c);
-    int32_t rc = onb_mcts_begin(x, cfg->c_puct, cfg->sims);
+    if (!d_games) return onb_mcts_begin(x, c_puct, sims);
+    if (!c->d_nodes) return fail(c, ONB_E_STATE, "search: context created with mcts_max_sims = 0");
+    if (sims > c->cfg.mcts_max_sims) return fail(c, ONB_E_INVALID, "search: sims %u > mcts_max_sims %u", sims, c->cfg.mcts_max_sims);
+    if (m <= 0 || m > c->n) return fail(c, ONB_E_INVALID, "search: bad subset size");
+    c->c_puct = c_puct;
+    c->sims_target = sims;
+    c->sims_done = 0;
+    c->n_act = m;
+    c->d_tree_game = d_games;
+    ONB_CUDA(c, launch_mcts_begin(c));
+    c->mcts_phase = 1;
+    return ONB_OK;
+}
+static int32_t self_play_search(Ctx* c, const onb_selfplay_config* cfg, const int32_t* d_games, int64_t m) {
+    onb_ctx* x = reinterpret_cast<onb_ctx*>(c);
+    int32_t rc = mcts_begin_subset(c, cfg->c_puct, cfg->sims, d_games, m);
     if (rc == ONB_OK) rc = onb_mcts_run(x, cfg->evaluator, cfg->sims);
     if (rc == ONB_OK) rc = onb_mcts_finish(x, nullptr, nullptr, nullptr, nullptr, nullptr);
     return rc;
@@ -546,10 +564,16 @@ int32_t onb_self_play(onb_ctx* ctx, const onb_selfplay_config* cfg, onb_selfplay
     if (rc != ONB_OK) return fail(c, rc, "%s", err);
     return ONB_OK;
 }
-static int32_t fight_move(Ctx* c, const onb_agent* ag, uint32_t ply) {
+// one agent chooses for the m games in which it is to move (d_games) and leaves the actions in d_out[game]
+static int32_t fight_move(Ctx* c, const onb_agent* ag, uint32_t ply, const int32_t* d_games, int64_t m, uint16_t* d_out) {
     onb_ctx* x = reinterpret_cast<onb_ctx*>(c);
-    if (ag->kind == ONB_AGENT_RANDOM) return onb_env_choose_random(x, ply, ONB_POLICY_AGENT);
-    int32_t rc = onb_mcts_begin(x, ag->c, ag->sims);
+    if (ag->kind == ONB_AGENT_RANDOM) {  // elementwise and cheap: chosen for every undecided game, the merge keeps this agent's games
+        const int32_t rc = onb_env_choose_random(x, ply, ONB_POLICY_AGENT);
+        if (rc != ONB_OK) return rc;
+        ONB_CUDA(c, cudaMemcpyAsync(d_out, c->d_actions, (size_t)c->n * 2, cudaMemcpyDeviceToDevice, c->stream));
+        return ONB_OK;
+    }
+    int32_t rc = mcts_begin_subset(c, ag->c, ag->sims, d_games, m);
     if (rc != ONB_OK) return rc;
     if (ag->kind == ONB_AGENT_PUCT) {
         if (ag->evaluator == ONB_EVAL_NET && (rc = onb_net_select(x, ag->net_slot)) != ONB_OK) return rc;
@@ -560,8 +584,7 @@ static int32_t fight_move(Ctx* c, const onb_agent* ag, uint32_t ply) {
     if (rc == ONB_OK) rc = onb_mcts_finish(x, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc != ONB_OK) return rc;
     // the chosen moves become the agent's actions (ONB_ACTION_NONE for decided roots)
-    cudaError_t e = cudaMemcpyAsync(c->d_actions, c->d_best, (size_t)c->n * 2, cudaMemcpyDeviceToDevice, c->stream);
-    if (e != cudaSuccess) return cuda_fail(c, e, "onb_fight");
+    ONB_CUDA(c, launch_mcts_scatter_best(c, d_out));
     return ONB_OK;
 }
 int32_t onb_fight(onb_ctx* ctx, const onb_agent* a, const onb_agent* b, const uint8_t* a_is_red_host, uint32_t max_plies, onb_fight_result* out,
@@ -586,6 +609,17 @@ int32_t onb_fight(onb_ctx* ctx, const onb_agent* a, const onb_agent* b, const ui
         ONB_CUDA(c, cudaMemcpyAsync(results_host, out->results, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
         ONB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
+    return ONB_OK;
+}
+int32_t onb_fight_stats(onb_ctx* ctx, double rating_a, double rating_b, onb_fight_statistics* out, double* history_host) {
+    ONB_CHECK_CTX(ctx);
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!out) return fail(c, ONB_E_INVALID, "onb_fight_stats: null output");
+    memset(out, 0, sizeof(*out));
+    char err[400];
+    err[0] = 0;
+    const int32_t rc = run_fight_statistics(c, rating_a, rating_b, out, history_host, err, sizeof(err));
+    if (rc != ONB_OK) return fail(c, rc, "%s", err);
     return ONB_OK;
 }
 int32_t onb_copy_to_host(onb_ctx* ctx, void* host, const void* device, int64_t bytes) {
@@ -719,7 +753,7 @@ int32_t onb_net_forward(onb_ctx* ctx, int32_t planes_buffer) {
     const float* planes = planes_buffer == ONB_BUF_LEAF_PLANES ? c->d_leaf_planes : planes_buffer == ONB_BUF_PLANES ? c->d_planes : nullptr;
     if (planes_buffer != ONB_BUF_LEAF_PLANES && planes_buffer != ONB_BUF_PLANES) return fail(c, ONB_E_INVALID, "onb_net_forward: not a plane buffer");
     if (!planes || !c->d_policy) return fail(c, ONB_E_STATE, "onb_net_forward: plane or policy/value buffers were not allocated by onb_create");
-    ONB_CUDA(c, launch_net_forward(c, planes, c->d_policy, c->d_value));
+    ONB_CUDA(c, launch_net_forward(c, planes, c->d_policy, c->d_value, c->n));
     return ONB_OK;
 }
 

@@ -65,6 +65,10 @@ struct Ctx {
     uint64_t noise_seed;
     uint32_t sims_target, sims_done;
     int mcts_phase;  // 0 idle, 1 begun/after expand, 2 after select
+    // subset search (onb_fight / onb_self_play): the first n_act trees search the games listed in d_tree_game (device, ascending);
+    // n_act == 0: every game is searched by the tree of the same index (the public onb_mcts_begin always selects this)
+    int64_t n_act;
+    const int32_t* d_tree_game;
     float* d_ln_table;  // logf(i) for the plain UCT search (filled by the host: the libm call behind Rust's f32::ln)
     uint32_t ln_cap;
     // policy/value network (onb_net.cu): weights in tensor-core operand layout, folded biases, head parameters
@@ -74,8 +78,9 @@ struct Ctx {
         float* head;  // head parameters
         int blocks, loaded, f16, x3;  // f16: f16 operands (else tf32); x3: split-operand f32-faithful mode (ONB_NET_F32)
     } net[2];         // two networks can be resident (an arena pits the new model against the previous one, evaluator.rs:355-399)
-    void* sp_buf[10];          // grow-only buffers of onb_self_play (samples, per-slot bookkeeping)
-    size_t sp_cap[10];
+    void* sp_buf[32];          // grow-only buffers of onb_self_play (slots 0-15) and onb_fight (16-31), see onb_selfplay.cu
+    size_t sp_cap[32];
+    int fight_valid;           // an onb_fight has left its per-game results on the device (onb_fight_statistics)
     void* d_net_scratch;       // residual scratch of the three-CTAs-per-SM network kernel
     size_t net_scratch_bytes;
     int net_cur;      // slot used by onb_net_load / onb_net_forward / ONB_EVAL_NET (onb_net_select)
@@ -86,6 +91,8 @@ struct Ctx {
     size_t scratch_cap[16];
     char err[512];
 };
+
+inline int64_t trees(const Ctx* c) { return c->n_act > 0 ? c->n_act : c->n; }
 
 // env (onb_env.cu)
 cudaError_t launch_env_reset(Ctx* c, const uint8_t* d_decks5, int64_t n_decks, uint32_t epoch);
@@ -110,17 +117,19 @@ cudaError_t launch_mcts_run(Ctx* c, int evaluator, uint32_t sims);
 cudaError_t launch_uct_run(Ctx* c, float exploration_c, uint32_t min_node_visits, uint32_t sims);
 cudaError_t launch_mcts_finish(Ctx* c);
 cudaError_t launch_mcts_play_best(Ctx* c, uint32_t out_flags);
+cudaError_t launch_mcts_scatter_best(Ctx* c, uint16_t* dst_actions);  // dst[game of tree t] = best[t]
 
 // network (onb_net.cu)
 int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel, std::string& err);
-cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value);
+cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value, int64_t count);  // count positions
 
 // native self-play driver (onb_selfplay.cu)
-int32_t run_self_play(Ctx* c, const onb_selfplay_config* cfg, onb_selfplay_result* out, int32_t (*search)(Ctx*, const onb_selfplay_config*), char* err,
-                      size_t err_len);
+int32_t run_self_play(Ctx* c, const onb_selfplay_config* cfg, onb_selfplay_result* out,
+                      int32_t (*search)(Ctx*, const onb_selfplay_config*, const int32_t* d_games, int64_t m), char* err, size_t err_len);
 
 int32_t run_fight(Ctx* c, const onb_agent* a, const onb_agent* b, const uint8_t* a_is_red_host, uint32_t max_plies, onb_fight_result* out,
-                  int32_t (*move)(Ctx*, const onb_agent*, uint32_t), char* err, size_t err_len);
+                  int32_t (*move)(Ctx*, const onb_agent*, uint32_t ply, const int32_t* d_games, int64_t m, uint16_t* d_out), char* err, size_t err_len);
+int32_t run_fight_statistics(Ctx* c, double rating_a, double rating_b, onb_fight_statistics* out, double* history_host, char* err, size_t err_len);
 
 constexpr int kModeActions = 2;  // env step modes: 0 = ONB_POLICY_UNIFORM, 1 = ONB_POLICY_AGENT, 2 = explicit actions
 

@@ -1219,7 +1219,7 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
 }
 
 template <int NACC, bool F16, bool X3 = false>
-static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
+static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
     using G = Geo<NACC, F16, X3>;
     static bool attr[64] = {};  // the opt-in is per device
     int dev = 0;
@@ -1230,13 +1230,13 @@ static cudaError_t launch_net_variant(Ctx* c, const float* planes, float* policy
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     const char* one = getenv("ONB_NET_ONE_CTA");  // experiment: a single CTA per SM (is the MMA issue time contention or a per-thread limit?)
-    const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * ((NACC == 2 && !X3 && !(one && one[0] == '1')) ? 2 : 1);
-    k_net_forward<NACC, F16, X3><<<(unsigned)(groups < slots ? groups : slots), 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
+    const int64_t groups = (count + G::NB - 1) / G::NB, slots = (int64_t)sms * ((NACC == 2 && !X3 && !(one && one[0] == '1')) ? 2 : 1);
+    k_net_forward<NACC, F16, X3><<<(unsigned)(groups < slots ? groups : slots), 256, G::SMEM, c->stream>>>(planes, policy, value, count, nd);
     return cudaGetLastError();
 }
 
 template <bool F16>
-static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
+static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
     using G = Geo2<F16>;
     static bool attr[64] = {};  // the opt-in is per device
     int dev = 0;
@@ -1246,12 +1246,12 @@ static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, flo
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
-    const int64_t pairs = ((c->n + G::NB - 1) / G::NB + 1) / 2;
-    k_net_forward2<F16><<<(unsigned)(pairs < sms ? pairs : sms), G::THREADS, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd);
+    const int64_t pairs = ((count + G::NB - 1) / G::NB + 1) / 2;
+    k_net_forward2<F16><<<(unsigned)(pairs < sms ? pairs : sms), G::THREADS, G::SMEM, c->stream>>>(planes, policy, value, count, nd);
     return cudaGetLastError();
 }
 
-static cudaError_t launch_net_v3(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms) {
+static cudaError_t launch_net_v3(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
     using G = Geo3;
     static bool attr[64] = {};
     int dev = 0;
@@ -1261,7 +1261,7 @@ static cudaError_t launch_net_v3(Ctx* c, const float* planes, float* policy, flo
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
-    const int64_t groups = (c->n + G::NB - 1) / G::NB, slots = (int64_t)sms * 3;
+    const int64_t groups = (count + G::NB - 1) / G::NB, slots = (int64_t)sms * 3;
     const unsigned grid = (unsigned)(groups < slots ? groups : slots);
     const size_t need = (size_t)grid * G::SCRATCH_FLOAT4 * sizeof(float4);
     if (c->net_scratch_bytes < need) {
@@ -1273,25 +1273,26 @@ static cudaError_t launch_net_v3(Ctx* c, const float* planes, float* policy, flo
         if (e != cudaSuccess) return e;
         c->net_scratch_bytes = need;
     }
-    k_net_forward3<<<grid, 256, G::SMEM, c->stream>>>(planes, policy, value, c->n, nd, reinterpret_cast<float4*>(c->d_net_scratch));
+    k_net_forward3<<<grid, 256, G::SMEM, c->stream>>>(planes, policy, value, count, nd, reinterpret_cast<float4*>(c->d_net_scratch));
     return cudaGetLastError();
 }
 
-cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value) {
+cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value, int64_t count) {
+    if (count <= 0) return cudaSuccess;
     const Ctx::NetSlot& ns = c->net[c->net_cur];
     const NetDev nd{reinterpret_cast<const uint8_t*>(ns.w), ns.bias, ns.head, ns.blocks};
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ns.x3) return launch_net_variant<2, true, true>(c, planes, policy, value, nd, sms);  // ONB_NET_F32: split operands, f32-faithful
+    if (ns.x3) return launch_net_variant<2, true, true>(c, planes, policy, value, nd, sms, count);  // ONB_NET_F32: split operands, f32-faithful
     const char* v3 = getenv("ONB_NET_V3");  // three CTAs per SM, residual in an L2-resident scratch (f16 operands only)
-    if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms);
+    if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms, count);
     const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)
-    if (v2 && v2[0] == '1') return ns.f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms) : launch_net_v2<false>(c, planes, policy, value, nd, sms);
+    if (v2 && v2[0] == '1') return ns.f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms, count) : launch_net_v2<false>(c, planes, policy, value, nd, sms, count);
     const char* wide = getenv("ONB_NET_WIDE");  // exploration knob: 14 boards per CTA, one CTA per SM
     const bool w = wide && wide[0] == '1';
-    if (ns.f16) return w ? launch_net_variant<4, true>(c, planes, policy, value, nd, sms) : launch_net_variant<2, true>(c, planes, policy, value, nd, sms);
-    return w ? launch_net_variant<4, false>(c, planes, policy, value, nd, sms) : launch_net_variant<2, false>(c, planes, policy, value, nd, sms);
+    if (ns.f16) return w ? launch_net_variant<4, true>(c, planes, policy, value, nd, sms, count) : launch_net_variant<2, true>(c, planes, policy, value, nd, sms, count);
+    return w ? launch_net_variant<4, false>(c, planes, policy, value, nd, sms, count) : launch_net_variant<2, false>(c, planes, policy, value, nd, sms, count);
 }
 
 }  // namespace onb

@@ -246,7 +246,24 @@ class Context:
         results = np.zeros(self.n, dtype=np.uint8)
         self._ck(self._lib.onb_fight(self._h, C.byref(agent_a), C.byref(agent_b), L.ptr(mask), max_plies, C.byref(res), L.ptr(results)))
         self.last_fight_results = results
+        self.last_fight_moves_chosen = int(res.moves_chosen)
+        self.last_fight_plies = int(res.plies_run)
         return int(res.a_wins), int(res.b_wins), int(res.draws), results
+
+    def fight_stats(self, rating_a=800.0, rating_b=800.0, history=False):
+        """onb_fight_stats: FightStatistics of the last fight_native (W/L/D overall and per colour of agent A, win rates, sequential Elo
+        updates), folded on the device in game order. Returns a dict; history=True adds the [n, 4] rating changes
+        (before_a, after_a, before_b, after_b)."""
+        st = L.FightStats()
+        hist = np.zeros((self.n, 4), dtype=np.float64) if history else None
+        self._ck(self._lib.onb_fight_stats(self._h, float(rating_a), float(rating_b), C.byref(st), L.ptr(hist)))
+        out = dict(n_games=int(st.n_games), general=dict(wins=int(st.wins), loses=int(st.loses), draws=int(st.draws)),
+                   color=[dict(wins=int(st.color_wins[k]), loses=int(st.color_loses[k]), draws=int(st.color_draws[k])) for k in range(2)],
+                   winrate=float(st.winrate), color_winrate=[float(st.color_winrate[0]), float(st.color_winrate[1])],
+                   rating_a=float(st.rating_a), rating_b=float(st.rating_b))
+        if history:
+            out["rating_change_history"] = hist
+        return out
 
     def uct_search(self, exploration_c=2.0 ** 0.5, min_node_visits=5, playouts=5000, to_host=True):
         """The reference's `Mcts` agent for every game at once: plain UCT with random rollouts (ai/mcts/mcts_arena.rs)."""

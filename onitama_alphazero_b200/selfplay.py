@@ -125,29 +125,47 @@ def self_play_continuous(ctx, c_puct, sims, n_games, max_plies=150, evaluator=L.
         rec = {"planes": [], "pi": [], "color": [], "serial": []}
         winners = {}   # serial -> 0 draw (ply cap), 1 Red, 2 Blue
         done, tick = 0, 0   # tick = plies played so far; a slot restarted after ply `tick` is dealt at epoch tick + 1 (as onb_self_play does)
-        while done < n_games:
+        # exactly max(n_games, slots) games are started and ALL of them are played to the end (dropping the games still running when a
+        # quota is reached would drop the long ones and bias z / pi): a finished slot starts its next game while games remain to be
+        # started -- slots in ascending order, as onb_self_play does -- and goes idle afterwards
+        target, started = max(int(n_games), n), n
+        idle = torch.zeros(n, dtype=torch.bool, device=dev)
+        acts_t, best_t = ctx.tensor(L.BUF_ACTIONS), ctx.tensor(L.BUF_BEST)
+        rec["live"] = []
+        while not bool(idle.all()):
             st = states_t.clone()
             ctx.encode(to_host=False)                       # create_tensor_from_state of the searched position (train.rs:58)
-            ctx.search_device(c_puct, sims, evaluator=evaluator, net=net)
+            ctx.search_device(c_puct, sims, evaluator=evaluator, net=net)   # (this driver searches idle slots too and ignores them)
             rec["planes"].append(ctx.tensor(L.BUF_PLANES).clone())
             rec["pi"].append(ctx.tensor(L.BUF_PI).clone())
             rec["color"].append(((st[:, 1] >> 30) & 1).to(torch.int8))
             rec["serial"].append(slots + n * generation)
-            ctx.mcts_play_best()
-            plies += 1
+            rec["live"].append(~idle)
+            acts_t.copy_(best_t)
+            acts_t[idle] = -1                                # ONB_ACTION_NONE: an idle slot (e.g. a game cut at the ply cap) is not stepped
+            ctx.step(None)
+            plies += (~idle).to(plies.dtype)
             result = (states_t.clone()[:, 2] >> 29) & 3
             # train.rs:74-79: the cap is checked after the move with max_plies counting down from 150 -> a game has at most max_plies + 2 plies
-            over = (result != 0) | (plies >= max_plies + 2)
+            over = ~idle & ((result != 0) | (plies >= max_plies + 2))
             if bool(over.any()):
                 idx = over.nonzero(as_tuple=True)[0]
                 ser = (idx + n * generation[idx]).tolist()
                 for s_, r_ in zip(ser, result[idx].tolist()):
                     winners[s_] = r_
                 done += len(ser)
-                ctx.reset_games(over.to(torch.uint8).cpu().numpy(), epoch=tick + 1)
-                generation[idx] += 1
+                k = min(len(ser), target - started)
+                again, stop = idx[:k], idx[k:]
+                if k:
+                    mask = torch.zeros(n, dtype=torch.uint8, device=dev)
+                    mask[again] = 1
+                    ctx.reset_games(mask.cpu().numpy(), epoch=tick + 1)
+                    generation[again] += 1
+                    started += k
+                idle[stop] = True
                 plies[idx] = 0
             tick += 1
+        live = torch.cat(rec["live"])
         planes = torch.cat(rec["planes"])
         pi = torch.cat(rec["pi"])
         color = torch.cat(rec["color"])
@@ -156,7 +174,7 @@ def self_play_continuous(ctx, c_puct, sims, n_games, max_plies=150, evaluator=L.
         keys = torch.tensor(list(winners.keys()), dtype=torch.int64, device=dev)
         table[keys] = torch.tensor(list(winners.values()), dtype=torch.int64, device=dev)
         r = table[serial]
-        keep = r >= 0                                         # games still running when the quota was reached are dropped
+        keep = (r >= 0) & live                                # every started game was completed; rows of idle slots are not samples
         r, color_k = r[keep], color[keep]
         z = torch.where(r == 0, 0.0, torch.where((r - 1) == color_k.to(r.dtype), 1.0, -1.0)).to(torch.float32)
         ctx.mcts_set_noise(False)

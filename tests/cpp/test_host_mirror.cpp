@@ -252,7 +252,7 @@ static void native_self_play() {
     tc.self_play_game_amnt = 40;
     tc.max_plies = 20;
     auto data = self_play_continuous(e, sp, tc);
-    CHECK(!data.empty() && data.size() <= 16u * 22u * 8u);
+    CHECK(!data.empty() && data.size() <= 16u * 22u * 40u);   // exactly 40 complete games of at most 22 plies
     size_t decided = 0;
     for (auto& d : data) {
         float ps = 0.f; for (float p : d.pi) ps += p;
@@ -286,8 +286,20 @@ static void native_fight() {
     FightStatistics a = fight_device(e, ec, puct, rnd);
     CHECK(a.wins + a.losses + a.draws == 24 && a.games_red == 12 && a.games_blue == 12);
     CHECK(a.wins > a.losses);
-    FightStatistics b = fight_device(e, ec, uct, rnd);
-    CHECK(b.wins + b.losses + b.draws == 24 && b.wins > b.losses);
+    // FightStatistics incl. Elo come from the device fold (onb_fight_stats): the host fold of the same per-game results
+    // (evaluator.rs:58-110) must agree -- counts exactly, ratings to rounding (device pow vs libm pow)
+    FightStatistics host(800., 800.);
+    for (size_t g = 0; g < 24; ++g) {
+        const uint8_t r = e.last_fight_results[g];
+        host.update(r == 1 ? MoveResult::RedWin : r == 2 ? MoveResult::BlueWin : MoveResult::InProgress, g % 2 == 0 ? PlayerColor::Red : PlayerColor::Blue);
+    }
+    CHECK(host.wins == a.wins && host.losses == a.losses && host.draws == a.draws && host.wins_red == a.wins_red && host.wins_blue == a.wins_blue);
+    CHECK(std::fabs(host.rating_a - a.rating_a) < 1e-9 && std::fabs(host.rating_b - a.rating_b) < 1e-9 && a.rating_a > 800. && a.rating_b < 800.);
+    CHECK(a.rating_change_history.size() == 24 && a.rating_change_history[0].before_a == 800.);
+    for (size_t g = 0; g < 24; ++g) CHECK(std::fabs(host.rating_change_history[g].after_a - a.rating_change_history[g].after_a) < 1e-9);
+    CHECK(std::fabs(host.winrate - a.winrate) < 1e-15);
+    FightStatistics b = fight_device(e, ec, uct, rnd, 900., 700.);
+    CHECK(b.wins + b.losses + b.draws == 24 && b.wins > b.losses && b.rating_change_history[0].before_a == 900.);
     bool threw = false;
     onb_agent bad = puct; bad.sims = 100000;   // more simulations than the engine was created for
     try { fight_device(e, ec, bad, rnd); } catch (const Error&) { threw = true; }

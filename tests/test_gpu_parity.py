@@ -1193,7 +1193,7 @@ def test_self_play_continuous_keeps_slots_busy(onb):
         changed = [i for i in range(n) if after[i].tobytes() != before[i].tobytes()]
         assert set(changed) <= {3, 7} and len(changed) >= 1          # a new deal almost surely differs
         assert ctx.reset_games(None, epoch=10) == 0                    # nothing is over yet
-    assert cont["games"] >= 3 * n
+    assert cont["games"] == 3 * n                                      # exactly the requested games, every one played to its end
     serial = cont["serial"].cpu().numpy()
     assert len(np.unique(serial)) == cont["games"]
     assert (serial >= n).any()                                         # slots were reused
@@ -1212,13 +1212,15 @@ def test_self_play_continuous_keeps_slots_busy(onb):
     checked = 0
     for s in range(n):
         a = torch.from_numpy(serial == s).to(zc.device)
-        if not bool(a.any()):
-            continue                                                   # still running when the quota was reached
+        assert bool(a.any())                                           # no started game is dropped (no short-game bias)
         b = torch.from_numpy(lock_game == s).to(zc.device)
         assert torch.equal(cont["planes"][a], lock["planes"][b]) and torch.equal(cont["pi"][a], lock["pi"][b])
         assert torch.equal(cont["z"][a], lock["z"][b])
         checked += 1
-    assert checked >= n // 2
+    assert checked == n
+    # the length distribution is that of complete games: the longest lockstep game (152 plies when it hits the cap) is in there
+    counts = np.bincount(serial)
+    assert counts[:n].max() == np.bincount(lock_game).max()
 
 
 @pytest.mark.gpu
@@ -1237,7 +1239,7 @@ def test_native_self_play_equals_the_python_driver(onb, evaluator):
         for train in (False, True):   # train mode: the root noise comes from the counter RNG, so both drivers still agree exactly
             py = onb.self_play_continuous(ctx, c, sims, n_games=games, max_plies=30, evaluator=ev, train=train, noise_seed=5)
             nat = ctx.self_play_native(c, sims, games, max_plies=30, evaluator=ev, train=train, noise_seed=5)
-            assert nat["games"] == py["games"] >= games and not nat["truncated"]
+            assert nat["games"] == py["games"] == games and not nat["truncated"]   # exactly the games asked for, all complete
             for k in ("planes", "pi", "z", "serial"):
                 assert torch.equal(nat[k], py[k]), (k, train)
             assert torch.equal(nat["color"], py["color"])
@@ -1388,8 +1390,26 @@ def test_native_fight_equals_the_python_driver(onb):
             assert a + b + d == n
             if cap == 3:
                 assert d > 0          # five plies are not enough to finish every game
+            # each ply an agent chooses ONLY for the undecided games in which it is to move (evaluator.rs:379): one choice per game
+            # and ply, never both agents' searches over all n games
+            assert 0 < ctx.last_fight_moves_chosen <= n * ctx.last_fight_plies
+            # FightStatistics folded on the device (onb_fight_stats) == the host fold of the same results (evaluator.rs:38-110)
+            dev = ctx.fight_stats(800.0, 812.5, history=True)
+            host = onb.fight_statistics(results, a_is_red, 800.0, 812.5)
+            assert dev["general"] == host.general and dev["color"] == host.color, name
+            assert dev["general"]["wins"] == a and dev["general"]["loses"] == b and dev["general"]["draws"] == d
+            assert abs(dev["winrate"] - host.winrate) < 1e-15
+            for k in range(2):
+                assert abs(dev["color_winrate"][k] - host.color_winrate[k]) < 1e-15
+            # pow() on the device is within 2 ulp of libm's: ratings agree far below anything Elo means
+            assert abs(dev["rating_a"] - host.rating_a) < 1e-9 and abs(dev["rating_b"] - host.rating_b) < 1e-9
+            assert np.abs(dev["rating_change_history"] - np.array(host.rating_change_history)).max() < 1e-9
         with pytest.raises(onb.OnbError):
             ctx.fight_native(ctx.agent_puct(10 ** 6), ctx.agent_random(), a_is_red)
+    with onb.Context(8, planes=False) as fresh:
+        with pytest.raises(onb.OnbError) as e:
+            fresh.fight_stats()
+        assert e.value.code == -4
 
 
 # ------------------------------------------------------------------ host-acted stepping pipelined inside the library (onb_actor_*)
@@ -1491,3 +1511,64 @@ def test_bad_host_actions_are_rejected_not_applied(onb):
         ctx.step(acts)
         assert ctx.get_states().tobytes() == before.tobytes()
         assert int(ctx.stats()[onb._lib.STAT_BAD_ACTIONS]) == 3
+
+
+# ------------------------------------------------------------------ the replay gather behind the C ABI (onb_comm_*, onb_gather_samples)
+@pytest.mark.gpu
+def test_gather_samples_single_rank_and_pack(onb):
+    """One-rank communicator (dlopen'ed NCCL, ncclCommInitRank, the count exchange, the local copy) and onb_selfplay_pack: the valid
+    samples of a native self-play as contiguous arrays == torch's gather of the same rows."""
+    import ctypes as C
+    import torch
+    from onitama_alphazero_b200.sharding import Comm
+    L = onb._lib
+    n, sims = 64, 8
+    with onb.Context(n, seed=12, mcts_max_sims=sims) as ctx:
+        res = ctx.self_play_native(2.0, sims, 100, max_plies=8)
+        with Comm(ctx, 1, 0, Comm.unique_id()) as comm:
+            got = comm.gather_samples(res["planes"], res["pi"], res["z"], dst=0)
+            assert torch.equal(got[0], res["planes"]) and torch.equal(got[1], res["pi"]) and torch.equal(got[2], res["z"])
+            assert comm.last_counts == [res["planes"].shape[0]]
+            empty = comm.gather_samples(res["planes"][:0], res["pi"][:0], res["z"][:0], dst=0)
+            assert empty[0].shape[0] == 0
+        # onb_selfplay_pack on the raw result
+        cfg = L.SelfPlayConfig(2.0, sims, onb.EVAL_UNIFORM, 100, 8, 0, 0, n * 10 * 4)
+        raw = L.SelfPlayResult()
+        ctx._ck(ctx._lib.onb_self_play(ctx._h, C.byref(cfg), C.byref(raw)))
+        p, q, z, m = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        ctx._ck(ctx._lib.onb_selfplay_pack(ctx._h, C.byref(raw), C.byref(p), C.byref(q), C.byref(z), C.byref(m)))
+        ctx.sync()
+        assert m.value == raw.n_valid == res["planes"].shape[0]
+        from onitama_alphazero_b200.engine import _DevBuf
+        with torch.cuda.stream(ctx.torch_stream()):
+            pp = torch.as_tensor(_DevBuf(p.value, (m.value, 21, 5, 5), "<f4"), device="cuda:0")
+            zz = torch.as_tensor(_DevBuf(z.value, (m.value,), "<f4"), device="cuda:0")
+            assert torch.equal(pp, res["planes"]) and torch.equal(zz, res["z"])
+
+
+@pytest.mark.gpu
+def test_gather_samples_two_gpus(onb):
+    """onb_gather_samples over a 2-rank NCCL communicator created through the C ABI == sharding.gather_replay (torch.distributed) on
+    the same samples, uneven and empty contributions, both destinations, and the collective overflow check. Needs two GPUs."""
+    import subprocess
+    import sys
+    import tempfile
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run on a gpurun --gpus 2 box; result recorded in profiles/)")
+    with tempfile.TemporaryDirectory() as d:
+        idfile = os.path.join(d, "nccl_id")
+        port = str(29600 + os.getpid() % 300)
+        procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_gather_worker.py"), str(r), "2", port, idfile],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+        outs = []
+        for p in procs:
+            try:
+                out, _ = p.communicate(timeout=300)
+            except subprocess.TimeoutExpired:
+                for q in procs:
+                    q.kill()
+                raise
+            outs.append(out)
+        for r, (p, out) in enumerate(zip(procs, outs)):
+            assert p.returncode == 0 and "rank %d ok" % r in out, out[-3000:]
