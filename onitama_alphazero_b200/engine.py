@@ -41,6 +41,7 @@ class Context:
             raise OnbError(rc, self._lib.onb_last_error(self._h).decode())
 
     def close(self):
+        self.__dict__.pop("_graphs", None)   # captured simulation rounds reference this context's buffers
         if getattr(self, "_h", None):
             self._lib.onb_destroy(self._h)
             self._h = None
@@ -189,6 +190,8 @@ class Context:
     def mcts_set_noise(self, enabled, epsilon=0.25, alpha=0.03, seed=0):
         """train mode: root exploration noise (AlphaZeroMctsConfig::train); statistical parity only."""
         self._ck(self._lib.onb_mcts_set_noise(self._h, int(bool(enabled)), float(epsilon), float(alpha), int(seed)))
+        # the select kernel's launch parameters include the noise settings: a captured simulation round is only valid for them
+        self._noise = (bool(enabled), float(epsilon), float(alpha), int(seed)) if enabled else (False,)
 
     def mcts_select(self):
         self._ck(self._lib.onb_mcts_select(self._h))
@@ -459,7 +462,10 @@ def _search_device(self, c_puct, sims, evaluator=L.EVAL_UNIFORM, net=None, use_g
                 for _ in range(sims):
                     one_round()
             else:
-                key = (id(net), float(c_puct))
+                # a captured round bakes in everything the launches were given: the evaluator, c_puct AND the root-noise settings
+                # (switching train mode after a capture must not replay the old setting). The cache holds a strong
+                # reference to `net`, so its id cannot be recycled for another module while the graph lives; close() drops it.
+                key = (id(net), float(c_puct), getattr(self, "_noise", (False,)))
                 cache = self.__dict__.setdefault("_graphs", {})
                 done = 0
                 if key not in cache:
@@ -469,8 +475,8 @@ def _search_device(self, c_puct, sims, evaluator=L.EVAL_UNIFORM, net=None, use_g
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=ts):
                         one_round()  # captured, not executed
-                    cache[key] = g
-                g = cache[key]
+                    cache[key] = (g, net)
+                g = cache[key][0]
                 for _ in range(sims - done):
                     g.replay()
     self.mcts_finish(to_host=False)

@@ -30,7 +30,7 @@ class _ResNetBlock(nn.Module):  # net.rs:40-66
 class ConvResNet(nn.Module):
     """ConvResNetConfig{hidden_channels, input_channels, resnet_block_amnt} (net.rs:74-90)."""
 
-    def __init__(self, hidden_channels=64, input_channels=21, resnet_block_amnt=3):
+    def __init__(self, hidden_channels=64, input_channels=21, resnet_block_amnt=5):  # ConvResNetConfig::default (net.rs:82-90)
         super().__init__()
         h = hidden_channels
         self.conv_init_1 = nn.Conv2d(input_channels, h, 3, stride=1, padding=1)
@@ -58,17 +58,69 @@ class ConvResNet(nn.Module):
         return p, v
 
     def load_ot(self, path):
-        """Load a libtorch named-tensor archive saved by VarStore::save (train.rs:414-430)."""
-        arch = torch.jit.load(path, map_location="cpu")
-        src = {n.replace("|", "."): p.detach() for n, p in arch.named_parameters()}
+        """Load a libtorch named-tensor archive saved by VarStore::save (train.rs:414-430) into THIS module. The archive must hold
+        exactly this architecture: missing tensors AND tensors this module has no place for (e.g. resnet_3/resnet_4 of a 5-block
+        checkpoint loaded into a 3-block module) are errors, never silently dropped. `ConvResNet.from_ot(path)` builds the module
+        the archive describes."""
+        src = read_ot(path)
         own = self.state_dict()
         missing = [k for k in own if k not in src and not k.endswith("num_batches_tracked")]
-        if missing:
-            raise KeyError("tensors missing from %s: %s" % (path, missing[:5]))
+        unexpected = [k for k in src if k not in own]
+        if missing or unexpected:
+            raise KeyError("%s does not match this ConvResNet (%d blocks): missing %s, unexpected %s"
+                           % (path, self.n_blocks, missing[:4], unexpected[:4]))
         for k in own:
             if k in src:
+                if own[k].shape != src[k].shape:
+                    raise KeyError("%s: tensor %s has shape %s, expected %s" % (path, k, tuple(src[k].shape), tuple(own[k].shape)))
                 own[k].copy_(src[k])
         return self
+
+    @classmethod
+    def from_ot(cls, path):
+        """The module an archive describes: hidden / input channels from conv_init_1.weight, the block count from the names."""
+        src = read_ot(path)
+        w = src["conv_init_1.weight"]
+        blocks = 0
+        while "resnet_%d.resnet_small_block1.small_block_conv.weight" % blocks in src:
+            blocks += 1
+        return cls(int(w.shape[0]), int(w.shape[1]), blocks).load_ot(path)
+
+    def save_ot(self, path):
+        """Write the archive VarStore::load expects (AlphaZeroMcts::from_model_file, alphazero_mcts/mod.rs:89-105; written by
+        VarStore::save, train.rs:414-430): a TorchScript module whose parameters carry the VarStore paths with '|' separators;
+        BatchNorm running statistics are parameters without gradient, num_batches_tracked is not part of a VarStore."""
+        write_ot(self.state_dict(), path)
+        return path
+
+
+def read_ot(path):
+    """name ('.'-separated) -> tensor of a libtorch named-tensor archive"""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        arch = torch.jit.load(path, map_location="cpu")
+    out = {n.replace("|", "."): p.detach() for n, p in arch.named_parameters()}
+    out.update({n.replace("|", "."): b.detach() for n, b in arch.named_buffers()})
+    return out
+
+
+class _VarStoreArchive(nn.Module):
+    """holder whose parameter names are VarStore paths (tch joins path components with '|')"""
+
+    def __init__(self, tensors):
+        super().__init__()
+        for name, t in tensors.items():
+            trainable = not (name.endswith("running_mean") or name.endswith("running_var"))
+            self.register_parameter(name.replace(".", "|"), nn.Parameter(t.detach().clone().float().contiguous(), requires_grad=trainable))
+
+
+def write_ot(state_dict, path):
+    import warnings
+    tensors = {k: v for k, v in state_dict.items() if not k.endswith("num_batches_tracked")}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.jit.script(_VarStoreArchive(tensors)).save(path)
 
 
 def alphaloss(v, p, pi, z):

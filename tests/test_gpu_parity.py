@@ -1572,3 +1572,32 @@ def test_gather_samples_two_gpus(onb):
             outs.append(out)
         for r, (p, out) in enumerate(zip(procs, outs)):
             assert p.returncode == 0 and "rank %d ok" % r in out, out[-3000:]
+
+
+@pytest.mark.gpu
+def test_cuda_graph_cache_follows_the_noise_setting(onb):
+    """the captured simulation round (search_device(use_graph=True)) bakes in the root-noise settings of its launches; the
+    cache is keyed by them, so switching train mode after a capture gives the same trees as the un-captured search in that mode."""
+    import torch
+    from onitama_alphazero_b200.net import make_evaluator
+    from test_net_cpu import lively_model
+    n, sims = 32, 24
+    net = make_evaluator(lively_model(1, seed=2).cuda())
+    with onb.Context(n, seed=8, mcts_max_sims=sims) as ctx:
+        ctx.reset()
+
+        def visits(use_graph):
+            with torch.cuda.stream(ctx.torch_stream()):
+                ctx.search_device(2.0, sims, net=net, use_graph=use_graph)
+            return ctx.mcts_finish()["child_visits"].copy()
+
+        eval_plain, eval_graph = visits(False), visits(True)
+        assert np.array_equal(eval_plain, eval_graph)
+        ctx.mcts_set_noise(True, 0.25, 0.03, 77)
+        train_plain, train_graph = visits(False), visits(True)
+        assert np.array_equal(train_plain, train_graph) and not np.array_equal(train_graph, eval_graph)
+        ctx.mcts_set_noise(True, 0.25, 0.03, 78)     # another seed is another graph
+        assert not np.array_equal(visits(True), train_graph)
+        ctx.mcts_set_noise(False)
+        assert np.array_equal(visits(True), eval_graph)
+        assert len(ctx._graphs) == 3

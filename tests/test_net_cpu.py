@@ -132,3 +132,72 @@ def test_oracle_network_on_the_reference_trained_weights_fixture():
         p2, v2 = m.eval()(torch.from_numpy(planes))
     assert np.abs(p2.reshape(-1, 50).numpy() - pol).max() < 1e-6 and np.abs(v2.reshape(-1).numpy() - val).max() < 1e-6
     assert pol.std(0).max() > 0.01          # the trained policy head does depend on the position
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/model_5e-3.ot"), reason="reference weights not present")
+def test_ot_archives_block_count_is_inferred_and_mismatches_are_errors():
+    """ADVICE r01: four of the reference's five checkpoints have 5 residual blocks (ConvResNetConfig::default, net.rs:82-90); loading one
+    into a 3-block module must not silently drop resnet_3 / resnet_4."""
+    from onitama_alphazero_b200.net import ConvResNet
+    assert ConvResNet().n_blocks == 5
+    assert ConvResNet.from_ot("/root/reference/models/model_5e-3.ot").n_blocks == 5
+    assert ConvResNet.from_ot("/root/reference/models/model_5e-3_3_resnet.ot").n_blocks == 3
+    with pytest.raises(KeyError, match="unexpected"):
+        ConvResNet(64, 21, 3).load_ot("/root/reference/models/model_5e-3.ot")
+    with pytest.raises(KeyError, match="missing"):
+        ConvResNet(64, 21, 5).load_ot("/root/reference/models/model_5e-3_3_resnet.ot")
+
+
+def test_ot_writer_round_trip(tmp_path):
+    """save_ot writes what VarStore::load reads (alphazero_mcts/mod.rs:89-105): a TorchScript archive whose parameters carry the VarStore
+    paths with '|' separators, running statistics as parameters without gradient; it reads back bit for bit."""
+    from onitama_alphazero_b200.net import ConvResNet, read_ot
+    m = lively_model(2, seed=5)
+    path = m.save_ot(str(tmp_path / "model_1_20240101_000000.ot"))
+    back = ConvResNet.from_ot(path)
+    sd, sd2 = m.state_dict(), back.state_dict()
+    for k in sd:
+        if not k.endswith("num_batches_tracked"):
+            assert torch.equal(sd[k], sd2[k]), k
+    arch = torch.jit.load(path)
+    names = {n: p.requires_grad for n, p in arch.named_parameters()}
+    assert "resnet_1|resnet_small_block2|small_block_bn|running_var" in names and "conv_init_1|weight" in names
+    assert not any("." in n or "num_batches_tracked" in n for n in names)
+    assert names["bn1|running_mean"] is False and names["bn1|weight"] is True
+    if os.path.exists("/root/reference/models/model_5e-3_3_resnet.ot"):   # same names, dtypes and shapes as an archive the reference wrote
+        ref = read_ot("/root/reference/models/model_5e-3_3_resnet.ot")
+        mine = ConvResNet(64, 21, 3)
+        p3 = mine.save_ot(str(tmp_path / "three.ot"))
+        got = read_ot(p3)
+        assert sorted(got) == sorted(ref) and all(got[k].shape == ref[k].shape and got[k].dtype == ref[k].dtype for k in ref)
+
+
+def test_stats_json_layout(tmp_path):
+    """stats.rs:14-80: the serde layout of the training log, written and read back"""
+    import datetime
+    import json
+    from onitama_alphazero_b200.selfplay import fight_statistics
+    from onitama_alphazero_b200.stats import Stats
+    now = datetime.datetime(2024, 6, 7, 12, 34, 56)
+    st = Stats(root=str(tmp_path), now=now)
+    assert st.dir.endswith("loss_20240607_123456")
+    st.push(0, 2.5, 1.0, 1.5)
+    st.push_games_played(1200, 33000)
+    fs = fight_statistics([1, 2, 0, 1], [True, False, True, False], 800.0, 800.0)
+    st.push_fight(True, self_fight=fs, random_fight=fs)
+    path = st.save(now)
+    assert os.path.basename(path) == "loss_stats_20240624_123456.json"   # the reference's "%Y%m%y" format string, reproduced
+    d = json.load(open(path))
+    assert list(d) == ["iteration", "loss", "policy_loss", "value_loss", "was_best_change", "fight_statistics", "games_played", "dir"]
+    assert d["loss"] == [2.5] and d["value_loss"] == [1.0] and d["policy_loss"] == [1.5] and d["was_best_change"] == [True]
+    assert d["games_played"] == [{"games_amnt": 1200, "positions_retrieved": 33000}]
+    pit = d["fight_statistics"][0]
+    assert list(pit) == ["self_fight", "random_fight", "alphabeta_fight", "mcts_fight"]
+    sf = pit["self_fight"]
+    assert list(sf) == ["general", "winrate", "color", "color_winrate", "rating_a", "rating_b", "rating_change_history"]
+    assert sf["general"] == {"wins": 2, "loses": 1, "draws": 1} and len(sf["rating_change_history"]) == 4
+    assert list(sf["rating_change_history"][0]) == ["before_a", "after_a", "before_b", "after_b"]
+    assert sf["rating_change_history"][0]["before_a"] == 800.0 and sf["rating_change_history"][0]["after_a"] == 816.0
+    assert pit["mcts_fight"]["general"] == {"wins": 0, "loses": 0, "draws": 0}
+    again = Stats.load(path)
+    assert again.to_dict() == d
