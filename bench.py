@@ -686,6 +686,13 @@ def main():
             res["nodes"], res["wins"], res["zero"] = ctx.perft(roots, 6)
 
         ms, clocks = timed(one, warmup, steps, between=lambda: flush.fill_(1))
+        # the same enumeration with EVERY leaf visited (k_perft_flat: register DFS below the frontier, no bulk counting of quiet replies):
+        # the like-for-like figure against the CPU arm, which enumerates every leaf too
+        os.environ["ONB_PERFT_DFS"] = "1"
+        counted = res["nodes"].copy()
+        ms_leaf, _ = timed(one, 1, max(1, min(steps, 3)), between=lambda: flush.fill_(1))
+        os.environ.pop("ONB_PERFT_DFS", None)
+        assert np.array_equal(counted, res["nodes"]), "bulk-counted and per-leaf enumeration disagree"
         total = int(res["nodes"].sum())
         tot_t = torch.tensor([total], device="cuda", dtype=torch.int64)
         if world > 1:
@@ -701,7 +708,14 @@ def main():
                 "frac": 40.0 * bfs_nodes / (ms / steps * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_perft_leaf2 (+ k_perft_expand)",
                 "note": "frontier of plies 1-4 in HBM (40 B/node written + read, chunked to < 7 GB); plies 5 and 6 are counted per frontier node in "
                         "registers by k_perft_leaf2 (issue-bound: quiet replies are counted in bulk), so the HBM fraction stays small by design",
-                "peak_source": peak_src, "nodes_per_call": total, "frontier_nodes_per_call": bfs_nodes}
+                "peak_source": peak_src, "nodes_per_call": total, "frontier_nodes_per_call": bfs_nodes,
+                "algorithms": {"bulk_counted": {"value": value, "unit": "nodes/s", "ms_per_step": ms / steps,
+                                                "what": "value of this line: the last two plies are COUNTED per frontier node (quiet replies in bulk), "
+                                                        "not visited one by one"},
+                               "per_leaf": {"value": total_all * max(1, min(steps, 3)) / (ms_leaf * 1e-3), "unit": "nodes/s",
+                                            "ms_per_step": ms_leaf / max(1, min(steps, 3)),
+                                            "what": "k_perft_flat: every leaf is generated and visited, as the CPU arm does -- the like-for-like "
+                                                    "comparison with cpu_baseline"}}}
         e2e = {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 24 * cnt, "d2h_bytes_per_step": 3 * 8 * 6 * cnt,
                "path": "onb_perft(host roots) -> host counters (the timed call itself copies both ways)"}
         return dict(metric="perft_nodes_per_sec", value=value, unit="nodes/s", ms_per_step=ms / steps, dtype="u32", roofline=roof, e2e=e2e,
@@ -919,7 +933,8 @@ def main():
                                       % (dt, cores, r["rollout_plies"] / (1024.0 * MCTS_SIMS))}
         elif wl == "perft":
             v, dt = cpu_perft(16 * cores, 5, cores)
-            cpu_baseline = {"value": v, "unit": "nodes/s", "cores": cores, "kind": "port",
+            cpu_baseline = {"value": v, "unit": "nodes/s", "cores": cores, "kind": "port", "algorithm": "per-leaf (recursive DFS visits every node; "
+                            "compare with roofline.algorithms.per_leaf)",
                             "sample": "%d random deals x depth 5, recursive DFS (%.1f s wall, %d threads)" % (16 * cores, dt, cores)}
         else:
             v, dt = cpu_playout(PLAYOUT_GAMES, 1)
