@@ -20,7 +20,10 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
+    """ONB_NVCC_EXTRA (optional): extra nvcc flags for measurement builds, e.g. ONB_NVCC_EXTRA=-DONB_NET_PROFILE with force=True
+    (per-phase cycle counters printed by the network kernel; rebuild without it afterwards)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("ONB_NVCC_EXTRA", "").split()
     deps = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
     logs = []
@@ -28,7 +31,7 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + deps):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             logs.append(r.stderr)
             if r.returncode != 0:

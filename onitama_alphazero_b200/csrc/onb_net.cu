@@ -50,7 +50,8 @@ struct Op {
     static constexpr int TAP_BYTES = KCH * 64 * 16;    // one tap of a 64 -> 64 layer: [KB][64 co][128 B], swizzled
     static constexpr int TAP_BYTES0 = 64 * 128;        // first layer: its K (32 | 24 channels) fits the first 128-byte block
     // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, A/B format, both K-major, N = 64, M = 128
-    static constexpr uint32_t IDESC = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    static constexpr uint32_t idesc(uint32_t n) { return (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+    static constexpr uint32_t IDESC = idesc(64), IDESC_N128 = idesc(128);
 };
 // head parameter blob (floats)
 constexpr int kHP0 = 0, kHP1 = 64, kHV = 128, kHB = 192, kPhW = 196, kPhB = 2696, kV1W = 2748, kV1B = 4348, kV2W = 4412, kV2B = 4476,
@@ -169,7 +170,7 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 template <bool F16>
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t accumulate) {
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t accumulate, uint32_t idesc = Op<F16>::IDESC) {
     const uint32_t a_lo = desc_lo(a_addr), a_hi = desc_hi(a_addr), b_lo = desc_lo(b_addr), b_hi = desc_hi(b_addr);
     if (F16)
         asm volatile(
@@ -178,7 +179,7 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_addr, uint32_
             "mov.b64 da, {%1, %2};\n\t"
             "mov.b64 db, {%3, %4};\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(Op<true>::IDESC), "r"(accumulate)
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
             : "memory");
     else
         asm volatile(
@@ -187,16 +188,20 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_addr, uint32_
             "mov.b64 da, {%1, %2};\n\t"
             "mov.b64 db, {%3, %4};\n\t"
             "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(Op<false>::IDESC), "r"(accumulate)
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
             : "memory");
 }
 // all MMAs of one tap: K steps of 32 bytes (4 per 128-byte block) x NACC accumulators of 128 rows
-// X3: a2_off / b2_off = byte distance of the second activation matrix / the tap's second weight copy (0 otherwise); D2 sits
-// NACC * 64 columns after D1 and starts from zero at the layer's first step (accumulate_second = false) whatever D1 was preloaded with.
+// X3: per step TWO instructions instead of three: a1 x [b1 ; b2] as ONE N = 128 MMA (the tap's two weight copies are adjacent in
+// the ring, so they are simply 128 consecutive B rows; its 128 result columns are D1 | D2 of the accumulator, which therefore sit
+// side by side in TMEM), then a2 x b1 (N = 64) onto D2. a1 is fetched from shared memory once for both of its products: 14 KB of
+// operands per step instead of 18 KB -- the operand fetch is what bounds this kernel. a2_off = byte distance of the second
+// activation matrix. D2 must hold zeros when D1 was preloaded with the residual (the epilogue that parks the residual writes them).
 template <bool F16, int NACC, bool X3 = false>
 __device__ __forceinline__ void issue_tap_mmas(bool elected, uint32_t dcol, uint32_t s_act, int R, int row0, uint32_t b_slot, int ksteps,
-                                               bool accumulate_first, uint32_t a2_off = 0, uint32_t b2_off = 0, bool accumulate_second = true) {
+                                               bool accumulate_first, uint32_t a2_off = 0) {
     using O = Op<F16>;
+    constexpr uint32_t ACC_COLS = X3 ? 128u : 64u;  // TMEM columns per accumulator
 #pragma unroll
     for (int j = 0; j < O::KCH / 2; ++j) {
         if (j < ksteps) {
@@ -207,10 +212,11 @@ __device__ __forceinline__ void issue_tap_mmas(bool elected, uint32_t dcol, uint
                 const uint32_t a_addr = s_act + koff * (uint32_t)R + (uint32_t)(row0 + a * 128) * 128u + (uint32_t)(j % 4) * 32u;
 #ifndef ONB_NET_DBG_NOMMA
                 if (elected) {
-                    mma_ss<F16>(dcol + a * 64, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u);
                     if (X3) {
-                        mma_ss<F16>(dcol + (NACC + a) * 64, a_addr, b_addr + b2_off, (accumulate_second || j > 0) ? 1u : 0u);  // a1 b2
-                        mma_ss<F16>(dcol + (NACC + a) * 64, a_addr + a2_off, b_addr, 1u);                                       // a2 b1
+                        mma_ss<F16>(dcol + a * ACC_COLS, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u, O::IDESC_N128);  // a1 b1 | a1 b2
+                        mma_ss<F16>(dcol + a * ACC_COLS + 64u, a_addr + a2_off, b_addr, 1u);                                    // a2 b1 -> D2
+                    } else {
+                        mma_ss<F16>(dcol + a * ACC_COLS, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u);
                     }
                 }
 #endif
@@ -357,7 +363,8 @@ __global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    constexpr uint32_t A2 = X3 ? (uint32_t)G::ACT_BYTES : 0u, B2 = X3 ? (uint32_t)O::TAP_BYTES : 0u;  // second activation matrix / weight copy
+    constexpr uint32_t A2 = X3 ? (uint32_t)G::ACT_BYTES : 0u;  // second activation matrix
+    constexpr uint32_t ACC = X3 ? 128u : 64u;                  // TMEM columns per accumulator (X3: D1 | D2 side by side)
     constexpr uint32_t SET = (uint32_t)G::SET_COLS;  // TMEM columns of one accumulator set (D1 [+ D2])
 
 #ifdef ONB_NET_PROFILE
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
                         const int t = g * TPS + tt;
                         issue_tap_mmas<F16, NACC, X3>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
                                                       s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
-                                                      use_s || t > 0, A2, B2, t > 0);
+                                                      use_s || t > 0, A2);
                     }
                     PF(3);  // issuing MMAs
                     if (elected) umma_commit(bar_empty(slot));  // the slot is free again once these MMAs have read it
@@ -463,8 +470,8 @@ __global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
                 const int cell = a * 128 + (warp & 3) * 32 + lane;
                 const Cell c = decode_cell(cell, CELLS);
                 const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-                const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * 64;
-                const uint32_t tskip = tlane + SET + a * 64;
+                const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * ACC;
+                const uint32_t tskip = tlane + SET + a * ACC;
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
                     tmem_ld32(tsrc + h * 32, v);
                     if (X3) {  // D1 + 2^-11 D2
                         uint32_t v2[32];
-                        tmem_ld32(tsrc + NACC * 64 + h * 32, v2);
+                        tmem_ld32(tsrc + 64 + h * 32, v2);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(v2[i]), kX3InvScale, __uint_as_float(v[i])));
                     }
@@ -500,6 +507,11 @@ __global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
                             v[4 * i + 3] = __float_as_uint(o[4 * i + 3] + b.w);
                         }
                         tmem_st32(tskip + h * 32, v);
+                        if (X3) {  // the D2 half of the preloaded accumulator starts the next-but-one layer from zero
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = 0u;
+                            tmem_st32(tskip + 64 + h * 32, v);
+                        }
                     }
                     if (last) {  // 1x1 convolutions of both heads (net.rs: policy_conv 64 -> 2, vh_conv 64 -> 1)
 #pragma unroll
