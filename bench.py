@@ -837,6 +837,10 @@ def main():
                             "useful multiply-add (split operands), so its tensor pipe does 3x this figure; the MMAs also compute the zero-padding "
                             "cells (25 of 36.6 rows are real squares) and are bound by shared-memory operand reads at N = 64; peak = dense bf16/f16",
                     "peak_source": tsrc}
+            if net_mode == "fused-f32":   # what the tensor pipe executes for those useful FLOPs: 3 f16 products per multiply-add
+                roof["split_products_per_multiply_add"] = 3
+                roof["tensor_pipe_tflops"] = 3 * ach
+                roof["tensor_pipe_frac"] = 3 * ach / tpeak
         else:
             roof = {"bound": "hbm", "achieved": per_sim * n * sims * steps / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": per_sim * n * sims * steps / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_mcts_select + k_mcts_expand_backup",
