@@ -9,7 +9,7 @@ import onitama_alphazero_b200 as onb
 
 n, sims = 1 << 14, 400
 s = torch.cuda.Stream(); torch.cuda.set_stream(s)
-ctx = onb.Context(n, seed=20240607, stream=s.cuda_stream, mcts_max_sims=sims, planes=False)
+ctx = onb.Context(n, seed=20240607, stream=s.cuda_stream, mcts_max_sims=sims, planes=False, mcts_node_cap=int(os.environ.get('ONB_TIME_NODE_CAP', '0')))
 ctx.reset()
 base = ctx.get_states(); cur = base.copy()
 for step in range(16):   # the config-4 roots: positions after (id mod 16) random plies
