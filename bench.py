@@ -32,6 +32,7 @@ MCTS_C = 2.0
 PLAYOUT_GAMES = 4096
 SELFPLAY_GAMES = 16384
 SELFPLAY_SIMS = 800
+GAMES_SLOTS = 2048     # `games` workload: slots per GPU (a step plays 2 x slots whole games)
 SEED = 20240607
 NET_PRECISION = {"fused-f32": "f32", "fused": "f16", "fused-tf32": "tf32", "torch": "torch"}
 NET_DTYPE = {"fused-f32": "f32-faithful network: split f16 operands (x = x1 + 2^-11 x2), 3 products per multiply-add, f32 accumulate",
@@ -320,9 +321,9 @@ def workload_config(wl):
                             % (SELFPLAY_SIMS, SELFPLAY_GAMES), "games_per_gpu": SELFPLAY_GAMES, "sims": SELFPLAY_SIMS, "c_puct": MCTS_C,
                 "l2": "node pools + leaf batches >> L2"}
     if wl == "games":
-        return {"workload": "whole self-play games inside the library (onb_self_play): %d slots/GPU, %d sims/move, 3-block ConvResNet on the tensor "
-                            "cores, finished slots restart at once, train-mode root noise" % (SELFPLAY_GAMES, SELFPLAY_SIMS),
-                "slots_per_gpu": SELFPLAY_GAMES, "sims": SELFPLAY_SIMS, "l2": "node pools + sample buffers >> L2"}
+        return {"workload": "whole self-play games inside the library (onb_self_play): %d slots/GPU, %d games per step, %d sims/move, 3-block ConvResNet "
+                            "on the tensor cores, every started game played to its end, train-mode root noise" % (GAMES_SLOTS, 2 * GAMES_SLOTS, SELFPLAY_SIMS),
+                "slots_per_gpu": GAMES_SLOTS, "sims": SELFPLAY_SIMS, "l2": "node pools + sample buffers >> L2"}
     if wl == "uct":
         return {"workload": "plain UCT with random rollouts (the reference's Mcts agent, evaluator.rs opponent): %d playouts/move, %d concurrent "
                             "trees/GPU, config-4 roots, c = sqrt(2), min_node_visits = 5" % (MCTS_SIMS, MCTS_TREES), "trees_per_gpu": MCTS_TREES,
@@ -376,7 +377,7 @@ def main():
                          "the reference computes in f32), fused = the f16 fast mode, fused-tf32 = tf32 operands -- or the PyTorch module as a black box")
     args = ap.parse_args()
     claim_stdout()
-    dflt = {"env": (1000, 50), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3), "games": (2, 3)}[args.workload]
+    dflt = {"env": (1000, 50), "mcts": (20, 5), "perft": (5, 3), "selfplay": (3, 3), "playout": (50, 5), "uct": (5, 3), "games": (1, 3)}[args.workload]
     if args.impl == "reference":
         dflt = (3, 1)
     args.steps_given = args.steps is not None
@@ -756,12 +757,12 @@ def main():
     # ---------------------------------------------------------------- whole self-play games, natively (onb_self_play)
     def bench_games(steps, warmup):
         from onitama_alphazero_b200.net import ConvResNet
-        n, sims = SELFPLAY_GAMES, SELFPLAY_SIMS
+        n, sims = GAMES_SLOTS, SELFPLAY_SIMS
         torch.manual_seed(1234)
         ctx = onb.Context(n, seed=SEED, device=local_rank, game_id_base=rank * n, stream=stream.cuda_stream, mcts_max_sims=sims)
         ctx.net_load(ConvResNet(64, 21, 3), precision=NET_PRECISION[args.net])
-        quota = n // 4          # a step = self-play until a quarter of the slots' worth of games is complete
-        cap = n * 64            # plies of sample buffer: far more than a step needs
+        quota = 2 * n           # a step = 2 games per slot, every one of them played to its end (onb_self_play never drops a started game)
+        cap = n * 400           # plies of sample buffer: two games of at most 152 plies per slot and slack
         tot = {"games": 0, "samples": 0, "plies": 0}
 
         def one(i):
@@ -778,11 +779,13 @@ def main():
         value = games / (ms * 1e-3)
         flop = 2.0 * 25 * 64 * 9 * (21 + 6 * 64) + 2.0 * (25 * 64 * 3 + 2500 + 1600 + 64)
         tpeak, tsrc = read_tensor_peak()
-        ach = flop * n * sims * (plies / world) / (ms * 1e-3) / 1e12
+        ach = flop * sims * (samples / world) / (ms * 1e-3) / 1e12   # one search of `sims` evaluations per recorded sample (= per live slot and ply)
         roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": read_traffic("k_net_forward"),
                 "kernel": "k_net_forward<2,%s>" % NET_PRECISION[args.net], "peak_source": tsrc,
                 "samples_per_sec": samples / (ms * 1e-3), "plies_per_step": plies / world / max(1, steps),
-                "note": "every ply searches all slots (16 384 x 800 network evaluations); finished slots restart at once; a step ends when n/4 games are complete"}
+                "note": "a step = 2 x slots complete games; every ply searches the slots with a game in progress (x 800 network evaluations); finished "
+                        "slots start their next game at once while games remain, idle slots are not searched",
+                "flop_basis": "recorded samples x sims network evaluations (idle slots are not searched)"}
         e2e = {"value": value, "unit": "games/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * plies / world / max(1, steps),
                "path": "onb_self_play: one 8-byte counter per ply crosses PCIe; samples stay in device buffers for the trainer"}
         return dict(metric="selfplay_games_per_sec", value=value, unit="games/s", ms_per_step=ms / steps,

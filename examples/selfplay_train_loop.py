@@ -34,6 +34,8 @@ def main(argv=None):
     ap.add_argument("--mcts-playouts", type=int, default=200, help="playouts of the plain-UCT arena opponent")
     ap.add_argument("--torch-net", action="store_true", help="evaluate with the PyTorch module as a black box instead of onb_net_load")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--out", default=None, help="directory for the reference's on-disk artefacts: loss_stats JSON (stats.rs) and .ot checkpoints (train.rs:414-430)")
+    ap.add_argument("--net-precision", default="f32", choices=["f32", "f16", "tf32"], help="arithmetic of the on-device network (f32 = the reference's)")
     args = ap.parse_args(argv)
 
     torch.manual_seed(args.seed)
@@ -41,12 +43,14 @@ def main(argv=None):
     opt = torch.optim.SGD(model.parameters(), lr=1e-2, weight_decay=1e-4)  # train.rs:181-186
     replay = onb.ReplayBuffer(200_000, device="cuda")
     log = []
+    from onitama_alphazero_b200.stats import Stats
+    stats_log = Stats(root=os.path.join(args.out, "loss_stats")) if args.out else None
 
     def evaluator_for(ctx):
         """(evaluator id, torch callable) for Context.search_device"""
         if args.torch_net:
             return onb.EVAL_UNIFORM, make_evaluator(model)
-        ctx.net_load(model)             # BatchNorm folded, weights laid out for the tensor cores
+        ctx.net_load(model, precision=args.net_precision)   # BatchNorm folded, weights laid out for the tensor cores
         return onb.EVAL_NET, None
 
     for it in range(args.iters):
@@ -70,7 +74,7 @@ def main(argv=None):
             opt.zero_grad()
             (vl + pl).backward()
             opt.step()
-            losses.append((float(vl), float(pl)))
+            losses.append((float(vl.detach()), float(pl.detach())))
         model.eval()
         # ---- evaluation (evaluator.rs:195-353): the network-guided search against the Random and the Mcts agent, colours alternate
         a_is_red = (np.arange(args.eval_games) % 2) == 0
@@ -97,8 +101,18 @@ def main(argv=None):
                     w, l, d, _ = ctx.fight_native(ctx.agent_puct(args.sims, 2.0, ev, 0), native, a_is_red, max_plies=150)
                 else:
                     w, l, d = onb.fight(ctx, az, opponent, a_is_red, max_plies=150)
-                stats = onb.fight_statistics(ctx.last_fight_results, a_is_red)
-                results[name] = dict(wins=w, losses=l, draws=d, elo=stats.rating_a)
+                # FightStatistics incl. the Elo fold: on the device for the native arena (onb_fight_stats), on the host otherwise
+                stats = ctx.fight_stats(history=True) if net is None else onb.fight_statistics(ctx.last_fight_results, a_is_red)
+                elo = stats["rating_a"] if isinstance(stats, dict) else stats.rating_a
+                results[name] = dict(wins=w, losses=l, draws=d, elo=elo, stats=stats)
+        if stats_log is not None:   # what train() leaves on disk: the loss / arena log and the checkpoint of the iteration
+            stats_log.push(it, losses[-1][0] + losses[-1][1], losses[-1][0], losses[-1][1])
+            stats_log.push_games_played(int(data["games"]), int(data["planes"].shape[0]))
+            stats_log.push_fight(False, random_fight=results["random"]["stats"], mcts_fight=results["mcts"]["stats"])
+            stats_log.save()
+            model.save_ot(os.path.join(args.out, "model_%d.ot" % it))
+        for r in results.values():
+            r.pop("stats")
         log.append(dict(iteration=it, games=int(data["games"]), samples=int(data["planes"].shape[0]), replay=replay.size,
                         value_loss=losses[-1][0], policy_loss=losses[-1][1], wins=results["random"]["wins"],
                         losses=results["random"]["losses"], draws=results["random"]["draws"], elo=results["random"]["elo"],

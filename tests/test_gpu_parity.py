@@ -868,13 +868,24 @@ def test_example_training_iteration_runs(onb):
     spec = importlib.util.spec_from_file_location("selfplay_train_loop", os.path.join(ROOT, "examples", "selfplay_train_loop.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    for extra in ([], ["--torch-net"]):   # the network inside the library (onb_net_load) and as a PyTorch black box
+    import glob
+    import tempfile
+    out = tempfile.mkdtemp()
+    for extra in (["--out", out], ["--torch-net"]):   # the network inside the library (onb_net_load) and as a PyTorch black box
         log = mod.main(["--slots", "48", "--games", "64", "--sims", "16", "--iters", "1", "--max-plies", "12", "--batch", "64", "--sgd-steps", "3",
                         "--eval-games", "16", "--mcts-playouts", "60"] + extra)
-        assert len(log) == 1 and log[0]["samples"] > 0 and log[0]["games"] >= 64
+        assert len(log) == 1 and log[0]["samples"] > 0 and log[0]["games"] == 64
         assert log[0]["wins"] + log[0]["losses"] + log[0]["draws"] == 16
         assert sum(log[0]["vs_mcts"][k] for k in ("wins", "losses", "draws")) == 16
         assert np.isfinite(log[0]["value_loss"]) and np.isfinite(log[0]["policy_loss"])
+    # the reference's on-disk artefacts: the stats JSON (stats.rs) and a checkpoint VarStore::load can read (train.rs:414-430)
+    from onitama_alphazero_b200.net import ConvResNet
+    stats_files = glob.glob(os.path.join(out, "loss_stats", "loss_*", "loss_stats_*.json"))
+    assert len(stats_files) == 1
+    d = json.load(open(stats_files[0]))
+    assert d["iteration"] == [0] and d["games_played"][0]["games_amnt"] == 64
+    assert sum(d["fight_statistics"][0]["random_fight"]["general"].values()) == 16 and len(d["fight_statistics"][0]["mcts_fight"]["rating_change_history"]) == 16
+    assert ConvResNet.from_ot(os.path.join(out, "model_0.ot")).n_blocks == 3
 
 
 @pytest.mark.gpu
