@@ -367,6 +367,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="env", choices=["env", "mcts", "playout", "perft", "selfplay", "uct", "games"])
     ap.add_argument("--subbatches", type=int, default=4, help="env e2e: sub-batches in flight inside onb_actor (>= 4 hides the copies under three kernels)")
+    ap.add_argument("--gather", default="abi", choices=["abi", "torch"],
+                    help="selfplay workload, N > 1: gather the replay samples with onb_gather_samples (C ABI) or torch.distributed")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary mcts measurement of the default env run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the config-5 section of the default env run (12 000 launches: too many for an ncu launch list)")
@@ -811,6 +813,17 @@ def main():
             ctx.mcts_set_noise(True, 0.25, 0.03, SEED)
         planes_t, pi_t = ctx.tensor(onb.BUF_PLANES), ctx.tensor(onb.BUF_PI)
         got = {"samples": 0}
+        # the replay gather of section 8e through the C ABI (onb_comm_* / onb_gather_samples: the library's own NCCL communicator, created
+        # from an id that rank 0 hands out); --gather torch keeps the torch.distributed twin (sharding.gather_replay)
+        comm = None
+        if world > 1 and args.gather == "abi":
+            from onitama_alphazero_b200.sharding import Comm
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, src=0)
+            torch.cuda.synchronize()
+            comm = Comm(ctx, world, rank, bytes(idt.cpu().numpy().tobytes()))
 
         def one_ply(i):
             ctx.encode(to_host=False)                      # sample planes of the searched position (train.rs:58)
@@ -819,13 +832,18 @@ def main():
             else:       # select -> torch module (zero-copy leaf batch, CUDA graph) -> expand/backup, x sims
                 ctx.search_device(MCTS_C, sims, net=net, use_graph=True)
             z = torch.zeros(n, device=planes_t.device)
-            out_s = onb.gather_replay(planes_t, pi_t, z, dst=0)   # NCCL gather of the ply's samples to the trainer GPU
+            if comm is not None:
+                out_s = comm.gather_samples(planes_t, pi_t, z, dst=0)   # onb_gather_samples: the ply's samples to the trainer GPU over NVLink
+            else:
+                out_s = onb.gather_replay(planes_t, pi_t, z, dst=0)
             if out_s is not None:
                 got["samples"] = int(out_s[0].shape[0])
             ctx.mcts_play_best()
 
         ms, clocks = timed(one_ply, warmup, steps)
         value = world * n * sims * steps / (ms * 1e-3)
+        if comm is not None:
+            comm.close()
         ctx.close()
         per_sim = 1217.0 + 2100 + 204
         if fused:
@@ -849,8 +867,9 @@ def main():
                     "frac": per_sim * n * sims * steps / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_mcts_select + k_mcts_expand_backup",
                     "note": "the step is dominated by the black-box network (library kernels, ~11.7 MFLOP per evaluation), not by these kernels",
                     "peak_source": peak_src}
-        e2e = {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "path": "device-resident self-play ply (search + sample gather + play); nothing crosses PCIe by design"}
+        e2e = {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * world if comm is not None else 0,
+               "path": "device-resident self-play ply (search + sample gather + play); nothing but the gather's sample counts crosses PCIe by design",
+               "gather": "onb_gather_samples (C ABI, NCCL send/recv over NVLink)" if comm is not None else ("torch.distributed gather" if world > 1 else "single rank")}
         roof["search_mode"] = "eval (no root noise)" if args.eval_mode else "train (root exploration noise, epsilon 0.25, alpha 0.03)"
         return dict(metric="mcts_sims_per_sec", value=value, unit="sims/s", ms_per_step=ms / steps, dtype="u32+f64 (search), " + NET_DTYPE[net_mode],
                     network=net_mode, roofline=roof, e2e=e2e, gpu_launches=((3 if fused else 2) * sims + 4) * steps, clocks=clocks,
