@@ -838,6 +838,308 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
     if (warp == 0) tmem_dealloc(*s_tmem, 512);
 }
 
+// ---- the split-operand (f32-faithful) network as TWO independent halves of one CTA that share one weight stream ----------------------
+// The one-CTA-per-SM split kernel above (k_net_forward<2, f16, X3>) spends 63 % of its time issuing MMAs and the rest with the tensor
+// pipe idle (epilogue, barriers, heads): TMEM (512 columns) and shared memory (219 KB) leave no room for a second CTA to fill the gaps.
+// Here a CTA is two halves of 8 warps, each with ONE 128-row accumulator = 3 boards whose cells never straddle an accumulator (so the
+// halves share nothing but the weights), its own activation matrices (a1, a2: 2 x 16 KB), 256 TMEM columns ({D1|D2} x {plain,
+// residual-preloaded}) and its own MMA-issuing lane; they run out of phase, so one half's MMAs cover the other's epilogue. Warp 16
+// streams the (b1, b2) weight copies into a ring of 3 slots x 3 taps that is refilled when BOTH halves' MMAs have read a slot. The 8
+// warps of a half split the epilogue by channels (warps 0-3: channels 0-31, warps 4-7: channels 32-63 of the same 128 cells), 16
+// columns at a time to stay within 120 registers. Same products and accumulation order per accumulator as the one-CTA kernel (the
+// heads add the two channel halves in a different order: last-bit differences). MEASURED (B200, 16 384 positions, 3 blocks): 0.876 ms
+// when the halves run freely (they fall into step: both issue, then both run epilogues), 0.794 ms when they take turns issuing a
+// layer -- against 0.745 ms for the one-CTA kernel, which wastes no accumulator rows (252 of 256 vs 108 of 128) and streams the
+// weights once per 7 boards instead of 6. Kept behind ONB_NET_X3_HALVES=1; not the default.
+struct Geo2X {
+    static constexpr int NB = 3;  // boards per half: 108 cells in one 128-row accumulator
+    static constexpr int CELLS = NB * kCellsPerBoard;
+    static constexpr int R = (kLead + 128 + kTrail + 7) / 8 * 8;  // 144: an MMA reads 128 rows from any of the 15 shifted windows
+    static constexpr int TPS = 3, UPL = 3, NSLOT = 3;
+    static constexpr int TAP_STRIDE = 2 * Op<true>::TAP_BYTES;  // [b1 tap][b2 tap]
+    static constexpr int SLOT_BYTES = TPS * TAP_STRIDE;
+    static constexpr int ACT_BYTES = R * Op<true>::KCH * 16;  // one activation matrix
+    static constexpr int HALF_ACT = 2 * ACT_BYTES;              // a1 + a2
+    static constexpr int OFF_RING = 2 * HALF_ACT;
+    static constexpr int RING_BYTES = NSLOT * SLOT_BYTES;
+    static constexpr int OFF_HEAD = OFF_RING + RING_BYTES;
+    static constexpr int HEAD_BYTES = ((2 * NB * 75 * 4 + 15) / 16) * 16;  // per half: two partial sums (channels 0-31 / 32-63) per head input
+    static constexpr int OFF_BAR = OFF_HEAD + 2 * HEAD_BYTES;
+    static constexpr int SMEM = OFF_BAR + (2 * NSLOT + 4) * 8 + 16;
+    static constexpr int THREADS = 17 * 32;
+    static_assert(CELLS <= 128 && R >= kLead + 128 + kTrail - 1, "one accumulator per half; shifted windows stay inside the matrix");
+    static_assert(ACT_BYTES % 1024 == 0 && OFF_RING % 1024 == 0, "swizzle period");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// 16 consecutive channels [c0, c0 + 16) of one cell as split operand chunks (two 16-byte chunks in each activation matrix)
+__device__ __forceinline__ void store_channels_x3_16(uint32_t s_act, uint32_t a2_off, int R, int row, int c0, const float (&o)[16]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float x0 = fminf(o[8 * i + 2 * q], 65504.f), x1 = fminf(o[8 * i + 2 * q + 1], 65504.f);
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
+            hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const uint32_t addr = act_addr(s_act, R, row, c0 / 8 + i);
+        st_shared_v4(addr, hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(addr + a2_off, lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+__global__ void __launch_bounds__(Geo2X::THREADS, 1)
+    k_net_forward2x(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
+    using G = Geo2X;
+    using O = Op<true>;
+    constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = G::NSLOT;
+    constexpr uint32_t A2 = (uint32_t)G::ACT_BYTES, SET = 128u;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t s_base = smem_u32(smem), s_ring = s_base + G::OFF_RING, s_bar = s_base + G::OFF_BAR;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + G::OFF_BAR + (2 * NSLOT + 4) * 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = 1 + 2 * net.n_blocks;
+    const int64_t n_groups = (n + NB - 1) / NB;
+    // iteration i of this CTA: half h works on group (blockIdx.x + i * gridDim.x) * 2 + h (possibly past the end: computed, not stored)
+    const int64_t n_pairs = (n_groups + 1) / 2;
+    if ((int64_t)blockIdx.x >= n_pairs) return;
+    const int64_t my_iters = (n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    constexpr int TPS = G::TPS, UPL = G::UPL;
+    const uint32_t total_units = (uint32_t)my_iters * (uint32_t)(UPL * L);
+    auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
+    auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 2);  // both halves' MMAs must have read the slot
+        }
+        mbar_init(s_bar + 2 * NSLOT * 8u, 1);
+        mbar_init(s_bar + (2 * NSLOT + 1) * 8u, 1);
+        // the halves take turns issuing a layer's MMAs (half 0 first): left alone they fall into step -- both issue, then both run
+        // their epilogues with the tensor pipe idle -- and the kernel is slower than the one-CTA version (measured 0.876 vs 0.745 ms)
+        mbar_init(s_bar + (2 * NSLOT + 2) * 8u, 1);
+        mbar_init(s_bar + (2 * NSLOT + 3) * 8u, 1);
+        fence_barrier_init();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_bar + (2 * NSLOT + 2) * 8u) : "memory");  // half 0 may start
+    }
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), 512);
+    for (int i = tid; i < 2 * G::HALF_ACT / 16; i += G::THREADS) st_shared_v4(s_base + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 16) {
+        // ---- weight producer (one lane): the ring is filled strictly in tap order, as far ahead as it has free slots
+        if (lane == 0) {
+            for (uint32_t u = 0; u < total_units; ++u) {
+                const uint32_t slot = u % NSLOT, use = u / NSLOT;
+                if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
+                const uint32_t ul = u % (uint32_t)(UPL * L), layer = ul / UPL, tap = (ul - layer * UPL) * TPS;
+                const uint8_t* src = net.wconv + (size_t)2 * (layer == 0 ? (size_t)tap * O::TAP_BYTES0
+                                                                          : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
+                const uint32_t bytes = (uint32_t)(2 * TPS) * (layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES);
+                mbar_expect_tx(bar_full(slot), bytes);
+                bulk_g2s(s_ring + slot * (uint32_t)G::SLOT_BYTES, src, bytes, bar_full(slot));
+            }
+        }
+        return;  // the workers only use named barriers from here on
+    }
+
+    const int half = warp >> 3, hwarp = warp & 7, htid = tid & 255;
+    const uint32_t s_act = s_base + (uint32_t)half * G::HALF_ACT;
+    float* s_head = reinterpret_cast<float*>(smem + G::OFF_HEAD + half * G::HEAD_BYTES);  // [2 channel halves][NB][75] partial sums
+    const uint32_t bar_acc = s_bar + (2 * NSLOT + half) * 8u;
+    const uint32_t bar_turn_mine = s_bar + (2 * NSLOT + 2 + half) * 8u, bar_turn_other = s_bar + (2 * NSLOT + 2 + (half ^ 1)) * 8u;
+    uint32_t turn_par = 0;
+    const uint32_t tmem = *s_tmem + (uint32_t)half * 256u;
+    const uint32_t bar_id = 1u + (uint32_t)half;
+
+    uint32_t q0 = 0, acc_par = 0;
+    for (int64_t gi = 0; gi < my_iters; ++gi) {
+        const int64_t board0 = (((int64_t)blockIdx.x + gi * gridDim.x) * 2 + half) * NB;
+        // ---- input planes -> the first channel chunks of both activation matrices (create_tensor_from_state layout [21][5][5])
+        if (htid < 128) {
+            const int cell = htid;
+            const Cell c = decode_cell(cell, CELLS);
+            if (c.real) {
+                const int64_t gb = board0 + c.board;
+                const float* src = planes + gb * 525 + c.pos;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    float x[16];  // the planes are 0 / 1: exact, the second operand part is zero
+#pragma unroll
+                    for (int ch = 0; ch < 16; ++ch) x[ch] = (part * 16 + ch < kInPlanes && gb < n) ? __ldg(src + (part * 16 + ch) * 25) : 0.f;
+                    store_channels_x3_16(s_act, A2, R, kLead + cell, part * 16, x);  // 32 channels: planes 21..31 are zero
+                }
+            }
+        }
+        fence_proxy_async();
+        for (int l = 0; l < L; ++l) {
+            tc_fence_before();
+            named_bar_sync(bar_id, 256);
+            tc_fence_after();
+            const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
+            const bool last = l == L - 1;
+            if (hwarp == 0) {
+                // ---- MMA issue: 9 taps x K steps x {a1 x [b1;b2] (N = 128), a2 x b1 (N = 64)} (the whole warp runs the loop, one lane issues)
+                const bool elected = elect_one();
+                const uint32_t dcol = tmem + (use_s ? SET : 0u);
+                mbar_wait(bar_turn_mine, turn_par);  // the other half has issued its layer: ours queues behind it while it runs its epilogue
+                turn_par ^= 1u;
+                auto issue_unit = [&](int g, int ksteps) {
+                    const uint32_t u = q0 + g, slot = u % NSLOT, use = u / NSLOT;
+                    mbar_wait(bar_full(slot), use & 1u);
+                    tc_fence_after();
+#pragma unroll
+                    for (int tt = 0; tt < TPS; ++tt) {
+                        const int t = g * TPS + tt;
+                        issue_tap_mmas<true, 1, true>(elected, dcol, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1),
+                                                      s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
+                                                      use_s || t > 0, A2);
+                    }
+                    if (elected) umma_commit(bar_empty(slot));  // the slot is free again once BOTH halves' MMAs have read it
+                };
+                if (l == 0) {
+#pragma unroll 1
+                    for (int g = 0; g < UPL; ++g) issue_unit(g, O::KCH0 / 2);
+                } else {
+#pragma unroll 1
+                    for (int g = 0; g < UPL; ++g) issue_unit(g, O::KCH / 2);
+                }
+                if (elected) {
+                    umma_commit(bar_acc);
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_turn_other) : "memory");
+                }
+            }
+            __syncwarp();
+            mbar_wait(bar_acc, acc_par);
+            acc_par ^= 1u;
+            tc_fence_after();
+            // ---- epilogue: this thread owns one cell (TMEM lane) and 32 of its 64 channels, 16 at a time
+            const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
+            const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
+            const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
+            const float4* hw = reinterpret_cast<const float4*>(net.head);
+            {
+                const int ch_half = hwarp >> 2;  // 0: channels 0-31, 1: channels 32-63
+                const int cell = (hwarp & 3) * 32 + lane;
+                const Cell c = decode_cell(cell, CELLS);
+                const uint32_t tlane = tmem + ((uint32_t)((hwarp & 3) * 32) << 16);
+                const uint32_t tsrc = tlane + (use_s ? SET : 0u);
+                const uint32_t tskip = tlane + SET;
+                float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c0 = ch_half * 32 + q * 16;  // first channel of this piece
+                    uint32_t v[16], v2[16];
+                    tmem_ld16_nowait(tsrc + c0, v);
+                    tmem_ld16_nowait(tsrc + 64 + c0, v2);
+                    tmem_wait_ld();
+                    float o[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!use_s) b = __ldg(bias_l + c0 / 4 + i);
+                        o[4 * i + 0] = fmaxf(fmaf(__uint_as_float(v2[4 * i + 0]), kX3InvScale, __uint_as_float(v[4 * i + 0])) + b.x, 0.f);
+                        o[4 * i + 1] = fmaxf(fmaf(__uint_as_float(v2[4 * i + 1]), kX3InvScale, __uint_as_float(v[4 * i + 1])) + b.y, 0.f);
+                        o[4 * i + 2] = fmaxf(fmaf(__uint_as_float(v2[4 * i + 2]), kX3InvScale, __uint_as_float(v[4 * i + 2])) + b.z, 0.f);
+                        o[4 * i + 3] = fmaxf(fmaf(__uint_as_float(v2[4 * i + 3]), kX3InvScale, __uint_as_float(v[4 * i + 3])) + b.w, 0.f);
+                    }
+                    if (!last && c.real) store_channels_x3_16(s_act, A2, R, kLead + cell, c0, o);
+                    if (preload) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = __ldg(bias_n + c0 / 4 + i);
+                            v[4 * i + 0] = __float_as_uint(o[4 * i + 0] + b.x);
+                            v[4 * i + 1] = __float_as_uint(o[4 * i + 1] + b.y);
+                            v[4 * i + 2] = __float_as_uint(o[4 * i + 2] + b.z);
+                            v[4 * i + 3] = __float_as_uint(o[4 * i + 3] + b.w);
+                        }
+                        tmem_st16(tskip + c0, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v2[i] = 0u;  // the D2 half of the preloaded accumulator starts from zero
+                        tmem_st16(tskip + 64 + c0, v2);
+                    }
+                    if (last) {  // 1x1 convolutions of both heads (net.rs: policy_conv 64 -> 2, vh_conv 64 -> 1), this thread's channels
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 w0 = __ldg(hw + (kHP0 / 4) + c0 / 4 + i), w1 = __ldg(hw + (kHP1 / 4) + c0 / 4 + i),
+                                         w2 = __ldg(hw + (kHV / 4) + c0 / 4 + i);
+                            hp0 = fmaf(o[4 * i + 0], w0.x, fmaf(o[4 * i + 1], w0.y, fmaf(o[4 * i + 2], w0.z, fmaf(o[4 * i + 3], w0.w, hp0))));
+                            hp1 = fmaf(o[4 * i + 0], w1.x, fmaf(o[4 * i + 1], w1.y, fmaf(o[4 * i + 2], w1.z, fmaf(o[4 * i + 3], w1.w, hp1))));
+                            hv = fmaf(o[4 * i + 0], w2.x, fmaf(o[4 * i + 1], w2.y, fmaf(o[4 * i + 2], w2.z, fmaf(o[4 * i + 3], w2.w, hv))));
+                        }
+                    }
+                }
+                if (last && c.real) {  // partial sums over this thread's 32 channels; the heads add the two halves, the bias and the ReLU
+                    float* hb = s_head + (ch_half * NB + c.board) * 75;
+                    hb[c.pos] = hp0;
+                    hb[25 + c.pos] = hp1;
+                    hb[50 + c.pos] = hv;
+                }
+            }
+            if (preload) tmem_wait_st();
+            fence_proxy_async();
+            q0 += (uint32_t)UPL;
+        }
+        // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
+        named_bar_sync(bar_id, 256);
+        for (int b = hwarp; b < NB; b += 8) {
+            const int64_t gb = board0 + b;
+            if (gb >= n) continue;
+            const float *h0p = s_head + b * 75, *h1p = s_head + (NB + b) * 75;
+            const float bp0 = __ldg(net.head + kHB + 0), bp1 = __ldg(net.head + kHB + 1), bv = __ldg(net.head + kHB + 2);
+            const bool two = lane + 32 < 50;
+            float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+#pragma unroll 10
+            for (int i = 0; i < 50; ++i) {
+                const float x = fmaxf(h0p[i] + h1p[i] + (i < 25 ? bp0 : bp1), 0.f);
+                l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
+                if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+            }
+            const float m = warp_max(two ? fmaxf(l0, l1) : l0);
+            const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
+            const float s = warp_sum(e0 + e1);
+            policy[gb * 50 + lane] = e0 / s;
+            if (two) policy[gb * 50 + 32 + lane] = e1 / s;
+            float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+#pragma unroll 5
+            for (int i = 0; i < 25; ++i) {
+                const float x = fmaxf(h0p[50 + i] + h1p[50 + i] + bv, 0.f);
+                h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
+                h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+            }
+            float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+            acc = warp_sum(acc);
+            if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+        }
+    }
+    tc_fence_before();
+    named_bar_sync(3, 512);  // both halves are done with TMEM
+    if (warp == 0) tmem_dealloc(*s_tmem, 512);
+}
+
 // ---- version 3: three CTAs per SM ---------------------------------------------------------------------------------------------
 // The phase timers of version 1 show ~4.2 k cycles per layer and CTA with no MMA in flight against 4.8 k of MMA issue, and TMEM (two
 // accumulators + two parked residuals = 256 columns per CTA) is what limits an SM to two CTAs. Here the residual lives in an
@@ -1263,6 +1565,21 @@ static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, flo
     return cudaGetLastError();
 }
 
+static cudaError_t launch_net_v2x(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
+    using G = Geo2X;
+    static bool attr[64] = {};  // the opt-in is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(k_net_forward2x, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+    const int64_t pairs = ((count + G::NB - 1) / G::NB + 1) / 2;
+    k_net_forward2x<<<(unsigned)(pairs < sms ? pairs : sms), G::THREADS, G::SMEM, c->stream>>>(planes, policy, value, count, nd);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_net_v3(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
     using G = Geo3;
     static bool attr[64] = {};
@@ -1296,7 +1613,13 @@ cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ns.x3) return launch_net_variant<2, true, true>(c, planes, policy, value, nd, sms, count);  // ONB_NET_F32: split operands, f32-faithful
+    if (ns.x3) {  // ONB_NET_F32: split operands, f32-faithful: the one-CTA-per-SM kernel (0.745 ms per 16 384 positions). Exploration knob
+                  // ONB_NET_X3_HALVES=1: two halves of 3 boards that share the weight stream and take turns issuing (0.794 ms: the overlap
+                  // of one half's epilogue with the other's MMAs does not pay for 6 instead of 7 boards per weight pass and 108 of 128 rows)
+        const char* halves = getenv("ONB_NET_X3_HALVES");
+        if (halves && halves[0] == '1') return launch_net_v2x(c, planes, policy, value, nd, sms, count);
+        return launch_net_variant<2, true, true>(c, planes, policy, value, nd, sms, count);
+    }
     const char* v3 = getenv("ONB_NET_V3");  // three CTAs per SM, residual in an L2-resident scratch (f16 operands only)
     if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms, count);
     const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)
