@@ -505,12 +505,24 @@ int32_t onb_mcts_run(onb_ctx* ctx, int32_t evaluator, uint32_t sims) {
         return fail(c, ONB_E_INVALID, "onb_mcts_run: unknown evaluator %d", evaluator);
     if (c->sims_done + sims > c->cfg.mcts_max_sims) return fail(c, ONB_E_INVALID, "onb_mcts_run: more simulations than mcts_max_sims");
     if (evaluator == ONB_EVAL_NET) {
-        // the network sits between select and expand: three launches per simulation round, all on the context's stream
+        // the network sits between select and expand: three launches per simulation round, all on the context's stream.
+        // ONB_MCTS_STEP_FUSION=1 (exploration knob): expand_backup(s) and select(s + 1) as ONE launch (k_mcts_step_g) -- measured SLOWER
+        // on B200 (config 5, f16 network: 304.8 vs 293.9 ms per ply): the fused kernel carries both halves' shared tables (36.6 KB, one
+        // CTA fewer per SM) and a block barrier between them, which costs more than the saved launch boundary
         if (!c->net[c->net_cur].loaded) return fail(c, ONB_E_STATE, "onb_mcts_run: no network loaded (onb_net_load)");
+        const char* fuse_env = getenv("ONB_MCTS_STEP_FUSION");
+        const bool fuse = fuse_env && fuse_env[0] == '1';
+        if (sims > 0) ONB_CUDA(c, launch_mcts_select(c));
         for (uint32_t s = 0; s < sims; ++s) {
-            ONB_CUDA(c, launch_mcts_select(c));
             ONB_CUDA(c, launch_net_forward(c, c->d_leaf_planes, c->d_policy, c->d_value, trees(c)));
-            ONB_CUDA(c, launch_mcts_expand_backup(c));
+            if (s + 1 == sims) {
+                ONB_CUDA(c, launch_mcts_expand_backup(c));
+            } else if (fuse) {
+                ONB_CUDA(c, launch_mcts_step(c));
+            } else {
+                ONB_CUDA(c, launch_mcts_expand_backup(c));
+                ONB_CUDA(c, launch_mcts_select(c));
+            }
         }
         c->sims_done += sims;
         return ONB_OK;

@@ -112,6 +112,7 @@ cudaError_t launch_selftest_div(Ctx* c, unsigned long long* d_mismatches);
 cudaError_t launch_mcts_begin(Ctx* c);
 cudaError_t launch_mcts_select(Ctx* c);
 cudaError_t launch_mcts_expand_backup(Ctx* c);
+cudaError_t launch_mcts_step(Ctx* c);  // expand_backup of this simulation + select of the next one, one launch
 cudaError_t launch_mcts_eval(Ctx* c, int evaluator);
 cudaError_t launch_mcts_run(Ctx* c, int evaluator, uint32_t sims);
 cudaError_t launch_uct_run(Ctx* c, float exploration_c, uint32_t min_node_visits, uint32_t sims);

@@ -1634,3 +1634,25 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
             outs.append((ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,))))
         assert np.abs(outs[-1][0] - want_p).max() <= 1e-5 and np.abs(outs[-1][1] - want_v).max() <= 1e-5
     assert np.abs(outs[0][0] - outs[1][0]).max() <= 1e-6 and np.abs(outs[0][1] - outs[1][1]).max() <= 2e-6   # a few f32 ulps of a probability
+
+
+@pytest.mark.gpu
+def test_step_fusion_knob_builds_the_same_trees(onb, monkeypatch):
+    """ONB_MCTS_STEP_FUSION=1 (expand_backup(s) + select(s+1) in one launch, an exploration knob) must not change a single tree: eval
+    and train mode, network evaluator, against the default three-launch rounds."""
+    from test_net_cpu import lively_model
+    n, sims = 96, 40
+    roots = _cfg4_roots(n, 9)
+    with onb.Context(n, seed=3, mcts_max_sims=sims, planes=False) as ctx:
+        ctx.net_load(lively_model(1, seed=6))
+        got = {}
+        for noise in (False, True):
+            ctx.mcts_set_noise(noise, 0.25, 0.03, 11)
+            for fuse in ("0", "1"):
+                monkeypatch.setenv("ONB_MCTS_STEP_FUSION", fuse)
+                ctx.set_states(roots)
+                res = ctx.search(2.0, sims, evaluator=onb.EVAL_NET)
+                got[(noise, fuse)] = (res["child_visits"].copy(), res["root_q"].copy(), ctx.mcts_tree_info()[0].copy())
+            for a, b in zip(got[(noise, "0")], got[(noise, "1")]):
+                assert np.array_equal(a, b)
+        assert not np.array_equal(got[(False, "0")][0], got[(True, "0")][0])
