@@ -1616,24 +1616,29 @@ def test_cuda_graph_cache_follows_the_noise_setting(onb):
 
 @pytest.mark.gpu
 def test_network_split_mode_variants_agree(onb, monkeypatch):
-    """The two-halves-per-CTA build of the f32-faithful network (ONB_NET_X3_HALVES=1, an exploration knob) computes the same products
-    in the same order per accumulator as the shipped one-CTA kernel: outputs agree to the last bits (the heads add the two channel
-    halves in a different order) and both meet the 1e-5 tolerance against the oracle."""
+    """The builds of the f32-faithful network compute the same products in the same order per accumulator: the warp-specialised
+    pipelined kernel (ONB_NET_X3_PIPE) is bit-identical to the plain one-CTA kernel, the two-halves build (ONB_NET_X3_HALVES=1, an
+    exploration knob) agrees to a few ulps (its heads add the two channel halves in a different order); all meet the 1e-5 tolerance."""
     from test_net_cpu import lively_model
-    model = lively_model(3, seed=9)
-    n = 100  # not a multiple of 3, 6 or 7
-    planes = O.encode(_positions(n, 5)).reshape(n, 21, 5, 5)
-    want_p, want_v = O.net_forward(model.state_dict(), planes)
-    outs = []
-    for halves in ("0", "1"):
-        monkeypatch.setenv("ONB_NET_X3_HALVES", halves)
-        with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
-            ctx.net_load(model, precision="f32")
-            ctx.write(onb.BUF_LEAF_PLANES, planes)
-            ctx.net_forward(onb.BUF_LEAF_PLANES)
-            outs.append((ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,))))
-        assert np.abs(outs[-1][0] - want_p).max() <= 1e-5 and np.abs(outs[-1][1] - want_v).max() <= 1e-5
-    assert np.abs(outs[0][0] - outs[1][0]).max() <= 1e-6 and np.abs(outs[0][1] - outs[1][1]).max() <= 2e-6   # a few f32 ulps of a probability
+    for blocks, n in ((3, 100), (0, 33), (5, 250)):   # n not a multiple of 3, 6 or 7
+        model = lively_model(blocks, seed=9)
+        planes = O.encode(_positions(n, 5)).reshape(n, 21, 5, 5)
+        want_p, want_v = O.net_forward(model.state_dict(), planes)
+        outs = {}
+        for name, env in (("plain", {"ONB_NET_X3_PIPE": "0"}), ("pipe", {"ONB_NET_X3_PIPE": "1"}), ("halves", {"ONB_NET_X3_HALVES": "1"})):
+            for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
+                ctx.net_load(model, precision="f32")
+                ctx.write(onb.BUF_LEAF_PLANES, planes)
+                ctx.net_forward(onb.BUF_LEAF_PLANES)
+                ctx.net_forward(onb.BUF_LEAF_PLANES)   # a second pass over the same buffers: barrier phases carry over correctly
+                outs[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
+            assert np.abs(outs[name][0] - want_p).max() <= 1e-5 and np.abs(outs[name][1] - want_v).max() <= 1e-5, (name, blocks)
+        assert np.array_equal(outs["plain"][0], outs["pipe"][0]) and np.array_equal(outs["plain"][1], outs["pipe"][1]), blocks
+        assert np.abs(outs["plain"][0] - outs["halves"][0]).max() <= 1e-6 and np.abs(outs["plain"][1] - outs["halves"][1]).max() <= 2e-6
 
 
 @pytest.mark.gpu
