@@ -591,6 +591,43 @@ __global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
     if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
 }
 
+// 16-column TMEM access and split-operand stores shared by the many-warp epilogues below
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// 16 consecutive channels [c0, c0 + 16) of one cell as split operand chunks (two 16-byte chunks in each activation matrix)
+__device__ __forceinline__ void store_channels_x3_16(uint32_t s_act, uint32_t a2_off, int R, int row, int c0, const float (&o)[16]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float x0 = fminf(o[8 * i + 2 * q], 65504.f), x1 = fminf(o[8 * i + 2 * q + 1], 65504.f);
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
+            hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const uint32_t addr = act_addr(s_act, R, row, c0 / 8 + i);
+        st_shared_v4(addr, hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(addr + a2_off, lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 // ---- the split-operand (f32-faithful) network, warp-specialised and software-pipelined over the two accumulators ------------------
 // k_net_forward<2, f16, X3> issues a layer's MMAs, waits, runs the epilogue with the tensor pipe idle, synchronises the CTA and
 // starts over: 63 % of its time is MMA issue (at the operand-fetch / tensor floor), the rest is exposed epilogue, barriers and
@@ -601,7 +638,10 @@ __global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
 //   warp 9           weight producer (one lane)
 // all connected by mbarriers (no CTA-wide barrier inside a board group). While accumulator 1's MMAs run, accumulator 0's epilogue
 // runs; accumulator 0's MMAs of the next layer start as soon as its own rows and the first 7 rows of accumulator 1 (the halo its
-// shifted windows reach into) are written, i.e. after warp 4's part of the epilogue, while warps 5-7 are still busy. In-place
+// shifted windows reach into) are written, i.e. after warp 4's part of the epilogue, while warps 5-7 are still busy. (Measured with
+// -DONB_X3P_PROFILE, 16 board groups per CTA: MMA issue 971 k cycles, waiting for accumulator 0's rows 350 k, for accumulator 1's
+// 9 k, for weights 46 k. A build with SIXTEEN epilogue warps -- every cell's channels split over two warps, half the instructions on
+// the critical warps -- ran 0.730 ms against 0.724 ms and was dropped: the wait is not the epilogue's instruction count.) In-place
 // activation hazards: rows 121..127 (accumulator 0's last cells) are still read by accumulator 1's MMAs of the same layer, so their
 // owners wait for accumulator 1's commit before storing. Same products, same accumulation order, same results as k_net_forward<2,f16,X3>.
 struct GeoX3P {
@@ -675,6 +715,12 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         // ---- MMA issue (the whole warp runs the loop so that descriptors stay in uniform registers; one elected lane issues)
         const bool elected = elect_one();
         uint32_t q0 = 0, stage = 0;  // stage = number of "rows ready" rounds consumed so far (input stage + epilogues)
+#ifdef ONB_X3P_PROFILE
+        long long t_rows0 = 0, t_rows1 = 0, t_full = 0, t_issue = 0, t_mark = clock64();
+#define XP(var) do { const long long now__ = clock64(); var += now__ - t_mark; t_mark = now__; } while (0)
+#else
+#define XP(var) do { } while (0)
+#endif
         for (int64_t gi = 0; gi < my_groups; ++gi) {
             for (int l = 0; l < L; ++l) {
                 const bool use_s = l >= 2 && (l & 1) == 0;
@@ -684,17 +730,22 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 for (int a = 0; a < NACC; ++a) {
                     // accumulator 0 needs its own rows and the first rows of accumulator 1 (its windows reach 7 rows further);
                     // accumulator 1 needs the rest as well
+                    XP(t_issue);
                     if (a == 0) {
                         mbar_wait(bar_rows(0), stage & 1u);
                         mbar_wait(bar_rows(1), stage & 1u);
+                        XP(t_rows0);
                     } else {
                         mbar_wait(bar_rows(2), stage & 1u);
+                        XP(t_rows1);
                     }
                     tc_fence_after();
 #pragma unroll 1
                     for (int g = 0; g < UPL; ++g) {
                         const uint32_t u = q0 + g, slot = u % NSLOT, use = u / NSLOT;
+                        XP(t_issue);
                         mbar_wait(bar_full(slot), use & 1u);
+                        XP(t_full);
                         tc_fence_after();
 #pragma unroll
                         for (int tt = 0; tt < TPS; ++tt) {
@@ -712,6 +763,12 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 stage += 1;
             }
         }
+#ifdef ONB_X3P_PROFILE
+        XP(t_issue);
+        if (blockIdx.x == 3 && lane == 0)
+            printf("x3p MMA warp, %lld groups: issue %lld, waiting rows for acc0 %lld, for acc1 %lld, waiting weights %lld\n", (long long)my_groups, t_issue,
+                   t_rows0, t_rows1, t_full);
+#endif
     } else {
         // ---- epilogue warps: group a = warp >> 2 owns accumulator a; this thread owns one cell (TMEM lane) and its 64 channels
         const int a = warp >> 2;
@@ -721,6 +778,12 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         const bool halo = a == 0 && cell >= 128 - 7;  // rows accumulator 1's MMAs of the SAME layer still read
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t acc_par = 0;  // parity of the layer counter (both accumulator barriers complete once per layer)
+#ifdef ONB_X3P_PROFILE
+        long long e_wait = 0, e_work = 0, e_halo = 0, e_mark = clock64();
+#define EP(var) do { const long long now__ = clock64(); var += now__ - e_mark; e_mark = now__; } while (0)
+#else
+#define EP(var) do { } while (0)
+#endif
         for (int64_t gi = 0; gi < my_groups; ++gi) {
             const int64_t board0 = ((int64_t)blockIdx.x + gi * gridDim.x) * NB;
             // ---- input planes -> channel chunks of both activation matrices (create_tensor_from_state layout [21][5][5]).
@@ -738,7 +801,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
             for (int l = 0; l < L; ++l) {
                 const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
                 const bool last = l == L - 1;
+                EP(e_work);
                 mbar_wait(bar_acc(a), acc_par);
+                EP(e_wait);
                 tc_fence_after();
                 const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
                 const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
@@ -770,7 +835,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     }
                     if (!last && c.real) {
                         // accumulator 1's MMAs of this layer read rows 121..127 through their negatively shifted windows: wait for them
-                        if (halo && h == 0) mbar_wait(bar_acc(1), acc_par);
+                        if (halo && h == 0) { EP(e_work); mbar_wait(bar_acc(1), acc_par); EP(e_halo); }
                         store_channels_x3(s_act, A2, R, kLead + cell, h * 32, o);
                     }
                     if (preload) {
@@ -847,6 +912,11 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
             }
             named_bar_sync(1, 256);  // s_head is free again before anybody's next last-layer epilogue
         }
+#ifdef ONB_X3P_PROFILE
+        EP(e_work);
+        if (blockIdx.x == 3 && (tid == 0 || tid == 127 || tid == 128 || tid == 160))
+            printf("x3p epilogue tid %d: waiting for the accumulator %lld, halo wait %lld, work (input, epilogue, heads) %lld\n", tid, e_wait, e_halo, e_work);
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -1147,42 +1217,6 @@ struct Geo2X {
     static_assert(ACT_BYTES % 1024 == 0 && OFF_RING % 1024 == 0, "swizzle period");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
-        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
-}
-// 16 consecutive channels [c0, c0 + 16) of one cell as split operand chunks (two 16-byte chunks in each activation matrix)
-__device__ __forceinline__ void store_channels_x3_16(uint32_t s_act, uint32_t a2_off, int R, int row, int c0, const float (&o)[16]) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float x0 = fminf(o[8 * i + 2 * q], 65504.f), x1 = fminf(o[8 * i + 2 * q + 1], 65504.f);
-            const __half2 h = __floats2half2_rn(x0, x1);
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
-            hi[q] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[q] = *reinterpret_cast<const uint32_t*>(&l);
-        }
-        const uint32_t addr = act_addr(s_act, R, row, c0 / 8 + i);
-        st_shared_v4(addr, hi[0], hi[1], hi[2], hi[3]);
-        st_shared_v4(addr + a2_off, lo[0], lo[1], lo[2], lo[3]);
-    }
-}
-
 __global__ void __launch_bounds__(Geo2X::THREADS, 1)
     k_net_forward2x(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
     using G = Geo2X;

@@ -1638,7 +1638,8 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
                 outs[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
             assert np.abs(outs[name][0] - want_p).max() <= 1e-5 and np.abs(outs[name][1] - want_v).max() <= 1e-5, (name, blocks)
         assert np.array_equal(outs["plain"][0], outs["pipe"][0]) and np.array_equal(outs["plain"][1], outs["pipe"][1]), blocks
-        assert np.abs(outs["plain"][0] - outs["halves"][0]).max() <= 1e-6 and np.abs(outs["plain"][1] - outs["halves"][1]).max() <= 2e-6
+        for other in ("halves",):   # its heads add the two channel halves' partial sums: a few ulps
+            assert np.abs(outs["plain"][0] - outs[other][0]).max() <= 1e-6 and np.abs(outs["plain"][1] - outs[other][1]).max() <= 2e-6, other
 
 
 @pytest.mark.gpu
