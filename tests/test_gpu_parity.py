@@ -1662,3 +1662,38 @@ def test_step_fusion_knob_builds_the_same_trees(onb, monkeypatch):
             for a, b in zip(got[(noise, "0")], got[(noise, "1")]):
                 assert np.array_equal(a, b)
         assert not np.array_equal(got[(False, "0")][0], got[(True, "0")][0])
+
+
+@pytest.mark.gpu
+def test_actor_and_comm_error_paths(onb):
+    """onb_actor_* / onb_comm_* argument checking: nothing hangs, every misuse is an error code with a message."""
+    import ctypes as C
+    from onitama_alphazero_b200.engine import Actor
+    L = onb._lib
+    with onb.Context(256, seed=1, planes=False) as ctx:
+        ctx.reset()
+        for bad in (0, 65):
+            with pytest.raises(onb.OnbError) as e:
+                Actor(ctx, n_sub=bad)
+            assert e.value.code == -1
+        with pytest.raises(onb.OnbError) as e:
+            Actor(ctx, host_flags=64)
+        assert e.value.code == -1
+        with pytest.raises(onb.OnbError) as e:
+            Actor(ctx, out_flags=onb.OUT_PLANES)            # the context has no plane buffer
+        assert e.value.code == -4
+        with Actor(ctx, n_sub=2, host_flags=L.HOST_MASKS) as act:
+            with pytest.raises(onb.OnbError):
+                act.submit(5, None)
+            with pytest.raises(onb.OnbError):
+                act.wait(-1)
+            assert act.views[0]["done"] is None and act.views[0]["masks"].shape == (128, 2)
+            act.wait(0)                                      # nothing in flight: returns at once
+            act.join()                                       # nothing submitted: no-op
+            v = L.ActorView()
+            assert ctx._lib.onb_actor_get_view(act._h, 7, C.byref(v)) == -1
+        # the communicator: bad ranks / missing id
+        h = C.c_void_p()
+        assert ctx._lib.onb_comm_create(ctx._h, 2, 2, None, None, C.byref(h)) == -1
+        assert ctx._lib.onb_comm_create(ctx._h, 0, 0, None, None, C.byref(h)) == -1
+        assert ctx._lib.onb_comm_unique_id(None) == -1
