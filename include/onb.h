@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ONB_VERSION 100
+#define ONB_VERSION 200 /* 200: round 2 (onb_actor_*, onb_comm_*, onb_fight_stats, onb_fight_result.moves_chosen, ONB_NET_F32) */
 
 #if defined(__GNUC__)
 #define ONB_API __attribute__((visibility("default")))

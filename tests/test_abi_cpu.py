@@ -32,7 +32,7 @@ def test_header_symbols_all_exported(lib):
         assert hasattr(lib, name), "libonb.so does not export %s" % name
     # the Python binding table covers exactly the header
     assert declared == set(_lib.SYMBOLS)
-    assert lib.onb_version() == 100
+    assert lib.onb_version() == 200
 
 
 def test_attack_table_matches_reference_hex(lib):
