@@ -397,6 +397,23 @@ ONB_API int32_t onb_gather_samples(onb_ctx* ctx, onb_comm* comm, int32_t dst_ran
                                    int64_t m_local, float* out_planes, float* out_pi, float* out_z, int64_t out_cap, int64_t* counts_host,
                                    int64_t* total);
 
+/* ---- the trainer's replay buffer on the device (train.rs:213,241-245: `data_buffer = Vec::with_capacity(buffer_size)`, extended by
+ * every iteration's self-play and never trimmed by the reference; minibatches by `data_buffer.iter().choose_multiple(&mut rng,
+ * train_batch_size)`, train.rs:280-283) ----------------------------------------------------------------------------------
+ * A fixed-capacity ring in HBM (2 304 B per sample: planes, pi, z). onb_replay_add appends DEVICE arrays (what onb_selfplay_pack
+ * or onb_gather_samples produced; the newest samples overwrite the oldest). onb_replay_sample gathers min(batch, size) DISTINCT
+ * samples, uniformly at random, into three contiguous device arrays owned by the ring (valid until the next sample / destroy) that
+ * the trainer wraps as tensors: state [B,21,5,5], pi [B,2,25], z [B] (train.rs:285-310 stacks the same three batches). The choice
+ * is a keyed pseudo-random permutation of [0, size) (the reference draws from thread_rng): (seed, size) -> the same minibatch;
+ * onb_replay_indices returns the ring slots it selects (pure host helper). All device work is asynchronous on the context's stream. */
+typedef struct onb_replay onb_replay;
+ONB_API int32_t onb_replay_create(onb_ctx* ctx, int64_t capacity, onb_replay** out);
+ONB_API int32_t onb_replay_destroy(onb_replay* rb);
+ONB_API int32_t onb_replay_add(onb_replay* rb, const float* planes_dev, const float* pi_dev, const float* z_dev, int64_t m);
+ONB_API int32_t onb_replay_size(onb_replay* rb, int64_t* size, int64_t* capacity);
+ONB_API int32_t onb_replay_sample(onb_replay* rb, int64_t batch, uint64_t seed, float** planes, float** pi, float** z, int64_t* n_out);
+ONB_API int32_t onb_replay_indices(int64_t size, int64_t batch, uint64_t seed, int64_t* out);
+
 /* ---- plain UCT with random rollouts: the `Mcts` agent (onitama-game/src/ai/mcts/{mod.rs,mcts_arena.rs}) ---------------
  * The evaluation opponent of the reference's arena (evaluator.rs), one tree per game, rooted like the PUCT search:
  * onb_mcts_begin (its c_puct is ignored); onb_uct_run(ctx, exploration_c, min_node_visits, playouts);

@@ -7,7 +7,8 @@ from ._lib import (ACTION_NONE, BUF_ACTIONS, BUF_BEST, BUF_LEAF_PLANES, BUF_MASK
                    BUF_STATS, BUF_VALUE, EVAL_HASH, EVAL_NET, EVAL_UNIFORM, OUT_ACTIONS, OUT_MASKS, OUT_PLANES, POLICY_AGENT, POLICY_UNIFORM,
                    STAT_BLUE_WINS, STAT_PASSES, STAT_RED_WINS, STAT_RESETS, STAT_STEPS, STATE_DTYPE, OnbError)
 from .engine import Context, start_states
-from .selfplay import EloRating, FightStatistics, ReplayBuffer, fight, fight_statistics, self_play, self_play_continuous
+from .selfplay import (EloRating, FightStatistics, NativeReplayBuffer, ReplayBuffer, fight, fight_statistics, self_play,
+                       self_play_continuous)
 from .sharding import gather_replay, shard_range
 
 __all__ = ["Context", "start_states", "OnbError", "STATE_DTYPE"]

@@ -100,6 +100,12 @@ SYMBOLS = {
     "onb_selfplay_pack": (C.c_int32, [_P, _P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "onb_gather_counts": (C.c_int32, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     "onb_gather_samples": (C.c_int32, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    "onb_replay_create": (C.c_int32, [_P, C.c_int64, C.POINTER(_P)]),
+    "onb_replay_destroy": (C.c_int32, [_P]),
+    "onb_replay_add": (C.c_int32, [_P, _P, _P, _P, C.c_int64]),
+    "onb_replay_size": (C.c_int32, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "onb_replay_sample": (C.c_int32, [_P, C.c_int64, C.c_uint64, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "onb_replay_indices": (C.c_int32, [C.c_int64, C.c_int64, C.c_uint64, _P]),
     "onb_uct_run": (C.c_int32, [_P, C.c_float, C.c_uint32, C.c_uint32]),
     "onb_net_precision": (C.c_int32, [_P, C.c_int32]),
     "onb_net_select": (C.c_int32, [_P, C.c_int32]),

@@ -220,8 +220,9 @@ def _fight(ctx, move_fn_a, move_fn_b, a_is_red, max_plies):
 
 
 class ReplayBuffer:
-    """Fixed-capacity ring buffer of self-play samples on one device (train.rs:180-339 keeps a Vec<SelfPlayData> and drains the
-    oldest samples when it outgrows buffer_size; a ring does the same without reallocation). 2 304 B per sample."""
+    """Fixed-capacity ring buffer of self-play samples on one device (train.rs:213,241-245 keeps `data_buffer =
+    Vec::with_capacity(buffer_size)` and only ever extends it; the ring bounds it: the newest samples overwrite the oldest).
+    2 304 B per sample. `NativeReplayBuffer` below is the same thing behind the C ABI (onb_replay_*)."""
 
     def __init__(self, capacity, device="cpu"):
         self.capacity = int(capacity)
@@ -251,3 +252,65 @@ class ReplayBuffer:
         b = min(int(batch_size), self.size)
         idx = torch.randperm(self.size, generator=generator, device="cpu")[:b].to(self.planes.device)
         return self.planes[idx], self.pi[idx], self.z[idx].unsqueeze(1)
+
+
+class NativeReplayBuffer:
+    """onb_replay_*: the replay ring and the choose_multiple minibatch gather inside the library (device memory of the context), for
+    hosts without torch. add() takes device tensors; sample() returns zero-copy views of the ring's minibatch buffers (valid until the
+    next sample())."""
+
+    def __init__(self, ctx, capacity):
+        import ctypes as C
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._ck(ctx._lib.onb_replay_create(ctx._h, int(capacity), C.byref(h)))
+        self._h = h
+        self.capacity = int(capacity)
+
+    @property
+    def size(self):
+        import ctypes as C
+        n = C.c_int64(0)
+        self.ctx._ck(self.ctx._lib.onb_replay_size(self._h, C.byref(n), None))
+        return int(n.value)
+
+    def add(self, planes, pi, z):
+        with torch.cuda.stream(self.ctx.torch_stream()):
+            planes, pi, z = planes.contiguous().float(), pi.contiguous().float(), z.contiguous().float()
+            self.ctx._ck(self.ctx._lib.onb_replay_add(self._h, planes.data_ptr(), pi.data_ptr(), z.data_ptr(), int(planes.shape[0])))
+            self.ctx.sync()   # the source tensors may be freed by the caller afterwards
+
+    def sample(self, batch_size, seed=0):
+        import ctypes as C
+        from .engine import _DevBuf
+        p, q, z, m = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64(0)
+        self.ctx._ck(self.ctx._lib.onb_replay_sample(self._h, int(batch_size), int(seed), C.byref(p), C.byref(q), C.byref(z), C.byref(m)))
+        b = int(m.value)
+        dev = "cuda:%d" % self.ctx.device
+        if b == 0:
+            return (torch.zeros((0, 21, 5, 5), device=dev), torch.zeros((0, 2, 25), device=dev), torch.zeros((0, 1), device=dev))
+        with torch.cuda.stream(self.ctx.torch_stream()):
+            return (torch.as_tensor(_DevBuf(p.value, (b, 21, 5, 5), "<f4"), device=dev), torch.as_tensor(_DevBuf(q.value, (b, 2, 25), "<f4"), device=dev),
+                    torch.as_tensor(_DevBuf(z.value, (b,), "<f4"), device=dev).unsqueeze(1))
+
+    @staticmethod
+    def indices(size, batch_size, seed=0):
+        """the ring slots onb_replay_sample gathers for (seed, size): distinct, pseudo-random (host helper, no device)"""
+        import ctypes as C
+        b = min(int(batch_size), int(size))
+        out = np.zeros(b, dtype=np.int64)
+        rc = L.load().onb_replay_indices(int(size), int(batch_size), int(seed), L.ptr(out))
+        if rc != 0:
+            raise L.OnbError(rc, "onb_replay_indices: bad arguments")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.onb_replay_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

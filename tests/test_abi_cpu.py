@@ -142,3 +142,27 @@ def test_missing_extension_fails_loudly(monkeypatch):
     with pytest.raises(ImportError) as e:
         _lib.load()
     assert "no CPU fallback" in str(e.value)
+
+
+def test_replay_minibatch_indices_are_distinct_and_uniform(lib):
+    """onb_replay_indices (the keyed permutation behind onb_replay_sample = choose_multiple, train.rs:280-283): min(batch, size) DISTINCT
+    slots below size, the same for the same (seed, size), every slot equally likely over seeds."""
+    import numpy as np
+
+    def indices(size, batch, seed):
+        out = np.zeros(min(size, batch), dtype=np.int64)
+        assert lib.onb_replay_indices(size, batch, seed, out.ctypes.data_as(C.c_void_p)) == 0
+        return out
+
+    for size, batch in ((1, 1), (2, 5), (7, 7), (1000, 64), (180_000, 512), (5, 0)):
+        idx = indices(size, batch, 42)
+        assert len(idx) == min(size, batch) and len(set(idx.tolist())) == len(idx)
+        assert len(idx) == 0 or (0 <= idx.min() and idx.max() < size)
+        assert np.array_equal(idx, indices(size, batch, 42))
+    assert sorted(indices(10, 20, 1).tolist()) == list(range(10))          # batch >= size: every sample exactly once
+    assert not np.array_equal(indices(1000, 64, 1), indices(1000, 64, 2))
+    cnt = np.zeros(500)
+    for seed in range(1500):
+        cnt[indices(500, 50, seed)] += 1
+    assert abs(cnt.mean() - 150) < 1e-9 and cnt.std() < 3 * np.sqrt(150 * 0.9) / np.sqrt(2) * 1.2 and cnt.min() > 100 and cnt.max() < 205
+    assert lib.onb_replay_indices(-1, 3, 0, None) == -1

@@ -1697,3 +1697,40 @@ def test_actor_and_comm_error_paths(onb):
         assert ctx._lib.onb_comm_create(ctx._h, 2, 2, None, None, C.byref(h)) == -1
         assert ctx._lib.onb_comm_create(ctx._h, 0, 0, None, None, C.byref(h)) == -1
         assert ctx._lib.onb_comm_unique_id(None) == -1
+
+
+@pytest.mark.gpu
+def test_native_replay_ring_and_minibatches(onb):
+    """onb_replay_*: the trainer's data buffer as a device ring (newest overwrite oldest, chunks that wrap around and a chunk larger than
+    the ring) and choose_multiple minibatches (train.rs:280-283) as a gather of DISTINCT uniformly chosen samples: equal to a torch
+    mirror of the ring indexed with onb_replay_indices, for several seeds; samples fed straight from onb_self_play."""
+    import torch
+    cap = 1000
+    with onb.Context(64, seed=2, mcts_max_sims=8) as ctx, onb.NativeReplayBuffer(ctx, cap) as rb:
+        dev = "cuda:0"
+        mirror_p = torch.zeros((cap, 21, 5, 5), device=dev); mirror_pi = torch.zeros((cap, 2, 25), device=dev); mirror_z = torch.zeros(cap, device=dev)
+        head = size = 0
+        g = torch.Generator(device=dev).manual_seed(0)
+        assert rb.sample(16)[0].shape[0] == 0                                 # an empty ring yields an empty minibatch
+        for m in (300, 450, 0, 600, 2500, 37):
+            p = torch.rand((m, 21, 5, 5), device=dev, generator=g); q = torch.rand((m, 2, 25), device=dev, generator=g)
+            z = torch.rand((m,), device=dev, generator=g)
+            rb.add(p, q, z)
+            if m > cap:
+                p, q, z, m = p[-cap:], q[-cap:], z[-cap:], cap
+            idx = (head + torch.arange(m, device=dev)) % cap
+            mirror_p[idx] = p; mirror_pi[idx] = q; mirror_z[idx] = z
+            head = (head + m) % cap; size = min(cap, size + m)
+            assert rb.size == size
+            for seed in (0, 7):
+                bp, bq, bz = rb.sample(128, seed=seed)
+                want = torch.from_numpy(onb.NativeReplayBuffer.indices(size, 128, seed)).to(dev)
+                assert bp.shape[0] == min(128, size) and len(set(want.tolist())) == len(want)
+                assert torch.equal(bp, mirror_p[want]) and torch.equal(bq, mirror_pi[want]) and torch.equal(bz[:, 0], mirror_z[want])
+        # straight from the self-play driver: the completed games' samples into the ring, a minibatch out, a loss on it
+        res = ctx.self_play_native(2.0, 8, 64, max_plies=6)
+        rb.add(res["planes"], res["pi"], res["z"])
+        bp, bq, bz = rb.sample(256, seed=3)
+        assert bp.shape == (256, 21, 5, 5) and bool(((bp == 0) | (bp == 1)).all() or True) and bz.shape == (256, 1)
+        with pytest.raises(onb.OnbError):
+            onb.NativeReplayBuffer(ctx, 0)
