@@ -88,3 +88,5 @@ def test_reference_arm_under_torchrun_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] == "env_steps_per_sec"
+    # the arm runs the config it prints: all 1 048 576 games, one lockstep step of them per timed step
+    assert d["config"]["games_per_gpu"] == 1 << 20 and d["cpu_baseline"]["sample"].startswith("1048576 games x 1 lockstep step")
