@@ -923,6 +923,254 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
     if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
 }
 
+// ---- the f16 fast mode with the same role pipeline, TWO CTAs per SM -------------------------------------------------------------
+// k_net_forward<2, f16> already overlaps one CTA's epilogue with the other CTA's MMAs, but each CTA still serialises issue ->
+// wait -> epilogue -> CTA barrier, and the tensor pipe is busy 46 % of the time (2 x 4 032 MMAs x 33.5 cycles of 581 k). Here
+// each of the two co-resident CTAs is the warp-specialised pipeline of k_net_forward_x3p (8 epilogue warps, one MMA warp, one
+// weight warp, mbarriers only), so an SM always has two MMA streams whose bubbles (the halo dependency between accumulators) fall
+// into each other's issue phases. The epilogue works 16 channels at a time to fit 96 registers (2 x 320 threads per SM).
+// Same products, accumulation order and head sums as k_net_forward<2, f16>: bit-identical results.
+__device__ __forceinline__ void store_channels_f16_16(uint32_t s_act, int R, int row, int c0, const float (&o)[16]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        st_shared_v4(act_addr(s_act, R, row, c0 / 8 + i), to_f16x2(o[8 * i + 0], o[8 * i + 1]), to_f16x2(o[8 * i + 2], o[8 * i + 3]),
+                     to_f16x2(o[8 * i + 4], o[8 * i + 5]), to_f16x2(o[8 * i + 6], o[8 * i + 7]));
+}
+__global__ void __launch_bounds__(GeoX3P::THREADS, 2)
+    k_net_forward_f16p(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
+    using G = Geo<2, true, false>;
+    using O = Op<true>;
+    constexpr int NACC = 2;
+    constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = G::NSLOT, TPS = G::TPS, UPL = G::UPL;
+    constexpr uint32_t ACC = 64u, SET = (uint32_t)G::SET_COLS;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t s_act = smem_u32(smem), s_ring = s_act + G::OFF_RING, s_bar = s_act + G::OFF_BAR;
+    float* s_head = reinterpret_cast<float*>(smem + G::OFF_HEAD);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + G::OFF_BAR + GeoX3P::N_BARS * 8);
+    static_assert(2 * (G::OFF_BAR + GeoX3P::N_BARS * 8 + 16 + 1024) <= 227 * 1024, "two CTAs per SM");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = 1 + 2 * net.n_blocks;
+    const int64_t n_groups = (n + NB - 1) / NB;
+    if ((int64_t)blockIdx.x >= n_groups) return;  // whole CTA, before any allocation
+    const int64_t my_groups = (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t total_units = (uint32_t)my_groups * (uint32_t)(UPL * L);
+    auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
+    auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
+    auto bar_acc = [&](uint32_t a) { return s_bar + (2 * NSLOT + a) * 8u; };
+    auto bar_rows = [&](uint32_t k) { return s_bar + (2 * NSLOT + 2 + k) * 8u; };  // 0: group 0, 1: warp 4, 2: warps 5-7
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_acc(0), 1);
+        mbar_init(bar_acc(1), 1);
+        mbar_init(bar_rows(0), 128);
+        mbar_init(bar_rows(1), 32);
+        mbar_init(bar_rows(2), 96);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
+    for (int i = tid; i < G::NMAT * G::ACT_BYTES / 16; i += GeoX3P::THREADS) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    auto arrive = [&](uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
+
+    if (warp == 9) {
+        // ---- weight producer: the ring is filled strictly in tap order, as far ahead as it has free slots
+        if (lane == 0) {
+            for (uint32_t u = 0; u < total_units; ++u) {
+                const uint32_t slot = u % NSLOT, use = u / NSLOT;
+                if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
+                const uint32_t ul = u % (uint32_t)(UPL * L), layer = ul / UPL, tap = (ul - layer * UPL) * TPS;
+                const uint8_t* src = net.wconv + (size_t)G::NMAT * (layer == 0 ? (size_t)tap * O::TAP_BYTES0
+                                                                              : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
+                const uint32_t bytes = (uint32_t)(TPS * G::NMAT) * (layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES);
+                mbar_expect_tx(bar_full(slot), bytes);
+                bulk_g2s(s_ring + slot * (uint32_t)G::SLOT_BYTES, src, bytes, bar_full(slot));
+            }
+        }
+    } else if (warp == 8) {
+        // ---- MMA issue (the whole warp runs the loop so that descriptors stay in uniform registers; one elected lane issues)
+        const bool elected = elect_one();
+        uint32_t q0 = 0, stage = 0;  // stage = number of "rows ready" rounds consumed so far (input stage + epilogues)
+        for (int64_t gi = 0; gi < my_groups; ++gi) {
+            for (int l = 0; l < L; ++l) {
+                const bool use_s = l >= 2 && (l & 1) == 0;
+                const uint32_t dcol = tmem + (use_s ? SET : 0u);
+                const int ksteps = l == 0 ? O::KCH0 / 2 : O::KCH / 2;
+#pragma unroll 1
+                for (int a = 0; a < NACC; ++a) {
+                    // accumulator 0 needs its own rows and the first rows of accumulator 1 (its windows reach 7 rows further);
+                    // accumulator 1 needs the rest as well
+                    if (a == 0) {
+                        mbar_wait(bar_rows(0), stage & 1u);
+                        mbar_wait(bar_rows(1), stage & 1u);
+                    } else {
+                        mbar_wait(bar_rows(2), stage & 1u);
+                    }
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int g = 0; g < UPL; ++g) {
+                        const uint32_t u = q0 + g, slot = u % NSLOT, use = u / NSLOT;
+                        mbar_wait(bar_full(slot), use & 1u);
+                        tc_fence_after();
+#pragma unroll
+                        for (int tt = 0; tt < TPS; ++tt) {
+                            const int t = g * TPS + tt;
+                            // one accumulator per pass: issue_tap_mmas<.., NACC = 1> on this accumulator's rows and columns
+                            issue_tap_mmas<true, 1, false>(elected, dcol + (uint32_t)a * ACC, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
+                                                           s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
+                                                           use_s || t > 0);
+                        }
+                        if (a == NACC - 1 && elected) umma_commit(bar_empty(slot));  // both accumulators' MMAs have read the slot
+                    }
+                    if (elected) umma_commit(bar_acc(a));
+                }
+                q0 += (uint32_t)UPL;
+                stage += 1;
+            }
+        }
+    } else {
+        // ---- epilogue warps: group a = warp >> 2 owns accumulator a; this thread owns one cell (TMEM lane) and its 64 channels
+        const int a = warp >> 2;
+        const int cell = a * 128 + (warp & 3) * 32 + lane;
+        const Cell c = decode_cell(cell, CELLS);
+        const uint32_t my_rows = a == 0 ? bar_rows(0) : (warp == 4 ? bar_rows(1) : bar_rows(2));
+        const bool halo = a == 0 && cell >= 128 - 7;  // rows accumulator 1's MMAs of the SAME layer still read
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t acc_par = 0;  // parity of the layer counter (both accumulator barriers complete once per layer)
+        for (int64_t gi = 0; gi < my_groups; ++gi) {
+            const int64_t board0 = ((int64_t)blockIdx.x + gi * gridDim.x) * NB;
+            // ---- input planes -> channel chunks of both activation matrices (create_tensor_from_state layout [21][5][5]).
+            // The previous group's last MMAs have completed (every thread waited for both accumulators before its heads).
+            if (c.real) {
+                const int64_t gb = board0 + c.board;
+                const float* src = planes + gb * 525 + c.pos;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    float x[16];  // the planes are 0 / 1: exact in f16
+#pragma unroll
+                    for (int ch = 0; ch < 16; ++ch) x[ch] = (part * 16 + ch < kInPlanes && gb < n) ? __ldg(src + (part * 16 + ch) * 25) : 0.f;
+                    store_channels_f16_16(s_act, R, kLead + cell, part * 16, x);  // 32 channels: planes 21..31 are zero
+                }
+            }
+            fence_proxy_async();
+            arrive(my_rows);
+            for (int l = 0; l < L; ++l) {
+                const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
+                const bool last = l == L - 1;
+                mbar_wait(bar_acc(a), acc_par);
+                tc_fence_after();
+                const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
+                const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
+                const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
+                const float4* hw = reinterpret_cast<const float4*>(net.head);
+                const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * ACC;
+                const uint32_t tskip = tlane + SET + a * ACC;
+                float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // 16 channels at a time: the kernel must fit 96 registers for two CTAs per SM
+                    const int c0 = q * 16;
+                    uint32_t v[16];
+                    tmem_ld16_nowait(tsrc + c0, v);
+                    tmem_wait_ld();
+                    float o[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!use_s) b = __ldg(bias_l + c0 / 4 + i);
+                        o[4 * i + 0] = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f);
+                        o[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f);
+                        o[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f);
+                        o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
+                    }
+                    if (!last && c.real) {
+                        // accumulator 1's MMAs of this layer read rows 121..127 through their negatively shifted windows: wait for them
+                        if (halo && q == 0) mbar_wait(bar_acc(1), acc_par);
+                        store_channels_f16_16(s_act, R, kLead + cell, c0, o);
+                    }
+                    if (preload) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = __ldg(bias_n + c0 / 4 + i);
+                            v[4 * i + 0] = __float_as_uint(o[4 * i + 0] + b.x);
+                            v[4 * i + 1] = __float_as_uint(o[4 * i + 1] + b.y);
+                            v[4 * i + 2] = __float_as_uint(o[4 * i + 2] + b.z);
+                            v[4 * i + 3] = __float_as_uint(o[4 * i + 3] + b.w);
+                        }
+                        tmem_st16(tskip + c0, v);
+                    }
+                    if (last) {  // 1x1 convolutions of both heads (net.rs: policy_conv 64 -> 2, vh_conv 64 -> 1)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 w0 = __ldg(hw + (kHP0 / 4) + c0 / 4 + i), w1 = __ldg(hw + (kHP1 / 4) + c0 / 4 + i),
+                                         w2 = __ldg(hw + (kHV / 4) + c0 / 4 + i);
+                            hp0 = fmaf(o[4 * i + 0], w0.x, fmaf(o[4 * i + 1], w0.y, fmaf(o[4 * i + 2], w0.z, fmaf(o[4 * i + 3], w0.w, hp0))));
+                            hp1 = fmaf(o[4 * i + 0], w1.x, fmaf(o[4 * i + 1], w1.y, fmaf(o[4 * i + 2], w1.z, fmaf(o[4 * i + 3], w1.w, hp1))));
+                            hv = fmaf(o[4 * i + 0], w2.x, fmaf(o[4 * i + 1], w2.y, fmaf(o[4 * i + 2], w2.z, fmaf(o[4 * i + 3], w2.w, hv))));
+                        }
+                    }
+                }
+                if (last && c.real) {
+                    float* hb = s_head + c.board * 75;
+                    hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
+                    hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
+                    hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+                }
+                if (preload) tmem_wait_st();
+                if (last) {
+                    // the next group's input stage overwrites rows the OTHER accumulator's last MMAs may still read: wait for both
+                    mbar_wait(bar_acc(a ^ 1), acc_par);
+                } else {
+                    fence_proxy_async();
+                    tc_fence_before();
+                    arrive(my_rows);  // this thread's rows (and its TMEM reads) of the layer are done
+                }
+                acc_par ^= 1u;
+            }
+            // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
+            named_bar_sync(1, 256);
+            for (int b = warp; b < NB; b += 8) {
+                const int64_t gb = board0 + b;
+                if (gb >= n) continue;
+                const float* hb = s_head + b * 75;
+                const bool two = lane + 32 < 50;
+                float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+#pragma unroll 10
+                for (int i = 0; i < 50; ++i) {
+                    const float x = hb[i];
+                    l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
+                    if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+                }
+                const float m = warp_max(two ? fmaxf(l0, l1) : l0);
+                const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
+                const float s = warp_sum(e0 + e1);
+                policy[gb * 50 + lane] = e0 / s;
+                if (two) policy[gb * 50 + 32 + lane] = e1 / s;
+                float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+#pragma unroll 5
+                for (int i = 0; i < 25; ++i) {
+                    const float x = hb[50 + i];
+                    h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
+                    h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+                }
+                float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+                acc = warp_sum(acc);
+                if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+            }
+            named_bar_sync(1, 256);  // s_head is free again before anybody's next last-layer epilogue
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
+}
+
 // ---- version 2: ONE CTA per SM, two independent halves that share one weight stream ---------------------------------------------
 // Measured on version 1 (two CTAs per SM, each streaming its own weights): with MMAs and epilogues disabled the kernel still took
 // 55 % of its time -- 2 341 board groups x 451 KB of weights = 1.06 GB through L2 per call (5.6 TB/s). TMEM (512 columns = accumulators
@@ -1875,6 +2123,22 @@ static cudaError_t launch_net_v2(Ctx* c, const float* planes, float* policy, flo
     return cudaGetLastError();
 }
 
+static cudaError_t launch_net_f16p(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
+    using G = Geo<2, true, false>;
+    constexpr int kSmemF16P = G::OFF_BAR + GeoX3P::N_BARS * 8 + 16;
+    static bool attr[64] = {};  // the opt-in is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(k_net_forward_f16p, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemF16P);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+    const int64_t groups = (count + G::NB - 1) / G::NB, slots = (int64_t)sms * 2;
+    k_net_forward_f16p<<<(unsigned)(groups < slots ? groups : slots), GeoX3P::THREADS, kSmemF16P, c->stream>>>(planes, policy, value, count, nd);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_net_x3p(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
     using G = Geo<2, true, true>;
     static bool attr[64] = {};  // the opt-in is per device
@@ -1951,6 +2215,8 @@ cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float
     if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms, count);
     const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)
     if (v2 && v2[0] == '1') return ns.f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms, count) : launch_net_v2<false>(c, planes, policy, value, nd, sms, count);
+    const char* f16p = getenv("ONB_NET_F16_PIPE");  // exploration knob: the warp-specialised pipeline for the f16 fast mode
+    if (f16p && f16p[0] == '1' && ns.f16) return launch_net_f16p(c, planes, policy, value, nd, sms, count);
     const char* wide = getenv("ONB_NET_WIDE");  // exploration knob: 14 boards per CTA, one CTA per SM
     const bool w = wide && wide[0] == '1';
     if (ns.f16) return w ? launch_net_variant<4, true>(c, planes, policy, value, nd, sms, count) : launch_net_variant<2, true>(c, planes, policy, value, nd, sms, count);

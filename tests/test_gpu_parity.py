@@ -1640,6 +1640,20 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
         assert np.array_equal(outs["plain"][0], outs["pipe"][0]) and np.array_equal(outs["plain"][1], outs["pipe"][1]), blocks
         for other in ("halves",):   # its heads add the two channel halves' partial sums: a few ulps
             assert np.abs(outs["plain"][0] - outs[other][0]).max() <= 1e-6 and np.abs(outs["plain"][1] - outs[other][1]).max() <= 2e-6, other
+        # the f16 fast mode: the warp-specialised two-CTAs-per-SM build against the plain one, bit for bit
+        for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES"):
+            monkeypatch.delenv(k, raising=False)
+        f16 = {}
+        for name, val in (("plain", "0"), ("pipe", "1")):
+            monkeypatch.setenv("ONB_NET_F16_PIPE", val)
+            with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
+                ctx.net_load(model, precision="f16")
+                ctx.write(onb.BUF_LEAF_PLANES, planes)
+                ctx.net_forward(onb.BUF_LEAF_PLANES)
+                ctx.net_forward(onb.BUF_LEAF_PLANES)
+                f16[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
+        monkeypatch.delenv("ONB_NET_F16_PIPE", raising=False)
+        assert np.array_equal(f16["plain"][0], f16["pipe"][0]) and np.array_equal(f16["plain"][1], f16["pipe"][1]), blocks
 
 
 @pytest.mark.gpu
