@@ -96,6 +96,7 @@ struct Geo {
 
 struct NetDev {
     const uint8_t* wconv;  // all conv taps in operand layout
+    const uint8_t* wpair;  // ONB_NET_F32 only: the taps as the CTA-pair kernel streams them, [rank][layer][tap][12 KB]
     const float* bias;   // [1 + 2 * n_blocks][64] folded biases
     const float* head;   // kHeadFloats
     int n_blocks;
@@ -310,6 +311,26 @@ __device__ __forceinline__ void store_channels_x3(uint32_t s_act, uint32_t a2_of
         const uint32_t addr = act_addr(s_act, R, row, c0 / 8 + i);
         st_shared_v4(addr, hi[0], hi[1], hi[2], hi[3]);
         st_shared_v4(addr + a2_off, lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+// the same in two steps, for owners that have to hold their chunks back until a reader of the old rows is done
+__device__ __forceinline__ void pack_channels_x3(const float (&o)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const float x0 = fminf(o[2 * q], 65504.f), x1 = fminf(o[2 * q + 1], 65504.f);
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
+        hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
+__device__ __forceinline__ void store_packed_x3(uint32_t s_act, uint32_t a2_off, int R, int row, int c0, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t addr = act_addr(s_act, R, row, c0 / 8 + i);
+        st_shared_v4(addr, hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+        st_shared_v4(addr + a2_off, lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
     }
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -582,7 +603,7 @@ __global__ void __launch_bounds__(256, (NACC == 2 && !X3) ? 2 : 1)
         PF(6);  // heads
     }
 #ifdef ONB_NET_PROFILE
-    if (blockIdx.x == 3 && (tid == 0 || tid == 64))
+    if (blockIdx.x == (CL ? 2 : 3) && (tid == 0 || tid == 64))
         printf("net profile tid %d groups %lld: input+fence %lld barrier+commit %lld weights %lld (late %lld) issue %lld acc %lld epilogue %lld heads %lld\n",
                tid, (long long)my_groups, pf[0], pf[1], pf[2], pf[7], pf[3], pf[4], pf[5], pf[6]);
 #endif
@@ -628,6 +649,83 @@ __device__ __forceinline__ void store_channels_x3_16(uint32_t s_act, uint32_t a2
     }
 }
 
+// ---- CTA-pair (cta_group::2) helpers: cluster-scope barrier traffic and the paired MMA / commit -------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {  // the same shared-memory offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // arrivals come from the peer CTA as well
+    if (mbar_try_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {  // the same warp of BOTH CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// M = 256 over the CTA pair: each CTA's tensor core takes 128 A rows from its own shared memory and writes 128 lanes of its own
+// TMEM; B's N rows are split in halves, the first from the leader's shared memory, the second from the peer's (same offsets)
+__device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t accumulate, uint32_t idesc) {
+    const uint32_t a_lo = desc_lo(a_addr), a_hi = desc_hi(a_addr), b_lo = desc_lo(b_addr), b_hi = desc_hi(b_addr);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+// one tap of the CTA-pair build: per K step a1 x [b1 ; b2] (N = 128: b1 from the leader, b2 from the peer) and a2 x b1 (N = 64: rows
+// 0..31 of b1 from the leader, 32..63 from the peer, both at byte 8192 of the tap)
+__device__ __forceinline__ void issue_tap_mmas_pair(bool elected, uint32_t dcol, uint32_t s_act, int row0, uint32_t b_tap, int ksteps, bool accumulate_first,
+                                                    uint32_t a2_off) {
+    constexpr uint32_t kIdesc128 = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24), kIdesc64 = (1u << 4) | ((64u >> 3) << 17) | ((256u >> 4) << 24);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < ksteps) {
+            const uint32_t a_addr = s_act + (uint32_t)row0 * 128u + (uint32_t)j * 32u, b_addr = b_tap + (uint32_t)j * 32u;
+            if (elected) {
+                mma_ss_pair(dcol, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u, kIdesc128);
+                mma_ss_pair(dcol + 64u, a_addr + a2_off, b_addr + 8192u, 1u, kIdesc64);
+            }
+        }
+    }
+}
+
 // ---- the split-operand (f32-faithful) network, warp-specialised and software-pipelined over the two accumulators ------------------
 // k_net_forward<2, f16, X3> issues a layer's MMAs, waits, runs the epilogue with the tensor pipe idle, synchronises the CTA and
 // starts over: 63 % of its time is MMA issue (at the operand-fetch / tensor floor), the rest is exposed epilogue, barriers and
@@ -644,58 +742,106 @@ __device__ __forceinline__ void store_channels_x3_16(uint32_t s_act, uint32_t a2
 // the critical warps -- ran 0.730 ms against 0.724 ms and was dropped: the wait is not the epilogue's instruction count.) In-place
 // activation hazards: rows 121..127 (accumulator 0's last cells) are still read by accumulator 1's MMAs of the same layer, so their
 // owners wait for accumulator 1's commit before storing. Same products, same accumulation order, same results as k_net_forward<2,f16,X3>.
-struct GeoX3P {
+template <bool CL>
+struct GeoX3PT {
     using G = Geo<2, true, true>;
     static constexpr int THREADS = 10 * 32;
-    // mbarriers: full[3], empty[3], acc_full[2], rows_ready[3] (group 0 | warp 4 | warps 5-7)
-    static constexpr int N_BARS = 2 * G::NSLOT + 2 + 3;
-    static constexpr int SMEM_USED = G::OFF_BAR + N_BARS * 8 + 16;
+    // CL (CTA pair, see below): a tap is [this CTA's 64 B rows of the N = 128 MMA][its 32 B rows of the N = 64 MMA]
+    static constexpr int TAP_STRIDE = CL ? 12 * 1024 : G::TAP_STRIDE;
+    static constexpr int NSLOT = G::NSLOT;
+    static constexpr int SLOT_BYTES = G::TPS * TAP_STRIDE;
+    static constexpr int OFF_HEAD = G::OFF_RING + NSLOT * SLOT_BYTES;
+    static constexpr int OFF_BAR = OFF_HEAD + G::HEAD_BYTES;
+    // mbarriers: full[3], empty[3], acc_full[2], rows_ready[3] (group 0 | warp 4 | warps 5-7), CL: peer_full[3]
+    static constexpr int N_BARS = 2 * NSLOT + 2 + 3 + (CL ? NSLOT : 0);
+    static constexpr int SMEM_USED = OFF_BAR + N_BARS * 8 + 16;
     static constexpr int SMEM = SMEM_USED;
     static_assert(SMEM_USED <= 227 * 1024, "shared memory");
+    static_assert(CL || (OFF_HEAD == G::OFF_HEAD && OFF_BAR == G::OFF_BAR), "the single-CTA build keeps Geo's layout");
 };
+using GeoX3P = GeoX3PT<false>;
 
+//
+// CL = true: the same pipeline on a PAIR of CTAs (a cluster of two SMs, tcgen05 cta_group::2). The kernel is bound by the tensor
+// cores' operand fetch from shared memory (14 KB per K step and SM above); a paired MMA has M = 256 -- each SM contributes its own
+// 128 activation rows and accumulates into its own TMEM -- while the weight rows are SPLIT between the two SMs' shared memories,
+// so that each SM stores and fetches only half of B: 11 KB per step. Every CTA keeps its own 7 boards, epilogue warps, weight
+// producer and weight ring (12 KB per tap: the leader holds b1 and b1[0:32], the peer b2 and b1[32:64]); only the leader's warp 8
+// issues MMAs. Cross-CTA traffic is barrier traffic only: the peer's epilogue threads arrive on the LEADER's rows barriers, the
+// peer's warp 8 relays "my share of slot s has landed" to the leader's peer_full[s], and the leader's commits are multicast to the
+// accumulator / empty barriers of both CTAs. Same products and accumulation order: results identical to the single-CTA build.
+template <bool CL>
 __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
     k_net_forward_x3p(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
     using G = Geo<2, true, true>;
+    using GP = GeoX3PT<CL>;
     using O = Op<true>;
     constexpr int NACC = 2;
-    constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = G::NSLOT, TPS = G::TPS, UPL = G::UPL;
+    constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = GP::NSLOT, TPS = G::TPS, UPL = G::UPL;
     constexpr uint32_t A2 = (uint32_t)G::ACT_BYTES, ACC = 128u, SET = (uint32_t)G::SET_COLS;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t s_act = smem_u32(smem), s_ring = s_act + G::OFF_RING, s_bar = s_act + G::OFF_BAR;
-    float* s_head = reinterpret_cast<float*>(smem + G::OFF_HEAD);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + G::OFF_BAR + GeoX3P::N_BARS * 8);
+    const uint32_t s_act = smem_u32(smem), s_ring = s_act + G::OFF_RING, s_bar = s_act + GP::OFF_BAR;
+    float* s_head = reinterpret_cast<float*>(smem + GP::OFF_HEAD);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GP::OFF_BAR + GP::N_BARS * 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = 1 + 2 * net.n_blocks;
-    const int64_t n_groups = (n + NB - 1) / NB;
-    if ((int64_t)blockIdx.x >= n_groups) return;  // whole CTA, before any allocation
-    const int64_t my_groups = (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x;
+#ifdef ONB_X3P_PROFILE
+    __shared__ long long s_tl[8][12];  // timeline of one board group (the 6th) of CTA 3: [layer][event], see the printout at the end
+    __shared__ long long s_t2[2][8];   // layer 4 of that group, per accumulator: wake, then (weights there, slot issued) x 3, commit issued
+#define TL(ev) do { if (blockIdx.x == (CL ? 2 : 3) && gi == 5 && l < 8) s_tl[l][ev] = clock64(); } while (0)
+#define TL2(ev) do { if (blockIdx.x == (CL ? 2 : 3) && gi == 5 && l == 4 && lane == 0) s_t2[a][ev] = clock64(); } while (0)
+#else
+#define TL(ev) do { } while (0)
+#define TL2(ev) do { } while (0)
+#endif
+    // CL: the pair works on two consecutive board groups at a time (leader 2 p, peer 2 p + 1; a group past the end computes on zeros
+    // and stores nothing), so both CTAs run the same number of rounds
+    const uint32_t crank = CL ? cluster_ctarank() : 0u;
+    const int64_t n_groups = CL ? ((n + NB - 1) / NB + 1) / 2 : (n + NB - 1) / NB;  // CL: pairs of groups
+    const int64_t worker = CL ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x, n_workers = CL ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+    if (worker >= n_groups) return;  // whole CTA (pair), before any allocation
+    const int64_t my_groups = (n_groups - worker + n_workers - 1) / n_workers;
     const uint32_t total_units = (uint32_t)my_groups * (uint32_t)(UPL * L);
     auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
     auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
     auto bar_acc = [&](uint32_t a) { return s_bar + (2 * NSLOT + a) * 8u; };
     auto bar_rows = [&](uint32_t k) { return s_bar + (2 * NSLOT + 2 + k) * 8u; };  // 0: group 0, 1: warp 4, 2: warps 5-7
+    auto bar_peer = [&](uint32_t s) { return s_bar + (2 * NSLOT + 5 + s) * 8u; };  // CL, leader's: the peer's share of slot s has landed
 
     if (tid == 0) {
         for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
+            if (CL) mbar_init(bar_peer(s), 1);
         }
         mbar_init(bar_acc(0), 1);
         mbar_init(bar_acc(1), 1);
-        mbar_init(bar_rows(0), 128);
-        mbar_init(bar_rows(1), 32);
-        mbar_init(bar_rows(2), 96);
+        mbar_init(bar_rows(0), CL ? 256 : 128);  // CL: the leader's rows barriers collect the epilogue threads of both CTAs
+        mbar_init(bar_rows(1), CL ? 64 : 32);
+        mbar_init(bar_rows(2), CL ? 192 : 96);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
+    if (warp == 0) {
+        if (CL)
+            tmem_alloc_pair(smem_u32(s_tmem), G::TMEM_COLS);
+        else
+            tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
+    }
     for (int i = tid; i < G::NMAT * G::ACT_BYTES / 16; i += GeoX3P::THREADS) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    auto arrive = [&](uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
+    // CL: rows barriers live in the leader; every epilogue thread of the pair arrives there with cluster scope
+    const uint32_t rows_base = CL ? mapa_shared(bar_rows(0), 0u) : bar_rows(0);
+    auto arrive = [&](uint32_t bar) {
+        if (CL)
+            mbar_arrive_cluster(rows_base + (bar - bar_rows(0)));
+        else
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    };
 
     if (warp == 9) {
         // ---- weight producer: the ring is filled strictly in tap order, as far ahead as it has free slots
@@ -704,11 +850,22 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 const uint32_t slot = u % NSLOT, use = u / NSLOT;
                 if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
                 const uint32_t ul = u % (uint32_t)(UPL * L), layer = ul / UPL, tap = (ul - layer * UPL) * TPS;
-                const uint8_t* src = net.wconv + (size_t)G::NMAT * (layer == 0 ? (size_t)tap * O::TAP_BYTES0
-                                                                              : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
-                const uint32_t bytes = (uint32_t)(TPS * G::NMAT) * (layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES);
+                const uint8_t* src = CL ? net.wpair + ((size_t)crank * (size_t)(9 * L) + (size_t)layer * 9 + tap) * (size_t)GP::TAP_STRIDE
+                                        : net.wconv + (size_t)G::NMAT * (layer == 0 ? (size_t)tap * O::TAP_BYTES0
+                                                                                    : (size_t)9 * O::TAP_BYTES0 + ((size_t)(layer - 1) * 9 + tap) * O::TAP_BYTES);
+                const uint32_t bytes = CL ? (uint32_t)GP::SLOT_BYTES : (uint32_t)(TPS * G::NMAT) * (layer == 0 ? O::TAP_BYTES0 : O::TAP_BYTES);
                 mbar_expect_tx(bar_full(slot), bytes);
-                bulk_g2s(s_ring + slot * (uint32_t)G::SLOT_BYTES, src, bytes, bar_full(slot));
+                bulk_g2s(s_ring + slot * (uint32_t)GP::SLOT_BYTES, src, bytes, bar_full(slot));
+            }
+        }
+    } else if (CL && warp == 8 && crank != 0u) {
+        // ---- peer CTA: no MMA issue here; relay "this CTA's share of the slot has landed" to the leader
+        if (lane == 0) {
+            const uint32_t peer0 = mapa_shared(bar_peer(0), 0u);
+            for (uint32_t u = 0; u < total_units; ++u) {
+                const uint32_t slot = u % NSLOT, use = u / NSLOT;
+                mbar_wait(bar_full(slot), use & 1u);
+                mbar_arrive_cluster(peer0 + slot * 8u);
             }
         }
     } else if (warp == 8) {
@@ -716,7 +873,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         const bool elected = elect_one();
         uint32_t q0 = 0, stage = 0;  // stage = number of "rows ready" rounds consumed so far (input stage + epilogues)
 #ifdef ONB_X3P_PROFILE
-        long long t_rows0 = 0, t_rows1 = 0, t_full = 0, t_issue = 0, t_mark = clock64();
+        long long t_rows0 = 0, t_rows0b = 0, t_rows1 = 0, t_full = 0, t_issue = 0, t_mark = clock64();
 #define XP(var) do { const long long now__ = clock64(); var += now__ - t_mark; t_mark = now__; } while (0)
 #else
 #define XP(var) do { } while (0)
@@ -728,36 +885,72 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 const int ksteps = l == 0 ? O::KCH0 / 2 : O::KCH / 2;
 #pragma unroll 1
                 for (int a = 0; a < NACC; ++a) {
-                    // accumulator 0 needs its own rows and the first rows of accumulator 1 (its windows reach 7 rows further);
-                    // accumulator 1 needs the rest as well
+                    // accumulator 0 needs its own rows and, from its sixth tap on, the first rows of accumulator 1: taps 0..4 shift
+                    // the window by -7, -6, -5, -1, 0 rows and stay inside rows 0..127, taps 5..8 (+1, +5, +6, +7) reach up to row
+                    // 134 (warp 4's cells). Accumulator 1 needs the rest as well. The MMA queue is shallow: every barrier test that
+                    // sits between two taps drains it, so all tests that can be made early are made while MMAs are queued -- the
+                    // next slot's weights after the first tap of a slot, accumulator 1's rows during accumulator 0's last slot -- and
+                    // accumulator 1 re-tests nothing (the same thread saw the same weights arrive for accumulator 0)
                     XP(t_issue);
                     if (a == 0) {
-                        mbar_wait(bar_rows(0), stage & 1u);
-                        mbar_wait(bar_rows(1), stage & 1u);
+                        if (CL) mbar_wait_cluster(bar_rows(0), stage & 1u); else mbar_wait(bar_rows(0), stage & 1u);
                         XP(t_rows0);
+                        if (lane == 0) TL(0);
+                        tc_fence_after();
                     } else {
-                        mbar_wait(bar_rows(2), stage & 1u);
-                        XP(t_rows1);
+                        if (lane == 0) TL(2);
                     }
-                    tc_fence_after();
+                    TL2(0);
+                    auto wait_weights = [&](uint32_t uu) {
+                        const uint32_t sl = uu % NSLOT, us = uu / NSLOT;
+                        XP(t_issue);
+                        mbar_wait(bar_full(sl), us & 1u);
+                        if (CL) mbar_wait_cluster(bar_peer(sl), us & 1u);
+                        XP(t_full);
+                    };
+                    if (a == 0) wait_weights(q0);
 #pragma unroll 1
                     for (int g = 0; g < UPL; ++g) {
-                        const uint32_t u = q0 + g, slot = u % NSLOT, use = u / NSLOT;
-                        XP(t_issue);
-                        mbar_wait(bar_full(slot), use & 1u);
-                        XP(t_full);
-                        tc_fence_after();
+                        const uint32_t u = q0 + g, slot = u % NSLOT;
+                        TL2(1 + 2 * g);
 #pragma unroll
                         for (int tt = 0; tt < TPS; ++tt) {
                             const int t = g * TPS + tt;
+                            if (a == 0 && t == 5) {  // the first window that reaches into accumulator 1's rows (see above)
+                                XP(t_issue);
+                                if (CL) mbar_wait_cluster(bar_rows(1), stage & 1u); else mbar_wait(bar_rows(1), stage & 1u);
+                                XP(t_rows0b);
+                                tc_fence_after();
+                            }
                             // one accumulator per pass: issue_tap_mmas<.., NACC = 1> on this accumulator's rows and columns
-                            issue_tap_mmas<true, 1, true>(elected, dcol + (uint32_t)a * ACC, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
-                                                          s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
-                                                          use_s || t > 0, A2);
+                            if (CL)
+                                issue_tap_mmas_pair(elected, dcol + (uint32_t)a * ACC, s_act, kLead + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
+                                                    s_ring + slot * (uint32_t)GP::SLOT_BYTES + (uint32_t)tt * (uint32_t)GP::TAP_STRIDE, ksteps, use_s || t > 0, A2);
+                            else
+                                issue_tap_mmas<true, 1, true>(elected, dcol + (uint32_t)a * ACC, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
+                                                              s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
+                                                              use_s || t > 0, A2);
+                            if (a == 0 && tt == 0) {
+                                if (g + 1 < UPL) {
+                                    wait_weights(u + 1);
+                                } else {  // accumulator 1's turn comes next: its rows (warps 5-7 of the previous stage) are long written
+                                    XP(t_issue);
+                                    if (CL) mbar_wait_cluster(bar_rows(2), stage & 1u); else mbar_wait(bar_rows(2), stage & 1u);
+                                    XP(t_rows1);
+                                    tc_fence_after();
+                                }
+                            }
                         }
-                        if (a == NACC - 1 && elected) umma_commit(bar_empty(slot));  // both accumulators' MMAs have read the slot
+                        if (a == NACC - 1 && elected) {  // both accumulators' MMAs have read the slot
+                            if (CL) umma_commit_pair(bar_empty(slot)); else umma_commit(bar_empty(slot));
+                        }
+                        TL2(2 + 2 * g);
                     }
-                    if (elected) umma_commit(bar_acc(a));
+                    if (elected) {
+                        if (CL) umma_commit_pair(bar_acc(a)); else umma_commit(bar_acc(a));
+                    }
+                    if (lane == 0) TL(a == 0 ? 1 : 3);
+                    TL2(7);
                 }
                 q0 += (uint32_t)UPL;
                 stage += 1;
@@ -765,9 +958,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         }
 #ifdef ONB_X3P_PROFILE
         XP(t_issue);
-        if (blockIdx.x == 3 && lane == 0)
-            printf("x3p MMA warp, %lld groups: issue %lld, waiting rows for acc0 %lld, for acc1 %lld, waiting weights %lld\n", (long long)my_groups, t_issue,
-                   t_rows0, t_rows1, t_full);
+        if (blockIdx.x == (CL ? 2 : 3) && lane == 0)
+            printf("x3p MMA warp, %lld groups: issue %lld, waiting rows for acc0 %lld (+ %lld before tap 5), for acc1 %lld, waiting weights %lld\n",
+                   (long long)my_groups, t_issue, t_rows0, t_rows0b, t_rows1, t_full);
 #endif
     } else {
         // ---- epilogue warps: group a = warp >> 2 owns accumulator a; this thread owns one cell (TMEM lane) and its 64 channels
@@ -775,7 +968,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         const int cell = a * 128 + (warp & 3) * 32 + lane;
         const Cell c = decode_cell(cell, CELLS);
         const uint32_t my_rows = a == 0 ? bar_rows(0) : (warp == 4 ? bar_rows(1) : bar_rows(2));
-        const bool halo = a == 0 && cell >= 128 - 7;  // rows accumulator 1's MMAs of the SAME layer still read
+        // warp 3 owns rows 121..127, which accumulator 1's MMAs of the SAME layer still read through their negatively shifted windows:
+        // it computes both channel halves first, holding the packed chunks in registers, waits for accumulator 1 and only then stores
+        const bool defer = warp == 3;
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t acc_par = 0;  // parity of the layer counter (both accumulator barriers complete once per layer)
 #ifdef ONB_X3P_PROFILE
@@ -785,7 +980,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
 #define EP(var) do { } while (0)
 #endif
         for (int64_t gi = 0; gi < my_groups; ++gi) {
-            const int64_t board0 = ((int64_t)blockIdx.x + gi * gridDim.x) * NB;
+            const int64_t board0 = CL ? (2 * (worker + gi * n_workers) + (int64_t)crank) * NB : ((int64_t)blockIdx.x + gi * gridDim.x) * NB;
             // ---- input planes -> channel chunks of both activation matrices (create_tensor_from_state layout [21][5][5]).
             // The previous group's last MMAs have completed (every thread waited for both accumulators before its heads).
             if (c.real) {
@@ -804,6 +999,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 EP(e_work);
                 mbar_wait(bar_acc(a), acc_par);
                 EP(e_wait);
+                if (tid == 0) TL(4);
+                if (tid == 128) TL(6);
+                if (tid == 224) TL(8);
                 tc_fence_after();
                 const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
                 const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
@@ -812,6 +1010,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * ACC;
                 const uint32_t tskip = tlane + SET + a * ACC;
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+                uint32_t keep_hi[16], keep_lo[16];  // defer: the first half's chunks
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t v[32];
@@ -833,10 +1032,22 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                         o[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f);
                         o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
                     }
-                    if (!last && c.real) {
-                        // accumulator 1's MMAs of this layer read rows 121..127 through their negatively shifted windows: wait for them
-                        if (halo && h == 0) { EP(e_work); mbar_wait(bar_acc(1), acc_par); EP(e_halo); }
-                        store_channels_x3(s_act, A2, R, kLead + cell, h * 32, o);
+                    if (!last) {
+                        if (!defer) {
+                            if (c.real) store_channels_x3(s_act, A2, R, kLead + cell, h * 32, o);
+                        } else if (h == 0) {
+                            pack_channels_x3(o, keep_hi, keep_lo);
+                        } else {
+                            uint32_t hi[16], lo[16];
+                            pack_channels_x3(o, hi, lo);
+                            EP(e_work);
+                            mbar_wait(bar_acc(1), acc_par);
+                            EP(e_halo);
+                            if (c.real) {
+                                store_packed_x3(s_act, A2, R, kLead + cell, 0, keep_hi, keep_lo);
+                                store_packed_x3(s_act, A2, R, kLead + cell, 32, hi, lo);
+                            }
+                        }
                     }
                     if (preload) {
 #pragma unroll
@@ -877,6 +1088,10 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     fence_proxy_async();
                     tc_fence_before();
                     arrive(my_rows);  // this thread's rows (and its TMEM reads) of the layer are done
+                    if (tid == 0) TL(5);
+                    if (tid == 128) TL(7);
+                    if (tid == 224) TL(9);
+                    if (tid == 127) TL(10);
                 }
                 acc_par ^= 1u;
             }
@@ -914,13 +1129,32 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         }
 #ifdef ONB_X3P_PROFILE
         EP(e_work);
-        if (blockIdx.x == 3 && (tid == 0 || tid == 127 || tid == 128 || tid == 160))
+        if (blockIdx.x == (CL ? 2 : 3) && (tid == 0 || tid == 127 || tid == 128 || tid == 160))
             printf("x3p epilogue tid %d: waiting for the accumulator %lld, halo wait %lld, work (input, epilogue, heads) %lld\n", tid, e_wait, e_halo, e_work);
 #endif
     }
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
+#ifdef ONB_X3P_PROFILE
+    if (blockIdx.x == (CL ? 2 : 3) && tid == 0 && my_groups > 5)
+        for (int l = 0; l < L && l < 8; ++l)
+            printf("layer %d: MMA wakes for acc0 %6lld, acc0 issued %6lld, wakes for acc1 %6lld, acc1 issued %6lld | acc0 done %6lld, warp 0 arrives %6lld, halo thread arrives %6lld | "
+                   "acc1 done %6lld, warp 4 arrives %6lld, warp 7 arrives %6lld\n", l, s_tl[l][0] - s_tl[0][0], s_tl[l][1] - s_tl[0][0], s_tl[l][2] - s_tl[0][0],
+                   s_tl[l][3] - s_tl[0][0], s_tl[l][4] - s_tl[0][0], s_tl[l][5] - s_tl[0][0], s_tl[l][10] - s_tl[0][0], s_tl[l][6] - s_tl[0][0],
+                   s_tl[l][7] - s_tl[0][0], s_tl[l][9] - s_tl[0][0]);
+    if (blockIdx.x == (CL ? 2 : 3) && tid == 0 && my_groups > 5)
+        for (int a = 0; a < 2; ++a)
+            printf("layer 4 acc %d: wake 0 | slot 0 weights %lld issued %lld | slot 1 weights %lld issued %lld | slot 2 weights %lld issued %lld | commit %lld\n", a,
+                   s_t2[a][1] - s_t2[a][0], s_t2[a][2] - s_t2[a][0], s_t2[a][3] - s_t2[a][0], s_t2[a][4] - s_t2[a][0], s_t2[a][5] - s_t2[a][0],
+                   s_t2[a][6] - s_t2[a][0], s_t2[a][7] - s_t2[a][0]);
+#endif
+    if (CL) {
+        cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal its barriers
+        if (warp == 0) tmem_dealloc_pair(tmem, G::TMEM_COLS);
+    } else if (warp == 0) {
+        tmem_dealloc(tmem, G::TMEM_COLS);
+    }
 }
 
 // ---- the f16 fast mode with the same role pipeline, TWO CTAs per SM -------------------------------------------------------------
@@ -1423,7 +1657,7 @@ __global__ void __launch_bounds__(Geo2<F16>::THREADS, 1)
         PF(6);
     }
 #ifdef ONB_NET_PROFILE
-    if (blockIdx.x == 3 && (htid == 0 || htid == 64))
+    if (blockIdx.x == (CL ? 2 : 3) && (htid == 0 || htid == 64))
         printf("net2 profile tid %d iters %lld: input %lld barrier %lld weights %lld issue %lld commit %lld acc %lld epilogue %lld heads %lld\n", tid,
                (long long)my_iters, pf[0], pf[1], pf[2], pf[3], pf[7], pf[4], pf[5], pf[6]);
 #endif
@@ -2064,6 +2298,23 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
         err = "a BatchNorm-folded convolution weight has magnitude " + std::to_string(w_absmax) + " > 65504 (f16 range): load this network with ONB_NET_TF32";
         return ONB_E_INVALID;
     }
+    // ONB_NET_F32: a second copy of the taps in the order the CTA-pair kernel streams them (k_net_forward_x3p<true>): per rank of
+    // the pair, per layer and tap, 12 KB = [b1 | b2 of the tap: this rank's 64 rows of the N = 128 MMA][rows 32 r .. 32 r + 31 of b1:
+    // its 32 rows of the N = 64 MMA]. Moving whole 8-row groups keeps the 128-byte swizzle phase of every row.
+    size_t pair_off = 0;
+    if (x3) {
+        static_assert(Op<true>::TAP_BYTES == 8192 && Op<true>::TAP_BYTES0 == 8192, "pair layout");
+        pair_off = (wconv.size() + 1023) / 1024 * 1024;
+        const size_t stride = (size_t)GeoX3PT<true>::TAP_STRIDE;
+        wconv.resize(pair_off + 2 * (size_t)(9 * L) * stride, 0);
+        for (int r = 0; r < 2; ++r)
+            for (int t = 0; t < 9 * L; ++t) {
+                const uint8_t* b1 = wconv.data() + (size_t)t * 2 * 8192;
+                uint8_t* dst = wconv.data() + pair_off + ((size_t)r * (size_t)(9 * L) + (size_t)t) * stride;
+                memcpy(dst, b1 + (size_t)r * 8192, 8192);
+                memcpy(dst + 8192, b1 + (size_t)r * 32 * 128, 4096);
+            }
+    }
     Ctx::NetSlot& ns = c->net[c->net_cur];
     cudaStreamSynchronize(c->stream);  // a forward pass with the old weights may still be running
     for (void** p : {(void**)&ns.w, (void**)&ns.bias, (void**)&ns.head})
@@ -2086,6 +2337,7 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
     ns.blocks = n_blocks;
     ns.f16 = f16 ? 1 : 0;
     ns.x3 = x3 ? 1 : 0;
+    ns.pair_off = pair_off;
     ns.loaded = 1;
     return ONB_OK;
 }
@@ -2145,13 +2397,47 @@ static cudaError_t launch_net_x3p(Ctx* c, const float* planes, float* policy, fl
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr[dev]) {
-        const cudaError_t e = cudaFuncSetAttribute(k_net_forward_x3p, cudaFuncAttributeMaxDynamicSharedMemorySize, GeoX3P::SMEM);
+        const cudaError_t e = cudaFuncSetAttribute(k_net_forward_x3p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GeoX3P::SMEM);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     const int64_t groups = (count + G::NB - 1) / G::NB;
-    k_net_forward_x3p<<<(unsigned)(groups < sms ? groups : sms), GeoX3P::THREADS, GeoX3P::SMEM, c->stream>>>(planes, policy, value, count, nd);
+    k_net_forward_x3p<false><<<(unsigned)(groups < sms ? groups : sms), GeoX3P::THREADS, GeoX3P::SMEM, c->stream>>>(planes, policy, value, count, nd);
     return cudaGetLastError();
+}
+
+// the CTA-pair build: clusters of two CTAs, as many as the device can hold at once (one CTA per SM)
+static cudaError_t launch_net_x3pair(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
+    using G = Geo<2, true, true>;
+    using GP = GeoX3PT<true>;
+    static int max_clusters[64] = {};  // per device; 0 = not asked yet
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(GP::THREADS);
+    cfg.dynamicSmemBytes = GP::SMEM;
+    cfg.stream = c->stream;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int mc = (dev >= 0 && dev < 64) ? max_clusters[dev] : 0;
+    if (mc == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_net_forward_x3p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GP::SMEM);
+        if (e != cudaSuccess) return e;
+        cfg.gridDim = dim3((unsigned)(sms & ~1));
+        e = cudaOccupancyMaxActiveClusters(&mc, k_net_forward_x3p<true>, &cfg);
+        if (e != cudaSuccess) return e;
+        if (mc <= 0) return cudaErrorLaunchOutOfResources;
+        if (mc > sms / 2) mc = sms / 2;
+        if (dev >= 0 && dev < 64) max_clusters[dev] = mc;
+    }
+    const int64_t pairs = ((count + G::NB - 1) / G::NB + 1) / 2;
+    cfg.gridDim = dim3(2u * (unsigned)(pairs < mc ? pairs : mc));
+    return cudaLaunchKernelEx(&cfg, k_net_forward_x3p<true>, planes, (float*)policy, (float*)value, (int64_t)count, nd);
 }
 
 static cudaError_t launch_net_v2x(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
@@ -2198,7 +2484,7 @@ static cudaError_t launch_net_v3(Ctx* c, const float* planes, float* policy, flo
 cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float* value, int64_t count) {
     if (count <= 0) return cudaSuccess;
     const Ctx::NetSlot& ns = c->net[c->net_cur];
-    const NetDev nd{reinterpret_cast<const uint8_t*>(ns.w), ns.bias, ns.head, ns.blocks};
+    const NetDev nd{reinterpret_cast<const uint8_t*>(ns.w), reinterpret_cast<const uint8_t*>(ns.w) + ns.pair_off, ns.bias, ns.head, ns.blocks};
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -2207,6 +2493,8 @@ cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float
                   // of one half's epilogue with the other's MMAs does not pay for 6 instead of 7 boards per weight pass and 108 of 128 rows)
         const char* halves = getenv("ONB_NET_X3_HALVES");
         if (halves && halves[0] == '1') return launch_net_v2x(c, planes, policy, value, nd, sms, count);
+        const char* pair = getenv("ONB_NET_X3_PAIR");  // the pipelined kernel on CTA pairs (tcgen05 cta_group::2): each SM fetches half of B
+        if (pair && pair[0] == '1') return launch_net_x3pair(c, planes, policy, value, nd, sms, count);
         const char* pipe = getenv("ONB_NET_X3_PIPE");  // default: the warp-specialised pipelined kernel (0.724 ms); 0 = the plain one (0.745 ms)
         if (!(pipe && pipe[0] == '0')) return launch_net_x3p(c, planes, policy, value, nd, sms, count);
         return launch_net_variant<2, true, true>(c, planes, policy, value, nd, sms, count);

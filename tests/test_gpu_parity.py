@@ -1625,8 +1625,9 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
         planes = O.encode(_positions(n, 5)).reshape(n, 21, 5, 5)
         want_p, want_v = O.net_forward(model.state_dict(), planes)
         outs = {}
-        for name, env in (("plain", {"ONB_NET_X3_PIPE": "0"}), ("pipe", {"ONB_NET_X3_PIPE": "1"}), ("halves", {"ONB_NET_X3_HALVES": "1"})):
-            for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES"):
+        for name, env in (("plain", {"ONB_NET_X3_PIPE": "0"}), ("pipe", {"ONB_NET_X3_PIPE": "1"}), ("halves", {"ONB_NET_X3_HALVES": "1"}),
+                          ("pair", {"ONB_NET_X3_PAIR": "1"})):
+            for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES", "ONB_NET_X3_PAIR"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
@@ -1638,10 +1639,11 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
                 outs[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
             assert np.abs(outs[name][0] - want_p).max() <= 1e-5 and np.abs(outs[name][1] - want_v).max() <= 1e-5, (name, blocks)
         assert np.array_equal(outs["plain"][0], outs["pipe"][0]) and np.array_equal(outs["plain"][1], outs["pipe"][1]), blocks
+        assert np.array_equal(outs["plain"][0], outs["pair"][0]) and np.array_equal(outs["plain"][1], outs["pair"][1]), blocks
         for other in ("halves",):   # its heads add the two channel halves' partial sums: a few ulps
             assert np.abs(outs["plain"][0] - outs[other][0]).max() <= 1e-6 and np.abs(outs["plain"][1] - outs[other][1]).max() <= 2e-6, other
         # the f16 fast mode: the warp-specialised two-CTAs-per-SM build against the plain one, bit for bit
-        for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES"):
+        for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES", "ONB_NET_X3_PAIR"):
             monkeypatch.delenv(k, raising=False)
         f16 = {}
         for name, val in (("plain", "0"), ("pipe", "1")):
