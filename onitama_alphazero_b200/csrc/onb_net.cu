@@ -750,14 +750,20 @@ struct GeoX3PT {
     static constexpr int TAP_STRIDE = CL ? 12 * 1024 : G::TAP_STRIDE;
     static constexpr int NSLOT = G::NSLOT;
     static constexpr int SLOT_BYTES = G::TPS * TAP_STRIDE;
-    static constexpr int OFF_HEAD = G::OFF_RING + NSLOT * SLOT_BYTES;
+    // drifting activation window (see the kernel): layer l's activations start DRIFT_ROWS rows below layer l - 1's, for WRAP
+    // layers in a row; the budget is what the weight ring leaves of the 227 KB
+    static constexpr int DRIFT_ROWS = 8, WRAP = CL ? 25 : 7;
+    static constexpr int R = G::R + DRIFT_ROWS * (WRAP - 1);
+    static constexpr int ACT_BYTES = R * 128;  // f16 operands: 64 channels = one 128-byte block per row
+    static constexpr int OFF_RING = G::NMAT * ACT_BYTES;
+    static constexpr int OFF_HEAD = OFF_RING + NSLOT * SLOT_BYTES;
     static constexpr int OFF_BAR = OFF_HEAD + G::HEAD_BYTES;
     // mbarriers: full[3], empty[3], acc_full[2], rows_ready[3] (group 0 | warp 4 | warps 5-7), CL: peer_full[3]
     static constexpr int N_BARS = 2 * NSLOT + 2 + 3 + (CL ? NSLOT : 0);
     static constexpr int SMEM_USED = OFF_BAR + N_BARS * 8 + 16;
     static constexpr int SMEM = SMEM_USED;
     static_assert(SMEM_USED <= 227 * 1024, "shared memory");
-    static_assert(CL || (OFF_HEAD == G::OFF_HEAD && OFF_BAR == G::OFF_BAR), "the single-CTA build keeps Geo's layout");
+    static_assert(Op<true>::KCH == 8 && ACT_BYTES % 1024 == 0, "one block per row; the ring stays aligned to the swizzle period");
 };
 using GeoX3P = GeoX3PT<false>;
 
@@ -777,10 +783,10 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
     using GP = GeoX3PT<CL>;
     using O = Op<true>;
     constexpr int NACC = 2;
-    constexpr int NB = G::NB, CELLS = G::CELLS, R = G::R, NSLOT = GP::NSLOT, TPS = G::TPS, UPL = G::UPL;
-    constexpr uint32_t A2 = (uint32_t)G::ACT_BYTES, ACC = 128u, SET = (uint32_t)G::SET_COLS;
+    constexpr int NB = G::NB, CELLS = G::CELLS, R = GP::R, NSLOT = GP::NSLOT, TPS = G::TPS, UPL = G::UPL;
+    constexpr uint32_t A2 = (uint32_t)GP::ACT_BYTES, ACC = 128u, SET = (uint32_t)G::SET_COLS;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t s_act = smem_u32(smem), s_ring = s_act + G::OFF_RING, s_bar = s_act + GP::OFF_BAR;
+    const uint32_t s_act = smem_u32(smem), s_ring = s_act + GP::OFF_RING, s_bar = s_act + GP::OFF_BAR;
     float* s_head = reinterpret_cast<float*>(smem + GP::OFF_HEAD);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GP::OFF_BAR + GP::N_BARS * 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -827,7 +833,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         else
             tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
     }
-    for (int i = tid; i < G::NMAT * G::ACT_BYTES / 16; i += GeoX3P::THREADS) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero
+    for (int i = tid; i < G::NMAT * GP::ACT_BYTES / 16; i += GeoX3P::THREADS) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -841,6 +847,24 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
             mbar_arrive_cluster(rows_base + (bar - bar_rows(0)));
         else
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    };
+
+    // Drifting activation window. Updating the activations in place has a write-after-read hazard: rows 121..127 of layer l are
+    // still read by accumulator 1's MMAs (their windows shift by up to -7 rows) when their owners want to store layer l + 1, and the
+    // next layer's accumulator 0 needs exactly those rows, so the tensor pipe drained at every layer boundary while warp 3 waited and
+    // stored (a quarter of the layer time in the first pipelined build). Here layer l + 1 is written 8 rows (one swizzle period)
+    // BELOW layer l: accumulator 0's owners then write over rows -8..119 of layer l, which accumulator 1 never reads, and the next
+    // layer's MMAs are queued behind the current one's with no wait in between. Because the layers slide over each other, zero
+    // rows and pad cells no longer keep themselves: pad cells are stored as zeros and the 8 rows before / 8 + 4 rows after the
+    // cells are cleared for every layer. After WRAP layers the window jumps back to the top; that one transition does overlap what
+    // accumulator 1 reads, and accumulator 0's owners wait for it (as all layer boundaries used to).
+    auto base_row = [&](int l) { return kLead + GP::DRIFT_ROWS * (GP::WRAP - 1 - (l % GP::WRAP)); };
+    auto zero_rows = [&](int row) {  // 8 rows of both matrices, by one warp
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = lane * 4 + k;  // matrix (1 bit) | row (3 bits) | chunk (3 bits)
+            st_shared_v4(s_act + (uint32_t)(idx >> 6) * A2 + (uint32_t)(row + ((idx >> 3) & 7)) * 128u + (uint32_t)(idx & 7) * 16u, 0u, 0u, 0u, 0u);
+        }
     };
 
     if (warp == 9) {
@@ -924,10 +948,10 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                             }
                             // one accumulator per pass: issue_tap_mmas<.., NACC = 1> on this accumulator's rows and columns
                             if (CL)
-                                issue_tap_mmas_pair(elected, dcol + (uint32_t)a * ACC, s_act, kLead + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
+                                issue_tap_mmas_pair(elected, dcol + (uint32_t)a * ACC, s_act, base_row(l) + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
                                                     s_ring + slot * (uint32_t)GP::SLOT_BYTES + (uint32_t)tt * (uint32_t)GP::TAP_STRIDE, ksteps, use_s || t > 0, A2);
                             else
-                                issue_tap_mmas<true, 1, true>(elected, dcol + (uint32_t)a * ACC, s_act, R, kLead + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
+                                issue_tap_mmas<true, 1, true>(elected, dcol + (uint32_t)a * ACC, s_act, R, base_row(l) + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
                                                               s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
                                                               use_s || t > 0, A2);
                             if (a == 0 && tt == 0) {
@@ -968,9 +992,6 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         const int cell = a * 128 + (warp & 3) * 32 + lane;
         const Cell c = decode_cell(cell, CELLS);
         const uint32_t my_rows = a == 0 ? bar_rows(0) : (warp == 4 ? bar_rows(1) : bar_rows(2));
-        // warp 3 owns rows 121..127, which accumulator 1's MMAs of the SAME layer still read through their negatively shifted windows:
-        // it computes both channel halves first, holding the packed chunks in registers, waits for accumulator 1 and only then stores
-        const bool defer = warp == 3;
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t acc_par = 0;  // parity of the layer counter (both accumulator barriers complete once per layer)
 #ifdef ONB_X3P_PROFILE
@@ -983,13 +1004,15 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
             const int64_t board0 = CL ? (2 * (worker + gi * n_workers) + (int64_t)crank) * NB : ((int64_t)blockIdx.x + gi * gridDim.x) * NB;
             // ---- input planes -> channel chunks of both activation matrices (create_tensor_from_state layout [21][5][5]).
             // The previous group's last MMAs have completed (every thread waited for both accumulators before its heads).
-            if (c.real) {
+            {
                 const int64_t gb = board0 + c.board;
                 const float* src = planes + gb * 525 + c.pos;
                 float x[32];  // the planes are 0 / 1: exact, the second operand part is zero
 #pragma unroll
-                for (int ch = 0; ch < 32; ++ch) x[ch] = (ch < kInPlanes && gb < n) ? __ldg(src + ch * 25) : 0.f;
-                store_channels_x3(s_act, A2, R, kLead + cell, 0, x);  // 32 channels: planes 21..31 are zero
+                for (int ch = 0; ch < 32; ++ch) x[ch] = (c.real && ch < kInPlanes && gb < n) ? __ldg(src + ch * 25) : 0.f;
+                store_channels_x3(s_act, A2, R, base_row(0) + cell, 0, x);  // 32 channels: planes 21..31 and pad cells are zero
+                if (warp == 0) zero_rows(base_row(0) - 8);
+                if (warp == 7) zero_rows(base_row(0) + 256);
             }
             fence_proxy_async();
             arrive(my_rows);
@@ -1003,6 +1026,16 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 if (tid == 128) TL(6);
                 if (tid == 224) TL(8);
                 tc_fence_after();
+                const int rn = base_row(l + 1);  // where the next layer's activations go
+                if (!last) {
+                    if (a == 0 && (l + 1) % GP::WRAP == 0) {  // the window jumps back up, over rows accumulator 1's MMAs may still read
+                        EP(e_work);
+                        mbar_wait(bar_acc(1), acc_par);
+                        EP(e_halo);
+                    }
+                    if (warp == 0) zero_rows(rn - 8);
+                    if (warp == 7) zero_rows(rn + 256);
+                }
                 const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
                 const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
                 const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
@@ -1010,7 +1043,6 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * ACC;
                 const uint32_t tskip = tlane + SET + a * ACC;
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
-                uint32_t keep_hi[16], keep_lo[16];  // defer: the first half's chunks
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t v[32];
@@ -1033,21 +1065,11 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                         o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
                     }
                     if (!last) {
-                        if (!defer) {
-                            if (c.real) store_channels_x3(s_act, A2, R, kLead + cell, h * 32, o);
-                        } else if (h == 0) {
-                            pack_channels_x3(o, keep_hi, keep_lo);
-                        } else {
-                            uint32_t hi[16], lo[16];
-                            pack_channels_x3(o, hi, lo);
-                            EP(e_work);
-                            mbar_wait(bar_acc(1), acc_par);
-                            EP(e_halo);
-                            if (c.real) {
-                                store_packed_x3(s_act, A2, R, kLead + cell, 0, keep_hi, keep_lo);
-                                store_packed_x3(s_act, A2, R, kLead + cell, 32, hi, lo);
-                            }
+                        if (!c.real) {  // pad cells are stored too, as zeros (their accumulators hold sums that mean nothing)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = 0.f;
                         }
+                        store_channels_x3(s_act, A2, R, rn + cell, h * 32, o);
                     }
                     if (preload) {
 #pragma unroll
