@@ -667,7 +667,7 @@ __device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) 
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -776,6 +776,10 @@ using GeoX3P = GeoX3PT<false>;
 // issues MMAs. Cross-CTA traffic is barrier traffic only: the peer's epilogue threads arrive on the LEADER's rows barriers, the
 // peer's warp 8 relays "my share of slot s has landed" to the leader's peer_full[s], and the leader's commits are multicast to the
 // accumulator / empty barriers of both CTAs. Same products and accumulation order: results identical to the single-CTA build.
+#ifdef ONB_X3P_PROFILE
+__device__ long long s_tl[8][12];  // timeline of one board group (the 6th) of one CTA: [layer][event], see the printout at the kernel's end
+__device__ long long s_t2[2][8];   // layer 4 of that group, per accumulator: wake, then (weights there, slot issued) x 3, commit issued
+#endif
 template <bool CL>
 __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
     k_net_forward_x3p(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
@@ -792,8 +796,6 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = 1 + 2 * net.n_blocks;
 #ifdef ONB_X3P_PROFILE
-    __shared__ long long s_tl[8][12];  // timeline of one board group (the 6th) of CTA 3: [layer][event], see the printout at the end
-    __shared__ long long s_t2[2][8];   // layer 4 of that group, per accumulator: wake, then (weights there, slot issued) x 3, commit issued
 #define TL(ev) do { if (blockIdx.x == (CL ? 2 : 3) && gi == 5 && l < 8) s_tl[l][ev] = clock64(); } while (0)
 #define TL2(ev) do { if (blockIdx.x == (CL ? 2 : 3) && gi == 5 && l == 4 && lane == 0) s_t2[a][ev] = clock64(); } while (0)
 #else
@@ -896,6 +898,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         // ---- MMA issue (the whole warp runs the loop so that descriptors stay in uniform registers; one elected lane issues)
         const bool elected = elect_one();
         uint32_t q0 = 0, stage = 0;  // stage = number of "rows ready" rounds consumed so far (input stage + epilogues)
+        int gl = 0;                  // layers issued so far, over all board groups: the activation window keeps drifting across groups
 #ifdef ONB_X3P_PROFILE
         long long t_rows0 = 0, t_rows0b = 0, t_rows1 = 0, t_full = 0, t_issue = 0, t_mark = clock64();
 #define XP(var) do { const long long now__ = clock64(); var += now__ - t_mark; t_mark = now__; } while (0)
@@ -948,10 +951,10 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                             }
                             // one accumulator per pass: issue_tap_mmas<.., NACC = 1> on this accumulator's rows and columns
                             if (CL)
-                                issue_tap_mmas_pair(elected, dcol + (uint32_t)a * ACC, s_act, base_row(l) + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
+                                issue_tap_mmas_pair(elected, dcol + (uint32_t)a * ACC, s_act, base_row(gl) + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
                                                     s_ring + slot * (uint32_t)GP::SLOT_BYTES + (uint32_t)tt * (uint32_t)GP::TAP_STRIDE, ksteps, use_s || t > 0, A2);
                             else
-                                issue_tap_mmas<true, 1, true>(elected, dcol + (uint32_t)a * ACC, s_act, R, base_row(l) + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
+                                issue_tap_mmas<true, 1, true>(elected, dcol + (uint32_t)a * ACC, s_act, R, base_row(gl) + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
                                                               s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
                                                               use_s || t > 0, A2);
                             if (a == 0 && tt == 0) {
@@ -978,6 +981,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 }
                 q0 += (uint32_t)UPL;
                 stage += 1;
+                gl = gl + 1 == GP::WRAP ? 0 : gl + 1;
             }
         }
 #ifdef ONB_X3P_PROFILE
@@ -1000,25 +1004,38 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
 #else
 #define EP(var) do { } while (0)
 #endif
-        for (int64_t gi = 0; gi < my_groups; ++gi) {
-            const int64_t board0 = CL ? (2 * (worker + gi * n_workers) + (int64_t)crank) * NB : ((int64_t)blockIdx.x + gi * gridDim.x) * NB;
-            // ---- input planes -> channel chunks of both activation matrices (create_tensor_from_state layout [21][5][5]).
-            // The previous group's last MMAs have completed (every thread waited for both accumulators before its heads).
-            {
-                const int64_t gb = board0 + c.board;
-                const float* src = planes + gb * 525 + c.pos;
-                float x[32];  // the planes are 0 / 1: exact, the second operand part is zero
+        auto group_board0 = [&](int64_t g) { return CL ? (2 * (worker + g * n_workers) + (int64_t)crank) * NB : ((int64_t)blockIdx.x + g * gridDim.x) * NB; };
+        // input planes -> channel chunks of both activation matrices (create_tensor_from_state layout [21][5][5]); pad cells and
+        // planes 21..31 are zero. The loads of the NEXT group are issued before the last layer's accumulator wait and stored from that
+        // layer's epilogue (it is simply the next stop of the drifting window), so the next group's MMAs queue up behind this one's
+        // while the heads are computed.
+        float xin[kInPlanes];
+        auto load_input = [&](int64_t g) {
+            const int64_t gb = group_board0(g) + c.board;
+            const float* src = planes + gb * 525 + c.pos;
 #pragma unroll
-                for (int ch = 0; ch < 32; ++ch) x[ch] = (c.real && ch < kInPlanes && gb < n) ? __ldg(src + ch * 25) : 0.f;
-                store_channels_x3(s_act, A2, R, base_row(0) + cell, 0, x);  // 32 channels: planes 21..31 and pad cells are zero
-                if (warp == 0) zero_rows(base_row(0) - 8);
-                if (warp == 7) zero_rows(base_row(0) + 256);
-            }
-            fence_proxy_async();
-            arrive(my_rows);
+            for (int ch = 0; ch < kInPlanes; ++ch) xin[ch] = (c.real && g < my_groups && gb < n) ? __ldg(src + ch * 25) : 0.f;
+        };
+        auto store_input = [&](int row) {
+            float x[32];
+#pragma unroll
+            for (int ch = 0; ch < 32; ++ch) x[ch] = ch < kInPlanes ? xin[ch] : 0.f;
+            store_channels_x3(s_act, A2, R, row + cell, 0, x);
+        };
+        int gl = 0;  // layers done so far modulo WRAP, over all board groups (the MMA warp counts the same)
+        load_input(0);
+        store_input(base_row(0));
+        if (warp == 0) zero_rows(base_row(0) - 8);
+        if (warp == 7) zero_rows(base_row(0) + 256);
+        fence_proxy_async();
+        arrive(my_rows);
+        for (int64_t gi = 0; gi < my_groups; ++gi) {
+            const int64_t board0 = group_board0(gi);
             for (int l = 0; l < L; ++l) {
                 const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
                 const bool last = l == L - 1;
+                const bool feeds = !last || gi + 1 < my_groups;  // this epilogue writes the next stop of the window (layer or input)
+                if (last && feeds) load_input(gi + 1);
                 EP(e_work);
                 mbar_wait(bar_acc(a), acc_par);
                 EP(e_wait);
@@ -1026,9 +1043,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 if (tid == 128) TL(6);
                 if (tid == 224) TL(8);
                 tc_fence_after();
-                const int rn = base_row(l + 1);  // where the next layer's activations go
-                if (!last) {
-                    if (a == 0 && (l + 1) % GP::WRAP == 0) {  // the window jumps back up, over rows accumulator 1's MMAs may still read
+                const int rn = base_row(gl + 1);  // where the next layer's activations (or the next group's input) go
+                if (feeds) {
+                    if (a == 0 && gl + 1 == GP::WRAP) {  // the window jumps back up, over rows accumulator 1's MMAs may still read
                         EP(e_work);
                         mbar_wait(bar_acc(1), acc_par);
                         EP(e_halo);
@@ -1103,10 +1120,8 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
                 }
                 if (preload) tmem_wait_st();
-                if (last) {
-                    // the next group's input stage overwrites rows the OTHER accumulator's last MMAs may still read: wait for both
-                    mbar_wait(bar_acc(a ^ 1), acc_par);
-                } else {
+                if (last && feeds) store_input(rn);
+                if (feeds) {
                     fence_proxy_async();
                     tc_fence_before();
                     arrive(my_rows);  // this thread's rows (and its TMEM reads) of the layer are done
@@ -1116,6 +1131,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     if (tid == 127) TL(10);
                 }
                 acc_par ^= 1u;
+                gl = gl + 1 == GP::WRAP ? 0 : gl + 1;
             }
             // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
             named_bar_sync(1, 256);
