@@ -2469,10 +2469,11 @@ static cudaError_t launch_net_x3pair(Ctx* c, const float* planes, float* policy,
         cfg.gridDim = dim3((unsigned)(sms & ~1));
         e = cudaOccupancyMaxActiveClusters(&mc, k_net_forward_x3p<true>, &cfg);
         if (e != cudaSuccess) return e;
-        if (mc <= 0) return cudaErrorLaunchOutOfResources;
         if (mc > sms / 2) mc = sms / 2;
+        if (20 * mc < 9 * sms) mc = -1;  // the clusters would leave more than a tenth of the SMs idle
         if (dev >= 0 && dev < 64) max_clusters[dev] = mc;
     }
+    if (mc < 0) return cudaErrorLaunchOutOfResources;
     const int64_t pairs = ((count + G::NB - 1) / G::NB + 1) / 2;
     cfg.gridDim = dim3(2u * (unsigned)(pairs < mc ? pairs : mc));
     return cudaLaunchKernelEx(&cfg, k_net_forward_x3p<true>, planes, (float*)policy, (float*)value, (int64_t)count, nd);
@@ -2526,16 +2527,23 @@ cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (ns.x3) {  // ONB_NET_F32: split operands, f32-faithful: one CTA per SM, warp-specialised (k_net_forward_x3p). Exploration knob
-                  // ONB_NET_X3_HALVES=1: two halves of 3 boards that share the weight stream and take turns issuing (0.794 ms: the overlap
-                  // of one half's epilogue with the other's MMAs does not pay for 6 instead of 7 boards per weight pass and 108 of 128 rows)
+    if (ns.x3) {
+        // ONB_NET_F32: split operands, f32-faithful, one CTA per SM. Default: the warp-specialised pipeline on CTA pairs
+        // (k_net_forward_x3p<true>, 0.600 ms per 16 384 positions); ONB_NET_X3_PAIR=0: the same pipeline on single CTAs (0.646 ms; also
+        // the fallback when the device cannot co-schedule the clusters); ONB_NET_X3_PIPE=0: the plain kernel (0.745 ms).
+        // Exploration knob ONB_NET_X3_HALVES=1: two halves of 3 boards that share the weight stream and take turns issuing (0.794 ms:
+        // the overlap of one half's epilogue with the other's MMAs does not pay for 6 instead of 7 boards per weight pass)
         const char* halves = getenv("ONB_NET_X3_HALVES");
         if (halves && halves[0] == '1') return launch_net_v2x(c, planes, policy, value, nd, sms, count);
-        const char* pair = getenv("ONB_NET_X3_PAIR");  // the pipelined kernel on CTA pairs (tcgen05 cta_group::2): each SM fetches half of B
-        if (pair && pair[0] == '1') return launch_net_x3pair(c, planes, policy, value, nd, sms, count);
-        const char* pipe = getenv("ONB_NET_X3_PIPE");  // default: the warp-specialised pipelined kernel (0.724 ms); 0 = the plain one (0.745 ms)
-        if (!(pipe && pipe[0] == '0')) return launch_net_x3p(c, planes, policy, value, nd, sms, count);
-        return launch_net_variant<2, true, true>(c, planes, policy, value, nd, sms, count);
+        const char* pipe = getenv("ONB_NET_X3_PIPE");
+        if (pipe && pipe[0] == '0') return launch_net_variant<2, true, true>(c, planes, policy, value, nd, sms, count);
+        const char* pair = getenv("ONB_NET_X3_PAIR");
+        if (!(pair && pair[0] == '0')) {
+            const cudaError_t e = launch_net_x3pair(c, planes, policy, value, nd, sms, count);
+            if (e != cudaErrorLaunchOutOfResources) return e;
+            (void)cudaGetLastError();  // no room for the clusters on this device: single CTAs
+        }
+        return launch_net_x3p(c, planes, policy, value, nd, sms, count);
     }
     const char* v3 = getenv("ONB_NET_V3");  // three CTAs per SM, residual in an L2-resident scratch (f16 operands only)
     if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms, count);

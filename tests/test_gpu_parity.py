@@ -1617,16 +1617,17 @@ def test_cuda_graph_cache_follows_the_noise_setting(onb):
 @pytest.mark.gpu
 def test_network_split_mode_variants_agree(onb, monkeypatch):
     """The builds of the f32-faithful network compute the same products in the same order per accumulator: the warp-specialised
-    pipelined kernel (ONB_NET_X3_PIPE) is bit-identical to the plain one-CTA kernel, the two-halves build (ONB_NET_X3_HALVES=1, an
-    exploration knob) agrees to a few ulps (its heads add the two channel halves in a different order); all meet the 1e-5 tolerance."""
+    pipelined kernel on CTA pairs (the default) and on single CTAs (ONB_NET_X3_PAIR=0) are bit-identical to the plain one-CTA kernel
+    (ONB_NET_X3_PIPE=0), the two-halves build (ONB_NET_X3_HALVES=1, an exploration knob) agrees to a few ulps (its heads add the two
+    channel halves in a different order); all meet the 1e-5 tolerance."""
     from test_net_cpu import lively_model
     for blocks, n in ((3, 100), (0, 33), (5, 250)):   # n not a multiple of 3, 6 or 7
         model = lively_model(blocks, seed=9)
         planes = O.encode(_positions(n, 5)).reshape(n, 21, 5, 5)
         want_p, want_v = O.net_forward(model.state_dict(), planes)
         outs = {}
-        for name, env in (("plain", {"ONB_NET_X3_PIPE": "0"}), ("pipe", {"ONB_NET_X3_PIPE": "1"}), ("halves", {"ONB_NET_X3_HALVES": "1"}),
-                          ("pair", {"ONB_NET_X3_PAIR": "1"})):
+        for name, env in (("plain", {"ONB_NET_X3_PIPE": "0"}), ("pipe", {}), ("halves", {"ONB_NET_X3_HALVES": "1"}),
+                          ("single", {"ONB_NET_X3_PAIR": "0"})):
             for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES", "ONB_NET_X3_PAIR"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
@@ -1639,7 +1640,7 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
                 outs[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
             assert np.abs(outs[name][0] - want_p).max() <= 1e-5 and np.abs(outs[name][1] - want_v).max() <= 1e-5, (name, blocks)
         assert np.array_equal(outs["plain"][0], outs["pipe"][0]) and np.array_equal(outs["plain"][1], outs["pipe"][1]), blocks
-        assert np.array_equal(outs["plain"][0], outs["pair"][0]) and np.array_equal(outs["plain"][1], outs["pair"][1]), blocks
+        assert np.array_equal(outs["plain"][0], outs["single"][0]) and np.array_equal(outs["plain"][1], outs["single"][1]), blocks
         for other in ("halves",):   # its heads add the two channel halves' partial sums: a few ulps
             assert np.abs(outs["plain"][0] - outs[other][0]).max() <= 1e-6 and np.abs(outs["plain"][1] - outs[other][1]).max() <= 2e-6, other
         # the f16 fast mode: the warp-specialised two-CTAs-per-SM build against the plain one, bit for bit
@@ -1656,6 +1657,31 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
                 f16[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
         monkeypatch.delenv("ONB_NET_F16_PIPE", raising=False)
         assert np.array_equal(f16["plain"][0], f16["pipe"][0]) and np.array_equal(f16["plain"][1], f16["pipe"][1]), blocks
+
+
+@pytest.mark.gpu
+def test_network_drifting_window_wraps(onb, monkeypatch):
+    """The pipelined f32-faithful kernels slide their activation window down by 8 rows per layer and jump back to the top after 25
+    (CTA pairs) / 7 (single CTAs) layers, across board groups: a 13-block network (27 layers) and enough boards for several groups per
+    CTA exercise every wrap; results must equal the plain kernel's bit for bit."""
+    from test_net_cpu import lively_model
+    model = lively_model(13, seed=4)
+    n = 148 * 7 * 3 + 5
+    planes = O.encode(_positions(n, 11)).reshape(n, 21, 5, 5)
+    outs = {}
+    for name, env in (("plain", {"ONB_NET_X3_PIPE": "0"}), ("pair", {}), ("single", {"ONB_NET_X3_PAIR": "0"})):
+        for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES", "ONB_NET_X3_PAIR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
+            ctx.net_load(model, precision="f32")
+            ctx.write(onb.BUF_LEAF_PLANES, planes)
+            ctx.net_forward(onb.BUF_LEAF_PLANES)
+            outs[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
+    assert np.isfinite(outs["plain"][0]).all() and outs["plain"][0].std(0).max() > 1e-4   # the boards still tell apart
+    for other in ("pair", "single"):
+        assert np.array_equal(outs["plain"][0], outs[other][0]) and np.array_equal(outs["plain"][1], outs[other][1]), other
 
 
 @pytest.mark.gpu
