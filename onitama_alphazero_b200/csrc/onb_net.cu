@@ -1022,6 +1022,42 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
             for (int ch = 0; ch < 32; ++ch) x[ch] = ch < kInPlanes ? xin[ch] : 0.f;
             store_channels_x3(s_act, A2, R, row + cell, 0, x);
         };
+        // heads of one board group: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh) from the 1x1
+        // convolution outputs the last layer's epilogue left in s_head. They are computed where the epilogue warps have slack -- after
+        // the second layer's epilogue of the NEXT group (its first layer has half the MMAs, its epilogue is already late) -- and right
+        // after the last layer only for the last group
+        auto run_heads = [&](int64_t hb0) {
+            named_bar_sync(1, 256);
+            for (int b = warp; b < NB; b += 8) {
+                const int64_t gb = hb0 + b;
+                if (gb >= n) continue;
+                const float* hb = s_head + b * 75;
+                const bool two = lane + 32 < 50;
+                float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+#pragma unroll 10
+                for (int i = 0; i < 50; ++i) {
+                    const float x = hb[i];
+                    l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
+                    if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+                }
+                const float m = warp_max(two ? fmaxf(l0, l1) : l0);
+                const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
+                const float s = warp_sum(e0 + e1);
+                policy[gb * 50 + lane] = e0 / s;
+                if (two) policy[gb * 50 + 32 + lane] = e1 / s;
+                float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+#pragma unroll 5
+                for (int i = 0; i < 25; ++i) {
+                    const float x = hb[50 + i];
+                    h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
+                    h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+                }
+                float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+                acc = warp_sum(acc);
+                if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+            }
+            named_bar_sync(1, 256);  // s_head is free again before anybody's next last-layer epilogue
+        };
         int gl = 0;  // layers done so far modulo WRAP, over all board groups (the MMA warp counts the same)
         load_input(0);
         store_input(base_row(0));
@@ -1130,40 +1166,11 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     if (tid == 224) TL(9);
                     if (tid == 127) TL(10);
                 }
+                if (l == 1 && L >= 3 && gi > 0) run_heads(group_board0(gi - 1));
                 acc_par ^= 1u;
                 gl = gl + 1 == GP::WRAP ? 0 : gl + 1;
             }
-            // ---- heads: one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
-            named_bar_sync(1, 256);
-            for (int b = warp; b < NB; b += 8) {
-                const int64_t gb = board0 + b;
-                if (gb >= n) continue;
-                const float* hb = s_head + b * 75;
-                const bool two = lane + 32 < 50;
-                float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
-#pragma unroll 10
-                for (int i = 0; i < 50; ++i) {
-                    const float x = hb[i];
-                    l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
-                    if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
-                }
-                const float m = warp_max(two ? fmaxf(l0, l1) : l0);
-                const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
-                const float s = warp_sum(e0 + e1);
-                policy[gb * 50 + lane] = e0 / s;
-                if (two) policy[gb * 50 + 32 + lane] = e1 / s;
-                float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
-#pragma unroll 5
-                for (int i = 0; i < 25; ++i) {
-                    const float x = hb[50 + i];
-                    h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
-                    h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
-                }
-                float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
-                acc = warp_sum(acc);
-                if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
-            }
-            named_bar_sync(1, 256);  // s_head is free again before anybody's next last-layer epilogue
+            if (L < 3 || gi + 1 == my_groups) run_heads(board0);
         }
 #ifdef ONB_X3P_PROFILE
         EP(e_work);
