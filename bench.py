@@ -35,6 +35,8 @@ SELFPLAY_SIMS = 800
 GAMES_SLOTS = 2048     # `games` workload: slots per GPU (a step plays 2 x slots whole games)
 SEED = 20240607
 NET_PRECISION = {"fused-f32": "f32", "fused": "f16", "fused-tf32": "tf32", "torch": "torch"}
+NET_KERNEL = {"fused-f32": "k_net_forward_x3p<true> (CTA pairs, tcgen05 cta_group::2)", "fused": "k_net_forward<2,f16>", "fused-tf32": "k_net_forward<2,tf32>",
+              "torch": "library kernels"}
 NET_DTYPE = {"fused-f32": "f32-faithful network: split f16 operands (x = x1 + 2^-11 x2), 3 products per multiply-add, f32 accumulate",
              "fused": "f16 x f16 -> f32 network (FAST MODE: operands rounded to 11 bits, not the reference's f32 arithmetic)",
              "fused-tf32": "tf32 x tf32 -> f32 network (operands rounded to 11 bits)", "torch": "f32/tf32 (network, cuDNN)"}
@@ -783,7 +785,7 @@ def main():
         tpeak, tsrc = read_tensor_peak()
         ach = flop * sims * (samples / world) / (ms * 1e-3) / 1e12   # one search of `sims` evaluations per recorded sample (= per live slot and ply)
         roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": read_traffic("k_net_forward"),
-                "kernel": "k_net_forward<2,%s>" % NET_PRECISION[args.net], "peak_source": tsrc,
+                "kernel": NET_KERNEL[args.net], "peak_source": tsrc,
                 "samples_per_sec": samples / (ms * 1e-3), "plies_per_step": plies / world / max(1, steps),
                 "note": "a step = 2 x slots complete games; every ply searches the slots with a game in progress (x 800 network evaluations); finished "
                         "slots start their next game at once while games remain, idle slots are not searched",
@@ -852,7 +854,7 @@ def main():
             tpeak, tsrc = read_tensor_peak()
             ach = flop * n * sims * steps / (ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": read_traffic("k_net_forward"),
-                    "kernel": "k_net_forward<2,%s>" % NET_PRECISION[net_mode], "flop_per_evaluation": flop,
+                    "kernel": NET_KERNEL[net_mode], "flop_per_evaluation": flop,
                     "note": "achieved = USEFUL network FLOPs (one f32 multiply-add per weight and square, as the reference computes) of the whole "
                             "ply / ply time, search kernels included in the time; the f32-faithful mode spends three f16 tensor-core products per "
                             "useful multiply-add (split operands), so its tensor pipe does 3x this figure; the MMAs also compute the zero-padding "
