@@ -705,6 +705,33 @@ __device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint32_t a_addr, ui
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same MMAs from precomputed descriptor words. The low word of a shared-memory descriptor -- (address >> 4) in 14 bits | the
+// leading-offset field -- is LINEAR in the byte address below 256 KB and the high word is a constant, so an issue loop can keep one
+// low word per operand base and add compile-time offsets (>> 4) instead of rebuilding both descriptors for every instruction: the
+// MMA warp's own instruction stream (not the tensor pipe) was what paced the pipelined kernels, ~ 100 instructions per tap.
+template <bool PAIR>
+__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate, uint32_t idesc) {
+    const uint32_t hi = desc_hi(0u);
+    static_assert(ONB_NET_BASEOFF == 0, "the descriptor high word must not depend on the address");
+    if (PAIR)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
                  : "memory");
@@ -1448,6 +1475,382 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 2)
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, G::TMEM_COLS);
+}
+
+// ---- the f16 fast mode as ONE CTA per SM with FOUR accumulators: the pipeline of k_net_forward_x3p with everything it learned ------
+// 14 boards (504 cells) per pass in four 128-row accumulators (TMEM: 4 x 64 columns x {plain, residual-preloaded} = 512), sixteen
+// epilogue warps (four per accumulator, 16 channels at a time: 576 threads leave 113 registers), one MMA warp, one weight warp.
+// The MMAs of a layer are issued accumulator after accumulator; accumulator a's epilogue has the other three accumulators' MMAs to
+// hide under. Taken over from k_net_forward_x3p: the drifting activation window (no write-after-read wait at layer boundaries, also
+// across board groups), the wait for the next accumulator's first warp only in front of tap 5, barrier tests behind queued MMAs,
+// the next group's input stored from the last layer's epilogue, heads computed in the next group's slack, and CL = CTA pairs
+// (tcgen05 cta_group::2: each SM keeps rows 32 r .. 32 r + 31 of every tap, 4 KB instead of 8 KB). Twice the boards per weight pass
+// of the two-CTAs-per-SM builds (and a quarter of their weight bytes per SM with CL): the L2 -> SM weight stream was 55 % of their
+// time. Same products, accumulation order and head sums as k_net_forward<2, f16>: bit-identical results.
+#ifdef ONB_F16Q_PROFILE
+__device__ long long q_tl[8][4][4];  // [layer][accumulator][issue start, issue end, accumulator done (first warp of its group), that warp arrives]
+#define QTL(l_, a_, e_) do { if (blockIdx.x == 2 && gi == 3 && (l_) < 8) q_tl[l_][a_][e_] = clock64(); } while (0)
+#else
+#define QTL(l_, a_, e_) do { } while (0)
+#endif
+template <bool CL>
+struct GeoF16Q {
+    static constexpr int NACC = 4, NB = 14, CELLS = NB * kCellsPerBoard;  // 504 of 512 rows
+    static constexpr int EPI_WARPS = 4 * NACC, THREADS = (EPI_WARPS + 2) * 32;
+    static constexpr int DRIFT_ROWS = 8, WRAP = CL ? 12 : 8;
+    static constexpr int R = kLead + NACC * 128 + kTrail + DRIFT_ROWS * (WRAP - 1);
+    static constexpr int ACT_BYTES = R * 128;
+    static constexpr int TAP_STRIDE = CL ? 4096 : 8192;
+    // the ring holds TWO layers: a slot is free again only when the LAST accumulator has read it, a third of an accumulator's MMAs
+    // before the next layer's first accumulator wants its successor -- with one layer of slots every layer waited for weights
+    static constexpr int TPS = 3, UPL = 3, NSLOT = 6;
+    static constexpr int SLOT_BYTES = TPS * TAP_STRIDE;
+    static constexpr int OFF_RING = ACT_BYTES;
+    static constexpr int OFF_HEAD = OFF_RING + NSLOT * SLOT_BYTES;
+    static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;
+    static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
+    // mbarriers: full[3], empty[3], acc[4], rows_first[4] (first warp of a group), rows_rest[4], CL: peer_full[3]
+    static constexpr int N_BARS = 2 * NSLOT + 3 * NACC + (CL ? NSLOT : 0);
+    static constexpr int SMEM = OFF_BAR + N_BARS * 8 + 16;
+    static constexpr int SET_COLS = NACC * 64, TMEM_COLS = 2 * SET_COLS;
+    static_assert(ACT_BYTES % 1024 == 0 && SMEM <= 227 * 1024 && TMEM_COLS == 512, "geometry");
+};
+
+template <bool CL>
+__global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
+    k_net_forward_f16q(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
+    using GP = GeoF16Q<CL>;
+    using O = Op<true>;
+    constexpr int NACC = GP::NACC, NB = GP::NB, CELLS = GP::CELLS, R = GP::R, NSLOT = GP::NSLOT, TPS = GP::TPS, UPL = GP::UPL, EW = GP::EPI_WARPS;
+    constexpr uint32_t ACC = 64u, SET = (uint32_t)GP::SET_COLS;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t s_act = smem_u32(smem), s_ring = s_act + GP::OFF_RING, s_bar = s_act + GP::OFF_BAR;
+    float* s_head = reinterpret_cast<float*>(smem + GP::OFF_HEAD);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GP::OFF_BAR + GP::N_BARS * 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = 1 + 2 * net.n_blocks;
+    const uint32_t crank = CL ? cluster_ctarank() : 0u;
+    const int64_t n_groups = CL ? ((n + NB - 1) / NB + 1) / 2 : (n + NB - 1) / NB;  // CL: pairs of groups (leader 2 p, peer 2 p + 1)
+    const int64_t worker = CL ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x, n_workers = CL ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+    if (worker >= n_groups) return;  // whole CTA (pair), before any allocation
+    const int64_t my_groups = (n_groups - worker + n_workers - 1) / n_workers;
+    const uint32_t total_units = (uint32_t)my_groups * (uint32_t)(UPL * L);
+    auto bar_full = [&](uint32_t s) { return s_bar + s * 8u; };
+    auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
+    auto bar_acc = [&](uint32_t a) { return s_bar + (2 * NSLOT + a) * 8u; };
+    auto bar_first = [&](uint32_t a) { return s_bar + (2 * NSLOT + NACC + a) * 8u; };      // rows of the first warp of group a
+    auto bar_rest = [&](uint32_t a) { return s_bar + (2 * NSLOT + 2 * NACC + a) * 8u; };   // rows of its other three warps
+    auto bar_peer = [&](uint32_t s) { return s_bar + (2 * NSLOT + 3 * NACC + s) * 8u; };   // CL, leader's: the peer's share of slot s landed
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+            if (CL) mbar_init(bar_peer(s), 1);
+        }
+        for (uint32_t a = 0; a < (uint32_t)NACC; ++a) {
+            mbar_init(bar_acc(a), 1);
+            mbar_init(bar_first(a), CL ? 64 : 32);  // CL: the leader's rows barriers collect the epilogue threads of both CTAs
+            mbar_init(bar_rest(a), CL ? 192 : 96);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        if (CL)
+            tmem_alloc_pair(smem_u32(s_tmem), GP::TMEM_COLS);
+        else
+            tmem_alloc(smem_u32(s_tmem), GP::TMEM_COLS);
+    }
+    for (int i = tid; i < GP::ACT_BYTES / 16; i += GP::THREADS) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (CL) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t rows_base = CL ? mapa_shared(bar_first(0), 0u) : bar_first(0);  // CL: rows barriers live in the leader
+    auto arrive = [&](uint32_t bar) {
+        if (CL)
+            mbar_arrive_cluster(rows_base + (bar - bar_first(0)));
+        else
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    };
+    auto wait_rows = [&](uint32_t bar, uint32_t parity) {
+        if (CL) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+    };
+    // drifting activation window, see k_net_forward_x3p: layer l + 1 is written 8 rows below layer l
+    auto base_row = [&](int l) { return kLead + GP::DRIFT_ROWS * (GP::WRAP - 1 - (l % GP::WRAP)); };
+    auto zero_rows = [&](int row) {  // 8 rows, by one warp
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int idx = lane * 2 + k;  // row (3 bits) | chunk (3 bits)
+            st_shared_v4(s_act + (uint32_t)(row + (idx >> 3)) * 128u + (uint32_t)(idx & 7) * 16u, 0u, 0u, 0u, 0u);
+        }
+    };
+
+    if (warp == EW + 1) {
+        // ---- weight producer: the ring is filled strictly in tap order, as far ahead as it has free slots
+        if (lane == 0) {
+            for (uint32_t u = 0; u < total_units; ++u) {
+                const uint32_t slot = u % NSLOT, use = u / NSLOT;
+                if (use >= 1) mbar_wait(bar_empty(slot), (use - 1u) & 1u);
+                const uint32_t ul = u % (uint32_t)(UPL * L), layer = ul / UPL, tap = (ul - layer * UPL) * TPS;
+                const uint8_t* src = CL ? net.wpair + ((size_t)crank * (size_t)(9 * L) + (size_t)layer * 9 + tap) * (size_t)GP::TAP_STRIDE
+                                        : net.wconv + ((size_t)layer * 9 + tap) * (size_t)O::TAP_BYTES;
+                mbar_expect_tx(bar_full(slot), (uint32_t)GP::SLOT_BYTES);
+                bulk_g2s(s_ring + slot * (uint32_t)GP::SLOT_BYTES, src, (uint32_t)GP::SLOT_BYTES, bar_full(slot));
+            }
+        }
+    } else if (CL && warp == EW && crank != 0u) {
+        // ---- peer CTA: no MMA issue here; relay "this CTA's share of the slot has landed" to the leader
+        if (lane == 0) {
+            const uint32_t peer0 = mapa_shared(bar_peer(0), 0u);
+            for (uint32_t u = 0; u < total_units; ++u) {
+                const uint32_t slot = u % NSLOT, use = u / NSLOT;
+                mbar_wait(bar_full(slot), use & 1u);
+                mbar_arrive_cluster(peer0 + slot * 8u);
+            }
+        }
+    } else if (warp == EW) {
+        // ---- MMA issue (the whole warp runs the loop so that descriptors stay in uniform registers; one elected lane issues)
+        const bool elected = elect_one();
+        constexpr uint32_t kIdescPair = (1u << 4) | ((64u >> 3) << 17) | ((256u >> 4) << 24);
+        uint32_t q0 = 0, stage = 0;  // stage = number of "rows ready" rounds consumed so far (input stage + epilogues)
+        int gl = 0;                  // layers issued so far modulo WRAP, over all board groups
+        auto wait_weights = [&](uint32_t uu) {
+            const uint32_t sl = uu % NSLOT, us = uu / NSLOT;
+            mbar_wait(bar_full(sl), us & 1u);
+            if (CL) mbar_wait_cluster(bar_peer(sl), us & 1u);
+        };
+        for (int64_t gi = 0; gi < my_groups; ++gi) {
+            for (int l = 0; l < L; ++l) {
+                const bool use_s = l >= 2 && (l & 1) == 0;
+                const uint32_t dcol = tmem + (use_s ? SET : 0u);
+                const int ksteps = l == 0 ? O::KCH0 / 2 : O::KCH / 2;
+                const int row_l = base_row(gl);
+                // accumulator a reads rows 128 a - 7 .. 128 a + 134: group a - 1 (tested when accumulator a - 1 was issued), group a,
+                // and from tap 5 on the first warp of group a + 1. Every test that can be made early sits behind queued MMAs.
+                wait_rows(bar_first(0), stage & 1u);
+                wait_rows(bar_rest(0), stage & 1u);
+                tc_fence_after();
+                wait_weights(q0);
+#pragma unroll 1
+                for (int a = 0; a < NACC; ++a) {
+                    if (lane == 0) QTL(l, a, 0);
+                    const uint32_t d_acc = dcol + (uint32_t)a * ACC;
+                    const uint32_t a_acc_lo = desc_lo(s_act) + (uint32_t)((row_l + a * 128) * 8);  // 128-byte rows: 8 per row in the address field
+#pragma unroll
+                    for (int g = 0; g < UPL; ++g) {  // unrolled: the tap number (window shift, which test sits where) is a compile-time constant
+                        const uint32_t u = q0 + g, slot = u % NSLOT;
+                        const uint32_t b_slot_lo = desc_lo(s_ring) + slot * (uint32_t)(GP::SLOT_BYTES >> 4);
+#pragma unroll
+                        for (int tt = 0; tt < TPS; ++tt) {
+                            const int t = g * TPS + tt;
+                            if (t == 5 && a + 1 < NACC) {  // the first window that reaches into the next accumulator's rows
+                                wait_rows(bar_first(a + 1), stage & 1u);
+                                tc_fence_after();
+                            }
+                            // descriptor low words of this tap (whole warp, uniform registers); K step j adds 32 bytes = 2 to both
+                            const uint32_t a_lo = a_acc_lo + (uint32_t)(((t / 3 - 1) * 6 + (t % 3 - 1)) * 8);
+                            const uint32_t b_lo = b_slot_lo + (uint32_t)(tt * (GP::TAP_STRIDE >> 4));
+                            if (elected) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (j < ksteps) mma_lo<CL>(d_acc, a_lo + 2u * j, b_lo + 2u * j, (use_s || t > 0 || j > 0) ? 1u : 0u, CL ? kIdescPair : O::IDESC);
+                            }
+                            if (tt == 0) {
+                                if (a == 0 && g + 1 < UPL) {
+                                    wait_weights(u + 1);
+                                } else if (g + 1 == UPL && a + 1 < NACC) {  // the next accumulator's other rows: long written
+                                    wait_rows(bar_rest(a + 1), stage & 1u);
+                                    tc_fence_after();
+                                }
+                            }
+                        }
+                        if (a == NACC - 1 && elected) {  // all accumulators' MMAs have read the slot
+                            if (CL) umma_commit_pair(bar_empty(slot)); else umma_commit(bar_empty(slot));
+                        }
+                    }
+                    if (elected) {
+                        if (CL) umma_commit_pair(bar_acc(a)); else umma_commit(bar_acc(a));
+                    }
+                    if (lane == 0) QTL(l, a, 1);
+                }
+                q0 += (uint32_t)UPL;
+                stage += 1;
+                gl = gl + 1 == GP::WRAP ? 0 : gl + 1;
+            }
+        }
+    } else {
+        // ---- epilogue warps: group a = warp >> 2 owns accumulator a; this thread owns one cell (TMEM lane) and its 64 channels
+        const int a = warp >> 2;
+        const int cell = a * 128 + (warp & 3) * 32 + lane;
+        const Cell c = decode_cell(cell, CELLS);
+        const uint32_t my_rows = (warp & 3) == 0 ? bar_first(a) : bar_rest(a);
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t acc_par = 0;  // parity of the layer counter (every accumulator barrier completes once per layer)
+        auto group_board0 = [&](int64_t g) { return CL ? (2 * (worker + g * n_workers) + (int64_t)crank) * NB : ((int64_t)blockIdx.x + g * gridDim.x) * NB; };
+        float xin[kInPlanes];  // the next input of this cell (create_tensor_from_state layout [21][5][5]); the planes are 0 / 1: exact in f16
+        auto load_input = [&](int64_t g) {
+            const int64_t gb = group_board0(g) + c.board;
+            const float* src = planes + gb * 525 + c.pos;
+#pragma unroll
+            for (int ch = 0; ch < kInPlanes; ++ch) xin[ch] = (c.real && g < my_groups && gb < n) ? __ldg(src + ch * 25) : 0.f;
+        };
+        auto store_input = [&](int row) {
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                float x[16];
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch) x[ch] = part * 16 + ch < kInPlanes ? xin[part * 16 + ch] : 0.f;
+                store_channels_f16_16(s_act, R, row + cell, part * 16, x);  // 32 channels: planes 21..31 and pad cells are zero
+            }
+        };
+        auto run_heads = [&](int64_t hb0) {  // one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
+            named_bar_sync(1, EW * 32);
+            for (int b = warp; b < NB; b += EW) {
+                const int64_t gb = hb0 + b;
+                if (gb >= n) continue;
+                const float* hb = s_head + b * 75;
+                const bool two = lane + 32 < 50;
+                float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+#pragma unroll 10
+                for (int i = 0; i < 50; ++i) {
+                    const float x = hb[i];
+                    l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
+                    if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+                }
+                const float m = warp_max(two ? fmaxf(l0, l1) : l0);
+                const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
+                const float s = warp_sum(e0 + e1);
+                policy[gb * 50 + lane] = e0 / s;
+                if (two) policy[gb * 50 + 32 + lane] = e1 / s;
+                float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+#pragma unroll 5
+                for (int i = 0; i < 25; ++i) {
+                    const float x = hb[50 + i];
+                    h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
+                    h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+                }
+                float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+                acc = warp_sum(acc);
+                if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+            }
+            named_bar_sync(1, EW * 32);  // s_head is free again before anybody's next last-layer epilogue
+        };
+        int gl = 0;  // layers done so far modulo WRAP, over all board groups (the MMA warp counts the same)
+        load_input(0);
+        store_input(base_row(0));
+        if (warp == 0) zero_rows(base_row(0) - 8);
+        if (warp == EW - 1) zero_rows(base_row(0) + NACC * 128);
+        fence_proxy_async();
+        arrive(my_rows);
+        for (int64_t gi = 0; gi < my_groups; ++gi) {
+            const int64_t board0 = group_board0(gi);
+            for (int l = 0; l < L; ++l) {
+                const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
+                const bool last = l == L - 1;
+                const bool feeds = !last || gi + 1 < my_groups;  // this epilogue writes the next stop of the window (layer or input)
+                if (last && feeds) load_input(gi + 1);
+                mbar_wait(bar_acc(a), acc_par);
+                if ((warp & 3) == 0 && lane == 0) QTL(l, a, 2);
+                tc_fence_after();
+                const int rn = base_row(gl + 1);  // where the next layer's activations (or the next group's input) go
+                if (feeds) {
+                    // the window jumps back up, over rows the later accumulators' MMAs of this layer may still read
+                    if (a + 1 < NACC && gl + 1 == GP::WRAP) mbar_wait(bar_acc(NACC - 1), acc_par);
+                    if (warp == 0) zero_rows(rn - 8);
+                    if (warp == EW - 1) zero_rows(rn + NACC * 128);
+                }
+                const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
+                const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
+                const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
+                const float4* hw = reinterpret_cast<const float4*>(net.head);
+                const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * ACC;
+                const uint32_t tskip = tlane + SET + a * ACC;
+                float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // 16 channels at a time
+                    const int c0 = q * 16;
+                    uint32_t v[16];
+                    tmem_ld16_nowait(tsrc + c0, v);
+                    tmem_wait_ld();
+                    float o[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!use_s) b = __ldg(bias_l + c0 / 4 + i);
+                        o[4 * i + 0] = fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f);
+                        o[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f);
+                        o[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f);
+                        o[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f);
+                    }
+                    if (!last) {
+                        if (!c.real) {  // pad cells are stored too, as zeros (their accumulators hold sums that mean nothing)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = 0.f;
+                        }
+                        store_channels_f16_16(s_act, R, rn + cell, c0, o);
+                    }
+                    if (preload) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = __ldg(bias_n + c0 / 4 + i);
+                            v[4 * i + 0] = __float_as_uint(o[4 * i + 0] + b.x);
+                            v[4 * i + 1] = __float_as_uint(o[4 * i + 1] + b.y);
+                            v[4 * i + 2] = __float_as_uint(o[4 * i + 2] + b.z);
+                            v[4 * i + 3] = __float_as_uint(o[4 * i + 3] + b.w);
+                        }
+                        tmem_st16(tskip + c0, v);
+                    }
+                    if (last) {  // 1x1 convolutions of both heads (net.rs: policy_conv 64 -> 2, vh_conv 64 -> 1)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 w0 = __ldg(hw + (kHP0 / 4) + c0 / 4 + i), w1 = __ldg(hw + (kHP1 / 4) + c0 / 4 + i),
+                                         w2 = __ldg(hw + (kHV / 4) + c0 / 4 + i);
+                            hp0 = fmaf(o[4 * i + 0], w0.x, fmaf(o[4 * i + 1], w0.y, fmaf(o[4 * i + 2], w0.z, fmaf(o[4 * i + 3], w0.w, hp0))));
+                            hp1 = fmaf(o[4 * i + 0], w1.x, fmaf(o[4 * i + 1], w1.y, fmaf(o[4 * i + 2], w1.z, fmaf(o[4 * i + 3], w1.w, hp1))));
+                            hv = fmaf(o[4 * i + 0], w2.x, fmaf(o[4 * i + 1], w2.y, fmaf(o[4 * i + 2], w2.z, fmaf(o[4 * i + 3], w2.w, hv))));
+                        }
+                    }
+                }
+                if (last && c.real) {
+                    float* hb = s_head + c.board * 75;
+                    hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
+                    hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
+                    hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+                }
+                if (preload) tmem_wait_st();
+                if (last && feeds) store_input(rn);
+                if (feeds) {
+                    fence_proxy_async();
+                    tc_fence_before();
+                    arrive(my_rows);  // this thread's rows (and its TMEM reads) of the layer are done
+                    if ((warp & 3) == 0 && lane == 0) QTL(l, a, 3);
+                }
+                if (l == 1 && L >= 3 && gi > 0) run_heads(group_board0(gi - 1));
+                acc_par ^= 1u;
+                gl = gl + 1 == GP::WRAP ? 0 : gl + 1;
+            }
+            if (L < 3 || gi + 1 == my_groups) run_heads(board0);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+#ifdef ONB_F16Q_PROFILE
+    if (blockIdx.x == 2 && tid == 0 && my_groups > 3)
+        for (int l = 0; l < L && l < 8; ++l)
+            for (int a = 0; a < NACC; ++a)
+                printf("f16q layer %d acc %d: issue %6lld .. %6lld | done %6lld, first warp arrives %6lld\n", l, a, q_tl[l][a][0] - q_tl[0][0][0],
+                       q_tl[l][a][1] - q_tl[0][0][0], q_tl[l][a][2] - q_tl[0][0][0], q_tl[l][a][3] - q_tl[0][0][0]);
+#endif
+    if (CL) {
+        cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal its barriers
+        if (warp == 0) tmem_dealloc_pair(tmem, GP::TMEM_COLS);
+    } else if (warp == 0) {
+        tmem_dealloc(tmem, GP::TMEM_COLS);
+    }
 }
 
 // ---- version 2: ONE CTA per SM, two independent halves that share one weight stream ---------------------------------------------
@@ -2347,6 +2750,14 @@ int32_t net_load(Ctx* c, int32_t n_tensors, const char* const* names, const floa
     // the pair, per layer and tap, 12 KB = [b1 | b2 of the tap: this rank's 64 rows of the N = 128 MMA][rows 32 r .. 32 r + 31 of b1:
     // its 32 rows of the N = 64 MMA]. Moving whole 8-row groups keeps the 128-byte swizzle phase of every row.
     size_t pair_off = 0;
+    if (f16 && !x3) {  // the f16 fast mode on CTA pairs (k_net_forward_f16q<true>): per rank, layer and tap the 32 B rows this rank holds
+        static_assert(Op<true>::TAP_BYTES == 8192 && Op<true>::TAP_BYTES0 == 8192, "pair layout");
+        pair_off = (wconv.size() + 1023) / 1024 * 1024;
+        wconv.resize(pair_off + 2 * (size_t)(9 * L) * 4096, 0);
+        for (int r = 0; r < 2; ++r)
+            for (int t = 0; t < 9 * L; ++t)
+                memcpy(wconv.data() + pair_off + ((size_t)r * (size_t)(9 * L) + (size_t)t) * 4096, wconv.data() + (size_t)t * 8192 + (size_t)r * 4096, 4096);
+    }
     if (x3) {
         static_assert(Op<true>::TAP_BYTES == 8192 && Op<true>::TAP_BYTES0 == 8192, "pair layout");
         pair_off = (wconv.size() + 1023) / 1024 * 1024;
@@ -2486,6 +2897,44 @@ static cudaError_t launch_net_x3pair(Ctx* c, const float* planes, float* policy,
     return cudaLaunchKernelEx(&cfg, k_net_forward_x3p<true>, planes, (float*)policy, (float*)value, (int64_t)count, nd);
 }
 
+// the four-accumulator f16 pipeline, on CTA pairs (clusters of two) or single CTAs
+template <bool CL>
+static cudaError_t launch_net_f16q(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
+    using GP = GeoF16Q<CL>;
+    static int max_workers[64] = {};  // per device; 0 = not asked yet, -1 = the clusters do not fit
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL ? 2 : 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(GP::THREADS);
+    cfg.dynamicSmemBytes = GP::SMEM;
+    cfg.stream = c->stream;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int mw = (dev >= 0 && dev < 64) ? max_workers[dev] : 0;
+    if (mw == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k_net_forward_f16q<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GP::SMEM);
+        if (e != cudaSuccess) return e;
+        mw = sms;
+        if (CL) {
+            cfg.gridDim = dim3((unsigned)(sms & ~1));
+            e = cudaOccupancyMaxActiveClusters(&mw, k_net_forward_f16q<CL>, &cfg);
+            if (e != cudaSuccess) return e;
+            if (mw > sms / 2) mw = sms / 2;
+            if (20 * mw < 9 * sms) mw = -1;  // the clusters would leave more than a tenth of the SMs idle
+        }
+        if (dev >= 0 && dev < 64) max_workers[dev] = mw;
+    }
+    if (mw < 0) return cudaErrorLaunchOutOfResources;
+    const int64_t groups = (count + GP::NB - 1) / GP::NB, work = CL ? (groups + 1) / 2 : groups;
+    cfg.gridDim = dim3((CL ? 2u : 1u) * (unsigned)(work < mw ? work : mw));
+    return cudaLaunchKernelEx(&cfg, k_net_forward_f16q<CL>, planes, (float*)policy, (float*)value, (int64_t)count, nd);
+}
+
 static cudaError_t launch_net_v2x(Ctx* c, const float* planes, float* policy, float* value, const NetDev& nd, int sms, int64_t count) {
     using G = Geo2X;
     static bool attr[64] = {};  // the opt-in is per device
@@ -2556,6 +3005,16 @@ cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float
     if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms, count);
     const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)
     if (v2 && v2[0] == '1') return ns.f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms, count) : launch_net_v2<false>(c, planes, policy, value, nd, sms, count);
+    // ONB_NET_F16: exploration knob ONB_NET_F16_QUAD=1|2: one CTA per SM with four accumulators (14 boards), the x3p pipeline: 1 = CTA pairs, 2 = single CTAs
+    const char* quad = getenv("ONB_NET_F16_QUAD");
+    if (quad && ns.f16 && (quad[0] == '1' || quad[0] == '2')) {
+        if (quad[0] == '1') {
+            const cudaError_t e = launch_net_f16q<true>(c, planes, policy, value, nd, sms, count);
+            if (e != cudaErrorLaunchOutOfResources) return e;
+            (void)cudaGetLastError();
+        }
+        return launch_net_f16q<false>(c, planes, policy, value, nd, sms, count);
+    }
     const char* f16p = getenv("ONB_NET_F16_PIPE");  // exploration knob: the warp-specialised pipeline for the f16 fast mode
     if (f16p && f16p[0] == '1' && ns.f16) return launch_net_f16p(c, planes, policy, value, nd, sms, count);
     const char* wide = getenv("ONB_NET_WIDE");  // exploration knob: 14 boards per CTA, one CTA per SM

@@ -1647,8 +1647,10 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
         for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES", "ONB_NET_X3_PAIR"):
             monkeypatch.delenv(k, raising=False)
         f16 = {}
-        for name, val in (("plain", "0"), ("pipe", "1")):
-            monkeypatch.setenv("ONB_NET_F16_PIPE", val)
+        for name, env in (("plain", {"ONB_NET_F16_PIPE": "0", "ONB_NET_F16_QUAD": "0"}), ("pipe", {"ONB_NET_F16_PIPE": "1", "ONB_NET_F16_QUAD": "0"}),
+                          ("quad_pair", {"ONB_NET_F16_QUAD": "1"}), ("quad_single", {"ONB_NET_F16_QUAD": "2"})):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
             with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
                 ctx.net_load(model, precision="f16")
                 ctx.write(onb.BUF_LEAF_PLANES, planes)
@@ -1656,7 +1658,9 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
                 ctx.net_forward(onb.BUF_LEAF_PLANES)
                 f16[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
         monkeypatch.delenv("ONB_NET_F16_PIPE", raising=False)
-        assert np.array_equal(f16["plain"][0], f16["pipe"][0]) and np.array_equal(f16["plain"][1], f16["pipe"][1]), blocks
+        monkeypatch.delenv("ONB_NET_F16_QUAD", raising=False)
+        for other in ("pipe", "quad_pair", "quad_single"):
+            assert np.array_equal(f16["plain"][0], f16[other][0]) and np.array_equal(f16["plain"][1], f16[other][1]), (blocks, other)
 
 
 @pytest.mark.gpu
