@@ -963,9 +963,16 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                         XP(t_full);
                     };
                     if (a == 0) wait_weights(q0);
-#pragma unroll 1
+                    // descriptor low words (see mma_lo): this accumulator's window of the current layer, the second activation matrix,
+                    // and per slot the weights; the slot loop is unrolled so that a tap's shift and tests are compile-time constants
+                    const uint32_t d_acc = dcol + (uint32_t)a * ACC;
+                    const uint32_t a_acc_lo = desc_lo(s_act) + (uint32_t)((base_row(gl) + a * 128) * 8);  // 128-byte rows: 8 per row in the address field
+                    constexpr uint32_t kA2Lo = A2 >> 4;
+                    constexpr uint32_t kPair128 = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24), kPair64 = (1u << 4) | ((64u >> 3) << 17) | ((256u >> 4) << 24);
+#pragma unroll
                     for (int g = 0; g < UPL; ++g) {
                         const uint32_t u = q0 + g, slot = u % NSLOT;
+                        const uint32_t b_slot_lo = desc_lo(s_ring) + slot * (uint32_t)(GP::SLOT_BYTES >> 4);
                         TL2(1 + 2 * g);
 #pragma unroll
                         for (int tt = 0; tt < TPS; ++tt) {
@@ -976,14 +983,23 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                                 XP(t_rows0b);
                                 tc_fence_after();
                             }
-                            // one accumulator per pass: issue_tap_mmas<.., NACC = 1> on this accumulator's rows and columns
-                            if (CL)
-                                issue_tap_mmas_pair(elected, dcol + (uint32_t)a * ACC, s_act, base_row(gl) + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
-                                                    s_ring + slot * (uint32_t)GP::SLOT_BYTES + (uint32_t)tt * (uint32_t)GP::TAP_STRIDE, ksteps, use_s || t > 0, A2);
-                            else
-                                issue_tap_mmas<true, 1, true>(elected, dcol + (uint32_t)a * ACC, s_act, R, base_row(gl) + (t / 3 - 1) * 6 + (t % 3 - 1) + a * 128,
-                                                              s_ring + slot * (uint32_t)G::SLOT_BYTES + (uint32_t)tt * (uint32_t)G::TAP_STRIDE, ksteps,
-                                                              use_s || t > 0, A2);
+                            // per K step: a1 x [b1 ; b2] (N = 128) into D1 | D2, then a2 x b1 (N = 64) onto D2 (issue_tap_mmas / _pair)
+                            const uint32_t a_lo = a_acc_lo + (uint32_t)(((t / 3 - 1) * 6 + (t % 3 - 1)) * 8);
+                            const uint32_t b_lo = b_slot_lo + (uint32_t)(tt * (GP::TAP_STRIDE >> 4));
+                            if (elected) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (j < ksteps) {
+                                        const uint32_t accum = (use_s || t > 0 || j > 0) ? 1u : 0u;
+                                        if (CL) {
+                                            mma_lo<true>(d_acc, a_lo + 2u * j, b_lo + 2u * j, accum, kPair128);
+                                            mma_lo<true>(d_acc + 64u, a_lo + kA2Lo + 2u * j, b_lo + (8192u >> 4) + 2u * j, 1u, kPair64);
+                                        } else {
+                                            mma_lo<false>(d_acc, a_lo + 2u * j, b_lo + 2u * j, accum, O::IDESC_N128);
+                                            mma_lo<false>(d_acc + 64u, a_lo + kA2Lo + 2u * j, b_lo + 2u * j, 1u, O::IDESC);
+                                        }
+                                    }
+                            }
                             if (a == 0 && tt == 0) {
                                 if (g + 1 < UPL) {
                                     wait_weights(u + 1);
