@@ -1525,8 +1525,8 @@ struct GeoF16Q {
     static constexpr int OFF_HEAD = OFF_RING + NSLOT * SLOT_BYTES;
     static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;
     static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
-    // mbarriers: full[3], empty[3], acc[4], rows_first[4] (first warp of a group), rows_rest[4], CL: peer_full[3]
-    static constexpr int N_BARS = 2 * NSLOT + 3 * NACC + (CL ? NSLOT : 0);
+    // mbarriers: full[6], empty[6], acc[4], rows_first[4] (first warp of a group), rows_rest[4], heads_full, heads_free, CL: peer_full[6]
+    static constexpr int N_BARS = 2 * NSLOT + 3 * NACC + 2 + (CL ? NSLOT : 0);
     static constexpr int SMEM = OFF_BAR + N_BARS * 8 + 16;
     static constexpr int SET_COLS = NACC * 64, TMEM_COLS = 2 * SET_COLS;
     static_assert(ACT_BYTES % 1024 == 0 && SMEM <= 227 * 1024 && TMEM_COLS == 512, "geometry");
@@ -1556,7 +1556,8 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
     auto bar_acc = [&](uint32_t a) { return s_bar + (2 * NSLOT + a) * 8u; };
     auto bar_first = [&](uint32_t a) { return s_bar + (2 * NSLOT + NACC + a) * 8u; };      // rows of the first warp of group a
     auto bar_rest = [&](uint32_t a) { return s_bar + (2 * NSLOT + 2 * NACC + a) * 8u; };   // rows of its other three warps
-    auto bar_peer = [&](uint32_t s) { return s_bar + (2 * NSLOT + 3 * NACC + s) * 8u; };   // CL, leader's: the peer's share of slot s landed
+    const uint32_t bar_hfull = s_bar + (2 * NSLOT + 3 * NACC) * 8u, bar_hfree = bar_hfull + 8u;  // s_head written by every cell | read by every head
+    auto bar_peer = [&](uint32_t s) { return s_bar + (2 * NSLOT + 3 * NACC + 2 + s) * 8u; };   // CL, leader's: the peer's share of slot s landed
 
     if (tid == 0) {
         for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
@@ -1569,6 +1570,8 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
             mbar_init(bar_first(a), CL ? 64 : 32);  // CL: the leader's rows barriers collect the epilogue threads of both CTAs
             mbar_init(bar_rest(a), CL ? 192 : 96);
         }
+        mbar_init(bar_hfull, EW * 32);
+        mbar_init(bar_hfree, EW * 32);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -1722,8 +1725,11 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
                 store_channels_f16_16(s_act, R, row + cell, part * 16, x);  // 32 channels: planes 21..31 and pad cells are zero
             }
         };
-        auto run_heads = [&](int64_t hb0) {  // one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh)
-            named_bar_sync(1, EW * 32);
+        // heads, one warp per board (ph_linear2 + softmax, vh_linear1 + ReLU + vh_linear2 + tanh). Two mbarriers instead of a CTA-wide
+        // barrier: the four groups reach this point up to three accumulator phases apart, and nobody should wait for the others
+        auto local_arrive = [&](uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
+        auto run_heads = [&](int64_t hb0, uint32_t parity) {
+            mbar_wait(bar_hfull, parity);  // every cell's 1x1 outputs of that group are in s_head
             for (int b = warp; b < NB; b += EW) {
                 const int64_t gb = hb0 + b;
                 if (gb >= n) continue;
@@ -1752,7 +1758,7 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
                 acc = warp_sum(acc);
                 if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
             }
-            named_bar_sync(1, EW * 32);  // s_head is free again before anybody's next last-layer epilogue
+            local_arrive(bar_hfree);  // s_head may be overwritten by the next last-layer epilogue once every thread has said so
         };
         int gl = 0;  // layers done so far modulo WRAP, over all board groups (the MMA warp counts the same)
         load_input(0);
@@ -1830,11 +1836,15 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
                         }
                     }
                 }
-                if (last && c.real) {
-                    float* hb = s_head + c.board * 75;
-                    hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
-                    hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
-                    hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+                if (last) {
+                    if (gi > 0) mbar_wait(bar_hfree, (uint32_t)(gi - 1) & 1u);  // the previous group's heads are done with s_head
+                    if (c.real) {
+                        float* hb = s_head + c.board * 75;
+                        hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
+                        hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
+                        hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+                    }
+                    local_arrive(bar_hfull);
                 }
                 if (preload) tmem_wait_st();
                 if (last && feeds) store_input(rn);
@@ -1844,11 +1854,11 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
                     arrive(my_rows);  // this thread's rows (and its TMEM reads) of the layer are done
                     if ((warp & 3) == 0 && lane == 0) QTL(l, a, 3);
                 }
-                if (l == 1 && L >= 3 && gi > 0) run_heads(group_board0(gi - 1));
+                if (l == 1 && L >= 3 && gi > 0) run_heads(group_board0(gi - 1), (uint32_t)(gi - 1) & 1u);
                 acc_par ^= 1u;
                 gl = gl + 1 == GP::WRAP ? 0 : gl + 1;
             }
-            if (L < 3 || gi + 1 == my_groups) run_heads(board0);
+            if (L < 3 || gi + 1 == my_groups) run_heads(board0, (uint32_t)gi & 1u);
         }
     }
     __syncwarp();
