@@ -1524,7 +1524,9 @@ struct GeoF16Q {
     static constexpr int OFF_RING = ACT_BYTES;
     static constexpr int OFF_HEAD = OFF_RING + NSLOT * SLOT_BYTES;
     static constexpr int HEAD_BYTES = ((NB * 75 * 4 + 15) / 16) * 16;
-    static constexpr int OFF_BAR = OFF_HEAD + HEAD_BYTES;
+    static constexpr int OFF_HW = OFF_HEAD + HEAD_BYTES;                 // CL (room to spare): the head parameters, copied once
+    static constexpr int HW_BYTES = CL ? kHeadFloats * 4 : 0;
+    static constexpr int OFF_BAR = OFF_HW + HW_BYTES;
     // mbarriers: full[6], empty[6], acc[4], rows_first[4] (first warp of a group), rows_rest[4], heads_full, heads_free, CL: peer_full[6]
     static constexpr int N_BARS = 2 * NSLOT + 3 * NACC + 2 + (CL ? NSLOT : 0);
     static constexpr int SMEM = OFF_BAR + N_BARS * 8 + 16;
@@ -1542,6 +1544,11 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s_act = smem_u32(smem), s_ring = s_act + GP::OFF_RING, s_bar = s_act + GP::OFF_BAR;
     float* s_head = reinterpret_cast<float*>(smem + GP::OFF_HEAD);
+    // head parameters: from shared memory in the pair build (the fully connected heads are latency chains of ~ 150 loads per lane; out
+    // of L1 / L2 one board cost a warp ~ 5 000 cycles), from global memory where the weight ring leaves no room
+    const float* s_hw = reinterpret_cast<const float*>(smem + GP::OFF_HW);
+    auto HW = [&](int i) { return CL ? s_hw[i] : __ldg(net.head + i); };
+    auto HW4 = [&](int i) { return CL ? reinterpret_cast<const float4*>(s_hw)[i] : __ldg(reinterpret_cast<const float4*>(net.head) + i); };
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GP::OFF_BAR + GP::N_BARS * 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = 1 + 2 * net.n_blocks;
@@ -1581,6 +1588,9 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
             tmem_alloc(smem_u32(s_tmem), GP::TMEM_COLS);
     }
     for (int i = tid; i < GP::ACT_BYTES / 16; i += GP::THREADS) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);
+    if (CL)
+        for (int i = tid; i < kHeadFloats / 4; i += GP::THREADS)
+            reinterpret_cast<float4*>(smem + GP::OFF_HW)[i] = __ldg(reinterpret_cast<const float4*>(net.head) + i);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -1735,28 +1745,28 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
                 if (gb >= n) continue;
                 const float* hb = s_head + b * 75;
                 const bool two = lane + 32 < 50;
-                float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+                float l0 = HW(kPhB + lane), l1 = two ? HW(kPhB + 32 + lane) : 0.f;
 #pragma unroll 10
                 for (int i = 0; i < 50; ++i) {
                     const float x = hb[i];
-                    l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
-                    if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+                    l0 = fmaf(x, HW(kPhW + i * 50 + lane), l0);
+                    if (two) l1 = fmaf(x, HW(kPhW + i * 50 + 32 + lane), l1);
                 }
                 const float m = warp_max(two ? fmaxf(l0, l1) : l0);
                 const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
                 const float s = warp_sum(e0 + e1);
                 policy[gb * 50 + lane] = e0 / s;
                 if (two) policy[gb * 50 + 32 + lane] = e1 / s;
-                float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+                float h0 = HW(kV1B + lane), h1 = HW(kV1B + 32 + lane);
 #pragma unroll 5
                 for (int i = 0; i < 25; ++i) {
                     const float x = hb[50 + i];
-                    h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
-                    h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+                    h0 = fmaf(x, HW(kV1W + i * 64 + lane), h0);
+                    h1 = fmaf(x, HW(kV1W + i * 64 + 32 + lane), h1);
                 }
-                float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+                float acc = fmaf(fmaxf(h0, 0.f), HW(kV2W + lane), fmaxf(h1, 0.f) * HW(kV2W + 32 + lane));
                 acc = warp_sum(acc);
-                if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+                if (lane == 0) value[gb] = tanhf(acc + HW(kV2B));
             }
             local_arrive(bar_hfree);  // s_head may be overwritten by the next last-layer epilogue once every thread has said so
         };
@@ -1787,7 +1797,6 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
                 const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
                 const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
                 const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
-                const float4* hw = reinterpret_cast<const float4*>(net.head);
                 const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * ACC;
                 const uint32_t tskip = tlane + SET + a * ACC;
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
@@ -1828,8 +1837,8 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
                     if (last) {  // 1x1 convolutions of both heads (net.rs: policy_conv 64 -> 2, vh_conv 64 -> 1)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float4 w0 = __ldg(hw + (kHP0 / 4) + c0 / 4 + i), w1 = __ldg(hw + (kHP1 / 4) + c0 / 4 + i),
-                                         w2 = __ldg(hw + (kHV / 4) + c0 / 4 + i);
+                            const float4 w0 = HW4((kHP0 / 4) + c0 / 4 + i), w1 = HW4((kHP1 / 4) + c0 / 4 + i),
+                                         w2 = HW4((kHV / 4) + c0 / 4 + i);
                             hp0 = fmaf(o[4 * i + 0], w0.x, fmaf(o[4 * i + 1], w0.y, fmaf(o[4 * i + 2], w0.z, fmaf(o[4 * i + 3], w0.w, hp0))));
                             hp1 = fmaf(o[4 * i + 0], w1.x, fmaf(o[4 * i + 1], w1.y, fmaf(o[4 * i + 2], w1.z, fmaf(o[4 * i + 3], w1.w, hp1))));
                             hv = fmaf(o[4 * i + 0], w2.x, fmaf(o[4 * i + 1], w2.y, fmaf(o[4 * i + 2], w2.z, fmaf(o[4 * i + 3], w2.w, hv))));
@@ -1840,9 +1849,9 @@ __global__ void __launch_bounds__(GeoF16Q<CL>::THREADS, 1)
                     if (gi > 0) mbar_wait(bar_hfree, (uint32_t)(gi - 1) & 1u);  // the previous group's heads are done with s_head
                     if (c.real) {
                         float* hb = s_head + c.board * 75;
-                        hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
-                        hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
-                        hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+                        hb[c.pos] = fmaxf(hp0 + HW(kHB + 0), 0.f);
+                        hb[25 + c.pos] = fmaxf(hp1 + HW(kHB + 1), 0.f);
+                        hb[50 + c.pos] = fmaxf(hv + HW(kHB + 2), 0.f);
                     }
                     local_arrive(bar_hfull);
                 }
