@@ -779,12 +779,14 @@ struct GeoX3PT {
     static constexpr int SLOT_BYTES = G::TPS * TAP_STRIDE;
     // drifting activation window (see the kernel): layer l's activations start DRIFT_ROWS rows below layer l - 1's, for WRAP
     // layers in a row; the budget is what the weight ring leaves of the 227 KB
-    static constexpr int DRIFT_ROWS = 8, WRAP = CL ? 25 : 7;
+    static constexpr int DRIFT_ROWS = 8, WRAP = CL ? 16 : 7;
     static constexpr int R = G::R + DRIFT_ROWS * (WRAP - 1);
     static constexpr int ACT_BYTES = R * 128;  // f16 operands: 64 channels = one 128-byte block per row
     static constexpr int OFF_RING = G::NMAT * ACT_BYTES;
     static constexpr int OFF_HEAD = OFF_RING + NSLOT * SLOT_BYTES;
-    static constexpr int OFF_BAR = OFF_HEAD + G::HEAD_BYTES;
+    static constexpr int OFF_HW = OFF_HEAD + G::HEAD_BYTES;  // CL: the head parameters, copied once (see k_net_forward_f16q)
+    static constexpr int HW_BYTES = CL ? kHeadFloats * 4 : 0;
+    static constexpr int OFF_BAR = OFF_HW + HW_BYTES;
     // mbarriers: full[3], empty[3], acc_full[2], rows_ready[3] (group 0 | warp 4 | warps 5-7), CL: peer_full[3]
     static constexpr int N_BARS = 2 * NSLOT + 2 + 3 + (CL ? NSLOT : 0);
     static constexpr int SMEM_USED = OFF_BAR + N_BARS * 8 + 16;
@@ -819,6 +821,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s_act = smem_u32(smem), s_ring = s_act + GP::OFF_RING, s_bar = s_act + GP::OFF_BAR;
     float* s_head = reinterpret_cast<float*>(smem + GP::OFF_HEAD);
+    const float* s_hw = reinterpret_cast<const float*>(smem + GP::OFF_HW);
+    auto HW = [&](int i) { return CL ? s_hw[i] : __ldg(net.head + i); };
+    auto HW4 = [&](int i) { return CL ? reinterpret_cast<const float4*>(s_hw)[i] : __ldg(reinterpret_cast<const float4*>(net.head) + i); };
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GP::OFF_BAR + GP::N_BARS * 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = 1 + 2 * net.n_blocks;
@@ -863,6 +868,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
             tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
     }
     for (int i = tid; i < G::NMAT * GP::ACT_BYTES / 16; i += GeoX3P::THREADS) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);
+    if (CL)
+        for (int i = tid; i < kHeadFloats / 4; i += GeoX3P::THREADS)
+            reinterpret_cast<float4*>(smem + GP::OFF_HW)[i] = __ldg(reinterpret_cast<const float4*>(net.head) + i);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -1076,28 +1084,28 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 if (gb >= n) continue;
                 const float* hb = s_head + b * 75;
                 const bool two = lane + 32 < 50;
-                float l0 = __ldg(net.head + kPhB + lane), l1 = two ? __ldg(net.head + kPhB + 32 + lane) : 0.f;
+                float l0 = HW(kPhB + lane), l1 = two ? HW(kPhB + 32 + lane) : 0.f;
 #pragma unroll 10
                 for (int i = 0; i < 50; ++i) {
                     const float x = hb[i];
-                    l0 = fmaf(x, __ldg(net.head + kPhW + i * 50 + lane), l0);
-                    if (two) l1 = fmaf(x, __ldg(net.head + kPhW + i * 50 + 32 + lane), l1);
+                    l0 = fmaf(x, HW(kPhW + i * 50 + lane), l0);
+                    if (two) l1 = fmaf(x, HW(kPhW + i * 50 + 32 + lane), l1);
                 }
                 const float m = warp_max(two ? fmaxf(l0, l1) : l0);
                 const float e0 = expf(l0 - m), e1 = two ? expf(l1 - m) : 0.f;
                 const float s = warp_sum(e0 + e1);
                 policy[gb * 50 + lane] = e0 / s;
                 if (two) policy[gb * 50 + 32 + lane] = e1 / s;
-                float h0 = __ldg(net.head + kV1B + lane), h1 = __ldg(net.head + kV1B + 32 + lane);
+                float h0 = HW(kV1B + lane), h1 = HW(kV1B + 32 + lane);
 #pragma unroll 5
                 for (int i = 0; i < 25; ++i) {
                     const float x = hb[50 + i];
-                    h0 = fmaf(x, __ldg(net.head + kV1W + i * 64 + lane), h0);
-                    h1 = fmaf(x, __ldg(net.head + kV1W + i * 64 + 32 + lane), h1);
+                    h0 = fmaf(x, HW(kV1W + i * 64 + lane), h0);
+                    h1 = fmaf(x, HW(kV1W + i * 64 + 32 + lane), h1);
                 }
-                float acc = fmaf(fmaxf(h0, 0.f), __ldg(net.head + kV2W + lane), fmaxf(h1, 0.f) * __ldg(net.head + kV2W + 32 + lane));
+                float acc = fmaf(fmaxf(h0, 0.f), HW(kV2W + lane), fmaxf(h1, 0.f) * HW(kV2W + 32 + lane));
                 acc = warp_sum(acc);
-                if (lane == 0) value[gb] = tanhf(acc + __ldg(net.head + kV2B));
+                if (lane == 0) value[gb] = tanhf(acc + HW(kV2B));
             }
             named_bar_sync(1, 256);  // s_head is free again before anybody's next last-layer epilogue
         };
@@ -1135,7 +1143,6 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 const bool preload = (l & 1) == 0 && !last;  // this layer's output is a block input: park it (+ next bias) in TMEM
                 const float4* bias_l = reinterpret_cast<const float4*>(net.bias + (size_t)l * 64);
                 const float4* bias_n = reinterpret_cast<const float4*>(net.bias + (size_t)(preload ? l + 2 : l) * 64);
-                const float4* hw = reinterpret_cast<const float4*>(net.head);
                 const uint32_t tsrc = tlane + (use_s ? SET : 0u) + a * ACC;
                 const uint32_t tskip = tlane + SET + a * ACC;
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
@@ -1184,8 +1191,8 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     if (last) {  // 1x1 convolutions of both heads (net.rs: policy_conv 64 -> 2, vh_conv 64 -> 1)
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float4 w0 = __ldg(hw + (kHP0 / 4) + h * 8 + i), w1 = __ldg(hw + (kHP1 / 4) + h * 8 + i),
-                                         w2 = __ldg(hw + (kHV / 4) + h * 8 + i);
+                            const float4 w0 = HW4((kHP0 / 4) + h * 8 + i), w1 = HW4((kHP1 / 4) + h * 8 + i),
+                                         w2 = HW4((kHV / 4) + h * 8 + i);
                             hp0 = fmaf(o[4 * i + 0], w0.x, fmaf(o[4 * i + 1], w0.y, fmaf(o[4 * i + 2], w0.z, fmaf(o[4 * i + 3], w0.w, hp0))));
                             hp1 = fmaf(o[4 * i + 0], w1.x, fmaf(o[4 * i + 1], w1.y, fmaf(o[4 * i + 2], w1.z, fmaf(o[4 * i + 3], w1.w, hp1))));
                             hv = fmaf(o[4 * i + 0], w2.x, fmaf(o[4 * i + 1], w2.y, fmaf(o[4 * i + 2], w2.z, fmaf(o[4 * i + 3], w2.w, hv))));
@@ -1194,9 +1201,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 }
                 if (last && c.real) {
                     float* hb = s_head + c.board * 75;
-                    hb[c.pos] = fmaxf(hp0 + __ldg(net.head + kHB + 0), 0.f);
-                    hb[25 + c.pos] = fmaxf(hp1 + __ldg(net.head + kHB + 1), 0.f);
-                    hb[50 + c.pos] = fmaxf(hv + __ldg(net.head + kHB + 2), 0.f);
+                    hb[c.pos] = fmaxf(hp0 + HW(kHB + 0), 0.f);
+                    hb[25 + c.pos] = fmaxf(hp1 + HW(kHB + 1), 0.f);
+                    hb[50 + c.pos] = fmaxf(hv + HW(kHB + 2), 0.f);
                 }
                 if (preload) tmem_wait_st();
                 if (last && feeds) store_input(rn);

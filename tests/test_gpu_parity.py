@@ -1665,7 +1665,7 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
 
 @pytest.mark.gpu
 def test_network_drifting_window_wraps(onb, monkeypatch):
-    """The pipelined f32-faithful kernels slide their activation window down by 8 rows per layer and jump back to the top after 25
+    """The pipelined f32-faithful kernels slide their activation window down by 8 rows per layer and jump back to the top after 16
     (CTA pairs) / 7 (single CTAs) layers, across board groups: a 13-block network (27 layers) and enough boards for several groups per
     CTA exercise every wrap; results must equal the plain kernel's bit for bit."""
     from test_net_cpu import lively_model
