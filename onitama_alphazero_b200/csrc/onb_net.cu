@@ -788,7 +788,7 @@ struct GeoX3PT {
     static constexpr int HW_BYTES = CL ? kHeadFloats * 4 : 0;
     static constexpr int OFF_BAR = OFF_HW + HW_BYTES;
     // mbarriers: full[3], empty[3], acc_full[2], rows_ready[3] (group 0 | warp 4 | warps 5-7), CL: peer_full[3]
-    static constexpr int N_BARS = 2 * NSLOT + 2 + 3 + (CL ? NSLOT : 0);
+    static constexpr int N_BARS = 2 * NSLOT + 2 + 3 + 2 + (CL ? NSLOT : 0);  // + heads_full, heads_free
     static constexpr int SMEM_USED = OFF_BAR + N_BARS * 8 + 16;
     static constexpr int SMEM = SMEM_USED;
     static_assert(SMEM_USED <= 227 * 1024, "shared memory");
@@ -846,7 +846,8 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
     auto bar_empty = [&](uint32_t s) { return s_bar + (NSLOT + s) * 8u; };
     auto bar_acc = [&](uint32_t a) { return s_bar + (2 * NSLOT + a) * 8u; };
     auto bar_rows = [&](uint32_t k) { return s_bar + (2 * NSLOT + 2 + k) * 8u; };  // 0: group 0, 1: warp 4, 2: warps 5-7
-    auto bar_peer = [&](uint32_t s) { return s_bar + (2 * NSLOT + 5 + s) * 8u; };  // CL, leader's: the peer's share of slot s has landed
+    const uint32_t bar_hfull = s_bar + (2 * NSLOT + 5) * 8u, bar_hfree = bar_hfull + 8u;  // s_head written by every cell | read by every head
+    auto bar_peer = [&](uint32_t s) { return s_bar + (2 * NSLOT + 7 + s) * 8u; };  // CL, leader's: the peer's share of slot s has landed
 
     if (tid == 0) {
         for (uint32_t s = 0; s < (uint32_t)NSLOT; ++s) {
@@ -859,6 +860,8 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         mbar_init(bar_rows(0), CL ? 256 : 128);  // CL: the leader's rows barriers collect the epilogue threads of both CTAs
         mbar_init(bar_rows(1), CL ? 64 : 32);
         mbar_init(bar_rows(2), CL ? 192 : 96);
+        mbar_init(bar_hfull, 256);
+        mbar_init(bar_hfree, 256);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -1077,8 +1080,9 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         // convolution outputs the last layer's epilogue left in s_head. They are computed where the epilogue warps have slack -- after
         // the second layer's epilogue of the NEXT group (its first layer has half the MMAs, its epilogue is already late) -- and right
         // after the last layer only for the last group
-        auto run_heads = [&](int64_t hb0) {
-            named_bar_sync(1, 256);
+        auto local_arrive = [&](uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); };
+        auto run_heads = [&](int64_t hb0, uint32_t parity) {
+            mbar_wait(bar_hfull, parity);  // every cell's 1x1 outputs of that group are in s_head (no CTA-wide barrier: the two groups are a phase apart)
             for (int b = warp; b < NB; b += 8) {
                 const int64_t gb = hb0 + b;
                 if (gb >= n) continue;
@@ -1107,7 +1111,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 acc = warp_sum(acc);
                 if (lane == 0) value[gb] = tanhf(acc + HW(kV2B));
             }
-            named_bar_sync(1, 256);  // s_head is free again before anybody's next last-layer epilogue
+            local_arrive(bar_hfree);  // s_head may be overwritten by the next last-layer epilogue once every thread has said so
         };
         int gl = 0;  // layers done so far modulo WRAP, over all board groups (the MMA warp counts the same)
         load_input(0);
@@ -1199,11 +1203,15 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                         }
                     }
                 }
-                if (last && c.real) {
-                    float* hb = s_head + c.board * 75;
-                    hb[c.pos] = fmaxf(hp0 + HW(kHB + 0), 0.f);
-                    hb[25 + c.pos] = fmaxf(hp1 + HW(kHB + 1), 0.f);
-                    hb[50 + c.pos] = fmaxf(hv + HW(kHB + 2), 0.f);
+                if (last) {
+                    if (gi > 0) mbar_wait(bar_hfree, (uint32_t)(gi - 1) & 1u);  // the previous group's heads are done with s_head
+                    if (c.real) {
+                        float* hb = s_head + c.board * 75;
+                        hb[c.pos] = fmaxf(hp0 + HW(kHB + 0), 0.f);
+                        hb[25 + c.pos] = fmaxf(hp1 + HW(kHB + 1), 0.f);
+                        hb[50 + c.pos] = fmaxf(hv + HW(kHB + 2), 0.f);
+                    }
+                    local_arrive(bar_hfull);
                 }
                 if (preload) tmem_wait_st();
                 if (last && feeds) store_input(rn);
@@ -1216,11 +1224,11 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     if (tid == 224) TL(9);
                     if (tid == 127) TL(10);
                 }
-                if (l == 1 && L >= 3 && gi > 0) run_heads(group_board0(gi - 1));
+                if (l == 1 && L >= 3 && gi > 0) run_heads(group_board0(gi - 1), (uint32_t)(gi - 1) & 1u);
                 acc_par ^= 1u;
                 gl = gl + 1 == GP::WRAP ? 0 : gl + 1;
             }
-            if (L < 3 || gi + 1 == my_groups) run_heads(board0);
+            if (L < 3 || gi + 1 == my_groups) run_heads(board0, (uint32_t)gi & 1u);
         }
 #ifdef ONB_X3P_PROFILE
         EP(e_work);
@@ -3047,10 +3055,17 @@ cudaError_t launch_net_forward(Ctx* c, const float* planes, float* policy, float
     if (v3 && v3[0] == '1' && c->net[c->net_cur].f16) return launch_net_v3(c, planes, policy, value, nd, sms, count);
     const char* v2 = getenv("ONB_NET_V2");  // exploration knob: one CTA per SM whose two halves share the weight stream (0.392 vs 0.343 ms)
     if (v2 && v2[0] == '1') return ns.f16 ? launch_net_v2<true>(c, planes, policy, value, nd, sms, count) : launch_net_v2<false>(c, planes, policy, value, nd, sms, count);
-    // ONB_NET_F16: exploration knob ONB_NET_F16_QUAD=1|2: one CTA per SM with four accumulators (14 boards), the x3p pipeline: 1 = CTA pairs, 2 = single CTAs
+    // ONB_NET_F16 default: one CTA per SM with four accumulators (14 boards), the pipeline of k_net_forward_x3p, on CTA pairs
+    // (k_net_forward_f16q<true>, 0.226 ms per 16 384 positions); ONB_NET_F16_QUAD=2: on single CTAs (0.269 ms; also the fallback when
+    // the clusters cannot be co-scheduled); ONB_NET_F16_QUAD=0: the round-1 build, two plain CTAs per SM (0.322 ms)
     const char* quad = getenv("ONB_NET_F16_QUAD");
-    if (quad && ns.f16 && (quad[0] == '1' || quad[0] == '2')) {
-        if (quad[0] == '1') {
+    const char* any_old = nullptr;
+    for (const char* knob : {"ONB_NET_V3", "ONB_NET_V2", "ONB_NET_F16_PIPE", "ONB_NET_WIDE", "ONB_NET_ONE_CTA"}) {
+        const char* v = getenv(knob);
+        if (v && v[0] == '1') any_old = v;  // an exploration knob of the older builds asks for them
+    }
+    if (ns.f16 && !any_old && !(quad && quad[0] == '0')) {
+        if (!(quad && quad[0] == '2')) {
             const cudaError_t e = launch_net_f16q<true>(c, planes, policy, value, nd, sms, count);
             if (e != cudaErrorLaunchOutOfResources) return e;
             (void)cudaGetLastError();

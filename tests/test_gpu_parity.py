@@ -1648,7 +1648,7 @@ def test_network_split_mode_variants_agree(onb, monkeypatch):
             monkeypatch.delenv(k, raising=False)
         f16 = {}
         for name, env in (("plain", {"ONB_NET_F16_PIPE": "0", "ONB_NET_F16_QUAD": "0"}), ("pipe", {"ONB_NET_F16_PIPE": "1", "ONB_NET_F16_QUAD": "0"}),
-                          ("quad_pair", {"ONB_NET_F16_QUAD": "1"}), ("quad_single", {"ONB_NET_F16_QUAD": "2"})):
+                          ("quad_pair", {"ONB_NET_F16_PIPE": "0", "ONB_NET_F16_QUAD": "1"}), ("quad_single", {"ONB_NET_F16_PIPE": "0", "ONB_NET_F16_QUAD": "2"})):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
