@@ -35,7 +35,7 @@ SELFPLAY_SIMS = 800
 GAMES_SLOTS = 2048     # `games` workload: slots per GPU (a step plays 2 x slots whole games)
 SEED = 20240607
 NET_PRECISION = {"fused-f32": "f32", "fused": "f16", "fused-tf32": "tf32", "torch": "torch"}
-NET_KERNEL = {"fused-f32": "k_net_forward_x3p<true> (CTA pairs, tcgen05 cta_group::2)", "fused": "k_net_forward<2,f16>", "fused-tf32": "k_net_forward<2,tf32>",
+NET_KERNEL = {"fused-f32": "k_net_forward_x3p<true> (CTA pairs, tcgen05 cta_group::2)", "fused": "k_net_forward_f16q<true> (CTA pairs, tcgen05 cta_group::2, four accumulators)", "fused-tf32": "k_net_forward<2,tf32>",
               "torch": "library kernels"}
 NET_DTYPE = {"fused-f32": "f32-faithful network: split f16 operands (x = x1 + 2^-11 x2), 3 products per multiply-add, f32 accumulate",
              "fused": "f16 x f16 -> f32 network (FAST MODE: operands rounded to 11 bits, not the reference's f32 arithmetic)",
