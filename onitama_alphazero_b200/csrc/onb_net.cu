@@ -772,7 +772,7 @@ __device__ __forceinline__ void issue_tap_mmas_pair(bool elected, uint32_t dcol,
 template <bool CL>
 struct GeoX3PT {
     using G = Geo<2, true, true>;
-    static constexpr int THREADS = 10 * 32;
+    static constexpr int THREADS = 11 * 32;  // 8 epilogue warps, warp 8: helper of warp 4 (see the kernel), warp 9: MMA issue, warp 10: weights
     // CL (CTA pair, see below): a tap is [this CTA's 64 B rows of the N = 128 MMA][its 32 B rows of the N = 64 MMA]
     static constexpr int TAP_STRIDE = CL ? 12 * 1024 : G::TAP_STRIDE;
     static constexpr int NSLOT = G::NSLOT;
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         mbar_init(bar_acc(0), 1);
         mbar_init(bar_acc(1), 1);
         mbar_init(bar_rows(0), CL ? 256 : 128);  // CL: the leader's rows barriers collect the epilogue threads of both CTAs
-        mbar_init(bar_rows(1), CL ? 64 : 32);
+        mbar_init(bar_rows(1), CL ? 128 : 64);  // warp 4 and its helper
         mbar_init(bar_rows(2), CL ? 192 : 96);
         mbar_init(bar_hfull, 256);
         mbar_init(bar_hfree, 256);
@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
         }
     };
 
-    if (warp == 9) {
+    if (warp == 10) {
         // ---- weight producer: the ring is filled strictly in tap order, as far ahead as it has free slots
         if (lane == 0) {
             for (uint32_t u = 0; u < total_units; ++u) {
@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 bulk_g2s(s_ring + slot * (uint32_t)GP::SLOT_BYTES, src, bytes, bar_full(slot));
             }
         }
-    } else if (CL && warp == 8 && crank != 0u) {
+    } else if (CL && warp == 9 && crank != 0u) {
         // ---- peer CTA: no MMA issue here; relay "this CTA's share of the slot has landed" to the leader
         if (lane == 0) {
             const uint32_t peer0 = mapa_shared(bar_peer(0), 0u);
@@ -932,7 +932,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 mbar_arrive_cluster(peer0 + slot * 8u);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 9) {
         // ---- MMA issue (the whole warp runs the loop so that descriptors stay in uniform registers; one elected lane issues)
         const bool elected = elect_one();
         uint32_t q0 = 0, stage = 0;  // stage = number of "rows ready" rounds consumed so far (input stage + epilogues)
@@ -1046,10 +1046,17 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
 #endif
     } else {
         // ---- epilogue warps: group a = warp >> 2 owns accumulator a; this thread owns one cell (TMEM lane) and its 64 channels
-        const int a = warp >> 2;
-        const int cell = a * 128 + (warp & 3) * 32 + lane;
+        // Warp 8 is the HELPER of warp 4: the cycle "accumulator 1 done -> warp 4's epilogue -> accumulator 0's taps 5..8 of the next
+        // layer -> accumulator 1's MMAs" is what paces a layer once everything else overlaps (timeline: ~ 900 idle tensor cycles per
+        // layer in front of tap 5), and a warp's epilogue is a latency chain, not a throughput problem. Warp 8 sits on the same TMEM
+        // lane quarter as warp 4 (warp id % 4 == 0) and takes channels 32..63 of cells 128..159, warp 4 keeps channels 0..31: the
+        // rows the next accumulator 0 waits for arrive in half the time. The last layer (heads: a sequential sum over all 64
+        // channels) stays with warp 4 alone.
+        const bool helper = warp == 8;
+        const int a = helper ? 1 : warp >> 2;
+        const int cell = helper ? 128 + lane : a * 128 + (warp & 3) * 32 + lane;
         const Cell c = decode_cell(cell, CELLS);
-        const uint32_t my_rows = a == 0 ? bar_rows(0) : (warp == 4 ? bar_rows(1) : bar_rows(2));
+        const uint32_t my_rows = a == 0 ? bar_rows(0) : ((warp == 4 || helper) ? bar_rows(1) : bar_rows(2));
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t acc_par = 0;  // parity of the layer counter (both accumulator barriers complete once per layer)
 #ifdef ONB_X3P_PROFILE
@@ -1114,8 +1121,10 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
             local_arrive(bar_hfree);  // s_head may be overwritten by the next last-layer epilogue once every thread has said so
         };
         int gl = 0;  // layers done so far modulo WRAP, over all board groups (the MMA warp counts the same)
-        load_input(0);
-        store_input(base_row(0));
+        if (!helper) {
+            load_input(0);
+            store_input(base_row(0));
+        }
         if (warp == 0) zero_rows(base_row(0) - 8);
         if (warp == 7) zero_rows(base_row(0) + 256);
         fence_proxy_async();
@@ -1126,7 +1135,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 const bool use_s = l >= 2 && (l & 1) == 0;  // second convolution of a block accumulates onto the parked residual
                 const bool last = l == L - 1;
                 const bool feeds = !last || gi + 1 < my_groups;  // this epilogue writes the next stop of the window (layer or input)
-                if (last && feeds) load_input(gi + 1);
+                if (last && feeds && !helper) load_input(gi + 1);
                 EP(e_work);
                 mbar_wait(bar_acc(a), acc_par);
                 EP(e_wait);
@@ -1152,6 +1161,8 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    // warp 4 and its helper share cells 128..159 by channel halves, except in the last layer (warp 4 alone)
+                    if (helper ? (last || h == 0) : (warp == 4 && !last && h == 1)) continue;
                     uint32_t v[32];
                     {
                         uint32_t v2[32];
@@ -1203,7 +1214,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                         }
                     }
                 }
-                if (last) {
+                if (last && !helper) {
                     if (gi > 0) mbar_wait(bar_hfree, (uint32_t)(gi - 1) & 1u);  // the previous group's heads are done with s_head
                     if (c.real) {
                         float* hb = s_head + c.board * 75;
@@ -1214,7 +1225,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     local_arrive(bar_hfull);
                 }
                 if (preload) tmem_wait_st();
-                if (last && feeds) store_input(rn);
+                if (last && feeds && !helper) store_input(rn);
                 if (feeds) {
                     fence_proxy_async();
                     tc_fence_before();
@@ -1224,11 +1235,11 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
                     if (tid == 224) TL(9);
                     if (tid == 127) TL(10);
                 }
-                if (l == 1 && L >= 3 && gi > 0) run_heads(group_board0(gi - 1), (uint32_t)(gi - 1) & 1u);
+                if (l == 1 && L >= 3 && gi > 0 && !helper) run_heads(group_board0(gi - 1), (uint32_t)(gi - 1) & 1u);
                 acc_par ^= 1u;
                 gl = gl + 1 == GP::WRAP ? 0 : gl + 1;
             }
-            if (L < 3 || gi + 1 == my_groups) run_heads(board0, (uint32_t)gi & 1u);
+            if ((L < 3 || gi + 1 == my_groups) && !helper) run_heads(board0, (uint32_t)gi & 1u);
         }
 #ifdef ONB_X3P_PROFILE
         EP(e_work);
@@ -1267,13 +1278,14 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 1)
 // weight warp, mbarriers only), so an SM always has two MMA streams whose bubbles (the halo dependency between accumulators) fall
 // into each other's issue phases. The epilogue works 16 channels at a time to fit 96 registers (2 x 320 threads per SM).
 // Same products, accumulation order and head sums as k_net_forward<2, f16>: bit-identical results.
+constexpr int kF16PThreads = 10 * 32;  // k_net_forward_f16p: 8 epilogue warps, MMA issue, weights
 __device__ __forceinline__ void store_channels_f16_16(uint32_t s_act, int R, int row, int c0, const float (&o)[16]) {
 #pragma unroll
     for (int i = 0; i < 2; ++i)
         st_shared_v4(act_addr(s_act, R, row, c0 / 8 + i), to_f16x2(o[8 * i + 0], o[8 * i + 1]), to_f16x2(o[8 * i + 2], o[8 * i + 3]),
                      to_f16x2(o[8 * i + 4], o[8 * i + 5]), to_f16x2(o[8 * i + 6], o[8 * i + 7]));
 }
-__global__ void __launch_bounds__(GeoX3P::THREADS, 2)
+__global__ void __launch_bounds__(kF16PThreads, 2)
     k_net_forward_f16p(const float* __restrict__ planes, float* __restrict__ policy, float* __restrict__ value, int64_t n, NetDev net) {
     using G = Geo<2, true, false>;
     using O = Op<true>;
@@ -1309,7 +1321,7 @@ __global__ void __launch_bounds__(GeoX3P::THREADS, 2)
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(smem_u32(s_tmem), G::TMEM_COLS);
-    for (int i = tid; i < G::NMAT * G::ACT_BYTES / 16; i += GeoX3P::THREADS) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero
+    for (int i = tid; i < G::NMAT * G::ACT_BYTES / 16; i += kF16PThreads) st_shared_v4(s_act + i * 16, 0u, 0u, 0u, 0u);  // pad cells stay zero
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -2893,7 +2905,7 @@ static cudaError_t launch_net_f16p(Ctx* c, const float* planes, float* policy, f
         if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     const int64_t groups = (count + G::NB - 1) / G::NB, slots = (int64_t)sms * 2;
-    k_net_forward_f16p<<<(unsigned)(groups < slots ? groups : slots), GeoX3P::THREADS, kSmemF16P, c->stream>>>(planes, policy, value, count, nd);
+    k_net_forward_f16p<<<(unsigned)(groups < slots ? groups : slots), kF16PThreads, kSmemF16P, c->stream>>>(planes, policy, value, count, nd);
     return cudaGetLastError();
 }
 
