@@ -759,16 +759,15 @@ __device__ __forceinline__ void issue_tap_mmas_pair(bool elected, uint32_t dcol,
 // waits, and neither TMEM (512 columns) nor shared memory (219 KB) leaves room for a second CTA to fill the gaps. Here the SAME
 // geometry (7 boards, two 128-row accumulators, a1/a2 activation matrices, 3 x 3-tap weight ring) runs as a pipeline of roles:
 //   warps 0-3 / 4-7  epilogue of accumulator 0 / 1 (one TMEM lane = one cell per thread, all 64 channels)
-//   warp 8           MMA issue (one elected lane): acc 0 of layer l, acc 1 of layer l, acc 0 of layer l + 1, ...
-//   warp 9           weight producer (one lane)
+//   warp 8           helper of warp 4: channels 32..63 of cells 128..159 (the rows the next layer's accumulator 0 waits for)
+//   warp 9           MMA issue (one elected lane): acc 0 of layer l, acc 1 of layer l, acc 0 of layer l + 1, ...
+//   warp 10          weight producer (one lane)
 // all connected by mbarriers (no CTA-wide barrier inside a board group). While accumulator 1's MMAs run, accumulator 0's epilogue
-// runs; accumulator 0's MMAs of the next layer start as soon as its own rows and the first 7 rows of accumulator 1 (the halo its
-// shifted windows reach into) are written, i.e. after warp 4's part of the epilogue, while warps 5-7 are still busy. (Measured with
-// -DONB_X3P_PROFILE, 16 board groups per CTA: MMA issue 971 k cycles, waiting for accumulator 0's rows 350 k, for accumulator 1's
-// 9 k, for weights 46 k. A build with SIXTEEN epilogue warps -- every cell's channels split over two warps, half the instructions on
-// the critical warps -- ran 0.730 ms against 0.724 ms and was dropped: the wait is not the epilogue's instruction count.) In-place
-// activation hazards: rows 121..127 (accumulator 0's last cells) are still read by accumulator 1's MMAs of the same layer, so their
-// owners wait for accumulator 1's commit before storing. Same products, same accumulation order, same results as k_net_forward<2,f16,X3>.
+// runs; accumulator 0's MMAs of the next layer are queued right behind accumulator 1's (the drifting activation window below removes
+// the write-after-read hazard of updating the activations in place) and wait for warp 4's rows only in front of their sixth tap.
+// The history of the kernel -- what a per-layer timeline (-DONB_X3P_PROFILE) showed at each step and what each change bought, from
+// 0.745 ms (plain build) to 0.514 ms -- is in DESIGN.md section 5b. Same products, same accumulation order, same results as
+// k_net_forward<2, f16, X3>.
 template <bool CL>
 struct GeoX3PT {
     using G = Geo<2, true, true>;
@@ -801,9 +800,9 @@ using GeoX3P = GeoX3PT<false>;
 // cores' operand fetch from shared memory (14 KB per K step and SM above); a paired MMA has M = 256 -- each SM contributes its own
 // 128 activation rows and accumulates into its own TMEM -- while the weight rows are SPLIT between the two SMs' shared memories,
 // so that each SM stores and fetches only half of B: 11 KB per step. Every CTA keeps its own 7 boards, epilogue warps, weight
-// producer and weight ring (12 KB per tap: the leader holds b1 and b1[0:32], the peer b2 and b1[32:64]); only the leader's warp 8
+// producer and weight ring (12 KB per tap: the leader holds b1 and b1[0:32], the peer b2 and b1[32:64]); only the leader's MMA warp
 // issues MMAs. Cross-CTA traffic is barrier traffic only: the peer's epilogue threads arrive on the LEADER's rows barriers, the
-// peer's warp 8 relays "my share of slot s has landed" to the leader's peer_full[s], and the leader's commits are multicast to the
+// peer's warp 9 relays "my share of slot s has landed" to the leader's peer_full[s], and the leader's commits are multicast to the
 // accumulator / empty barriers of both CTAs. Same products and accumulation order: results identical to the single-CTA build.
 #ifdef ONB_X3P_PROFILE
 __device__ long long s_tl[8][12];  // timeline of one board group (the 6th) of one CTA: [layer][event], see the printout at the kernel's end
