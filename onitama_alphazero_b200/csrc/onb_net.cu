@@ -192,6 +192,43 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint32_t a_addr, uint32_
             "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
             : "memory");
 }
+// The same MMAs from precomputed descriptor words. The low word of a shared-memory descriptor -- (address >> 4) in 14 bits | the
+// leading-offset field -- is LINEAR in the byte address below 256 KB and the high word is a constant, so an issue loop can keep one
+// low word per operand base and add compile-time offsets (>> 4) instead of rebuilding both descriptors for every instruction: the
+// MMA warp's own instruction stream (not the tensor pipe) was what paced the pipelined kernels, ~ 100 instructions per tap.
+template <bool PAIR, bool F16 = true>
+__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate, uint32_t idesc) {
+    const uint32_t hi = desc_hi(0u);
+    static_assert(ONB_NET_BASEOFF == 0, "the descriptor high word must not depend on the address");
+    static_assert(F16 || !PAIR, "the CTA-pair kernels use f16 operands");
+    if (!F16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else if (PAIR)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
 // all MMAs of one tap: K steps of 32 bytes (4 per 128-byte block) x NACC accumulators of 128 rows
 // X3: per step TWO instructions instead of three: a1 x [b1 ; b2] as ONE N = 128 MMA (the tap's two weight copies are adjacent in
 // the ring, so they are simply 128 consecutive B rows; its 128 result columns are D1 | D2 of the accumulator, which therefore sit
@@ -203,27 +240,29 @@ __device__ __forceinline__ void issue_tap_mmas(bool elected, uint32_t dcol, uint
                                                bool accumulate_first, uint32_t a2_off = 0) {
     using O = Op<F16>;
     constexpr uint32_t ACC_COLS = X3 ? 128u : 64u;  // TMEM columns per accumulator
-#pragma unroll
-    for (int j = 0; j < O::KCH / 2; ++j) {
-        if (j < ksteps) {
-            const uint32_t koff = (uint32_t)(j / 4) * 128u;  // block index * rows * 128 is added per operand below
-            const uint32_t b_addr = b_slot + (uint32_t)(j / 4) * (64u * 128u) + (uint32_t)(j % 4) * 32u;
-#pragma unroll
-            for (int a = 0; a < NACC; ++a) {
-                const uint32_t a_addr = s_act + koff * (uint32_t)R + (uint32_t)(row0 + a * 128) * 128u + (uint32_t)(j % 4) * 32u;
+    // descriptor low words of the tap's operand bases (whole warp: uniform registers); steps, blocks and accumulators add constants
+    const uint32_t a_lo = desc_lo(s_act + (uint32_t)row0 * 128u), b_lo = desc_lo(b_slot), a2_lo = a2_off >> 4;
 #ifndef ONB_NET_DBG_NOMMA
-                if (elected) {
+    if (elected) {
+#pragma unroll
+        for (int j = 0; j < O::KCH / 2; ++j) {
+            if (j < ksteps) {
+                const uint32_t kb = (uint32_t)(j / 4), ks = (uint32_t)(j % 4) * 2u;  // 128-byte block of the row, 32-byte step inside it
+                const uint32_t bj = b_lo + kb * (64u * 128u >> 4) + ks;
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) {
+                    const uint32_t aj = a_lo + kb * (uint32_t)(R * 8) + (uint32_t)(a * 128 * 8) + ks;
                     if (X3) {
-                        mma_ss<F16>(dcol + a * ACC_COLS, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u, O::IDESC_N128);  // a1 b1 | a1 b2
-                        mma_ss<F16>(dcol + a * ACC_COLS + 64u, a_addr + a2_off, b_addr, 1u);                                    // a2 b1 -> D2
+                        mma_lo<false, F16>(dcol + a * ACC_COLS, aj, bj, (accumulate_first || j > 0) ? 1u : 0u, O::IDESC_N128);  // a1 b1 | a1 b2
+                        mma_lo<false, F16>(dcol + a * ACC_COLS + 64u, aj + a2_lo, bj, 1u, O::IDESC);                           // a2 b1 -> D2
                     } else {
-                        mma_ss<F16>(dcol + a * ACC_COLS, a_addr, b_addr, (accumulate_first || j > 0) ? 1u : 0u);
+                        mma_lo<false, F16>(dcol + a * ACC_COLS, aj, bj, (accumulate_first || j > 0) ? 1u : 0u, O::IDESC);
                     }
                 }
-#endif
             }
         }
     }
+#endif
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -704,33 +743,6 @@ __device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint32_t a_addr, ui
         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-// The same MMAs from precomputed descriptor words. The low word of a shared-memory descriptor -- (address >> 4) in 14 bits | the
-// leading-offset field -- is LINEAR in the byte address below 256 KB and the high word is a constant, so an issue loop can keep one
-// low word per operand base and add compile-time offsets (>> 4) instead of rebuilding both descriptors for every instruction: the
-// MMA warp's own instruction stream (not the tensor pipe) was what paced the pipelined kernels, ~ 100 instructions per tap.
-template <bool PAIR>
-__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate, uint32_t idesc) {
-    const uint32_t hi = desc_hi(0u);
-    static_assert(ONB_NET_BASEOFF == 0, "the descriptor high word must not depend on the address");
-    if (PAIR)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "setp.ne.b32 p, %5, 0;\n\t"
-            "mov.b64 da, {%1, %3};\n\t"
-            "mov.b64 db, {%2, %3};\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
-            : "memory");
-    else
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "setp.ne.b32 p, %5, 0;\n\t"
-            "mov.b64 da, {%1, %3};\n\t"
-            "mov.b64 db, {%2, %3};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
-            : "memory");
 }
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on the barrier at this offset in BOTH CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
