@@ -1689,6 +1689,36 @@ def test_network_drifting_window_wraps(onb, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_network_pipelines_match_plain_builds_on_ragged_sizes(onb, monkeypatch):
+    """The shipped role pipelines (CTA pairs: two board groups of 7 / 14 boards per cluster and round) against the plain round-1 builds,
+    bit for bit, on sizes around every grouping boundary: fewer boards than one group, one group and one board, an odd number of
+    groups (the peer CTA of the last pair computes on zeros), more groups than one round of clusters, and 0 / 1 / 3 blocks (0 blocks:
+    the only layer is the last one, heads run at once)."""
+    from test_net_cpu import lively_model
+    knobs = ("ONB_NET_X3_PIPE", "ONB_NET_X3_PAIR", "ONB_NET_X3_HALVES", "ONB_NET_F16_QUAD", "ONB_NET_F16_PIPE")
+    sizes = (1, 6, 7, 8, 13, 14, 15, 27, 28, 29, 43, 148 * 7 + 3, 148 * 14 + 1, 4099)
+    for blocks in (0, 1, 3):
+        model = lively_model(blocks, seed=21 + blocks)
+        for precision, plain_env in (("f32", {"ONB_NET_X3_PIPE": "0"}), ("f16", {"ONB_NET_F16_QUAD": "0"})):
+            for n in sizes:
+                planes = O.encode(_positions(n, 3 + n % 5)).reshape(n, 21, 5, 5)
+                outs = []
+                for env in (plain_env, {}):
+                    for k in knobs:
+                        monkeypatch.delenv(k, raising=False)
+                    for k, v in env.items():
+                        monkeypatch.setenv(k, v)
+                    with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
+                        ctx.net_load(model, precision=precision)
+                        ctx.write(onb.BUF_LEAF_PLANES, planes)
+                        ctx.net_forward(onb.BUF_LEAF_PLANES)
+                        outs.append((ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,))))
+                assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (blocks, precision, n)
+    for k in knobs:
+        monkeypatch.delenv(k, raising=False)
+
+
+@pytest.mark.gpu
 def test_step_fusion_knob_builds_the_same_trees(onb, monkeypatch):
     """ONB_MCTS_STEP_FUSION=1 (expand_backup(s) + select(s+1) in one launch, an exploration knob) must not change a single tree: eval
     and train mode, network evaluator, against the default three-launch rounds."""
