@@ -305,10 +305,14 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ uint32_t to_f16x2(float lo, float hi) {  // post-ReLU values: only the upper end can overflow
-    const __half2 h = __floats2half2_rn(fminf(lo, 65504.f), fminf(hi, 65504.f));
-    return *reinterpret_cast<const uint32_t*>(&h);
+// two f32 -> packed f16, round to nearest, SATURATING at +-65504 in the conversion itself (F2FP.SATFINITE: one instruction where a
+// clamp + convert was three); activations past f16's range saturate instead of becoming inf
+__device__ __forceinline__ uint32_t to_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
+__device__ __forceinline__ float2 f16x2_to_float2(uint32_t h) { return __half22float2(*reinterpret_cast<const __half2*>(&h)); }
 // store 32 consecutive channels [c0, c0 + 32) of one cell as operand chunks
 template <bool F16>
 __device__ __forceinline__ void store_channels(uint32_t s_act, int R, int row, int c0, const float (&o)[32]);
@@ -340,12 +344,10 @@ __device__ __forceinline__ void store_channels_x3(uint32_t s_act, uint32_t a2_of
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float x0 = fminf(o[8 * i + 2 * q], 65504.f), x1 = fminf(o[8 * i + 2 * q + 1], 65504.f);
-            const __half2 h = __floats2half2_rn(x0, x1);
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
-            hi[q] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+            const float x0 = o[8 * i + 2 * q], x1 = o[8 * i + 2 * q + 1];
+            hi[q] = to_f16x2(x0, x1);  // saturating
+            const float2 hf = f16x2_to_float2(hi[q]);
+            lo[q] = to_f16x2((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
         }
         const uint32_t addr = act_addr(s_act, R, row, c0 / 8 + i);
         st_shared_v4(addr, hi[0], hi[1], hi[2], hi[3]);
@@ -356,12 +358,10 @@ __device__ __forceinline__ void store_channels_x3(uint32_t s_act, uint32_t a2_of
 __device__ __forceinline__ void pack_channels_x3(const float (&o)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-        const float x0 = fminf(o[2 * q], 65504.f), x1 = fminf(o[2 * q + 1], 65504.f);
-        const __half2 h = __floats2half2_rn(x0, x1);
-        const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
-        hi[q] = *reinterpret_cast<const uint32_t*>(&h);
-        lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+        const float x0 = o[2 * q], x1 = o[2 * q + 1];
+        hi[q] = to_f16x2(x0, x1);  // saturating
+        const float2 hf = f16x2_to_float2(hi[q]);
+        lo[q] = to_f16x2((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
     }
 }
 __device__ __forceinline__ void store_packed_x3(uint32_t s_act, uint32_t a2_off, int R, int row, int c0, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
@@ -675,12 +675,10 @@ __device__ __forceinline__ void store_channels_x3_16(uint32_t s_act, uint32_t a2
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float x0 = fminf(o[8 * i + 2 * q], 65504.f), x1 = fminf(o[8 * i + 2 * q + 1], 65504.f);
-            const __half2 h = __floats2half2_rn(x0, x1);
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
-            hi[q] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+            const float x0 = o[8 * i + 2 * q], x1 = o[8 * i + 2 * q + 1];
+            hi[q] = to_f16x2(x0, x1);  // saturating
+            const float2 hf = f16x2_to_float2(hi[q]);
+            lo[q] = to_f16x2((x0 - hf.x) * kX3Scale, (x1 - hf.y) * kX3Scale);
         }
         const uint32_t addr = act_addr(s_act, R, row, c0 / 8 + i);
         st_shared_v4(addr, hi[0], hi[1], hi[2], hi[3]);
