@@ -1686,6 +1686,21 @@ def test_network_drifting_window_wraps(onb, monkeypatch):
     assert np.isfinite(outs["plain"][0]).all() and outs["plain"][0].std(0).max() > 1e-4   # the boards still tell apart
     for other in ("pair", "single"):
         assert np.array_equal(outs["plain"][0], outs[other][0]) and np.array_equal(outs["plain"][1], outs[other][1]), other
+    # the f16 pipeline (four accumulators, window wraps after 12 / 8 layers) against the round-1 build
+    f16 = {}
+    for name, env in (("plain", {"ONB_NET_F16_QUAD": "0"}), ("pair", {}), ("single", {"ONB_NET_F16_QUAD": "2"})):
+        for k in ("ONB_NET_X3_PIPE", "ONB_NET_X3_HALVES", "ONB_NET_X3_PAIR", "ONB_NET_F16_QUAD", "ONB_NET_F16_PIPE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with onb.Context(n, mcts_max_sims=2, planes=False) as ctx:
+            ctx.net_load(model, precision="f16")
+            ctx.write(onb.BUF_LEAF_PLANES, planes)
+            ctx.net_forward(onb.BUF_LEAF_PLANES)
+            f16[name] = (ctx.read(onb.BUF_POLICY, np.float32, (n, 50)), ctx.read(onb.BUF_VALUE, np.float32, (n,)))
+    monkeypatch.delenv("ONB_NET_F16_QUAD", raising=False)
+    for other in ("pair", "single"):
+        assert np.array_equal(f16["plain"][0], f16[other][0]) and np.array_equal(f16["plain"][1], f16[other][1]), ("f16", other)
 
 
 @pytest.mark.gpu
